@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""oracle/make_golden.py — TEST INFRASTRUCTURE ONLY.
+
+Mints golden input/output vectors from the UNMODIFIED reference (imported from
+/root/reference via oracle/ref_import.py) and freezes them under tests/golden/.  The
+reference cannot travel to the GPU box, so these fixtures are what the `-m gpu` parity tests
+and the oracle pin (tests/test_oracle_golden.py) compare against.
+
+    python oracle/make_golden.py            # the small cases (seconds each)
+    python oracle/make_golden.py --full     # + full-size BASELINE configs C1..C5 (minutes;
+                                            #   only RTF + hashes + scalars are stored)
+
+Small cases store every array the reference's Numba kernels receive and the
+complex128 RTF that run_DEISM returned.  Full-size cases store the scalars needed to rebuild
+the inputs (room, positions, T60, impedance, wave numbers, seeds), the RTF and SHA-256
+digests of the image lists.
+
+Synthetic directivity coefficients (the real .mat inputs are absent, .MISSING_LARGE_BLOBS):
+rng = default_rng(seed); source drawn first, then receiver; (N(0,1) + i N(0,1)).astype(c64),
+shape [K, N+1, 2N+1]   (SURVEY.md §8d).
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import os
+import sys
+import time
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, _HERE)
+import ref_import  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(_HERE), "tests", "golden")
+
+
+def synth_coeffs(K, N, V, seed=0):
+    rng = np.random.default_rng(seed)
+    cs = (rng.standard_normal((K, N + 1, 2 * N + 1))
+          + 1j * rng.standard_normal((K, N + 1, 2 * N + 1))).astype(np.complex64)
+    cr = (rng.standard_normal((K, V + 1, 2 * V + 1))
+          + 1j * rng.standard_normal((K, V + 1, 2 * V + 1))).astype(np.complex64)
+    return cs, cr
+
+
+def sha(arr) -> str:
+    a = np.ascontiguousarray(arr)
+    return hashlib.sha256(a.tobytes()).hexdigest()
+
+
+def inject_directivities(d, N, V, seed=0):
+    """Replace update_directivities() by synthetic coefficients."""
+    from deism.core_deism import pre_calc_Wigner, vectorize_C_nm_s, vectorize_C_vu_r
+
+    p = d.params
+    K = len(p["waveNumbers"])
+    cs, cr = synth_coeffs(K, N, V, seed)
+    p["sourceOrder"], p["receiverOrder"] = N, V
+    p["C_nm_s"], p["C_vu_r"] = cs, cr
+    if p["DEISM_method"] in ("LC", "MIX"):
+        d.params = vectorize_C_nm_s(d.params)
+        d.params = vectorize_C_vu_r(d.params)
+    if p["DEISM_method"] in ("ORG", "MIX"):
+        d.params = pre_calc_Wigner(d.params)
+
+
+_SCALARS = ["soundSpeed", "reverberationTime", "angDepFlag", "maxReflOrder", "mixEarlyOrder",
+            "ifRemoveDirectPath", "numParaImages", "sourceOrder", "receiverOrder",
+            "sampleRate", "RIRLength"]
+_ARRAYS = ["roomSize", "posSource", "posReceiver", "impedance", "waveNumbers", "freqs",
+           "C_nm_s", "C_vu_r", "C_nm_s_vec", "C_vu_r_vec", "n_all", "m_all", "v_all", "u_all",
+           "vertices", "wallCenters", "C_nm_s_ARG", "C_nm_s_ARG_vec", "reflection_matrix"]
+
+
+def pack(d, extra=None, store_images=True, store_inputs=True):
+    p = d.params
+    out = {"RTF": np.asarray(p["RTF"]), "meta/method": np.array(p["DEISM_method"]),
+           "meta/roomtype": np.array(d.roomtype), "meta/mode": np.array(d.mode)}
+    for key in _SCALARS:
+        if key in p and p[key] is not None:
+            out["params/" + key] = np.asarray(p[key])
+    if store_inputs:
+        for key in _ARRAYS:
+            if key in p and p[key] is not None:
+                out["params/" + key] = np.asarray(p[key])
+        if "Wigner" in p:
+            out["wigner/W_1_all"] = p["Wigner"]["W_1_all"]
+            out["wigner/W_2_all"] = p["Wigner"]["W_2_all"]
+    if "images" in p:
+        for key, val in p["images"].items():
+            if key == "storage":
+                out["images/storage"] = np.array(val)
+            elif store_images:
+                out["images/" + key] = np.asarray(val)
+            else:
+                a = np.asarray(val)
+                out["imagehash/" + key] = np.array(sha(a))
+                out["imageshape/" + key] = np.array(a.shape)
+    if extra:
+        out.update(extra)
+    return out
+
+
+def save(name, blob):
+    os.makedirs(GOLDEN, exist_ok=True)
+    path = os.path.join(GOLDEN, name + ".npz")
+    np.savez_compressed(path, **blob)
+    print(f"  wrote {path}  ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
+# --------------------------------------------------------------------------------------
+# shoebox
+# --------------------------------------------------------------------------------------
+def shoebox_case(name, mode, method, order, N=None, V=None, overrides=None, materials=None,
+                 store_images=True, store_inputs=True, compact=False, seed=0, room=None):
+    t0 = time.time()
+    d = ref_import.make_deism(mode, "shoebox")
+    p = d.params
+    p["DEISM_method"] = method
+    p["maxReflOrder"] = order
+    for key, val in (overrides or {}).items():
+        p[key] = val
+    if room is not None:
+        d.update_room(roomDimensions=np.asarray(room, dtype=float))
+    if compact:
+        p["shoeboxCompactImages"] = True
+    if materials is None:
+        d.update_wall_materials()
+    else:
+        d.update_wall_materials(*materials)
+    d.update_freqs()
+    if N is None:
+        d.update_directivities()
+    else:
+        inject_directivities(d, N, V, seed)
+    t1 = time.time()
+    d.update_source_receiver()
+    t2 = time.time()
+    d.run_DEISM(if_clean_up=False)
+    t3 = time.time()
+    K = len(p["waveNumbers"])
+    im = p["images"]
+    nimg = len(im["A"]) if "A" in im else len(im["A_early"]) + len(im["A_late"])
+    print(f"[{name}] {method} order {order}: I={nimg} K={K} T60={p['reverberationTime']:.6f} "
+          f"images {t2 - t1:.2f}s run {t3 - t2:.2f}s (cold) setup {t1 - t0:.2f}s")
+    extra = {"meta/n_images": np.array(nimg), "meta/seed": np.array(seed),
+             "meta/t_images_s": np.array(t2 - t1), "meta/t_run_cold_s": np.array(t3 - t2)}
+    save(name, pack(d, extra, store_images, store_inputs))
+    return d
+
+
+# --------------------------------------------------------------------------------------
+# convex
+# --------------------------------------------------------------------------------------
+def convex_case(name, mode, method, order, N=None, overrides=None, store_inputs=True,
+                seed=0):
+    ref_import.import_reference()
+    from deism.core_deism import (pre_calc_Wigner, vectorize_C_nm_s_ARG, vectorize_C_vu_r)
+
+    t0 = time.time()
+    d = ref_import.make_deism(mode, "convex")
+    p = d.params
+    p["DEISM_method"] = method
+    p["maxReflOrder"] = order
+    for key, val in (overrides or {}).items():
+        p[key] = val
+    d.update_wall_materials()
+    d.update_freqs()
+    t1 = time.time()
+    d.update_source_receiver()
+    t2 = time.time()
+    if N is None:
+        d.update_directivities()
+    else:
+        # synthetic per-image source coefficients C_nm_s_ARG[K, N+1, 2N+1, I] (cd:1608-1836
+        # needs directivity .mat data that is absent); receiver shared C_vu_r[K, V+1, 2V+1]
+        K = len(p["waveNumbers"])
+        nimg = max(p["images"]["R_sI_r_all"].shape)
+        rng = np.random.default_rng(seed)
+        shp = (K, N + 1, 2 * N + 1, nimg)
+        p["C_nm_s_ARG"] = (rng.standard_normal(shp)
+                           + 1j * rng.standard_normal(shp)).astype(np.complex64)
+        shp = (K, N + 1, 2 * N + 1)
+        p["C_vu_r"] = (rng.standard_normal(shp)
+                       + 1j * rng.standard_normal(shp)).astype(np.complex64)
+        p["sourceOrder"] = p["receiverOrder"] = N
+        if method in ("LC", "MIX"):
+            d.params = vectorize_C_nm_s_ARG(d.params)
+            d.params = vectorize_C_vu_r(d.params)
+        if method in ("ORG", "MIX"):
+            d.params = pre_calc_Wigner(d.params)
+    d.run_DEISM(if_clean_up=False)
+    t3 = time.time()
+    eng = d.room_convex.room_engine
+    walls = d.room_convex.walls
+    extra = {
+        "engine/sources": np.asarray(eng.sources), "engine/orders": np.asarray(eng.orders),
+        "engine/gen_walls": np.asarray(eng.gen_walls),
+        "engine/attenuations": np.asarray(eng.attenuations),
+        "engine/reflection_matrix": np.asarray(eng.reflection_matrix, dtype=np.float32),
+        "engine/visible_mics": np.asarray(eng.visible_mics),
+        "walls/n": np.array(len(walls)),
+        "meta/n_images": np.array(np.asarray(eng.sources).shape[1]),
+        "meta/t_images_s": np.array(t2 - t1), "meta/t_run_cold_s": np.array(t3 - t2),
+    }
+    for i, w in enumerate(walls):
+        lw = w.libroom_walls
+        extra[f"walls/{i}/corners"] = np.asarray(lw.corners, dtype=np.float32)
+        extra[f"walls/{i}/normal"] = np.asarray(lw.normal, dtype=np.float32)
+        extra[f"walls/{i}/origin"] = np.asarray(lw.origin, dtype=np.float32)
+        extra[f"walls/{i}/basis"] = np.asarray(lw.basis, dtype=np.float32)
+        extra[f"walls/{i}/flat_corners"] = np.asarray(lw.flat_corners, dtype=np.float32)
+        extra[f"walls/{i}/reflection_matrix"] = np.asarray(lw.reflection_matrix,
+                                                           dtype=np.float32)
+        extra[f"walls/{i}/impedance"] = np.asarray(w.impedence_bands)
+    K = len(p["waveNumbers"])
+    print(f"[{name}] convex {method} order {order}: I={extra['meta/n_images']} K={K} "
+          f"T60={p['reverberationTime']:.6f} images {t2 - t1:.2f}s run {t3 - t2:.2f}s")
+    save(name, pack(d, extra, True, store_inputs))
+    return d
+
+
+def small_cases():
+    # S1: the reference's own smoke configuration (SURVEY §8c smoke values)
+    shoebox_case("s1_shoebox_rtf_mix_o5_mono", "RTF", "MIX", 5, overrides={"endFreq": 200})
+    # S2: LC, non-monopole, frequency-dependent complex impedance on 3 bands (PCHIP path)
+    Zb = np.array([[18, 20, 8, 5, 30, 19], [12 + 3j, 25 - 2j, 9 + 1j, 6, 28 + 4j, 15 - 1j],
+                   [10, 30, 7, 4, 35, 12]]).T
+    shoebox_case("s2_shoebox_rtf_lc_o6_N3", "RTF", "LC", 6, N=3, V=3,
+                 overrides={"startFreq": 20, "endFreq": 1280, "freqStep": 20},
+                 materials=(Zb, np.array([100.0, 500.0, 1000.0]), "impedance"))
+    # S3: ORG with asymmetric orders (N=3, V=2), angle-dependent beta
+    shoebox_case("s3_shoebox_rtf_org_o4_N3V2", "RTF", "ORG", 4, N=3, V=2,
+                 overrides={"startFreq": 50, "endFreq": 2000, "freqStep": 50})
+    # S4: RIR mode, T60 input (C5-like), MIX with N=V=2, direct path removed, distance cut
+    shoebox_case("s4_shoebox_rir_mix_o9_N2", "RIR", "MIX", 9, N=2, V=2,
+                 overrides={"sampleRate": 1500, "ifRemoveDirectPath": 1},
+                 materials=(0.08, None, "reverberationTime"))
+    # S5: angle-independent beta, LC monopole, odd room
+    shoebox_case("s5_shoebox_rtf_lc_o7_mono_noang", "RTF", "LC", 7,
+                 overrides={"endFreq": 300, "angDepFlag": 0}, room=[5.3, 3.1, 2.7])
+    # S6: compact image storage (beta from f32 angles, pb:140-186)
+    shoebox_case("s6_shoebox_rtf_mix_o5_compact", "RTF", "MIX", 5, N=1, V=1,
+                 overrides={"endFreq": 120}, compact=True)
+    # X1..X3: convex room (shipped ARG RIR yaml, smaller sampling rate)
+    convex_case("x1_convex_rir_mix_o4_mono", "RIR", "MIX", 4, overrides={"sampleRate": 4000})
+    convex_case("x2_convex_rir_lc_o5_N2", "RIR", "LC", 5, N=2, overrides={"sampleRate": 250})
+    convex_case("x3_convex_rir_org_o3_N2", "RIR", "ORG", 3, N=2, overrides={"sampleRate": 500})
+
+
+def full_cases(which):
+    if "c1" in which:
+        shoebox_case("c1_full", "RTF", "MIX", 25, store_images=False, store_inputs=False)
+    if "c2" in which:
+        shoebox_case("c2_full_mono", "RIR", "LC", 20, store_images=False, store_inputs=False,
+                     overrides={"sampleRate": 48000},
+                     materials=(1.0 / 3.0, None, "reverberationTime"))
+        shoebox_case("c2_full_N5", "RIR", "LC", 20, N=5, V=5, store_images=False,
+                     store_inputs=False, overrides={"sampleRate": 48000},
+                     materials=(1.0 / 3.0, None, "reverberationTime"))
+    if "c3" in which:
+        # C3 sub-sampled in frequency: the full image list of the order-25 ORG N=V=10 sum on
+        # every 20th frequency of 2:2:4000 Hz (the full 2000-frequency reference run costs
+        # ~50 CPU-minutes).  Coefficients drawn for K=100.
+        shoebox_case("c3_sub100", "RTF", "ORG", 25, N=10, V=10, store_images=False,
+                     store_inputs=False,
+                     overrides={"startFreq": 40, "endFreq": 4000, "freqStep": 40})
+    if "c4" in which:
+        convex_case("c4_full", "RIR", "MIX", 10, store_inputs=False)
+    if "c5" in which:
+        shoebox_case("c5_full_N5", "RIR", "MIX", 40, N=5, V=5, store_images=False,
+                     store_inputs=False, overrides={"sampleRate": 48000},
+                     materials=(2.0 / 3.0, None, "reverberationTime"))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", nargs="*", default=None,
+                    help="full-size configs to mint (c1 c2 c3 c4 c5); no value = all")
+    ap.add_argument("--skip-small", action="store_true")
+    args = ap.parse_args()
+    if not args.skip_small:
+        small_cases()
+    if args.full is not None:
+        full_cases(args.full or ["c1", "c2", "c3", "c4", "c5"])
