@@ -1,0 +1,331 @@
+"""Host side of the accumulation hot path: the drop-in for the reference's Numba backend.
+
+Mirrors ``deism/parallel_backends.py``:
+
+    run_DEISM(params)      ~ pb:1572 -> run_DEISM_numba      pb:912-922   (shoebox)
+    run_DEISM_ARG(params)  ~ pb:1577 -> run_DEISM_ARG_numba  pb:925-935   (convex)
+
+Same ``params`` keys, same return value (``complex128[K]``), same error behaviour
+(``ValueError`` for an unknown ``DEISM_method``; zero images -> zeros).  The work is done by
+the sm_100a kernels of ``libdeism_b200.so`` through its C ABI; PyTorch is only the carrier of
+device memory and streams.  NumPy inputs are staged host->device here and the result is read
+back, so a call is end-to-end comparable with the reference's.
+
+``params["images"]`` may be
+  * the reference's own dict with a materialised ``atten_all*`` (complex64[I,K]) — streamed to
+    the GPU in image batches (reference layout, 8 B/term of PCIe+HBM traffic);
+  * the reference's "compact" dict (no ``atten_all*``, ``storage == "compact"``) — attenuation
+    rebuilt in-kernel from the f32 angles (numerics of pb:140-186);
+  * this package's dict (``storage == "fused"``, deism_b200.images) — attenuation fused
+    in-kernel from A + room geometry with the complex64 rounding of the default reference
+    storage reproduced (numerics of cd:2847-2928).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (ATTEN_C64, ATTEN_C128, ATTEN_FUSED_ANGLES, ATTEN_FUSED_ROOM, ShoeboxAtten,
+                   check, lib)
+
+# Device bytes a streamed batch of materialised attenuation may take (pb:34-35 uses 256 MB of
+# host temporaries; HBM affords more).
+ATTEN_BATCH_BYTES = 1 << 30
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("deism_b200 needs a CUDA (sm_100) device; there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def to_device(x, dtype, dev=None):
+    """NumPy / torch (host or device) -> contiguous device tensor of ``dtype``."""
+    dev = dev or _device()
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        a = np.asarray(x)
+        if not a.flags["C_CONTIGUOUS"] or not a.flags["ALIGNED"]:
+            a = np.ascontiguousarray(a)
+        if not a.flags["WRITEABLE"]:
+            a = a.copy()
+        t = torch.from_numpy(a)
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.to(dev, non_blocking=True).contiguous()
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _host_i64(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.int64))
+
+
+def _vec3(x):
+    a = np.asarray(x, dtype=np.float64).reshape(3)
+    return (C.c_double * 3)(float(a[0]), float(a[1]), float(a[2]))
+
+
+def _c64_on_device(x, dev):
+    """Directivity coefficients travel as complex64 — the reference stores them as complex64
+    (cd:1184,1236,1258,1329) and only up-casts inside the kernels (pb:556-557)."""
+    if isinstance(x, torch.Tensor):
+        if x.dtype == torch.complex128:
+            raise NotImplementedError("complex128 directivity coefficients are not supported; the "
+                                      "reference stores complex64 (core_deism.py:1184)")
+        return to_device(x, torch.complex64, dev)
+    a = np.asarray(x)
+    if a.dtype != np.complex64:
+        a64 = a.astype(np.complex64)
+        if not np.array_equal(a64.astype(np.complex128), a.astype(np.complex128)):
+            raise NotImplementedError("directivity coefficients must be complex64-representable "
+                                      "(core_deism.py:1184)")
+        a = a64
+    return to_device(a, torch.complex64, dev)
+
+
+class _AttenSpec:
+    """Builds struct deism_shoebox_atten and keeps the device tensors it points at alive."""
+
+    def __init__(self, params, images, suffix, dev, lo=None, hi=None):
+        self.keep = []
+        s = ShoeboxAtten()
+        s.ang_dep_flag = int(params["angDepFlag"])
+        atten = images.get("atten_all" + suffix)
+        storage = images.get("storage")
+        sl = slice(lo, hi)
+        if atten is not None:
+            n_img = len(images["A" + suffix])
+            a = atten
+            if not isinstance(a, torch.Tensor):
+                a = np.atleast_2d(np.asarray(a))           # pb:525-529
+                if a.shape[0] != n_img and a.shape[1] == n_img:
+                    a = a.T
+            a = a[sl]
+            is128 = (a.dtype == torch.complex128) if isinstance(a, torch.Tensor) \
+                else (a.dtype == np.complex128)
+            t = to_device(a, torch.complex128 if is128 else torch.complex64, dev)
+            s.mode = ATTEN_C128 if is128 else ATTEN_C64
+            s.d_atten = t.data_ptr()
+            self.keep.append(t)
+        else:
+            if storage == "compact":
+                s.mode = ATTEN_FUSED_ANGLES
+            elif storage == "fused":
+                s.mode = ATTEN_FUSED_ROOM
+            else:
+                raise KeyError(f"images has no 'atten_all{suffix}' and storage={storage!r}")
+            A = to_device(images["A" + suffix][sl], torch.int32, dev)
+            Z = to_device(np.asarray(params["impedance"], dtype=np.complex128)
+                          if not isinstance(params["impedance"], torch.Tensor)
+                          else params["impedance"], torch.complex128, dev)
+            if Z.dim() != 2 or Z.shape[0] != 6:
+                raise ValueError("params['impedance'] must have shape [6, K]")
+            s.d_A, s.d_Z_S = A.data_ptr(), Z.data_ptr()
+            self.keep += [A, Z]
+            if s.mode == ATTEN_FUSED_ANGLES:
+                R = to_device(images["R_sI_r_all" + suffix][sl], torch.float32, dev)
+                s.d_R_sI_r = R.data_ptr()
+                self.keep.append(R)
+            s.room_size = _vec3(params["roomSize"])
+            s.pos_source = _vec3(params["posSource"])
+            s.pos_receiver = _vec3(params["posReceiver"])
+        self.struct = s
+
+    def ref(self):
+        return C.byref(self.struct)
+
+
+def _image_batches(params, images, suffix, n_images, K):
+    """Image ranges per kernel call: everything at once when the attenuation is fused, bounded
+    slabs when a materialised atten[I,K] has to be streamed to the device (pb:471-522)."""
+    atten = images.get("atten_all" + suffix)
+    if atten is None or isinstance(atten, torch.Tensor) and atten.is_cuda:
+        return [(0, n_images)]
+    per_image = K * 16
+    step = max(1, ATTEN_BATCH_BYTES // per_image)
+    return [(s, min(s + step, n_images)) for s in range(0, n_images, step)]
+
+
+def _run_lc(params, images, suffix, out, accumulate, dev):
+    """pb:594-654 _run_numba_lc_matrix_in_batches."""
+    Rs_all = images["R_s_rI_all" + suffix]
+    n_images = int(Rs_all.shape[0])
+    k = to_device(params["waveNumbers"], torch.float64, dev)
+    K = int(k.shape[0])
+    if n_images == 0:
+        if not accumulate:
+            out.zero_()
+        return
+    n_all, m_all = _host_i64(params["n_all"]), _host_i64(params["m_all"])
+    v_all, u_all = _host_i64(params["v_all"]), _host_i64(params["u_all"])
+    Cs = _c64_on_device(params["C_nm_s_vec"], dev)
+    Cr = _c64_on_device(params["C_vu_r_vec"], dev)
+    if Cs.shape != (K, n_all.shape[0]) or Cr.shape != (K, v_all.shape[0]):
+        raise ValueError("C_nm_s_vec / C_vu_r_vec must be [K, (N+1)^2] / [K, (V+1)^2]")
+    for lo, hi in _image_batches(params, images, suffix, n_images, K):
+        Rs = to_device(Rs_all[lo:hi], torch.float32, dev)
+        Rr = to_device(images["R_r_sI_all" + suffix][lo:hi], torch.float32, dev)
+        spec = _AttenSpec(params, images, suffix, dev, lo, hi)
+        rc = lib().deism_lc_shoebox(
+            hi - lo, K, int(n_all.shape[0]), int(v_all.shape[0]),
+            n_all.ctypes.data, m_all.ctypes.data, v_all.ctypes.data, u_all.ctypes.data,
+            _ptr(Cs), _ptr(Cr), _ptr(Rs), _ptr(Rr), spec.ref(), _ptr(k), _ptr(out),
+            1 if (accumulate or lo > 0) else 0, _stream_ptr())
+        check(rc, "deism_lc_shoebox")
+        del spec, Rs, Rr
+
+
+def _wigner_host(Wigner):
+    W1 = np.ascontiguousarray(np.asarray(Wigner["W_1_all"]).astype(np.complex64))
+    W2 = np.ascontiguousarray(np.asarray(Wigner["W_2_all"]).astype(np.complex64))
+    return W1, W2
+
+
+def _run_org(params, images, suffix, out, accumulate, dev):
+    """pb:543-591 _run_numba_org_in_batches."""
+    A_all = images["A" + suffix]
+    n_images = len(A_all)
+    k = to_device(params["waveNumbers"], torch.float64, dev)
+    K = int(k.shape[0])
+    if n_images == 0:
+        if not accumulate:
+            out.zero_()
+        return
+    N, V = int(params["sourceOrder"]), int(params["receiverOrder"])
+    Cs = _c64_on_device(params["C_nm_s"], dev)
+    Cr = _c64_on_device(params["C_vu_r"], dev)
+    if tuple(Cs.shape) != (K, N + 1, 2 * N + 1) or tuple(Cr.shape) != (K, V + 1, 2 * V + 1):
+        raise ValueError("C_nm_s / C_vu_r must be [K, N+1, 2N+1] / [K, V+1, 2V+1]")
+    W1, W2 = _wigner_host(params["Wigner"])
+    if W2.shape != (N + 1, V + 1, N + V + 1, 2 * N + 1, 2 * V + 1):
+        raise ValueError("Wigner tables do not match sourceOrder/receiverOrder")
+    algo = int(params.get("b200OrgAlgo", 0))
+    for lo, hi in _image_batches(params, images, suffix, n_images, K):
+        A = to_device(A_all[lo:hi], torch.int32, dev)
+        R = to_device(images["R_sI_r_all" + suffix][lo:hi], torch.float32, dev)
+        spec = _AttenSpec(params, images, suffix, dev, lo, hi)
+        rc = lib().deism_org_shoebox(
+            hi - lo, K, N, V, _ptr(Cs), _ptr(Cr), W1.ctypes.data, W2.ctypes.data, _ptr(A),
+            _ptr(R), spec.ref(), _ptr(k), _ptr(out), 1 if (accumulate or lo > 0) else 0, algo,
+            _stream_ptr())
+        check(rc, "deism_org_shoebox")
+        del spec, A, R
+
+
+def run_DEISM_device(params, dev=None):
+    """As run_DEISM but returns the complex128[K] result as a device tensor (no read-back)."""
+    dev = dev or _device()
+    method = params["DEISM_method"]
+    images = params["images"]
+    K = int(np.asarray(params["waveNumbers"]).shape[0]) \
+        if not isinstance(params["waveNumbers"], torch.Tensor) else int(params["waveNumbers"].shape[0])
+    out = torch.zeros(K, dtype=torch.complex128, device=dev)
+    if method == "ORG":
+        _run_org(params, images, "", out, False, dev)
+    elif method == "LC":
+        _run_lc(params, images, "", out, False, dev)
+    elif method == "MIX":
+        # pb:725-777: early images -> ORG, late images -> LC, results added
+        _run_org(params, images, "_early", out, False, dev)
+        _run_lc(params, images, "_late", out, True, dev)
+    else:
+        raise ValueError(f"Unknown DEISM method: {method}")
+    return out
+
+
+def run_DEISM(params):
+    """Drop-in for deism.parallel_backends.run_DEISM (pb:1572): complex128[K] NumPy array."""
+    return run_DEISM_device(params).cpu().numpy()
+
+
+# --------------------------------------------------------------------------------------
+# convex (DEISM-ARG)
+# --------------------------------------------------------------------------------------
+def _arg_common(params, dev):
+    images = params["images"]
+    R = to_device(images["R_sI_r_all"], torch.float32, dev)
+    if R.dim() != 2 or R.shape[0] != 3:
+        raise ValueError("images['R_sI_r_all'] must be [3, I]")
+    att = images["atten_all"]
+    att = to_device(att, torch.complex64, dev)
+    k = to_device(params["waveNumbers"], torch.float64, dev)
+    return images, R, att, k
+
+
+def _idx(sel):
+    if sel is None:
+        return None, 0, C.c_void_p(0)
+    a = _host_i64(sel)
+    return a, int(a.shape[0]), C.c_void_p(a.ctypes.data)
+
+
+def _run_arg_lc(params, out, accumulate, dev, sel=None):
+    images, R, att, k = _arg_common(params, dev)
+    K, n_images = int(k.shape[0]), int(R.shape[1])
+    n_all, m_all = _host_i64(params["n_all"]), _host_i64(params["m_all"])
+    v_all, u_all = _host_i64(params["v_all"]), _host_i64(params["u_all"])
+    Cs = _c64_on_device(params["C_nm_s_ARG_vec"], dev)
+    Cr = _c64_on_device(params["C_vu_r_vec"], dev)
+    if tuple(Cs.shape) != (K, n_all.shape[0], n_images):
+        raise ValueError("C_nm_s_ARG_vec must be [K, (N+1)^2, I]")
+    keep, n_sel, p_sel = _idx(sel)
+    rc = lib().deism_lc_arg(n_images, K, int(n_all.shape[0]), int(v_all.shape[0]),
+                            n_all.ctypes.data, m_all.ctypes.data, v_all.ctypes.data,
+                            u_all.ctypes.data, _ptr(Cs), _ptr(Cr), _ptr(R), _ptr(att), _ptr(k),
+                            p_sel, n_sel, _ptr(out), 1 if accumulate else 0, _stream_ptr())
+    check(rc, "deism_lc_arg")
+    del keep
+
+
+def _run_arg_org(params, out, accumulate, dev, sel=None):
+    images, R, att, k = _arg_common(params, dev)
+    K, n_images = int(k.shape[0]), int(R.shape[1])
+    N, V = int(params["sourceOrder"]), int(params["receiverOrder"])
+    Cs = _c64_on_device(params["C_nm_s_ARG"], dev)
+    Cr = _c64_on_device(params["C_vu_r"], dev)
+    if tuple(Cs.shape) != (K, N + 1, 2 * N + 1, n_images):
+        raise ValueError("C_nm_s_ARG must be [K, N+1, 2N+1, I]")
+    W1, W2 = _wigner_host(params["Wigner"])
+    keep, n_sel, p_sel = _idx(sel)
+    rc = lib().deism_org_arg(n_images, K, N, V, _ptr(Cs), _ptr(Cr), W1.ctypes.data, W2.ctypes.data,
+                             _ptr(R), _ptr(att), _ptr(k), p_sel, n_sel, _ptr(out),
+                             1 if accumulate else 0, _stream_ptr())
+    check(rc, "deism_org_arg")
+    del keep
+
+
+def run_DEISM_ARG_device(params, dev=None):
+    dev = dev or _device()
+    method = params["DEISM_method"]
+    K = int(np.asarray(params["waveNumbers"]).shape[0])
+    out = torch.zeros(K, dtype=torch.complex128, device=dev)
+    if method == "LC":
+        _run_arg_lc(params, out, False, dev)
+    elif method == "ORG":
+        _run_arg_org(params, out, False, dev)
+    elif method == "MIX":
+        im = params["images"]
+        early, late = im["early_indices"], im["late_indices"]
+        if len(early) > 0:
+            _run_arg_org(params, out, False, dev, early)
+        if len(late) > 0:
+            _run_arg_lc(params, out, True, dev, late)
+    else:
+        raise ValueError(f"Unknown DEISM method: {method}")
+    return out
+
+
+def run_DEISM_ARG(params):
+    """Drop-in for deism.parallel_backends.run_DEISM_ARG (pb:1577)."""
+    return run_DEISM_ARG_device(params).cpu().numpy()

@@ -1,0 +1,223 @@
+// api.cu — library plumbing of libdeism_b200: error reporting, device checks, cached device
+// scratch, launch counting and the FP64 roofline micro-benchmarks (DFMA / DMMA).
+#include <mutex>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace deism {
+
+static thread_local char g_err[512] = "";
+static uint64_t g_launches = 0;
+static std::mutex g_mu;
+
+int set_error(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+void count_launch(int n) { __atomic_add_fetch(&g_launches, (uint64_t)n, __ATOMIC_RELAXED); }
+
+struct DeviceState {
+    bool checked = false;
+    bool ok = false;
+    int sms = 0;
+    void *ws[WS_NSLOTS] = {};
+    size_t ws_bytes[WS_NSLOTS] = {};
+};
+static DeviceState g_dev[64];
+
+static DeviceState *state() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    return &g_dev[dev];
+}
+
+int check_device() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess)
+        return set_error(DEISM_ERR_CUDA, "no CUDA device: %s (there is no CPU fallback)",
+                         cudaGetErrorString(e));
+    if (dev < 0 || dev >= 64) return set_error(DEISM_ERR_CUDA, "device index %d unsupported", dev);
+    DeviceState &s = g_dev[dev];
+    if (!s.checked) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        cudaDeviceProp p;
+        e = cudaGetDeviceProperties(&p, dev);
+        if (e != cudaSuccess)
+            return set_error(DEISM_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+        s.ok = (p.major == 10);
+        s.sms = p.multiProcessorCount;
+        s.checked = true;
+        if (!s.ok)
+            return set_error(DEISM_ERR_CUDA,
+                             "device %d is sm_%d%d; libdeism_b200 carries sm_100a code only", dev,
+                             p.major, p.minor);
+    }
+    if (!s.ok) return set_error(DEISM_ERR_CUDA, "device %d is not sm_100", dev);
+    return DEISM_OK;
+}
+
+int sm_count() {
+    DeviceState *s = state();
+    return (s && s->sms > 0) ? s->sms : 148;
+}
+
+void *workspace(int slot, size_t bytes) {
+    DeviceState *s = state();
+    if (!s || slot < 0 || slot >= WS_NSLOTS) {
+        set_error(DEISM_ERR_INVALID, "bad workspace slot %d", slot);
+        return nullptr;
+    }
+    if (bytes < 256) bytes = 256;
+    if (s->ws_bytes[slot] >= bytes) return s->ws[slot];
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (s->ws[slot]) {
+        cudaFree(s->ws[slot]);   // synchronises: no kernel still reads the old buffer
+        s->ws[slot] = nullptr;
+        s->ws_bytes[slot] = 0;
+    }
+    size_t want = bytes + bytes / 4;   // head-room so that growing inputs do not thrash
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMalloc(&p, bytes);
+        want = bytes;
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error(DEISM_ERR_NOMEM, "cudaMalloc(%zu bytes) for scratch slot %d failed: %s", bytes, slot,
+                  cudaGetErrorString(e));
+        return nullptr;
+    }
+    s->ws[slot] = p;
+    s->ws_bytes[slot] = want;
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------
+// FP64 roofline micro-benchmarks.  MEASURED_PEAKS.json carries HBM and bf16 numbers only; the
+// kernels of this library are bound by the FP64 FMA pipe, so bench.py measures that pipe.
+// ---------------------------------------------------------------------------------------
+constexpr int PEAK_THREADS = 256;
+constexpr int PEAK_ILP = 8;
+
+__global__ void __launch_bounds__(PEAK_THREADS)
+dfma_peak_kernel(int iters, double seed, double *sink) {
+    double a[PEAK_ILP], b = 1.0000001 + seed, c = 1e-9 + seed;
+#pragma unroll
+    for (int i = 0; i < PEAK_ILP; ++i) a[i] = seed + i + threadIdx.x * 1e-3;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int i = 0; i < PEAK_ILP; ++i) a[i] = fma(a[i], b, c);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < PEAK_ILP; ++i) s += a[i];
+    if (s == 123.456) sink[0] = s;   // never true; keeps the loop alive
+}
+
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(PEAK_THREADS)
+dmma_peak_kernel(int iters, double seed, double *sink) {
+    double d[PEAK_ILP][2];
+    double a = 1e-3 * (threadIdx.x & 31) + seed, b = 1e-3 + seed;
+#pragma unroll
+    for (int i = 0; i < PEAK_ILP; ++i) { d[i][0] = seed + i; d[i][1] = seed - i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < PEAK_ILP; ++i) dmma_m8n8k4(d[i][0], d[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < PEAK_ILP; ++i) s += d[i][0] + d[i][1];
+    if (s == 123.456) sink[0] = s;
+}
+
+}  // namespace deism
+
+using namespace deism;
+
+extern "C" int deism_b200_version(void) { return 100; }   // 0.1.0
+
+extern "C" const char *deism_last_error(void) { return g_err; }
+
+extern "C" uint64_t deism_kernel_launch_count(void) {
+    return __atomic_load_n(&g_launches, __ATOMIC_RELAXED);
+}
+
+extern "C" int deism_device_info(int device, int *sm_count_out, size_t *hbm_bytes, int *cc_major,
+                                 int *cc_minor) {
+    int dev = device;
+    if (dev < 0) DEISM_CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    DEISM_CUDA_TRY(cudaGetDeviceProperties(&p, dev));
+    if (sm_count_out) *sm_count_out = p.multiProcessorCount;
+    if (hbm_bytes) *hbm_bytes = p.totalGlobalMem;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return DEISM_OK;
+}
+
+extern "C" int deism_release_workspace(void) {
+    DeviceState *s = state();
+    if (!s) return set_error(DEISM_ERR_CUDA, "no current device");
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (int i = 0; i < WS_NSLOTS; ++i) {
+        if (s->ws[i]) cudaFree(s->ws[i]);
+        s->ws[i] = nullptr;
+        s->ws_bytes[i] = 0;
+    }
+    return DEISM_OK;
+}
+
+extern "C" int deism_fp64_peak(int kind, int iters, double *tflops, double *ms_out) {
+    int rc = check_device();
+    if (rc) return rc;
+    if (iters <= 0) iters = 2000;
+    double *sink = (double *)workspace(WS_BENCH, 256);
+    if (!sink) return DEISM_ERR_NOMEM;
+    int blocks = sm_count() * 8;
+    cudaEvent_t e0, e1;
+    DEISM_CUDA_TRY(cudaEventCreate(&e0));
+    DEISM_CUDA_TRY(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {   // first rep is the warm-up
+        DEISM_CUDA_TRY(cudaEventRecord(e0, 0));
+        if (kind == 0)
+            dfma_peak_kernel<<<blocks, PEAK_THREADS>>>(iters, 0.0, sink);
+        else
+            dmma_peak_kernel<<<blocks, PEAK_THREADS>>>(iters, 0.0, sink);
+        DEISM_LAUNCH_CHECK("fp64_peak_kernel");
+        DEISM_CUDA_TRY(cudaEventRecord(e1, 0));
+        DEISM_CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        DEISM_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    double fmas;
+    if (kind == 0)
+        fmas = (double)blocks * PEAK_THREADS * (double)iters * 8.0 * PEAK_ILP;
+    else   // one m8n8k4 = 8*8*4 FMAs per warp
+        fmas = (double)blocks * (PEAK_THREADS / 32) * (double)iters * 4.0 * PEAK_ILP * 256.0;
+    if (tflops) *tflops = 2.0 * fmas / ((double)best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return DEISM_OK;
+}

@@ -1,0 +1,240 @@
+// common.cuh — shared device/host helpers of libdeism_b200 (sm_100a only).
+//
+// Device math here restates the scalar helpers of the reference's Numba backend
+// (deism/parallel_backends.py, "pb"): _sph_harm_numba pb:40-83, _sphankel2_numba pb:86-118,
+// _shoebox_ref_coef_from_cos_numba pb:121, _shoebox_complex_pow_int_numba pb:125.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/deism_b200.h"
+
+namespace deism {
+
+// ---------------------------------------------------------------------------------------
+// host-side error / bookkeeping (api.cu)
+// ---------------------------------------------------------------------------------------
+int set_error(int code, const char *fmt, ...);
+void count_launch(int n = 1);
+int check_device();                       // DEISM_OK iff current device is sm_100
+void *workspace(int slot, size_t bytes);  // cached device scratch; nullptr on failure
+int sm_count();
+
+enum WsSlot {
+    WS_LC_IMG = 0, WS_LC_YS, WS_LC_YR, WS_PARTIAL, WS_FLAGS, WS_SMALL, WS_ORG_B, WS_ORG_IMG,
+    WS_ORG_Y, WS_ORG_LIST, WS_ARG_IDX, WS_CONVEX_A, WS_CONVEX_B, WS_CONVEX_C, WS_CONVEX_D,
+    WS_CONVEX_E, WS_BENCH, WS_NSLOTS
+};
+
+#define DEISM_CUDA_TRY(expr)                                                                  \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return deism::set_error(DEISM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,           \
+                                    cudaGetErrorString(_e), __FILE__, __LINE__);              \
+    } while (0)
+
+#define DEISM_LAUNCH_CHECK(name)                                                              \
+    do {                                                                                      \
+        deism::count_launch();                                                                \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess)                                                                \
+            return deism::set_error(DEISM_ERR_CUDA, "launch of %s failed: %s", name,          \
+                                    cudaGetErrorString(_e));                                  \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// complex128 as double2
+// ---------------------------------------------------------------------------------------
+typedef double2 cplx;
+
+__host__ __device__ __forceinline__ cplx cmake(double re, double im) { return make_double2(re, im); }
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return cmake(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+    return cmake(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ cplx cscale(cplx a, double s) { return cmake(a.x * s, a.y * s); }
+__device__ __forceinline__ cplx cconj(cplx a) { return cmake(a.x, -a.y); }
+// acc += a*b  (4 DFMA)
+__device__ __forceinline__ void cfma(cplx &acc, cplx a, cplx b) {
+    acc.x = fma(a.x, b.x, acc.x);
+    acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y);
+    acc.y = fma(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
+    double inv = 1.0 / fma(b.x, b.x, b.y * b.y);
+    return cmake(fma(a.x, b.x, a.y * b.y) * inv, fma(a.y, b.x, -a.x * b.y) * inv);
+}
+// multiply by i^n
+__device__ __forceinline__ cplx cmul_ipow(cplx a, int n) {
+    switch (n & 3) {
+    case 0: return a;
+    case 1: return cmake(-a.y, a.x);
+    case 2: return cmake(-a.x, -a.y);
+    default: return cmake(a.y, -a.x);
+    }
+}
+// round to complex64 and back (the reference's Q2 quantisation point, cd:2921-2928)
+__device__ __forceinline__ cplx round_c64(cplx a) {
+    return cmake((double)__double2float_rn(a.x), (double)__double2float_rn(a.y));
+}
+
+// ---------------------------------------------------------------------------------------
+// sincos with a 3-term Cody-Waite reduction (exactly-rounded differences via FMA) and the
+// fdlibm minimax kernels; |error| < 2 ulp for |x| < 2^30.  CUDA's own sincos() drops into a
+// slow Payne-Hanek path above |x| = 105615, which k*r reaches (k up to 440 rad/m, r to 350 m).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void sincos_cw(double x, double *sp, double *cp) {
+    double q = rint(x * 0.6366197723675814);
+    int n = (int)q;
+    double r = fma(-q, 1.5707963267948966, x);
+    r = fma(-q, 6.123233995736766e-17, r);
+    r = fma(-q, -1.4973849048591698e-33, r);
+    double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    double s = fma(z * r, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    double c = fma(z * z, pc, fma(z, -0.5, 1.0));
+    if (n & 1) { double t = s; s = c; c = -t; }
+    if (n & 2) { s = -s; c = -c; }
+    *sp = s;
+    *cp = c;
+}
+
+// ---------------------------------------------------------------------------------------
+// pb:40-83  Y_n^m(theta = polar, phi = azimuth), scipy convention.
+// ct = cos(theta); (sphi_m, cphi_m) supplied by the caller would save work, but n <= ~10 and
+// this runs once per image, never per term.
+// ---------------------------------------------------------------------------------------
+__device__ inline cplx sph_harm_dev(int m, int n, double phi, double ct) {
+    int am = m < 0 ? -m : m;
+    double pmm = 1.0;
+    if (am > 0) {
+        double somx2 = sqrt(fma(-ct, ct, 1.0));
+        double fact = 1.0;
+        for (int i = 1; i <= am; ++i) {
+            pmm *= -fact * somx2;
+            fact += 2.0;
+        }
+    }
+    double p_val;
+    if (n == am) {
+        p_val = pmm;
+    } else {
+        double pmm1 = ct * (double)(2 * am + 1) * pmm;
+        for (int ll = am + 2; ll <= n; ++ll) {
+            double pll = (ct * (double)(2 * ll - 1) * pmm1 - (double)(ll + am - 1) * pmm) /
+                         (double)(ll - am);
+            pmm = pmm1;
+            pmm1 = pll;
+        }
+        p_val = pmm1;
+    }
+    double ratio = 1.0;
+    for (int i = n - am + 1; i <= n + am; ++i) ratio *= (double)i;
+    double norm = sqrt((double)(2 * n + 1) / (4.0 * 3.14159265358979323846) / ratio);
+    double s, c;
+    sincos_cw((double)am * phi, &s, &c);
+    double np_ = norm * p_val;
+    cplx pos = cmake(np_ * c, np_ * s);
+    if (m < 0) {
+        double sign = (am & 1) ? -1.0 : 1.0;
+        return cmake(sign * pos.x, -sign * pos.y);
+    }
+    return pos;
+}
+
+// ---------------------------------------------------------------------------------------
+// Shoebox wall reflection factor (pb:121 / cd:2635) and its integer power (pb:125 / cd:2641;
+// the reference multiplies `e` times, here by squaring: identical to ~e*1e-16 relative, far
+// below the 6e-8 complex64 rounding step that follows — see DESIGN.md "quantisation").
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ cplx ref_coef(double cos_t, cplx zeta) {
+    double zr = zeta.x * cos_t, zi = zeta.y * cos_t;
+    return cdiv(cmake(zr - 1.0, zi), cmake(zr + 1.0, zi));
+}
+__device__ __forceinline__ cplx cpow_uint(cplx base, unsigned e) {
+    cplx out = cmake(1.0, 0.0);
+    while (e) {
+        if (e & 1u) out = cmul(out, base);
+        e >>= 1;
+        if (e) base = cmul(base, base);
+    }
+    return out;
+}
+// atten = bx1^e0 * bx2^e1 * by1^e2 * by2^e3 * bz1^e4 * bz2^e5   (cd:2921-2928)
+// Z points at Z_S[0][k]; zstride = K (row stride in complex elements).
+__device__ __forceinline__ cplx shoebox_atten(const cplx *__restrict__ Z, long zstride, double cx,
+                                              double cy, double cz, const unsigned char *e) {
+    cplx a = cpow_uint(ref_coef(cx, Z[0]), e[0]);
+    a = cmul(a, cpow_uint(ref_coef(cx, Z[zstride]), e[1]));
+    a = cmul(a, cpow_uint(ref_coef(cy, Z[2 * zstride]), e[2]));
+    a = cmul(a, cpow_uint(ref_coef(cy, Z[3 * zstride]), e[3]));
+    a = cmul(a, cpow_uint(ref_coef(cz, Z[4 * zstride]), e[4]));
+    a = cmul(a, cpow_uint(ref_coef(cz, Z[5 * zstride]), e[5]));
+    return a;
+}
+
+// Per-image attenuation geometry shared by images.cu / lc.cu / org.cu
+struct AttenGeom {
+    double cx, cy, cz;
+    unsigned char e[8];  // e[0..5] exponents; e[6], e[7] padding
+};
+
+// Direction cosines exactly as the reference fill computes them (cd:2804-2851): FP64, no FMA
+// contraction (Numba/LLVM does not contract), from A and the room geometry.
+__device__ __forceinline__ void atten_geom_room(const int32_t *A6, const double *LL, const double *xs,
+                                                const double *xr, int angdep, AttenGeom &g) {
+    int qx = A6[0], qy = A6[1], qz = A6[2], px = A6[3], py = A6[4], pz = A6[5];
+    g.e[0] = (unsigned char)abs(qx - px); g.e[1] = (unsigned char)abs(qx);
+    g.e[2] = (unsigned char)abs(qy - py); g.e[3] = (unsigned char)abs(qy);
+    g.e[4] = (unsigned char)abs(qz - pz); g.e[5] = (unsigned char)abs(qz);
+    g.e[6] = g.e[7] = 0;
+    if (angdep != 1) { g.cx = g.cy = g.cz = 1.0; return; }
+    double sox = __dsub_rn(xs[0], __dmul_rn((double)(2 * px), xs[0]));
+    double soy = __dsub_rn(xs[1], __dmul_rn((double)(2 * py), xs[1]));
+    double soz = __dsub_rn(xs[2], __dmul_rn((double)(2 * pz), xs[2]));
+    double Isx = __dadd_rn(__dmul_rn((double)(2 * qx), LL[0]), sox);
+    double Isy = __dadd_rn(__dmul_rn((double)(2 * qy), LL[1]), soy);
+    double Isz = __dadd_rn(__dmul_rn((double)(2 * qz), LL[2]), soz);
+    double dx = __dsub_rn(Isx, xr[0]), dy = __dsub_rn(Isy, xr[1]), dz = __dsub_rn(Isz, xr[2]);
+    double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    double rn = __dsqrt_rn(d2);
+    g.cx = __ddiv_rn(fabs(__dsub_rn(xr[0], Isx)), rn);
+    g.cy = __ddiv_rn(fabs(__dsub_rn(xr[1], Isy)), rn);
+    g.cz = __ddiv_rn(fabs(__dsub_rn(xr[2], Isz)), rn);
+}
+// Compact-storage variant (pb:131-137): cosines from the f32-rounded angles.
+__device__ __forceinline__ void atten_geom_angles(const int32_t *A6, const float *R3, int angdep,
+                                                  AttenGeom &g) {
+    int qx = A6[0], qy = A6[1], qz = A6[2], px = A6[3], py = A6[4], pz = A6[5];
+    g.e[0] = (unsigned char)abs(qx - px); g.e[1] = (unsigned char)abs(qx);
+    g.e[2] = (unsigned char)abs(qy - py); g.e[3] = (unsigned char)abs(qy);
+    g.e[4] = (unsigned char)abs(qz - pz); g.e[5] = (unsigned char)abs(qz);
+    g.e[6] = g.e[7] = 0;
+    if (angdep != 1) { g.cx = g.cy = g.cz = 1.0; return; }
+    double sp, cp, st, ct;
+    sincos_cw((double)R3[0], &sp, &cp);
+    sincos_cw((double)R3[1], &st, &ct);
+    g.cx = fabs(st * cp);
+    g.cy = fabs(st * sp);
+    g.cz = fabs(ct);
+}
+
+// Device copy of the room part of deism_shoebox_atten (passed by value to kernels)
+struct RoomGeom {
+    double LL[3], xs[3], xr[3];
+};
+
+}  // namespace deism

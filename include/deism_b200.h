@@ -1,0 +1,206 @@
+/*
+ * deism_b200.h — C ABI of libdeism_b200.so: the B200-native (sm_100a) engine for the
+ * image x frequency hot path behind deism.core_deism.DEISM.run_DEISM() of audiolabs/DEISM.
+ *
+ * Every entry point names the reference interface it replaces ("pb" =
+ * deism/parallel_backends.py, "cd" = deism/core_deism.py, "room.cpp" etc. =
+ * deism/libroom_src/*), so a maintainer can bind it with ctypes / cffi / pybind11 at that call
+ * site (INTEGRATION.md shows the stubs).  Signatures use only plain pointers, sizes and PODs.
+ *
+ * Conventions
+ *   - complex128 = interleaved (re, im) doubles; complex64 = interleaved floats (NumPy layout).
+ *   - all arrays are C-contiguous with the reference's own shapes and dtypes, so the
+ *     reference's arrays can be handed over without transposition;
+ *   - "d_" pointers are DEVICE pointers on the current CUDA device, "h_" pointers are HOST
+ *     pointers (small tables and scalars only).  Bulk host<->device staging is the caller's
+ *     job; deism_b200/backend.py does it with pinned torch buffers for NumPy callers;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream);
+ *     device-pointer entry points are asynchronous with respect to the host unless noted;
+ *   - return value: DEISM_OK (0) or a DEISM_ERR_* code; deism_last_error() gives the message
+ *     (thread-local).  There is no CPU fallback: without a usable sm_100 device every compute
+ *     entry point fails with DEISM_ERR_CUDA;
+ *   - the caller owns every buffer it passes; the library keeps no pointer after a call
+ *     returns (device scratch is library-owned, cached per device, freed by
+ *     deism_release_workspace()).
+ */
+#ifndef DEISM_B200_H
+#define DEISM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DEISM_API __attribute__((visibility("default")))
+#else
+#define DEISM_API
+#endif
+
+#define DEISM_OK 0
+#define DEISM_ERR_INVALID 1 /* bad argument (the ValueError cases of pb:922,935) */
+#define DEISM_ERR_CUDA 2    /* CUDA runtime / launch failure, or no sm_100 device */
+#define DEISM_ERR_NOMEM 3   /* device or host allocation failed */
+
+/* ------------------------------------------------------------------------------------ */
+/* library / device                                                                      */
+/* ------------------------------------------------------------------------------------ */
+DEISM_API int deism_b200_version(void);          /* 10000*major + 100*minor + patch */
+DEISM_API const char *deism_last_error(void);    /* message of the last failing call */
+/* Fills SM count, HBM bytes and compute capability of `device` (or the current one if <0). */
+DEISM_API int deism_device_info(int device, int *sm_count, size_t *hbm_bytes, int *cc_major,
+                                int *cc_minor);
+DEISM_API int deism_release_workspace(void);     /* frees cached device scratch */
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+DEISM_API uint64_t deism_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------------------ */
+/* Shoebox wall attenuation source (what the reference calls images["atten_all"])        */
+/* ------------------------------------------------------------------------------------ */
+/*
+ * The reference materialises atten[I,K] as complex64 while it enumerates images
+ * (cd:2900-2928; 8 bytes per term of HBM/host traffic) or, in "compact" storage, rebuilds it
+ * per batch from the f32-rounded angles (pb:140-186).  This engine can also FUSE the factor
+ * into the accumulation kernels, reproducing either numerics:
+ */
+#define DEISM_ATTEN_C64 0        /* d_atten: complex64[I,K]  (reference default storage)      */
+#define DEISM_ATTEN_C128 1       /* d_atten: complex128[I,K]                                   */
+#define DEISM_ATTEN_FUSED_ROOM 2 /* in-kernel from A + room geometry in FP64, rounded to c64:
+                                    bit-for-bit the values of cd:2847-2928 (default storage)   */
+#define DEISM_ATTEN_FUSED_ANGLES 3 /* in-kernel from A + f32 angles R_sI_r, NOT rounded:
+                                    the values of pb:140-186 (compact storage)                 */
+
+typedef struct deism_shoebox_atten {
+    int32_t mode;            /* DEISM_ATTEN_*                                                  */
+    int32_t ang_dep_flag;    /* params["angDepFlag"] (1 = angle dependent)                     */
+    const void *d_atten;     /* modes 0/1: [I,K]                                               */
+    const int32_t *d_A;      /* modes 2/3: int32[I,6] = (q_x,q_y,q_z,p_x,p_y,p_z)              */
+    const float *d_R_sI_r;   /* mode 3: float32[I,3] = (phi, theta, r)                         */
+    const double *d_Z_S;     /* modes 2/3: complex128[6,K], wall rows x1,x2,y1,y2,z1,z2        */
+    double room_size[3];     /* mode 2: params["roomSize"]                                     */
+    double pos_source[3];    /* mode 2: params["posSource"]                                    */
+    double pos_receiver[3];  /* mode 2: params["posReceiver"]                                  */
+} deism_shoebox_atten;
+
+/* ------------------------------------------------------------------------------------ */
+/* (1) Shoebox image lattice   — replaces cd:2649-2728 (_count_shoebox_images_nofs_v2_numba),
+ *     cd:2731-2928 (_fill_...), the prefix sum of cd:3390-3394, the direct-path removal of
+ *     cd:3442-3451, and deism/count_reflections.cpp                                         */
+/* ------------------------------------------------------------------------------------ */
+/* Counts images per task t = (4p_x+2p_y+p_z)*(N_o+1) + order.  d_early/d_late: int64[8*(N_o+1)].
+ * remove_direct != 0 drops the (q=0,p=0) image (params["ifRemoveDirectPath"]). */
+DEISM_API int deism_shoebox_count_images(const double h_room_size[3], const double h_pos_source[3],
+                                         const double h_pos_receiver[3], double max_dist_sq,
+                                         int N_o, int N_o_ORG, int remove_direct,
+                                         int64_t *d_early_counts, int64_t *d_late_counts,
+                                         void *stream);
+/* Fills the compacted lists in the reference order.  Offsets are the exclusive
+ * prefix sums of the counts (computed on the device).  Any output pointer may be NULL. */
+DEISM_API int deism_shoebox_fill_images(const double h_room_size[3], const double h_pos_source[3],
+                                        const double h_pos_receiver[3], double max_dist_sq,
+                                        int N_o, int N_o_ORG, int remove_direct,
+                                        const int64_t *d_early_counts, const int64_t *d_late_counts,
+                                        int32_t *d_A_early, float *d_R_sI_r_early,
+                                        float *d_R_s_rI_early, float *d_R_r_sI_early,
+                                        int32_t *d_A_late, float *d_R_sI_r_late,
+                                        float *d_R_s_rI_late, float *d_R_r_sI_late, void *stream);
+/* Materialises atten[I,K] (complex64 if out_c128 == 0, else complex128) from a FUSED_* spec —
+ * the array the reference stores as images["atten_all_*"] (cd:2900-2928) or rebuilds per
+ * batch (pb:140-186). */
+DEISM_API int deism_shoebox_attenuation(int64_t n_images, int64_t K, const deism_shoebox_atten *spec,
+                                        void *d_out, int out_c128, void *stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* (2) Accumulation kernels — replace the Numba kernels of pb:189-460                     */
+/* ------------------------------------------------------------------------------------ */
+/* Shoebox DEISM-LC  (pb:264-325 _numba_LC_matrix_batch + batching of pb:594-654).
+ * h_n_all..h_u_all: HOST int64[Js]/[Jr] (params["n_all"] ...); d_C_s/d_C_r: complex64[K,Js],
+ * [K,Jr] (kept complex64 as at pb:619-620); d_R_s_rI/d_R_r_sI: float32[I,3]; d_k: float64[K];
+ * d_out: complex128[K]; accumulate != 0 adds to d_out instead of overwriting. */
+DEISM_API int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr,
+                               const int64_t *h_n_all, const int64_t *h_m_all,
+                               const int64_t *h_v_all, const int64_t *h_u_all,
+                               const float *d_C_s_vec, const float *d_C_r_vec,
+                               const float *d_R_s_rI, const float *d_R_r_sI,
+                               const deism_shoebox_atten *atten, const double *d_k,
+                               double *d_out, int accumulate, void *stream);
+
+/* Shoebox DEISM-ORG (pb:189-261 _numba_ORG_batch + batching of pb:543-591).
+ * d_C_nm_s: complex64[K,N+1,2N+1], d_C_vu_r: complex64[K,V+1,2V+1] (signed m/u wrap as in
+ * NumPy); h_W1: HOST complex64[N+1,V+1,N+V+1]; h_W2: HOST complex64[N+1,V+1,N+V+1,2N+1,2V+1]
+ * (params["Wigner"]); d_A: int32[I,6]; d_R_sI_r: float32[I,3].
+ * algo: 0 = auto, 1 = factorised B[parity,k,l,mu] table, 2 = direct quintuple sum. */
+DEISM_API int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V,
+                                const float *d_C_nm_s, const float *d_C_vu_r,
+                                const float *h_W1, const float *h_W2, const int32_t *d_A,
+                                const float *d_R_sI_r, const deism_shoebox_atten *atten,
+                                const double *d_k, double *d_out, int accumulate, int algo,
+                                void *stream);
+
+/* Convex DEISM-ARG LC (pb:328-385).  d_C_s_ARG_vec: complex64[K,Js,I] (image index innermost,
+ * cd:1193-1217), d_C_r_vec: complex64[K,Jr], d_R_sI_r: float32[3,I] (component-major),
+ * d_atten: complex64[K,I].  h_image_index (HOST int64[n_sel] or NULL = all) selects the columns
+ * processed (the late_indices of pb:886-899). */
+DEISM_API int deism_lc_arg(int64_t n_images, int64_t K, int Js, int Jr, const int64_t *h_n_all,
+                           const int64_t *h_m_all, const int64_t *h_v_all, const int64_t *h_u_all,
+                           const float *d_C_s_ARG_vec, const float *d_C_r_vec,
+                           const float *d_R_sI_r, const float *d_atten, const double *d_k,
+                           const int64_t *h_image_index, int64_t n_sel, double *d_out,
+                           int accumulate, void *stream);
+
+/* Convex DEISM-ARG ORG (pb:388-460).  d_C_nm_s_ARG: complex64[K,N+1,2N+1,I]. */
+DEISM_API int deism_org_arg(int64_t n_images, int64_t K, int N, int V, const float *d_C_nm_s_ARG,
+                            const float *d_C_vu_r, const float *h_W1, const float *h_W2,
+                            const float *d_R_sI_r, const float *d_atten, const double *d_k,
+                            const int64_t *h_image_index, int64_t n_sel, double *d_out,
+                            int accumulate, void *stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* (3) Precompute — replaces cd:1842-1913 pre_calc_Wigner (sympy, 169 s at N=V=10)        */
+/* ------------------------------------------------------------------------------------ */
+/* Exact (big-rational) Wigner 3j tables rounded to float32 exactly like the reference
+ * (float64 -> complex64).  Host buffers: h_W1 complex64[N+1,V+1,N+V+1],
+ * h_W2 complex64[N+1,V+1,N+V+1,2N+1,2V+1], W2[n,v,l,m,u] = (n v l; -m u m-u), negative m/u
+ * stored with NumPy wrap-around.  CPU code (setup, not the hot path). */
+DEISM_API int deism_wigner_tables(int N, int V, float *h_W1, float *h_W2);
+
+/* ------------------------------------------------------------------------------------ */
+/* (4) Convex-room reflection tree — replaces Room_deism<3>::image_source_model            */
+/*     (room.cpp:271-511) behind libroom_deism (libroom.cpp:58-127)                        */
+/* ------------------------------------------------------------------------------------ */
+typedef struct deism_convex_walls {
+    int32_t n_walls;
+    int32_t max_corners;        /* row stride of h_flat_corners                             */
+    const float *h_normal;      /* float32[n_walls,3]   Wall_deism.normal                   */
+    const float *h_origin;      /* float32[n_walls,3]   Wall_deism.origin                   */
+    const float *h_basis;       /* float32[n_walls,3,2] Wall_deism.basis (row-major 3x2)    */
+    const float *h_flat_corners;/* float32[n_walls,2,max_corners] Wall_deism.flat_corners   */
+    const int32_t *h_n_corners; /* int32[n_walls]                                           */
+    const float *h_reflection;  /* float32[n_walls,3,3] Wall_deism.reflection_matrix        */
+    const float *h_impedance;   /* float32[n_walls,K]  real impedance per band (wall.cpp:428) */
+} deism_convex_walls;
+
+/* Phase 1: enumerate the visible images (pre-order DFS order of room.cpp:351-420).
+ * Returns the count in *h_n_images; results stay in library scratch until phase 2. */
+DEISM_API int deism_convex_images_count(const deism_convex_walls *walls, const float h_source[3],
+                                        const float h_mic[3], int ism_order, int64_t *h_n_images,
+                                        void *stream);
+/* Phase 2: export.  d_sources float32[3,I], d_orders int32[I], d_gen_walls int32[I],
+ * d_attenuations float32[K,I], d_reflection float32[I,3,3].  Any pointer may be NULL. */
+DEISM_API int deism_convex_images_fill(const deism_convex_walls *walls, int64_t K, float *d_sources,
+                                       int32_t *d_orders, int32_t *d_gen_walls,
+                                       float *d_attenuations, float *d_reflection, void *stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* (5) Micro-benchmarks used by bench.py to measure the FP64 roofline denominators         */
+/* ------------------------------------------------------------------------------------ */
+/* Runs a register-resident DFMA (kind 0) or DMMA m8n8k4 (kind 1) loop on every SM and returns
+ * the achieved TFLOP/s (2 flops per FMA) in *tflops, timed with CUDA events. */
+DEISM_API int deism_fp64_peak(int kind, int iters, double *tflops, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEISM_B200_H */

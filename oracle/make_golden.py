@@ -74,6 +74,23 @@ _ARRAYS = ["roomSize", "posSource", "posReceiver", "impedance", "waveNumbers", "
            "vertices", "wallCenters", "C_nm_s_ARG", "C_nm_s_ARG_vec", "reflection_matrix"]
 
 
+def small_inputs(p):
+    """Inputs every case keeps (also the full-size ones): geometry, wave numbers, and the
+    impedance (one column + a flag when it is frequency-flat)."""
+    out = {}
+    for key in ("roomSize", "posSource", "posReceiver", "vertices", "wallCenters",
+                "waveNumbers", "freqs"):
+        if key in p and p[key] is not None:
+            out["params/" + key] = np.asarray(p[key])
+    Z = np.asarray(p["impedance"])
+    flat = bool(Z.ndim == 2 and np.all(Z == Z[:, :1]))
+    out["meta/impedance_flat"] = np.array(flat)
+    out["params/impedance_col0"] = np.ascontiguousarray(Z[:, 0]) if Z.ndim == 2 else Z
+    if not flat:
+        out["params/impedance"] = Z
+    return out
+
+
 def pack(d, extra=None, store_images=True, store_inputs=True):
     p = d.params
     out = {"RTF": np.asarray(p["RTF"]), "meta/method": np.array(p["DEISM_method"]),
@@ -81,6 +98,7 @@ def pack(d, extra=None, store_images=True, store_inputs=True):
     for key in _SCALARS:
         if key in p and p[key] is not None:
             out["params/" + key] = np.asarray(p[key])
+    out.update(small_inputs(p))
     if store_inputs:
         for key in _ARRAYS:
             if key in p and p[key] is not None:
@@ -275,12 +293,42 @@ def full_cases(which):
                      materials=(2.0 / 3.0, None, "reverberationTime"))
 
 
+def augment_full():
+    """Add the small inputs to full-size fixtures minted before small_inputs() existed
+    (re-derives them from the reference without re-running the minutes-long solves)."""
+    specs = {
+        "c3_sub100": ("RTF", {"startFreq": 40, "endFreq": 4000, "freqStep": 40}, None),
+        "c5_full_N5": ("RIR", {"sampleRate": 48000}, (2.0 / 3.0, None, "reverberationTime")),
+    }
+    for name, (mode, overrides, materials) in specs.items():
+        path = os.path.join(GOLDEN, name + ".npz")
+        if not os.path.exists(path):
+            continue
+        d = ref_import.make_deism(mode, "shoebox")
+        for key, val in overrides.items():
+            d.params[key] = val
+        if materials is None:
+            d.update_wall_materials()
+        else:
+            d.update_wall_materials(*materials)
+        d.update_freqs()
+        old = dict(np.load(path))
+        assert abs(float(old["params/reverberationTime"]) - d.params["reverberationTime"]) == 0
+        old.update(small_inputs(d.params))
+        np.savez_compressed(path, **old)
+        print("  augmented", path, os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", nargs="*", default=None,
                     help="full-size configs to mint (c1 c2 c3 c4 c5); no value = all")
     ap.add_argument("--skip-small", action="store_true")
+    ap.add_argument("--augment", action="store_true")
     args = ap.parse_args()
+    if args.augment:
+        augment_full()
+        sys.exit(0)
     if not args.skip_small:
         small_cases()
     if args.full is not None:

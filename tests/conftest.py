@@ -46,6 +46,12 @@ class Golden:
         p = {}
         for k, v in self.group("params").items():
             p[k] = v.item() if v.ndim == 0 else v
+        if "impedance" not in p and "impedance_col0" in p:
+            # frequency-flat impedance is stored as one column (oracle/make_golden.py)
+            K = int(np.asarray(p["waveNumbers"]).shape[0])
+            p["impedance"] = np.ascontiguousarray(
+                np.repeat(np.asarray(p["impedance_col0"]).reshape(-1, 1), K, axis=1))
+        p.pop("impedance_col0", None)
         p["DEISM_method"] = str(self.z["meta/method"])
         p["silentMode"] = 1
         img = {}

@@ -1,0 +1,90 @@
+"""CPU-only: the C-ABI library loads, exports every symbol include/deism_b200.h declares, the
+host-side pieces (Wigner tables) are exact, and compute entry points fail loudly without a GPU."""
+import ctypes as C
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, Golden
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "deism_b200.h")).read()
+    return sorted(set(re.findall(r"DEISM_API\s+[\w\s\*]+?\b(deism_\w+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    from deism_b200 import _lib
+
+    handle = _lib.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert set(declared) == set(_lib.EXPORTED)
+    assert handle.deism_b200_version() >= 100
+
+
+def test_no_cpu_fallback():
+    import torch
+    from deism_b200 import backend
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        backend.run_DEISM({"DEISM_method": "LC", "images": {}, "waveNumbers": [1.0]})
+    from deism_b200._lib import lib
+
+    rc = lib().deism_fp64_peak(0, 10, None, None)
+    assert rc == 2 and b"no CPU fallback" in lib().deism_last_error()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "deism_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), os.path.join(dirpath, f)
+
+
+@pytest.mark.parametrize("key", ["0_0", "3_2", "2_4", "5_5", "10_10"])
+def test_native_wigner_tables_equal_sympy(key):
+    """Hashes of the sympy tables (core_deism.py:1842-1913 run via the oracle) vs native."""
+    from deism_b200 import wigner
+
+    z = np.load(os.path.join(GOLDEN, "wigner_hashes.npz"))
+    N, V = map(int, key.split("_"))
+    W = wigner.wigner_tables(N, V)
+    assert W["W_1_all"].dtype == np.complex64
+    assert hashlib.sha256(W["W_1_all"].tobytes()).hexdigest() == str(z[key + "/sha_W1"])
+    assert hashlib.sha256(W["W_2_all"].tobytes()).hexdigest() == str(z[key + "/sha_W2"])
+    assert int(np.count_nonzero(W["W_2_all"])) == int(z[key + "/nnz_W2"])
+
+
+def test_native_wigner_matches_reference_fixture_tables():
+    from deism_b200 import wigner
+
+    g = Golden("s3_shoebox_rtf_org_o4_N3V2")
+    ref = g.group("wigner")
+    p = {"sourceOrder": 3, "receiverOrder": 2, "track_updated_where": True, "updated_where": {}}
+    p = wigner.pre_calc_Wigner(p)
+    assert np.array_equal(p["Wigner"]["W_1_all"], ref["W_1_all"])
+    assert np.array_equal(p["Wigner"]["W_2_all"], ref["W_2_all"])
+    assert p["updated_where"]["Wigner"] == ["pre_calc_Wigner"]
+
+
+def test_wigner_orthogonality():
+    """sum_{m,u} (n v l; -m u m-u)^2 = 1 for every valid (n,v,l) (3j completeness)."""
+    from deism_b200 import wigner
+
+    N = V = 6
+    W2 = wigner.wigner_tables(N, V)["W_2_all"].real.astype(np.float64)
+    for n in range(N + 1):
+        for v in range(V + 1):
+            for l in range(abs(n - v), n + v + 1):
+                s = np.sum(W2[n, v, l] ** 2)
+                assert abs(s - 1.0) < 1e-6
