@@ -1,13 +1,832 @@
-// org.cu — DEISM-ORG accumulation (placeholder until the factorised / direct kernels land).
+// org.cu — DEISM-ORG accumulation: the Wigner-3j coupled bilinear sum over source and receiver
+// spherical-harmonic directivity coefficients.
+//
+// Replaces _numba_ORG_batch (deism/parallel_backends.py:189-261), _numba_ARG_ORG_batch
+// (pb:388-460) and the batching driver pb:543-591.
+//
+// Reference form, one image:
+//   P[k] = sum_{n,m,v,u} mirror * atten[k] * C_s[k,n,m] * S * C_r[k,v,-u] * (i/k) * (-1)^u
+//   S    = 4pi i^{v-n} (-1)^{m'} sum_l i^l h_l(kr) Y_l^{m'-u}(theta,phi) W1[n,v,l] W2[n,v,l,m',u] Xi
+//   mirror = (-1)^{(p_y+p_z) m + p_z n},  m' = (-1)^{p_x+p_y} m,  Xi = sqrt((2n+1)(2v+1)(2l+1)/4pi)
+//
+// W1 = (n v l; 0 0 0) vanishes unless n+v+l is even, so i^{v-n+l} = +-1 and every quintuple
+// carries a REAL coefficient  G = 4pi (-1)^{(v-n+l)/2} (-1)^{m'+u} W1 W2 Xi.  Re-ordering the
+// sum by (l, mu = m'-u):
+//
+//   P[img,k] = atten[img,k] * sum_l h_l(k r_img) sum_mu Y_l^mu(img) * B[par(img)][l,mu][k]
+//   B[par][l,mu][k] = (i/k) sum_{(n,m,v,u): m'-u = mu} mirror*G * C_s[k,n,m] * C_r[k,v,-u]
+//
+// Kernels:
+//   org_btable_kernel   B for the 8 parity classes (image independent)          [algo 1]
+//   org_sort/prep       images grouped by parity class, Y_l^mu(img) table, attenuation geometry
+//   org_consume_kernel  32 freq x 32 image CTA tile, 4x2 register tile; per l: a (2l+1)-long
+//                       complex contraction from shared memory, h_l recurrence in registers
+//   org_direct_kernel   the quintuple sum done per (image, frequency) pair with per-image
+//                       source coefficients: the ARG form (pb:388-460) and the shoebox
+//                       cross-check [algo 2]
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
-using namespace deism;
-extern "C" int deism_org_shoebox(int64_t, int64_t, int, int, const float *, const float *, const float *,
-                                 const float *, const int32_t *, const float *,
-                                 const deism_shoebox_atten *, const double *, double *, int, int, void *) {
-    return set_error(DEISM_ERR_INVALID, "deism_org_shoebox: not implemented yet");
+
+namespace deism {
+
+int launch_reduce_partials(const cplx *partial, long n_chunks, long K, double *d_out, int accumulate,
+                           cudaStream_t st);
+int validate_atten(const deism_shoebox_atten *at);
+int launch_z_flat(const deism_shoebox_atten *at, long K, int *flags, cudaStream_t st);
+
+// One non-zero quintuple (n,m,v,u,l) of the coupling, stored in the segment of its (l,mu).
+struct OrgEntry {
+    double G;        // real coefficient without the mirror sign
+    int16_t idx_s;   // n*(2N+1) + wrap(m)      -> C_s[k, n, m]
+    int16_t idx_r;   // v*(2V+1) + wrap(-u)     -> C_r[k, v, -u]
+    int8_t m, n;     // for the mirror sign (-1)^{b m + c n}
+    int16_t pad;
+};
+static_assert(sizeof(OrgEntry) == 16, "OrgEntry must be 16 bytes");
+
+// one 128-bit load + register decode (a struct copy with int8 fields goes through local memory)
+struct OrgEntryReg { double G; int idx_s, idx_r, m, n; };
+__device__ __forceinline__ OrgEntryReg load_entry(const OrgEntry *p) {
+    int4 raw = __ldg(reinterpret_cast<const int4 *>(p));
+    OrgEntryReg e;
+    e.G = __hiloint2double(raw.y, raw.x);
+    e.idx_s = (int)(short)(raw.z & 0xffff);
+    e.idx_r = (int)(short)((raw.z >> 16) & 0xffff);
+    e.m = (int)(signed char)(raw.w & 0xff);
+    e.n = (int)(signed char)((raw.w >> 8) & 0xff);
+    return e;
 }
-extern "C" int deism_org_arg(int64_t, int64_t, int, int, const float *, const float *, const float *,
-                             const float *, const float *, const float *, const double *,
-                             const int64_t *, int64_t, double *, int, void *) {
-    return set_error(DEISM_ERR_INVALID, "deism_org_arg: not implemented yet");
+
+struct OrgLists {
+    // class a = (p_x+p_y)&1 selects m' = m (a=0) or -m (a=1)
+    std::vector<OrgEntry> entries[2];
+    std::vector<int> seg[2];   // Lmax^2 + 1 offsets, segment index = l*l + l + mu
+    long nnz = 0;
+};
+
+static void build_lists(int N, int V, const float *W1, const float *W2, OrgLists &L) {
+    const int Lmax = N + V + 1, M2 = 2 * N + 1, U2 = 2 * V + 1, nseg = Lmax * Lmax;
+    for (int a = 0; a < 2; ++a) {
+        std::vector<std::vector<OrgEntry>> buckets(nseg);
+        for (int n = 0; n <= N; ++n)
+        for (int m = -n; m <= n; ++m) {
+            int mp = a ? -m : m;
+            for (int v = 0; v <= V; ++v)
+            for (int u = -v; u <= v; ++u)
+            for (int l = abs(n - v); l <= n + v; ++l) {
+                if (abs(u - mp) > l) continue;
+                long i1 = ((long)n * (V + 1) + v) * Lmax + l;
+                long i2 = (i1 * M2 + (mp < 0 ? mp + M2 : mp)) * U2 + (u < 0 ? u + U2 : u);
+                // complex64 tables: a value counts as zero only if both parts are (pb:229)
+                double w1 = (double)W1[2 * i1], w1i = (double)W1[2 * i1 + 1];
+                double w2 = (double)W2[2 * i2], w2i = (double)W2[2 * i2 + 1];
+                if ((w1 == 0.0 && w1i == 0.0) || (w2 == 0.0 && w2i == 0.0)) continue;
+                double Xi = sqrt((double)((2 * n + 1) * (2 * v + 1) * (2 * l + 1)) /
+                                 (4.0 * 3.14159265358979323846));
+                // i^{v-n+l}: real (+-1) whenever W1 != 0; guard the impossible odd case
+                int e = v - n + l;
+                if (e & 1) continue;
+                double ph = ((e / 2) & 1) ? -1.0 : 1.0;
+                double sg = ((mp + u) & 1) ? -1.0 : 1.0;
+                OrgEntry en;
+                en.G = 4.0 * 3.14159265358979323846 * ph * sg * w1 * w2 * Xi;
+                en.idx_s = (int16_t)(n * M2 + (m < 0 ? m + M2 : m));
+                en.idx_r = (int16_t)(v * U2 + ((-u) < 0 ? -u + U2 : -u));
+                en.m = (int8_t)m; en.n = (int8_t)n; en.pad = 0;
+                int mu = mp - u;
+                buckets[l * l + l + mu].push_back(en);
+            }
+        }
+        L.seg[a].assign(nseg + 1, 0);
+        L.entries[a].clear();
+        for (int s = 0; s < nseg; ++s) {
+            L.seg[a][s] = (int)L.entries[a].size();
+            L.entries[a].insert(L.entries[a].end(), buckets[s].begin(), buckets[s].end());
+        }
+        L.seg[a][nseg] = (int)L.entries[a].size();
+    }
+    L.nnz = (long)L.entries[0].size();
+}
+
+// ---------------------------------------------------------------------------------------
+// coefficient transposes: complex64 [K][J] -> complex128 [J][K]
+// ---------------------------------------------------------------------------------------
+__global__ void transpose_c64_kernel(const float2 *__restrict__ in, long K, int J, cplx *out) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * J) return;
+    long k = i / J;
+    int j = (int)(i % J);
+    float2 v = in[i];
+    out[(long)j * K + k] = cmake((double)v.x, (double)v.y);
+}
+
+// ---------------------------------------------------------------------------------------
+// B table: grid (ceil(K/128), Lmax^2, 8 parity classes)
+// ---------------------------------------------------------------------------------------
+struct BtableArgs {
+    long K;
+    int nseg, nm_s, nm_r;
+    const OrgEntry *ent[2];
+    const int *seg[2];
+    const cplx *CsT, *CrT;   // [nm][K]
+    const double *k;
+    cplx *B;                 // [8][nseg][K]
+};
+
+__global__ void __launch_bounds__(128) org_btable_kernel(BtableArgs a) {
+    long k = (long)blockIdx.x * 128 + threadIdx.x;
+    int s = blockIdx.y, par = blockIdx.z;
+    int px = par >> 2, py = (par >> 1) & 1, pz = par & 1;
+    int cls = (px + py) & 1, b = (py + pz) & 1, c = pz;
+    if (k >= a.K) return;
+    const OrgEntry *ent = cls ? a.ent[1] : a.ent[0];
+    const int *segp = cls ? a.seg[1] : a.seg[0];
+    int lo = segp[s], hi = segp[s + 1];
+    cplx acc = cmake(0.0, 0.0);
+    for (int j = lo; j < hi; ++j) {
+        OrgEntryReg e = load_entry(ent + j);
+        int sgn = (b * e.m + c * e.n) & 1;
+        double g = sgn ? -e.G : e.G;
+        cplx d = cmul(a.CsT[(long)e.idx_s * a.K + k], a.CrT[(long)e.idx_r * a.K + k]);
+        acc.x = fma(g, d.x, acc.x);
+        acc.y = fma(g, d.y, acc.y);
+    }
+    double ik = 1.0 / a.k[k];
+    a.B[((long)par * a.nseg + s) * a.K + k] = cmake(-acc.y * ik, acc.x * ik);   // * (i/k)
+}
+
+// ---------------------------------------------------------------------------------------
+// image grouping by parity class (stable counting sort, one CTA) and per-image tables
+// ---------------------------------------------------------------------------------------
+constexpr int ORG_TI = 32;    // images per tile
+constexpr int ORG_TF = 32;    // frequencies per tile
+constexpr int ORG_THREADS = 128;
+constexpr int SORT_THREADS = 1024;
+
+struct OrgImage {   // 80 bytes
+    double r, inv_r;
+    double cx, cy, cz;
+    unsigned char e[8];
+    double2 atten_flat;
+    long orig;      // index in the caller's image list (-1 = padding)
+    int par, pad;
+};
+
+// meta[0..8]   : first padded position of class c (multiple of ORG_TI); meta[8] = total padded
+// perm[pos]    : original image index or -1
+__global__ void __launch_bounds__(SORT_THREADS)
+org_sort_kernel(const int32_t *__restrict__ A, long n_images, long *perm, long *meta, long perm_cap) {
+    __shared__ long cnt[8], base[8];
+    __shared__ int wtot[SORT_THREADS / 32][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 8) cnt[tid] = 0;
+    __syncthreads();
+    // pass 1: counts
+    long local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long i = tid; i < n_images; i += SORT_THREADS) {
+        const int32_t *a = A + i * 6;
+        int par = ((a[3] & 1) << 2) | ((a[4] & 1) << 1) | (a[5] & 1);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) local[c] += (par == c);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        long v = local[c];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) atomicAdd((unsigned long long *)&cnt[c], (unsigned long long)v);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        long pos = 0;
+        for (int c = 0; c < 8; ++c) {
+            meta[c] = pos;
+            base[c] = pos;
+            pos += (cnt[c] + ORG_TI - 1) / ORG_TI * ORG_TI;
+        }
+        meta[8] = pos;
+    }
+    __syncthreads();
+    for (long i = tid; i < perm_cap; i += SORT_THREADS) perm[i] = -1;
+    __syncthreads();
+    // pass 2: stable placement, chunk by chunk
+    for (long i0 = 0; i0 < n_images; i0 += SORT_THREADS) {
+        long i = i0 + tid;
+        int par = -1;
+        if (i < n_images) {
+            const int32_t *a = A + i * 6;
+            par = ((a[3] & 1) << 2) | ((a[4] & 1) << 1) | (a[5] & 1);
+        }
+        int rank = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            unsigned ball = __ballot_sync(0xffffffffu, par == c);
+            if (par == c) rank = __popc(ball & ((1u << lane) - 1u));
+            if (lane == 0) wtot[warp][c] = __popc(ball);
+        }
+        __syncthreads();
+        if (par >= 0) {
+            long off = base[par];
+            for (int w = 0; w < warp; ++w) off += wtot[w][par];
+            perm[off + rank] = i;
+        }
+        __syncthreads();
+        if (tid < 8) {
+            long t = 0;
+            for (int w = 0; w < SORT_THREADS / 32; ++w) t += wtot[w][tid];
+            base[tid] += t;
+        }
+        __syncthreads();
+    }
+}
+
+struct OrgPrepArgs {
+    long n_images, n_pad_cap;   // Y row stride = n_pad_cap
+    int Lmax;
+    const long *perm, *meta;    // nullptr perm = identity (direct kernel)
+    const float *R_sI_r;        // [I,3] (shoebox) or [3,I] (ARG, component_major = 1)
+    int component_major;
+    int mode, angdep;
+    const int32_t *A;
+    const cplx *Z;
+    long K;
+    RoomGeom room;
+};
+
+__global__ void __launch_bounds__(128)
+org_prep_kernel(OrgPrepArgs a, OrgImage *rec_out, cplx *Y) {
+    long pos = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long total = a.perm ? a.meta[8] : a.n_images;
+    if (pos >= total) return;
+    long img = a.perm ? a.perm[pos] : pos;
+    OrgImage rec;
+    rec.orig = img; rec.pad = 0; rec.par = 0;
+    rec.cx = rec.cy = rec.cz = 1.0;
+    for (int i = 0; i < 8; ++i) rec.e[i] = 0;
+    rec.atten_flat = cmake(1.0, 0.0);
+    if (img < 0) {   // padding: contributes exactly zero
+        rec.r = 1.0; rec.inv_r = 1.0; rec.atten_flat = cmake(0.0, 0.0);
+        rec_out[pos] = rec;
+        for (int s = 0; s < a.Lmax * a.Lmax; ++s) Y[(long)s * a.n_pad_cap + pos] = cmake(0.0, 0.0);
+        return;
+    }
+    double phi, theta;
+    if (a.component_major) {
+        phi = (double)a.R_sI_r[img]; theta = (double)a.R_sI_r[a.n_images + img];
+        rec.r = (double)a.R_sI_r[2 * a.n_images + img];
+    } else {
+        phi = (double)a.R_sI_r[img * 3 + 0]; theta = (double)a.R_sI_r[img * 3 + 1];
+        rec.r = (double)a.R_sI_r[img * 3 + 2];
+    }
+    rec.inv_r = 1.0 / rec.r;
+    if (a.A) {
+        const int32_t *A6 = a.A + img * 6;
+        rec.par = ((A6[3] & 1) << 2) | ((A6[4] & 1) << 1) | (A6[5] & 1);
+    }
+    if (a.mode == DEISM_ATTEN_FUSED_ROOM || a.mode == DEISM_ATTEN_FUSED_ANGLES) {
+        AttenGeom g;
+        if (a.mode == DEISM_ATTEN_FUSED_ROOM)
+            atten_geom_room(a.A + img * 6, a.room.LL, a.room.xs, a.room.xr, a.angdep, g);
+        else
+            atten_geom_angles(a.A + img * 6, a.R_sI_r + img * 3, a.angdep, g);
+        cplx at = shoebox_atten(a.Z, a.K, g.cx, g.cy, g.cz, g.e);
+        rec.atten_flat = a.mode == DEISM_ATTEN_FUSED_ROOM ? round_c64(at) : at;
+        rec.cx = g.cx; rec.cy = g.cy; rec.cz = g.cz;
+        for (int i = 0; i < 8; ++i) rec.e[i] = g.e[i];
+    }
+    rec_out[pos] = rec;
+    double st, ct;
+    sincos_cw(theta, &st, &ct);
+    for (int l = 0; l < a.Lmax; ++l)
+        for (int mu = -l; mu <= l; ++mu)
+            Y[(long)(l * l + l + mu) * a.n_pad_cap + pos] = sph_harm_dev(mu, l, phi, ct);
+}
+
+// ---------------------------------------------------------------------------------------
+// consume kernel (factorised form)
+// ---------------------------------------------------------------------------------------
+struct OrgConsumeArgs {
+    long K, n_pad_cap;
+    int Lmax, nseg;
+    const cplx *B;            // [8][nseg][K]
+    const cplx *Y;            // [nseg][n_pad_cap]
+    const OrgImage *rec;      // [n_pad]
+    const long *meta;         // class starts + total
+    const double *k;
+    int mode;
+    const void *atten;
+    const cplx *Z;
+    const int *flags;
+    long tiles_per_chunk;
+    cplx *partial;            // [n_chunks][K]
+};
+
+// dynamic shared memory layout (sizes depend on Lmax)
+struct OrgSmemFixed {
+    double2 fac[ORG_TI][ORG_TF + 1];
+    double2 red[16][ORG_TF];
+    double2 Z[6][ORG_TF];
+    double2 aflat[ORG_TI];
+    double r[ORG_TI], invr[ORG_TI];
+    double cosd[3][ORG_TI];
+    long orig[ORG_TI];
+    unsigned char e[ORG_TI][8];
+};
+
+__global__ void __launch_bounds__(ORG_THREADS, 2)
+org_consume_kernel(OrgConsumeArgs a) {
+    extern __shared__ __align__(16) unsigned char org_smem_raw[];
+    OrgSmemFixed &sm = *reinterpret_cast<OrgSmemFixed *>(org_smem_raw);
+    const int MW = 2 * a.Lmax - 1;                                  // max 2l+1
+    double2 *B_sm = reinterpret_cast<double2 *>(org_smem_raw + sizeof(OrgSmemFixed));  // [MW][TF]
+    double2 *Y_sm = B_sm + (size_t)MW * ORG_TF;                     // [MW][TI]
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 7;      // freqs f0 + tx + 8q, q < 4
+    const int ty = tid >> 3;     // images ty + 16b, b < 2
+    const long f0 = (long)blockIdx.x * ORG_TF;
+    const long n_tiles = a.meta[8] / ORG_TI;
+    long tile_lo = (long)blockIdx.y * a.tiles_per_chunk;
+    long tile_hi = tile_lo + a.tiles_per_chunk;
+    if (tile_hi > n_tiles) tile_hi = n_tiles;
+
+    const bool fused = a.mode == DEISM_ATTEN_FUSED_ROOM || a.mode == DEISM_ATTEN_FUSED_ANGLES;
+    const bool flat = fused && a.flags[0] != 0;
+
+    double kf[4], invk[4];
+    bool fvalid[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        long f = f0 + tx + 8 * q;
+        fvalid[q] = f < a.K;
+        kf[q] = fvalid[q] ? a.k[f] : 1.0;
+        invk[q] = 1.0 / kf[q];
+    }
+    if (fused && !flat) {
+        for (int i = tid; i < 6 * ORG_TF; i += ORG_THREADS) {
+            int w = i / ORG_TF, q = i % ORG_TF;
+            long f = f0 + q;
+            sm.Z[w][q] = f < a.K ? a.Z[(long)w * a.K + f] : cmake(1.0, 0.0);
+        }
+    }
+    cplx P[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) P[q] = cmake(0.0, 0.0);
+
+    for (long tile = tile_lo; tile < tile_hi; ++tile) {
+        const long p0 = tile * ORG_TI;
+        int par = 0;
+#pragma unroll
+        for (int c = 1; c < 8; ++c) par += (p0 >= a.meta[c]);
+        __syncthreads();
+        for (int i = tid; i < ORG_TI; i += ORG_THREADS) {
+            OrgImage rec = a.rec[p0 + i];
+            sm.r[i] = rec.r; sm.invr[i] = rec.inv_r;
+            sm.cosd[0][i] = rec.cx; sm.cosd[1][i] = rec.cy; sm.cosd[2][i] = rec.cz;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) sm.e[i][b] = rec.e[b];
+            sm.aflat[i] = rec.atten_flat;
+            sm.orig[i] = rec.orig;
+        }
+        __syncthreads();
+        // attenuation factor per pair (registers dead during the contraction)
+#pragma unroll 1
+        for (int b = 0; b < 2; ++b) {
+            const int il = ty + 16 * b;
+            const long orig = sm.orig[il];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                cplx att;
+                if (orig < 0) {
+                    att = cmake(0.0, 0.0);
+                } else if (flat) {
+                    att = sm.aflat[il];
+                } else if (fused) {
+                    att = shoebox_atten(&sm.Z[0][tx + 8 * q], ORG_TF, sm.cosd[0][il], sm.cosd[1][il],
+                                        sm.cosd[2][il], sm.e[il]);
+                    if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
+                } else {
+                    long f = f0 + tx + 8 * q;
+                    att = cmake(0.0, 0.0);
+                    if (fvalid[q]) {
+                        if (a.mode == DEISM_ATTEN_C64) {
+                            float2 v = ((const float2 *)a.atten)[orig * a.K + f];
+                            att = cmake((double)v.x, (double)v.y);
+                        } else {
+                            att = ((const cplx *)a.atten)[orig * a.K + f];
+                        }
+                    }
+                }
+                sm.fac[il][tx + 8 * q] = att;
+            }
+        }
+
+        // h_l(k r) recurrences, one per pair (pb:86-118 with j and y carried as one complex)
+        cplx hm[4][2], hc[4][2], Pp[4][2];
+        double ix[4][2];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const double r = sm.r[ty + 16 * b], ir = sm.invr[ty + 16 * b];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                double s, c;
+                sincos_cw(kf[q] * r, &s, &c);
+                double i1 = invk[q] * ir;
+                ix[q][b] = i1;
+                hm[q][b] = cmake(s * i1, c * i1);                              // h_0
+                hc[q][b] = cmake(fma(s * i1, i1, -c * i1), fma(c * i1, i1, s * i1));   // h_1
+                Pp[q][b] = cmake(0.0, 0.0);
+            }
+        }
+
+#pragma unroll 1
+        for (int l = 0; l < a.Lmax; ++l) {
+            const int W = 2 * l + 1;
+            __syncthreads();
+            const cplx *Bg = a.B + ((long)par * a.nseg + l * l) * a.K;
+            for (int i = tid; i < W * ORG_TF; i += ORG_THREADS) {
+                int mu = i / ORG_TF, q = i % ORG_TF;
+                long f = f0 + q;
+                B_sm[mu * ORG_TF + q] = f < a.K ? Bg[(long)mu * a.K + f] : cmake(0.0, 0.0);
+            }
+            const cplx *Yg = a.Y + (long)(l * l) * a.n_pad_cap + p0;
+            for (int i = tid; i < W * ORG_TI; i += ORG_THREADS) {
+                int mu = i / ORG_TI, ii = i % ORG_TI;
+                Y_sm[mu * ORG_TI + ii] = Yg[(long)mu * a.n_pad_cap + ii];
+            }
+            __syncthreads();
+            cplx T[4][2];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { T[q][0] = cmake(0.0, 0.0); T[q][1] = cmake(0.0, 0.0); }
+#pragma unroll 2
+            for (int mu = 0; mu < W; ++mu) {
+                cplx bq[4], yb[2];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) bq[q] = B_sm[mu * ORG_TF + tx + 8 * q];
+                yb[0] = Y_sm[mu * ORG_TI + ty];
+                yb[1] = Y_sm[mu * ORG_TI + ty + 16];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { cfma(T[q][0], bq[q], yb[0]); cfma(T[q][1], bq[q], yb[1]); }
+            }
+            // advance h_l and accumulate
+            const double cl = (double)(2 * l - 1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    cplx h;
+                    if (l == 0) h = hm[q][b];
+                    else if (l == 1) h = hc[q][b];
+                    else {
+                        double c = cl * ix[q][b];
+                        h = cmake(fma(c, hc[q][b].x, -hm[q][b].x), fma(c, hc[q][b].y, -hm[q][b].y));
+                        hm[q][b] = hc[q][b];
+                        hc[q][b] = h;
+                    }
+                    cfma(Pp[q][b], h, T[q][b]);
+                }
+        }
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cfma(P[q], sm.fac[ty + 16 * b][tx + 8 * q], Pp[q][b]);
+    }
+
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sm.red[ty][tx + 8 * q] = P[q];
+    __syncthreads();
+    if (tid < ORG_TF) {
+        cplx s = cmake(0.0, 0.0);
+#pragma unroll
+        for (int y = 0; y < 16; ++y) s = cadd(s, sm.red[y][tid]);
+        long f = f0 + tid;
+        if (f < a.K) a.partial[(long)blockIdx.y * a.K + f] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// direct kernel: thread = image, blockIdx.y = frequency.  Source coefficients are addressed
+// as Cs[k*sk + nm*snm + img*si] (complex64): shoebox [K][NM] (si = 0) or ARG [K][NM][I].
+// ---------------------------------------------------------------------------------------
+struct OrgDirectArgs {
+    long n_sel, n_images, K;
+    int Lmax, nseg, NMr;
+    const OrgEntry *ent[2];
+    const int *seg[2];
+    const float2 *Cs;
+    long sk, snm, si;
+    const float2 *Cr;          // [K][NMr]
+    const cplx *Y;             // [nseg][n_images]
+    const OrgImage *rec;       // [n_images]
+    const long *sel;           // [n_sel] or nullptr
+    const double *k;
+    int mode;                  // DEISM_ATTEN_* (shoebox) or -1: ARG atten complex64 [K][I]
+    const void *atten;
+    const cplx *Z;
+    int shoebox;
+    cplx *partial;             // [gridDim.x][K]
+};
+
+__global__ void __launch_bounds__(128) org_direct_kernel(OrgDirectArgs a) {
+    __shared__ double2 red[128];
+    const long kidx = blockIdx.y;
+    const long s = (long)blockIdx.x * 128 + threadIdx.x;
+    cplx P = cmake(0.0, 0.0);
+    if (s < a.n_sel) {
+        const long img = a.sel ? a.sel[s] : s;
+        const OrgImage rec = a.rec[img];
+        const double kk = a.k[kidx];
+        int cls = 0, b = 0, c = 0;
+        if (a.shoebox) {
+            int px = rec.par >> 2, py = (rec.par >> 1) & 1, pz = rec.par & 1;
+            cls = (px + py) & 1; b = (py + pz) & 1; c = pz;
+        }
+        const OrgEntry *ent = cls ? a.ent[1] : a.ent[0];
+        const int *seg = cls ? a.seg[1] : a.seg[0];
+        const float2 *Cs = a.Cs + kidx * a.sk + img * a.si;
+        const float2 *Cr = a.Cr + kidx * a.NMr;
+        double sn, cs;
+        sincos_cw(kk * rec.r, &sn, &cs);
+        const double ix = 1.0 / (kk * rec.r);
+        cplx hm = cmake(sn * ix, cs * ix);
+        cplx hc = cmake(fma(sn * ix, ix, -cs * ix), fma(cs * ix, ix, sn * ix));
+        cplx acc = cmake(0.0, 0.0);
+        for (int l = 0; l < a.Lmax; ++l) {
+            cplx h;
+            if (l == 0) h = hm;
+            else if (l == 1) h = hc;
+            else {
+                double cf = (double)(2 * l - 1) * ix;
+                h = cmake(fma(cf, hc.x, -hm.x), fma(cf, hc.y, -hm.y));
+                hm = hc; hc = h;
+            }
+            for (int mu = -l; mu <= l; ++mu) {
+                int sg = l * l + l + mu;
+                int lo = seg[sg], hi = seg[sg + 1];
+                if (lo == hi) continue;
+                cplx bsum = cmake(0.0, 0.0);
+                for (int j = lo; j < hi; ++j) {
+                    OrgEntryReg e = load_entry(ent + j);
+                    double g = ((b * e.m + c * e.n) & 1) ? -e.G : e.G;
+                    float2 c1 = Cs[(long)e.idx_s * a.snm], c2 = Cr[e.idx_r];
+                    cplx d = cmul(cmake((double)c1.x, (double)c1.y), cmake((double)c2.x, (double)c2.y));
+                    bsum.x = fma(g, d.x, bsum.x);
+                    bsum.y = fma(g, d.y, bsum.y);
+                }
+                cfma(acc, cmul(h, a.Y[(long)sg * a.n_images + img]), bsum);
+            }
+        }
+        // * (i/k) * atten
+        const double ik = 1.0 / kk;
+        cplx v = cmake(-acc.y * ik, acc.x * ik);
+        cplx att;
+        if (a.mode == -1) {
+            float2 t = ((const float2 *)a.atten)[kidx * a.n_images + img];
+            att = cmake((double)t.x, (double)t.y);
+        } else if (a.mode == DEISM_ATTEN_C64) {
+            float2 t = ((const float2 *)a.atten)[img * a.K + kidx];
+            att = cmake((double)t.x, (double)t.y);
+        } else if (a.mode == DEISM_ATTEN_C128) {
+            att = ((const cplx *)a.atten)[img * a.K + kidx];
+        } else {
+            att = shoebox_atten(a.Z + kidx, a.K, rec.cx, rec.cy, rec.cz, rec.e);
+            if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
+        }
+        P = cmul(att, v);
+    }
+    red[threadIdx.x] = P;
+    __syncthreads();
+    for (int st = 64; st > 0; st >>= 1) {
+        if (threadIdx.x < st) red[threadIdx.x] = cadd(red[threadIdx.x], red[threadIdx.x + st]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) a.partial[(long)blockIdx.x * a.K + kidx] = red[0];
+}
+
+// upload the two entry lists into one scratch slot; returns device pointers
+static int upload_lists(const OrgLists &L, int nseg, const OrgEntry *d_ent[2], const int *d_seg[2],
+                        cudaStream_t st) {
+    size_t ent_bytes = (L.entries[0].size() + L.entries[1].size()) * sizeof(OrgEntry);
+    size_t seg_bytes = 2 * (size_t)(nseg + 1) * sizeof(int);
+    unsigned char *base = (unsigned char *)workspace(WS_ORG_LIST, ent_bytes + seg_bytes + 64);
+    if (!base) return DEISM_ERR_NOMEM;
+    OrgEntry *e0 = (OrgEntry *)base;
+    OrgEntry *e1 = e0 + L.entries[0].size();
+    int *s0 = (int *)(base + ent_bytes);
+    int *s1 = s0 + nseg + 1;
+    // pageable -> device async copies are staged by the runtime before returning
+    if (!L.entries[0].empty())
+        DEISM_CUDA_TRY(cudaMemcpyAsync(e0, L.entries[0].data(), L.entries[0].size() * sizeof(OrgEntry),
+                                       cudaMemcpyHostToDevice, st));
+    if (!L.entries[1].empty())
+        DEISM_CUDA_TRY(cudaMemcpyAsync(e1, L.entries[1].data(), L.entries[1].size() * sizeof(OrgEntry),
+                                       cudaMemcpyHostToDevice, st));
+    DEISM_CUDA_TRY(cudaMemcpyAsync(s0, L.seg[0].data(), (nseg + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    DEISM_CUDA_TRY(cudaMemcpyAsync(s1, L.seg[1].data(), (nseg + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    DEISM_CUDA_TRY(cudaStreamSynchronize(st));   // host vectors may die after return
+    d_ent[0] = e0; d_ent[1] = e1; d_seg[0] = s0; d_seg[1] = s1;
+    return DEISM_OK;
+}
+
+static void fill_room(RoomGeom &room, const deism_shoebox_atten *at) {
+    for (int i = 0; i < 3; ++i) {
+        room.LL[i] = at->room_size[i]; room.xs[i] = at->pos_source[i]; room.xr[i] = at->pos_receiver[i];
+    }
+}
+
+}  // namespace deism
+
+using namespace deism;
+
+extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, const float *d_C_nm_s,
+                                 const float *d_C_vu_r, const float *h_W1, const float *h_W2,
+                                 const int32_t *d_A, const float *d_R_sI_r,
+                                 const deism_shoebox_atten *atten, const double *d_k, double *d_out,
+                                 int accumulate, int algo, void *stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (K <= 0) return DEISM_OK;
+    if (!d_out || !d_k) return set_error(DEISM_ERR_INVALID, "null d_out/d_k");
+    if (n_images <= 0) {   // pb:546-547
+        if (!accumulate) DEISM_CUDA_TRY(cudaMemsetAsync(d_out, 0, (size_t)K * 16, st));
+        return DEISM_OK;
+    }
+    if (N < 0 || V < 0 || N > 20 || V > 20) return set_error(DEISM_ERR_INVALID, "orders must be 0..20");
+    if (!d_C_nm_s || !d_C_vu_r || !h_W1 || !h_W2 || !d_A || !d_R_sI_r)
+        return set_error(DEISM_ERR_INVALID, "null input pointer");
+    if (algo < 0 || algo > 2) return set_error(DEISM_ERR_INVALID, "algo must be 0, 1 or 2");
+    rc = validate_atten(atten);
+    if (rc) return rc;
+
+    const int Lmax = N + V + 1, nseg = Lmax * Lmax;
+    const int NMs = (N + 1) * (2 * N + 1), NMr = (V + 1) * (2 * V + 1);
+    OrgLists L;
+    build_lists(N, V, h_W1, h_W2, L);
+    const OrgEntry *d_ent[2];
+    const int *d_seg[2];
+    rc = upload_lists(L, nseg, d_ent, d_seg, st);
+    if (rc) return rc;
+
+    int *flags = (int *)workspace(WS_FLAGS, 64);
+    if (!flags) return DEISM_ERR_NOMEM;
+    rc = launch_z_flat(atten, K, flags, st);
+    if (rc) return rc;
+
+    if (algo == 2) {
+        // ---- direct quintuple sum per (image, frequency) ----
+        OrgImage *rec = (OrgImage *)workspace(WS_ORG_IMG, (size_t)n_images * sizeof(OrgImage));
+        cplx *Y = (cplx *)workspace(WS_ORG_Y, (size_t)nseg * n_images * sizeof(cplx));
+        long nblk = (n_images + 127) / 128;
+        cplx *partial = (cplx *)workspace(WS_PARTIAL, (size_t)nblk * K * sizeof(cplx));
+        if (!rec || !Y || !partial) return DEISM_ERR_NOMEM;
+        OrgPrepArgs pa;
+        pa.n_images = n_images; pa.n_pad_cap = n_images; pa.Lmax = Lmax; pa.perm = nullptr;
+        pa.meta = nullptr; pa.R_sI_r = d_R_sI_r; pa.component_major = 0; pa.mode = atten->mode;
+        pa.angdep = atten->ang_dep_flag; pa.A = d_A; pa.Z = (const cplx *)atten->d_Z_S; pa.K = K;
+        fill_room(pa.room, atten);
+        org_prep_kernel<<<(unsigned)((n_images + 127) / 128), 128, 0, st>>>(pa, rec, Y);
+        DEISM_LAUNCH_CHECK("org_prep_kernel");
+        OrgDirectArgs da;
+        da.n_sel = n_images; da.n_images = n_images; da.K = K; da.Lmax = Lmax; da.nseg = nseg;
+        da.NMr = NMr;
+        for (int i = 0; i < 2; ++i) { da.ent[i] = d_ent[i]; da.seg[i] = d_seg[i]; }
+        da.Cs = (const float2 *)d_C_nm_s; da.sk = NMs; da.snm = 1; da.si = 0;
+        da.Cr = (const float2 *)d_C_vu_r; da.Y = Y; da.rec = rec; da.sel = nullptr; da.k = d_k;
+        da.mode = atten->mode; da.atten = atten->d_atten; da.Z = (const cplx *)atten->d_Z_S;
+        da.shoebox = 1; da.partial = partial;
+        if (K > 65535) return set_error(DEISM_ERR_INVALID, "direct ORG supports K <= 65535");
+        dim3 grid((unsigned)nblk, (unsigned)K);
+        org_direct_kernel<<<grid, 128, 0, st>>>(da);
+        DEISM_LAUNCH_CHECK("org_direct_kernel");
+        return launch_reduce_partials(partial, nblk, K, d_out, accumulate, st);
+    }
+
+    // ---- factorised path ----
+    cplx *CsT = (cplx *)workspace(WS_SMALL, (size_t)(NMs + NMr) * K * sizeof(cplx));
+    cplx *B = (cplx *)workspace(WS_ORG_B, (size_t)8 * nseg * K * sizeof(cplx));
+    if (!CsT || !B) return DEISM_ERR_NOMEM;
+    cplx *CrT = CsT + (size_t)NMs * K;
+    transpose_c64_kernel<<<(unsigned)(((long)K * NMs + 255) / 256), 256, 0, st>>>(
+        (const float2 *)d_C_nm_s, K, NMs, CsT);
+    DEISM_LAUNCH_CHECK("transpose_c64_kernel");
+    transpose_c64_kernel<<<(unsigned)(((long)K * NMr + 255) / 256), 256, 0, st>>>(
+        (const float2 *)d_C_vu_r, K, NMr, CrT);
+    DEISM_LAUNCH_CHECK("transpose_c64_kernel");
+    BtableArgs ba;
+    ba.K = K; ba.nseg = nseg; ba.nm_s = NMs; ba.nm_r = NMr;
+    for (int i = 0; i < 2; ++i) { ba.ent[i] = d_ent[i]; ba.seg[i] = d_seg[i]; }
+    ba.CsT = CsT; ba.CrT = CrT; ba.k = d_k; ba.B = B;
+    {
+        dim3 grid((unsigned)((K + 127) / 128), (unsigned)nseg, 8);
+        org_btable_kernel<<<grid, 128, 0, st>>>(ba);
+        DEISM_LAUNCH_CHECK("org_btable_kernel");
+    }
+
+    const long n_pad_cap = (n_images + ORG_TI - 1) / ORG_TI * ORG_TI + 8 * ORG_TI;
+    long *perm = (long *)workspace(WS_ARG_IDX, (size_t)(n_pad_cap + 16) * sizeof(long));
+    OrgImage *rec = (OrgImage *)workspace(WS_ORG_IMG, (size_t)n_pad_cap * sizeof(OrgImage));
+    cplx *Y = (cplx *)workspace(WS_ORG_Y, (size_t)nseg * n_pad_cap * sizeof(cplx));
+    if (!perm || !rec || !Y) return DEISM_ERR_NOMEM;
+    long *meta = perm + n_pad_cap;
+    org_sort_kernel<<<1, SORT_THREADS, 0, st>>>(d_A, n_images, perm, meta, n_pad_cap);
+    DEISM_LAUNCH_CHECK("org_sort_kernel");
+    OrgPrepArgs pa;
+    pa.n_images = n_images; pa.n_pad_cap = n_pad_cap; pa.Lmax = Lmax; pa.perm = perm; pa.meta = meta;
+    pa.R_sI_r = d_R_sI_r; pa.component_major = 0; pa.mode = atten->mode; pa.angdep = atten->ang_dep_flag;
+    pa.A = d_A; pa.Z = (const cplx *)atten->d_Z_S; pa.K = K;
+    fill_room(pa.room, atten);
+    org_prep_kernel<<<(unsigned)((n_pad_cap + 127) / 128), 128, 0, st>>>(pa, rec, Y);
+    DEISM_LAUNCH_CHECK("org_prep_kernel");
+
+    const long n_tiles_cap = n_pad_cap / ORG_TI;
+    const long n_ftiles = (K + ORG_TF - 1) / ORG_TF;
+    long n_chunks = (long)sm_count() * 3 * 8 / n_ftiles;
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > n_tiles_cap) n_chunks = n_tiles_cap;
+    if (n_chunks > 65535) n_chunks = 65535;
+    long tiles_per_chunk = (n_tiles_cap + n_chunks - 1) / n_chunks;
+    n_chunks = (n_tiles_cap + tiles_per_chunk - 1) / tiles_per_chunk;
+    cplx *partial = (cplx *)workspace(WS_PARTIAL, (size_t)n_chunks * K * sizeof(cplx));
+    if (!partial) return DEISM_ERR_NOMEM;
+
+    OrgConsumeArgs ca;
+    ca.K = K; ca.n_pad_cap = n_pad_cap; ca.Lmax = Lmax; ca.nseg = nseg; ca.B = B; ca.Y = Y;
+    ca.rec = rec; ca.meta = meta; ca.k = d_k; ca.mode = atten->mode; ca.atten = atten->d_atten;
+    ca.Z = (const cplx *)atten->d_Z_S; ca.flags = flags; ca.tiles_per_chunk = tiles_per_chunk;
+    ca.partial = partial;
+    const int MW = 2 * Lmax - 1;
+    size_t smem = sizeof(OrgSmemFixed) + (size_t)MW * (ORG_TF + ORG_TI) * sizeof(double2);
+    DEISM_CUDA_TRY(cudaFuncSetAttribute(org_consume_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    dim3 grid((unsigned)n_ftiles, (unsigned)n_chunks);
+    org_consume_kernel<<<grid, ORG_THREADS, smem, st>>>(ca);
+    DEISM_LAUNCH_CHECK("org_consume_kernel");
+    return launch_reduce_partials(partial, n_chunks, K, d_out, accumulate, st);
+}
+
+extern "C" int deism_org_arg(int64_t n_images, int64_t K, int N, int V, const float *d_C_nm_s_ARG,
+                             const float *d_C_vu_r, const float *h_W1, const float *h_W2,
+                             const float *d_R_sI_r, const float *d_atten, const double *d_k,
+                             const int64_t *h_image_index, int64_t n_sel, double *d_out, int accumulate,
+                             void *stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (K <= 0) return DEISM_OK;
+    if (!d_out || !d_k) return set_error(DEISM_ERR_INVALID, "null d_out/d_k");
+    if (!h_image_index) n_sel = n_images;
+    if (n_images <= 0 || n_sel <= 0) {
+        if (!accumulate) DEISM_CUDA_TRY(cudaMemsetAsync(d_out, 0, (size_t)K * 16, st));
+        return DEISM_OK;
+    }
+    if (N < 0 || V < 0 || N > 20 || V > 20) return set_error(DEISM_ERR_INVALID, "orders must be 0..20");
+    if (!d_C_nm_s_ARG || !d_C_vu_r || !h_W1 || !h_W2 || !d_R_sI_r || !d_atten)
+        return set_error(DEISM_ERR_INVALID, "null input pointer");
+    if (K > 65535) return set_error(DEISM_ERR_INVALID, "ARG ORG supports K <= 65535");
+    const int Lmax = N + V + 1, nseg = Lmax * Lmax;
+    const int NMs = (N + 1) * (2 * N + 1), NMr = (V + 1) * (2 * V + 1);
+    OrgLists L;
+    build_lists(N, V, h_W1, h_W2, L);
+    const OrgEntry *d_ent[2];
+    const int *d_seg[2];
+    rc = upload_lists(L, nseg, d_ent, d_seg, st);
+    if (rc) return rc;
+
+    OrgImage *rec = (OrgImage *)workspace(WS_ORG_IMG, (size_t)n_images * sizeof(OrgImage));
+    cplx *Y = (cplx *)workspace(WS_ORG_Y, (size_t)nseg * n_images * sizeof(cplx));
+    long nblk = (n_sel + 127) / 128;
+    cplx *partial = (cplx *)workspace(WS_PARTIAL, (size_t)nblk * K * sizeof(cplx));
+    long *sel = nullptr;
+    if (h_image_index) {
+        for (int64_t i = 0; i < n_sel; ++i)
+            if (h_image_index[i] < 0 || h_image_index[i] >= n_images)
+                return set_error(DEISM_ERR_INVALID, "image index %lld out of range",
+                                 (long long)h_image_index[i]);
+        sel = (long *)workspace(WS_ARG_IDX, (size_t)n_sel * sizeof(long));
+        if (!sel) return DEISM_ERR_NOMEM;
+        DEISM_CUDA_TRY(cudaMemcpyAsync(sel, h_image_index, (size_t)n_sel * sizeof(long),
+                                       cudaMemcpyHostToDevice, st));
+        DEISM_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    if (!rec || !Y || !partial) return DEISM_ERR_NOMEM;
+    OrgPrepArgs pa;
+    pa.n_images = n_images; pa.n_pad_cap = n_images; pa.Lmax = Lmax; pa.perm = nullptr; pa.meta = nullptr;
+    pa.R_sI_r = d_R_sI_r; pa.component_major = 1; pa.mode = DEISM_ATTEN_C64; pa.angdep = 0;
+    pa.A = nullptr; pa.Z = nullptr; pa.K = K;
+    for (int i = 0; i < 3; ++i) pa.room.LL[i] = pa.room.xs[i] = pa.room.xr[i] = 0.0;
+    org_prep_kernel<<<(unsigned)((n_images + 127) / 128), 128, 0, st>>>(pa, rec, Y);
+    DEISM_LAUNCH_CHECK("org_prep_kernel");
+    OrgDirectArgs da;
+    da.n_sel = n_sel; da.n_images = n_images; da.K = K; da.Lmax = Lmax; da.nseg = nseg; da.NMr = NMr;
+    for (int i = 0; i < 2; ++i) { da.ent[i] = d_ent[i]; da.seg[i] = d_seg[i]; }
+    da.Cs = (const float2 *)d_C_nm_s_ARG; da.sk = (long)NMs * n_images; da.snm = n_images; da.si = 1;
+    da.Cr = (const float2 *)d_C_vu_r; da.Y = Y; da.rec = rec; da.sel = sel; da.k = d_k;
+    da.mode = -1; da.atten = d_atten; da.Z = nullptr; da.shoebox = 0; da.partial = partial;
+    dim3 grid((unsigned)nblk, (unsigned)K);
+    org_direct_kernel<<<grid, 128, 0, st>>>(da);
+    DEISM_LAUNCH_CHECK("org_direct_kernel");
+    return launch_reduce_partials(partial, nblk, K, d_out, accumulate, st);
 }

@@ -163,3 +163,118 @@ def test_fp64_peak_microbenchmarks_run():
         check(lib().deism_fp64_peak(kind, 2000, C.byref(tf), C.byref(ms)), "fp64_peak")
         print(f"fp64 peak kind={kind}: {tf.value:.2f} TFLOP/s in {ms.value:.3f} ms")
         assert 1.0 < tf.value < 200.0
+
+
+# --------------------------------------------------------------------------------------
+# ORG / MIX
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", [n for n in SHOEBOX if "_org_" in n or "_mix_" in n])
+@pytest.mark.parametrize("algo", [1, 2])
+def test_org_mix_reference_layout(name, algo):
+    """Reference images dict as-is; factorised (1) and direct quintuple-sum (2) ORG kernels."""
+    from deism_b200 import backend
+
+    g = Golden(name)
+    p = g.params()
+    p["b200OrgAlgo"] = algo
+    got = backend.run_DEISM(p)
+    assert rel_l2(got, g.rtf) < RTF_TOL
+
+
+@pytest.mark.parametrize("name", [n for n in SHOEBOX if ("_org_" in n or "_mix_" in n) and "compact" not in n])
+def test_org_mix_fused(name):
+    from deism_b200 import backend, wigner
+
+    g = Golden(name)
+    p = g.params()
+    p.pop("images")
+    p.pop("Wigner")
+    p = wigner.pre_calc_Wigner(p)           # native tables instead of the fixture's sympy ones
+    p["images"] = _images_from_params(p, p["DEISM_method"])
+    got = backend.run_DEISM(p)
+    assert rel_l2(got, g.rtf) < RTF_TOL
+
+
+def test_org_vs_oracle_random_inputs():
+    """Random parities / geometry / complex attenuation, N != V, ragged sizes."""
+    from deism_b200 import backend, wigner
+    from oracle import oracle
+
+    rng = np.random.default_rng(11)
+    for (I, K, N, V) in [(1, 1, 0, 0), (45, 37, 2, 3), (130, 33, 4, 4), (67, 20, 6, 1)]:
+        cs = (rng.standard_normal((K, N + 1, 2 * N + 1)) + 1j * rng.standard_normal((K, N + 1, 2 * N + 1))).astype(np.complex64)
+        cr = (rng.standard_normal((K, V + 1, 2 * V + 1)) + 1j * rng.standard_normal((K, V + 1, 2 * V + 1))).astype(np.complex64)
+        A = rng.integers(-3, 4, size=(I, 6)).astype(np.int32)
+        A[:, 3:] = rng.integers(0, 2, size=(I, 3))
+        R = np.stack([rng.uniform(-np.pi, np.pi, I), rng.uniform(0.05, 3.0, I),
+                      rng.uniform(0.5, 60.0, I)], axis=1).astype(np.float32)
+        atten = (rng.standard_normal((I, K)) + 1j * rng.standard_normal((I, K))).astype(np.complex64)
+        params = {"DEISM_method": "ORG", "waveNumbers": np.sort(rng.uniform(0.5, 100.0, K)),
+                  "sourceOrder": N, "receiverOrder": V, "C_nm_s": cs, "C_vu_r": cr,
+                  "Wigner": wigner.wigner_tables(N, V), "silentMode": 1, "angDepFlag": 1,
+                  "numParaImages": 50,
+                  "images": {"A": A, "R_sI_r_all": R, "R_s_rI_all": R, "R_r_sI_all": R, "atten_all": atten}}
+        want = oracle.run_DEISM(params)
+        for algo in (1, 2):
+            params["b200OrgAlgo"] = algo
+            got = backend.run_DEISM(params)
+            assert rel_l2(got, want) < RTF_TOL, (I, K, N, V, algo)
+
+
+def _synth(K, N, V, seed=0):
+    rng = np.random.default_rng(seed)
+    cs = (rng.standard_normal((K, N + 1, 2 * N + 1)) + 1j * rng.standard_normal((K, N + 1, 2 * N + 1))).astype(np.complex64)
+    cr = (rng.standard_normal((K, V + 1, 2 * V + 1)) + 1j * rng.standard_normal((K, V + 1, 2 * V + 1))).astype(np.complex64)
+    return cs, cr
+
+
+def _full_case(name, method, N, V):
+    """Rebuild a full-size BASELINE config from the scalars in its fixture, run it end to end
+    (GPU image enumeration + fused accumulation), check hashes and the RTF."""
+    from deism_b200 import backend, wigner
+    from oracle import oracle
+
+    g = Golden(name)
+    p = _full_params(g)
+    k = p["waveNumbers"]
+    K = len(k)
+    p["DEISM_method"] = method
+    if N == 0:
+        p["C_nm_s"] = oracle.monopole_coefficients(k)
+        p["C_vu_r"] = oracle.monopole_coefficients(k)
+    else:
+        p["C_nm_s"], p["C_vu_r"] = _synth(K, N, V)
+    p["sourceOrder"], p["receiverOrder"] = N, V
+    if method in ("LC", "MIX"):
+        p["n_all"], p["m_all"], p["C_nm_s_vec"] = oracle.vectorize(p["C_nm_s"], N)
+        p["v_all"], p["u_all"], p["C_vu_r_vec"] = oracle.vectorize(p["C_vu_r"], V)
+    if method in ("ORG", "MIX"):
+        p = wigner.pre_calc_Wigner(p)
+    im = _images_from_params(p, method)
+    hashes = g.group("imagehash")
+    for key, h in hashes.items():
+        if key.startswith("atten"):
+            continue
+        assert hashlib.sha256(np.ascontiguousarray(im[key]).tobytes()).hexdigest() == str(h), key
+    p["images"] = im
+    got = backend.run_DEISM(p)
+    err = rel_l2(got, g.rtf)
+    print(f"{name}: rel L2 error vs reference run_DEISM = {err:.3e}")
+    assert err < RTF_TOL
+    return err
+
+
+def test_full_c1_shipped_rtf_yaml_mix():
+    _full_case("c1_full", "MIX", 0, 0)
+
+
+def test_full_c2_lc_order20_N5():
+    _full_case("c2_full_N5", "LC", 5, 5)
+
+
+def test_full_c3_org_order25_N10_subsampled():
+    _full_case("c3_sub100", "ORG", 10, 10)
+
+
+def test_full_c5_mix_order40_N5():
+    _full_case("c5_full_N5", "MIX", 5, 5)
