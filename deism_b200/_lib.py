@@ -57,6 +57,9 @@ _SIGNATURES = {
     "deism_device_info": (C.c_int, [_i32, _vp, _vp, _vp, _vp]),
     "deism_release_workspace": (C.c_int, []),
     "deism_kernel_launch_count": (C.c_uint64, []),
+    "deism_profile_enable": (C.c_int, [_i32]),
+    "deism_profile_reset": (C.c_int, []),
+    "deism_profile_get": (C.c_int, [C.c_char_p, _vp, _vp]),
     "deism_shoebox_count_images": (C.c_int, [_vp, _vp, _vp, _dbl, _i32, _i32, _i32, _vp, _vp, _vp]),
     "deism_shoebox_fill_images": (C.c_int, [_vp, _vp, _vp, _dbl, _i32, _i32, _i32, _vp, _vp]
                                   + [_vp] * 8 + [_vp]),

@@ -1,6 +1,7 @@
 // api.cu — library plumbing of libdeism_b200: error reporting, device checks, cached device
 // scratch, launch counting and the FP64 roofline micro-benchmarks (DFMA / DMMA).
 #include <mutex>
+#include <vector>
 #include <stdarg.h>
 #include <string.h>
 
@@ -102,6 +103,40 @@ void *workspace(int slot, size_t bytes) {
 }
 
 // ---------------------------------------------------------------------------------------
+// per-kernel event timing
+// ---------------------------------------------------------------------------------------
+struct ProfSlot {
+    char name[32];
+    std::vector<cudaEvent_t> ev;   // start/stop pairs
+    size_t used = 0;
+};
+static bool g_prof_on = false;
+static std::vector<ProfSlot *> g_prof;
+
+static ProfSlot *prof_slot(const char *name) {
+    for (ProfSlot *s : g_prof)
+        if (strncmp(s->name, name, sizeof(s->name)) == 0) return s;
+    ProfSlot *s = new ProfSlot();
+    strncpy(s->name, name, sizeof(s->name) - 1);
+    s->name[sizeof(s->name) - 1] = 0;
+    g_prof.push_back(s);
+    return s;
+}
+static void prof_record(const char *name, cudaStream_t st) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    ProfSlot *s = prof_slot(name);
+    if (s->used == s->ev.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        s->ev.push_back(e);
+    }
+    cudaEventRecord(s->ev[s->used++], st);
+}
+void prof_begin(const char *name, cudaStream_t st) { prof_record(name, st); }
+void prof_end(const char *name, cudaStream_t st) { prof_record(name, st); }
+
+// ---------------------------------------------------------------------------------------
 // FP64 roofline micro-benchmarks.  MEASURED_PEAKS.json carries HBM and bf16 numbers only; the
 // kernels of this library are bound by the FP64 FMA pipe, so bench.py measures that pipe.
 // ---------------------------------------------------------------------------------------
@@ -183,6 +218,37 @@ extern "C" int deism_release_workspace(void) {
         s->ws[i] = nullptr;
         s->ws_bytes[i] = 0;
     }
+    return DEISM_OK;
+}
+
+extern "C" int deism_profile_enable(int on) {
+    g_prof_on = on != 0;
+    return DEISM_OK;
+}
+
+extern "C" int deism_profile_reset(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (ProfSlot *s : g_prof) s->used = 0;
+    return DEISM_OK;
+}
+
+extern "C" int deism_profile_get(const char *kernel, double *ms_total, int *launches) {
+    if (!kernel) return set_error(DEISM_ERR_INVALID, "null kernel name");
+    double total = 0.0;
+    int n = 0;
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (ProfSlot *s : g_prof) {
+        if (strncmp(s->name, kernel, sizeof(s->name)) != 0) continue;
+        for (size_t i = 0; i + 1 < s->used; i += 2) {
+            DEISM_CUDA_TRY(cudaEventSynchronize(s->ev[i + 1]));
+            float ms = 0.f;
+            DEISM_CUDA_TRY(cudaEventElapsedTime(&ms, s->ev[i], s->ev[i + 1]));
+            total += ms;
+            ++n;
+        }
+    }
+    if (ms_total) *ms_total = total;
+    if (launches) *launches = n;
     return DEISM_OK;
 }
 

@@ -163,7 +163,9 @@ extern "C" int deism_lc_arg(int64_t n_images, int64_t K, int Js, int Jr, const i
     ma.Cs = (const float2 *)d_C_s_ARG_vec; ma.Cr = (const float2 *)d_C_r_vec; ma.Ys = Ys; ma.Yr = Yr;
     ma.r = r; ma.atten = (const float2 *)d_atten; ma.k = d_k; ma.sel = sel; ma.partial = partial;
     dim3 grid((unsigned)nblk, (unsigned)K);
+    prof_begin("arg_lc", st);
     arg_lc_kernel<<<grid, 128, 0, st>>>(ma);
+    prof_end("arg_lc", st);
     DEISM_LAUNCH_CHECK("arg_lc_kernel");
     return launch_reduce_partials(partial, nblk, K, d_out, accumulate, st);
 }

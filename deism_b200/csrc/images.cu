@@ -254,9 +254,11 @@ extern "C" int deism_shoebox_fill_images(const double h_room_size[3], const doub
                       remove_direct);
     if (rc) return rc;
     if (!d_early_counts || !d_late_counts) return set_error(DEISM_ERR_INVALID, "null count buffer");
+    prof_begin("shoebox_fill", (cudaStream_t)stream);
     shoebox_fill_kernel<<<8 * (N_o + 1), IMG_THREADS, 0, (cudaStream_t)stream>>>(
         P, d_early_counts, d_late_counts, d_A_early, d_R_sI_r_early, d_R_s_rI_early, d_R_r_sI_early,
         d_A_late, d_R_sI_r_late, d_R_s_rI_late, d_R_r_sI_late);
+    prof_end("shoebox_fill", (cudaStream_t)stream);
     DEISM_LAUNCH_CHECK("shoebox_fill_kernel");
     return DEISM_OK;
 }

@@ -452,7 +452,9 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
     dim3 grid((unsigned)n_ftiles, (unsigned)n_chunks);
     DEISM_CUDA_TRY(cudaFuncSetAttribute(lc_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)sizeof(LcSmem)));
+    prof_begin("lc_main", st);
     lc_main_kernel<<<grid, LC_THREADS, sizeof(LcSmem), st>>>(ma);
+    prof_end("lc_main", st);
     DEISM_LAUNCH_CHECK("lc_main_kernel");
 
     return launch_reduce_partials(partial, n_chunks, K, d_out, accumulate, st);

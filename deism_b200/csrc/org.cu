@@ -699,7 +699,9 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
         da.shoebox = 1; da.partial = partial;
         if (K > 65535) return set_error(DEISM_ERR_INVALID, "direct ORG supports K <= 65535");
         dim3 grid((unsigned)nblk, (unsigned)K);
-        org_direct_kernel<<<grid, 128, 0, st>>>(da);
+        prof_begin("org_direct", st);
+    org_direct_kernel<<<grid, 128, 0, st>>>(da);
+    prof_end("org_direct", st);
         DEISM_LAUNCH_CHECK("org_direct_kernel");
         return launch_reduce_partials(partial, nblk, K, d_out, accumulate, st);
     }
@@ -721,7 +723,9 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
     ba.CsT = CsT; ba.CrT = CrT; ba.k = d_k; ba.B = B;
     {
         dim3 grid((unsigned)((K + 127) / 128), (unsigned)nseg, 8);
+        prof_begin("org_btable", st);
         org_btable_kernel<<<grid, 128, 0, st>>>(ba);
+        prof_end("org_btable", st);
         DEISM_LAUNCH_CHECK("org_btable_kernel");
     }
 
@@ -762,7 +766,9 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
     DEISM_CUDA_TRY(cudaFuncSetAttribute(org_consume_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
     dim3 grid((unsigned)n_ftiles, (unsigned)n_chunks);
+    prof_begin("org_consume", st);
     org_consume_kernel<<<grid, ORG_THREADS, smem, st>>>(ca);
+    prof_end("org_consume", st);
     DEISM_LAUNCH_CHECK("org_consume_kernel");
     return launch_reduce_partials(partial, n_chunks, K, d_out, accumulate, st);
 }
@@ -826,7 +832,9 @@ extern "C" int deism_org_arg(int64_t n_images, int64_t K, int N, int V, const fl
     da.Cr = (const float2 *)d_C_vu_r; da.Y = Y; da.rec = rec; da.sel = sel; da.k = d_k;
     da.mode = -1; da.atten = d_atten; da.Z = nullptr; da.shoebox = 0; da.partial = partial;
     dim3 grid((unsigned)nblk, (unsigned)K);
+    prof_begin("org_direct", st);
     org_direct_kernel<<<grid, 128, 0, st>>>(da);
+    prof_end("org_direct", st);
     DEISM_LAUNCH_CHECK("org_direct_kernel");
     return launch_reduce_partials(partial, nblk, K, d_out, accumulate, st);
 }

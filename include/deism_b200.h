@@ -55,6 +55,14 @@ DEISM_API int deism_device_info(int device, int *sm_count, size_t *hbm_bytes, in
 DEISM_API int deism_release_workspace(void);     /* frees cached device scratch */
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 DEISM_API uint64_t deism_kernel_launch_count(void);
+/* Per-kernel device timing for the roofline report: when enabled, the accumulation entry points
+ * bracket their dominant kernels with CUDA events on the launching stream.
+ * deism_profile_get("lc_main" | "org_consume" | "org_btable" | "org_direct" | "arg_lc" |
+ * "shoebox_fill" | "convex_expand", ...) synchronises those events and returns the summed
+ * milliseconds and the number of launches since the last deism_profile_reset(). */
+DEISM_API int deism_profile_enable(int on);
+DEISM_API int deism_profile_reset(void);
+DEISM_API int deism_profile_get(const char *kernel, double *ms_total, int *launches);
 
 /* ------------------------------------------------------------------------------------ */
 /* Shoebox wall attenuation source (what the reference calls images["atten_all"])        */

@@ -438,3 +438,89 @@ def vectorize(Cnm, order):
             m_all[n * n + n + m] = m
             vec[:, n * n + n + m] = Cnm[:, n, m]
     return n_all, m_all, vec.astype(np.complex64)
+
+
+# --------------------------------------------------------------------------------------
+# convex room (libroom_deism restatement, oracle/convex_oracle.c)
+# --------------------------------------------------------------------------------------
+def walls_from_libroom(walls, K=None):
+    """Pack a list of libroom Wall_deism objects (or anything with .normal/.origin/.basis/
+    .flat_corners/.reflection_matrix/.impedence_bands) into the flat float32 tables used by the
+    oracle and by the C ABI (struct deism_convex_walls)."""
+    W = len(walls)
+    mc = max(np.asarray(w.flat_corners).shape[1] for w in walls)
+    out = {
+        "normal": np.zeros((W, 3), np.float32), "origin": np.zeros((W, 3), np.float32),
+        "basis": np.zeros((W, 3, 2), np.float32), "flat_corners": np.zeros((W, 2, mc), np.float32),
+        "n_corners": np.zeros(W, np.int32), "reflection": np.zeros((W, 3, 3), np.float32),
+    }
+    imp = []
+    for i, w in enumerate(walls):
+        out["normal"][i] = np.asarray(w.normal, np.float32).reshape(3)
+        out["origin"][i] = np.asarray(w.origin, np.float32).reshape(3)
+        out["basis"][i] = np.asarray(w.basis, np.float32)
+        fc = np.asarray(w.flat_corners, np.float32)
+        out["flat_corners"][i, :, :fc.shape[1]] = fc
+        out["n_corners"][i] = fc.shape[1]
+        out["reflection"][i] = np.asarray(w.reflection_matrix, np.float32)
+        imp.append(np.real(np.asarray(w.impedence_bands)).astype(np.float32))   # wall.cpp:428
+    out["impedance"] = np.ascontiguousarray(np.stack(imp, axis=0))
+    return out
+
+
+def walls_from_golden(g):
+    """Same tables from a tests/golden convex fixture (walls/<i>/...)."""
+    grp = g.group("walls")
+    W = int(grp["n"])
+
+    class _W:
+        pass
+
+    ws = []
+    for i in range(W):
+        w = _W()
+        w.normal, w.origin = grp[f"{i}/normal"], grp[f"{i}/origin"]
+        w.basis, w.flat_corners = grp[f"{i}/basis"], grp[f"{i}/flat_corners"]
+        w.reflection_matrix, w.impedence_bands = grp[f"{i}/reflection_matrix"], grp[f"{i}/impedance"]
+        ws.append(w)
+    return walls_from_libroom(ws)
+
+
+def convex_images(wt, source, mic, ism_order):
+    """room.cpp:271-511: returns dict(sources[3,I], orders[I], gen_walls[I], attenuations[K,I],
+    reflection_matrix[I,3,3], n_nodes)."""
+    L = lib()
+    L.oracle_convex_run.restype = C.c_void_p
+    K = wt["impedance"].shape[1]
+    src = _c(source, np.float32)
+    m = _c(mic, np.float32)
+    n, nodes = C.c_long(0), C.c_long(0)
+    h = L.oracle_convex_run(
+        C.c_int(wt["normal"].shape[0]), C.c_int(wt["flat_corners"].shape[2]),
+        _p(wt["normal"], _f32p), _p(wt["origin"], _f32p), _p(wt["basis"], _f32p),
+        _p(wt["flat_corners"], _f32p), _p(wt["n_corners"], _i32p), _p(wt["reflection"], _f32p),
+        _p(wt["impedance"], _f32p), C.c_int(K), _p(src, _f32p), _p(m, _f32p), C.c_int(ism_order),
+        C.byref(n), C.byref(nodes))
+    if not h:
+        raise MemoryError("oracle_convex_run")
+    I = n.value
+    out = {"sources": np.zeros((3, I), np.float32), "orders": np.zeros(I, np.int32),
+           "gen_walls": np.zeros(I, np.int32), "attenuations": np.zeros((K, I), np.float32),
+           "reflection_matrix": np.zeros((I, 3, 3), np.float32), "n_nodes": nodes.value}
+    L.oracle_convex_export(C.c_void_p(h), _p(out["sources"], _f32p), _p(out["orders"], _i32p),
+                           _p(out["gen_walls"], _i32p), _p(out["attenuations"], _f32p),
+                           _p(out["reflection_matrix"], _f32p))
+    L.oracle_convex_free(C.c_void_p(h))
+    return out
+
+
+def acosf(x):
+    L = lib()
+    L.oracle_acosf.restype = C.c_float
+    return float(L.oracle_acosf(C.c_float(x)))
+
+
+def cosf(x):
+    L = lib()
+    L.oracle_cosf.restype = C.c_float
+    return float(L.oracle_cosf(C.c_float(x)))
