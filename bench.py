@@ -193,7 +193,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from deism_b200 import _lib, backend, images as gimages
+    from deism_b200 import _lib, backend, distributed, images as gimages
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -208,12 +208,9 @@ def main():
     terms = I * K
 
     # frequency slab of this rank
-    lo, hi = (K * rank) // world, (K * (rank + 1)) // world
-    ps = workloads.slice_frequencies(p, lo, hi) if world > 1 else dict(p)
+    ps, lo, hi = distributed.shard_frequencies(p, rank, world)
     ps["images"] = full_images
     Ks = hi - lo
-    counts = [(K * (r + 1)) // world - (K * r) // world for r in range(world)]
-    equal_slabs = len(set(counts)) == 1
 
     def pin(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -261,26 +258,9 @@ def main():
             p_dev[key] = torch.from_numpy(np.ascontiguousarray(ps[key])).to(dt).to(dev)
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    gather_buf = [torch.empty(Ks, dtype=torch.complex128, device=dev) for _ in range(world)] \
-        if (world > 1 and equal_slabs) else None
-    full_out = torch.empty(K, dtype=torch.complex128, device=dev) if world > 1 else None
-
     def combine(slab):
         """The one collective of the path: frequency slabs -> full RTF on every rank."""
-        if world == 1:
-            return slab
-        if equal_slabs:
-            dist.all_gather_into_tensor(full_out, slab)
-        else:
-            padded = torch.zeros(max(counts), dtype=torch.complex128, device=dev)
-            padded[:Ks] = slab
-            bufs = [torch.empty_like(padded) for _ in range(world)]
-            dist.all_gather(bufs, padded)
-            off = 0
-            for r, c in enumerate(counts):
-                full_out[off:off + c] = bufs[r][:c]
-                off += c
-        return full_out
+        return distributed.gather_frequency_slabs(slab, K)
 
     def step_device():
         return combine(backend.run_DEISM_device(p_dev, dev))

@@ -1,0 +1,133 @@
+"""Multi-GPU sharding of the run_DEISM hot path.
+
+Every (image, frequency) term is independent and the only coupling is the sum over images per
+frequency (parallel_backends.py:257-261), so the path shards without any data-path exchange:
+
+  * primary: every rank owns a contiguous FREQUENCY slab [lo, hi) and all images; the slabs
+    are concatenated with one all_gather of hi-lo complex128 values per rank;
+  * secondary (few frequencies, many images): contiguous IMAGE slabs, all frequencies, one
+    all_reduce(sum) over 2K doubles.
+
+One process per GPU, ``torch.distributed`` for the plumbing (NCCL on GPUs; the same code runs
+over gloo with CPU tensors, which is how the host logic is tested without GPUs).  The compute
+callback is injected so that this module never decides *how* a slab is computed.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+_FREQ_KEYS = ("waveNumbers", "freqs", "C_nm_s", "C_vu_r", "C_nm_s_vec", "C_vu_r_vec",
+              "C_nm_s_ARG", "C_nm_s_ARG_vec", "pointSrcStrength")
+_IMAGE_KEYS = ("A", "R_sI_r_all", "R_s_rI_all", "R_r_sI_all", "atten_all")
+
+
+def slab_bounds(n: int, world: int, rank: int):
+    """Contiguous, balanced [lo, hi) of ``n`` items for ``rank`` (sizes differ by at most 1)."""
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def slab_counts(n: int, world: int):
+    return [slab_bounds(n, world, r)[1] - slab_bounds(n, world, r)[0] for r in range(world)]
+
+
+def _slice0(x, lo, hi):
+    if isinstance(x, torch.Tensor):
+        return x[lo:hi].contiguous()
+    return np.ascontiguousarray(np.asarray(x)[lo:hi])
+
+
+def shard_frequencies(params, rank: int, world: int):
+    """params restricted to this rank's frequency slab (images are shared, not copied)."""
+    K = int(np.asarray(params["waveNumbers"]).shape[0]) \
+        if not isinstance(params["waveNumbers"], torch.Tensor) else int(params["waveNumbers"].shape[0])
+    lo, hi = slab_bounds(K, world, rank)
+    q = dict(params)
+    for key in _FREQ_KEYS:
+        if key in q and q[key] is not None:
+            q[key] = _slice0(q[key], lo, hi)
+    Z = q.get("impedance")
+    if Z is not None:
+        q["impedance"] = Z[:, lo:hi].contiguous() if isinstance(Z, torch.Tensor) \
+            else np.ascontiguousarray(np.asarray(Z)[:, lo:hi])
+    images = q.get("images")
+    if images is not None:
+        im = dict(images)
+        shoebox = "A" in images or "A_early" in images
+        for key, val in images.items():
+            if key.startswith("atten_all") and val is not None:
+                if shoebox:      # materialised shoebox attenuation is [I, K]
+                    im[key] = val[:, lo:hi].contiguous() if isinstance(val, torch.Tensor) \
+                        else np.ascontiguousarray(np.asarray(val)[:, lo:hi])
+                else:            # convex attenuation is [K, I]
+                    im[key] = _slice0(val, lo, hi)
+        q["images"] = im
+    return q, lo, hi
+
+
+def shard_images(params, rank: int, world: int):
+    """params restricted to this rank's slab of a merged (ORG / LC) shoebox image list."""
+    images = params["images"]
+    if "A" not in images:
+        raise ValueError("image sharding needs the merged ORG/LC image dict")
+    n = len(images["A"])
+    lo, hi = slab_bounds(n, world, rank)
+    q = dict(params)
+    im = dict(images)
+    for key in _IMAGE_KEYS:
+        if key in im and im[key] is not None:
+            im[key] = _slice0(im[key], lo, hi)
+    q["images"] = im
+    return q, lo, hi
+
+
+def gather_frequency_slabs(slab: torch.Tensor, K: int, group=None) -> torch.Tensor:
+    """The one collective of the frequency-sharded path: every rank ends up with the full
+    complex128[K] result.  Equal slabs use all_gather_into_tensor; ragged ones are padded."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return slab
+    counts = slab_counts(K, world)
+    slab = slab.contiguous()
+    if len(set(counts)) == 1:
+        out = torch.empty(K, dtype=slab.dtype, device=slab.device)
+        if slab.is_complex():
+            dist.all_gather_into_tensor(torch.view_as_real(out), torch.view_as_real(slab), group=group)
+        else:
+            dist.all_gather_into_tensor(out, slab, group=group)
+        return out
+    width = max(counts)
+    padded = torch.zeros(width, dtype=slab.dtype, device=slab.device)
+    padded[:slab.shape[0]] = slab
+    bufs = [torch.empty((width, 2), dtype=torch.float64, device=slab.device) for _ in range(world)]
+    dist.all_gather(bufs, torch.view_as_real(padded).contiguous(), group=group)
+    parts = [torch.view_as_complex(b.contiguous())[:c] for b, c in zip(bufs, counts)]
+    return torch.cat(parts)
+
+
+def reduce_image_slabs(partial: torch.Tensor, group=None) -> torch.Tensor:
+    """Image-sharded path: sum of the per-rank partial RTFs (one all_reduce over 2K doubles)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return partial
+    buf = torch.view_as_real(partial.contiguous()).clone()
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return torch.view_as_complex(buf)
+
+
+def run_sharded(params, compute, mode: str = "frequency", group=None) -> torch.Tensor:
+    """Run ``compute(params_slab) -> complex128 tensor`` on this rank's slab and combine.
+
+    ``compute`` is e.g. ``deism_b200.backend.run_DEISM_device``; ``mode`` is "frequency"
+    (all_gather) or "image" (all_reduce)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if mode == "frequency":
+        K = int(np.asarray(params["waveNumbers"]).shape[0]) \
+            if not isinstance(params["waveNumbers"], torch.Tensor) else int(params["waveNumbers"].shape[0])
+        q, lo, hi = shard_frequencies(params, rank, world)
+        return gather_frequency_slabs(compute(q), K, group)
+    if mode == "image":
+        q, lo, hi = shard_images(params, rank, world)
+        return reduce_image_slabs(compute(q), group)
+    raise ValueError(f"unknown sharding mode: {mode}")

@@ -1,0 +1,79 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: frequency-slab sharding + the one
+all_gather, image-slab sharding + all_reduce.  The per-slab compute is the CPU oracle here (no
+GPU in this container); on the GPU box bench.py runs the same code path over NCCL."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, Golden, rel_l2
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, name, mode, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from conftest import Golden as G
+    from deism_b200 import distributed as D
+    from oracle import oracle
+
+    oracle.set_num_threads(1)
+    g = G(name)
+    p = g.params()
+
+    def compute(q):
+        if "R_s_rI_all" in q["images"] or "A_early" in q["images"] or "A" in q["images"]:
+            return torch.from_numpy(oracle.run_DEISM(q))
+        return torch.from_numpy(oracle.run_DEISM_ARG(q))
+
+    full = D.run_sharded(p, compute, mode=mode)
+    np.save(os.path.join(out_dir, f"r{rank}.npy"), full.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,mode,world", [
+    ("s2_shoebox_rtf_lc_o6_N3", "frequency", 2),
+    ("s4_shoebox_rir_mix_o9_N2", "frequency", 2),
+    ("s1_shoebox_rtf_mix_o5_mono", "frequency", 3),     # ragged slabs: 100 freqs over 3 ranks
+    ("s3_shoebox_rtf_org_o4_N3V2", "image", 2),
+    ("x1_convex_rir_mix_o4_mono", "frequency", 2),
+])
+def test_sharded_run_equals_single(tmp_path, name, mode, world):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, name, mode, str(tmp_path)), nprocs=world, join=True)
+    g = Golden(name)
+    for r in range(world):
+        got = np.load(tmp_path / f"r{r}.npy")
+        assert got.shape == g.rtf.shape
+        assert rel_l2(got, g.rtf) < 1e-12, (name, r)
+
+
+def test_slab_bounds_cover_everything():
+    from deism_b200 import distributed as D
+
+    for n in (0, 1, 7, 100, 16000):
+        for world in (1, 2, 3, 4, 8):
+            prev = 0
+            for r in range(world):
+                lo, hi = D.slab_bounds(n, world, r)
+                assert lo == prev and hi >= lo
+                prev = hi
+            assert prev == n
+            c = D.slab_counts(n, world)
+            assert sum(c) == n and max(c) - min(c) <= 1
