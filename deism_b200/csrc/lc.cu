@@ -7,23 +7,38 @@
 //   S[img,k] = sum_j i^{n_j} C_s[k,j] Y_{n_j}^{m_j}(theta_s,phi_s)       (source->receiver image)
 //   R[img,k] = sum_j i^{v_j} C_r[k,j] Y_{v_j}^{u_j}(theta_r,phi_r)       (receiver->source image)
 //
-// Structure:
-//   lc_prep_kernel   one thread per image: phase-folded harmonics Ys'[img,j], Yr'[img,j],
+// S and R are dense complex contractions [I x J] . [J x K] whose [I x K] result must never reach
+// memory (22 GB for the order-40 / 16k-frequency config), so they are computed tile by tile on
+// the FP64 tensor cores and consumed in registers:
+//
+//   lc_prep_kernel   one thread per image: phase-folded harmonics Y'[img,j] (i^n folded in),
 //                    r, 1/r, direction cosines + wall exponents, flat-impedance attenuation.
-//   lc_main_kernel   CTA tile = 32 frequencies x 64 images, 128 threads, 4x4 (freq x image)
-//                    register tile per thread: S and R are [I x J] . [J x K] complex
-//                    contractions streamed through shared memory in chunks of JC harmonics;
-//                    the epilogue applies exp(-ikr), 1/(k^2 r) and atten and accumulates
-//                    P[k] in registers over the CTA's image chunk.
-//   lc_reduce_kernel deterministic sum of the per-chunk partials into out[K].
+//   lc_coef_kernel   C[k,j] complex64 -> FP64 operand planes.
+//   lc_main_kernel   CTA tile = 64 images x 32 frequencies, 4 warps (16 images each).
+//                    The complex product uses the 3-multiplication form
+//                        T1 = Yr.Cr   T2 = Yi.Ci   T3 = (Yr+Yi).(Cr+Ci)
+//                        S = (T1 - T2) + i (T3 - T1 - T2)
+//                    i.e. three REAL GEMMs per pass, each issued as mma.sync m8n8k4 f64 (DMMA):
+//                    25 % fewer FP64 FMAs than the 4-multiplication form, error ~1e-16 relative.
+//                    Operand planes (Yr | Yi | Yr+Yi and Cr | Ci | Cr+Ci) are laid out in global
+//                    memory exactly as the kernel wants them in shared memory (row stride
+//                    = 4 mod 16 doubles -> conflict-free fragment loads), so one harmonic chunk of
+//                    one tile is ONE contiguous block staged by a single TMA bulk copy
+//                    (cp.async.bulk -> UBLKCP) per operand, double buffered on mbarriers.
+//                    Epilogue in registers: fac = -atten * 4pi/k^2/r * exp(-ikr) (computed per
+//                    tile before the contraction), S' = fac*S parked in shared memory, then
+//                    P[k] += S'*R accumulated over the CTA's image chunk.
+//   reduce_partials  deterministic sum of the per-chunk partials into out[K].
 #include "common.cuh"
 
 namespace deism {
 
-constexpr int LC_TF = 32;       // frequencies per CTA tile
-constexpr int LC_TI = 64;       // images per inner tile
-constexpr int LC_JC = 16;       // harmonics per shared-memory chunk
-constexpr int LC_THREADS = 128; // 8 (freq) x 16 (image) threads, 4x4 pairs each
+constexpr int LC_TF = 32;        // frequencies per CTA tile
+constexpr int LC_TI = 64;        // images per tile
+constexpr int LC_JC = 12;        // max harmonics per staged chunk (multiple of 4)
+constexpr int LC_THREADS = 128;  // 4 warps x 16 images
+constexpr int LC_YS = LC_TI + 4; // Y plane row stride (doubles): 68 = 4 mod 16
+constexpr int LC_CS = LC_TF + 4; // C plane row stride (doubles): 36 = 4 mod 16
 
 struct LcImage {        // 64 bytes per image
     double r, inv_r;
@@ -60,25 +75,38 @@ __global__ void z_flat_kernel(const cplx *__restrict__ Z, long K, int *flags) {
     if (__syncthreads_or(diff) && threadIdx.x == 0) atomicExch(flags, 0);
 }
 
-// Per-image tables, padded to whole tiles: rows >= n_images and columns >= J are zero so that
-// the main kernel's bulk copies never need a bounds check.
+// Y planes: [tile][j < J_pad][plane 0..2][LC_YS] doubles, plane = Re | Im | Re+Im of
+// i^{n_j} Y_j(image); image index within the tile fastest.  Rows >= n_images, columns >= J and
+// the 4 pad doubles are zero, so the main kernel's bulk copies never need a bounds check.
+__device__ __forceinline__ void store_y(double *Y, long base, int j, cplx v) {
+    double *p = Y + base + (long)j * 3 * LC_YS;
+    p[0] = v.x;
+    p[LC_YS] = v.y;
+    p[2 * LC_YS] = v.x + v.y;
+}
+
 __global__ void __launch_bounds__(128)
-lc_prep_kernel(LcPrepArgs a, LcImage *img_out, cplx *Ys, cplx *Yr) {
+lc_prep_kernel(LcPrepArgs a, LcImage *img_out, double *Ys, double *Yr) {
     long img = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (img >= a.n_pad) return;
     LcImage rec;
     rec.cx = rec.cy = rec.cz = 1.0;
     for (int i = 0; i < 8; ++i) rec.e[i] = 0;
-    // Y tables are tile-major [tile][j][image in tile]: a chunk of harmonics of one image tile is
-    // one contiguous block (a single bulk copy) and lands conflict-free in shared memory
-    const long ys_base = (img / LC_TI) * (long)a.Js_pad * LC_TI + (img % LC_TI);
-    const long yr_base = (img / LC_TI) * (long)a.Jr_pad * LC_TI + (img % LC_TI);
+    const long tile = img / LC_TI, it = img % LC_TI;
+    const long ys_base = tile * (long)a.Js_pad * 3 * LC_YS + it;
+    const long yr_base = tile * (long)a.Jr_pad * 3 * LC_YS + it;
+    if (it < 4) {   // the pad columns of this tile's rows
+        for (int j = 0; j < a.Js_pad * 3; ++j)
+            Ys[tile * (long)a.Js_pad * 3 * LC_YS + (long)j * LC_YS + LC_TI + it] = 0.0;
+        for (int j = 0; j < a.Jr_pad * 3; ++j)
+            Yr[tile * (long)a.Jr_pad * 3 * LC_YS + (long)j * LC_YS + LC_TI + it] = 0.0;
+    }
     if (img >= a.n_images) {
         rec.r = 1.0; rec.inv_r = 0.0;           // weight 0: contributes exactly nothing
         rec.atten_flat = cmake(0.0, 0.0);
         img_out[img] = rec;
-        for (int j = 0; j < a.Js_pad; ++j) Ys[ys_base + (long)j * LC_TI] = cmake(0.0, 0.0);
-        for (int j = 0; j < a.Jr_pad; ++j) Yr[yr_base + (long)j * LC_TI] = cmake(0.0, 0.0);
+        for (int j = 0; j < a.Js_pad; ++j) store_y(Ys, ys_base, j, cmake(0.0, 0.0));
+        for (int j = 0; j < a.Jr_pad; ++j) store_y(Yr, yr_base, j, cmake(0.0, 0.0));
         return;
     }
     double phi_s = (double)a.R_s_rI[img * 3 + 0], th_s = (double)a.R_s_rI[img * 3 + 1];
@@ -89,11 +117,11 @@ lc_prep_kernel(LcPrepArgs a, LcImage *img_out, cplx *Ys, cplx *Yr) {
     sincos_cw(th_s, &s, &ct_s);
     sincos_cw(th_r, &s, &ct_r);
     for (int j = 0; j < a.Js_pad; ++j)
-        Ys[ys_base + (long)j * LC_TI] = j < a.Js
-            ? cmul_ipow(sph_harm_dev(c_lc_m[j], c_lc_n[j], phi_s, ct_s), c_lc_n[j]) : cmake(0.0, 0.0);
+        store_y(Ys, ys_base, j, j < a.Js
+            ? cmul_ipow(sph_harm_dev(c_lc_m[j], c_lc_n[j], phi_s, ct_s), c_lc_n[j]) : cmake(0.0, 0.0));
     for (int j = 0; j < a.Jr_pad; ++j)
-        Yr[yr_base + (long)j * LC_TI] = j < a.Jr
-            ? cmul_ipow(sph_harm_dev(c_lc_u[j], c_lc_v[j], phi_r, ct_r), c_lc_v[j]) : cmake(0.0, 0.0);
+        store_y(Yr, yr_base, j, j < a.Jr
+            ? cmul_ipow(sph_harm_dev(c_lc_u[j], c_lc_v[j], phi_r, ct_r), c_lc_v[j]) : cmake(0.0, 0.0));
     AttenGeom g;
     g.cx = g.cy = g.cz = 1.0;
     for (int i = 0; i < 8; ++i) g.e[i] = 0;
@@ -111,24 +139,29 @@ lc_prep_kernel(LcPrepArgs a, LcImage *img_out, cplx *Ys, cplx *Yr) {
     img_out[img] = rec;
 }
 
-// complex64 [K][J] -> complex128 [K_pad/32][J_pad][32], zero padded: the harmonics j0..j0+JC of
-// one frequency tile are one contiguous block (a single bulk copy)
+// C planes: complex64 [K][J] -> [K_pad/32][j < J_pad][plane 0..2][LC_CS] doubles
+// (plane = Re | Im | Re+Im, frequency within the tile fastest, zero padded)
 __global__ void __launch_bounds__(256)
-lc_coef_kernel(const float2 *__restrict__ in, long K, int J, long K_pad, int J_pad, cplx *out) {
+lc_coef_kernel(const float2 *__restrict__ in, long K, int J, long n_ftiles, int J_pad, double *out) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= K_pad * J_pad) return;
-    long ft = i / ((long)J_pad * LC_TF);
-    int j = (int)((i / LC_TF) % J_pad);
-    long k = ft * LC_TF + (i % LC_TF);
-    cplx v = cmake(0.0, 0.0);
-    if (j < J && k < K) {
+    long total = n_ftiles * J_pad * LC_CS;
+    if (i >= total) return;
+    int q = (int)(i % LC_CS);
+    int j = (int)((i / LC_CS) % J_pad);
+    long ft = i / ((long)LC_CS * J_pad);
+    long k = ft * LC_TF + q;
+    double re = 0.0, im = 0.0;
+    if (q < LC_TF && j < J && k < K) {
         float2 c = in[k * J + j];
-        v = cmake((double)c.x, (double)c.y);
+        re = (double)c.x; im = (double)c.y;
     }
-    out[i] = v;
+    double *p = out + (ft * J_pad + j) * 3 * LC_CS + q;
+    p[0] = re;
+    p[LC_CS] = im;
+    p[2 * LC_CS] = re + im;
 }
 
-// ---- mbarrier / bulk-copy (TMA) primitives ----------------------------------------------
+// ---- mbarrier / bulk-copy (TMA) / DMMA primitives ---------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) {
     return (unsigned)__cvta_generic_to_shared(p);
 }
@@ -162,13 +195,19 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// D(8x8) += A(8x4) * B(4x8), FP64 tensor core
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
 
 struct LcMainArgs {
-    long n_images, n_pad, K, K_pad;
+    long n_images, n_pad, K;
     int Js_pad, Jr_pad;      // padded harmonic counts = ncs*JCs, ncr*JCr
-    int ncs, ncr, JCs, JCr;  // chunks per pass and harmonics per chunk
-    const cplx *CTs, *CTr;   // [K_pad/32][J_pad][32]
-    const cplx *Ys, *Yr;     // [n_pad/64][J_pad][64]
+    int ncs, ncr, JCs, JCr;  // chunks per pass and harmonics per chunk (multiples of 4)
+    const double *CTs, *CTr; // [K_pad/32][J_pad][3][LC_CS]
+    const double *Ys, *Yr;   // [n_pad/64][J_pad][3][LC_YS]
     const LcImage *img;      // [n_pad]
     const double *k;
     int mode;                // DEISM_ATTEN_*
@@ -181,20 +220,23 @@ struct LcMainArgs {
 
 constexpr int LC_STAGES = 2;
 struct LcStage {
-    double2 C[LC_JC][LC_TF];
-    double2 Y[LC_JC][LC_TI];
+    double C[LC_JC][3][LC_CS];
+    double Y[LC_JC][3][LC_YS];
 };
 struct LcSmem {
     LcStage st[LC_STAGES];
-    double2 fac[LC_TI][LC_TF + 1];   // factor[img][freq] of the current tile
-    double2 red[16][LC_TF];
+    double2 fac[LC_TI][LC_TF + 1];   // factor[img][freq], then S' = factor * S, of the current tile
     double2 Z[6][LC_TF];
     double2 aflat[LC_TI];
     double r[LC_TI], invr[LC_TI];
     double cosd[3][LC_TI];
+    double kf[LC_TF], wk[LC_TF];
     unsigned char e[LC_TI][8];
     unsigned long long full[LC_STAGES];
 };
+static_assert(sizeof(LcStage) % 16 == 0, "stage must keep 16-byte alignment");
+static_assert(sizeof(double2) * 32 * LC_TF <= sizeof(LcStage) * LC_STAGES,
+              "final reduction aliases the stages");
 
 __global__ void __launch_bounds__(LC_THREADS, 2)
 lc_main_kernel(LcMainArgs a) {
@@ -202,8 +244,8 @@ lc_main_kernel(LcMainArgs a) {
     LcSmem &sm = *reinterpret_cast<LcSmem *>(lc_smem_raw);
 
     const int tid = threadIdx.x;
-    const int tx = tid & 7;        // frequency lane: freqs f0 + tx + 8*q
-    const int ty = tid >> 3;       // image lane:     images i0 + ty + 16*b
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;          // DMMA fragment coordinates
     const long f0 = (long)blockIdx.x * LC_TF;
     const long chunk = blockIdx.y;
     const long n_img_tiles = a.n_pad / LC_TI;
@@ -220,35 +262,11 @@ lc_main_kernel(LcMainArgs a) {
         for (int s = 0; s < LC_STAGES; ++s) mbar_init(&sm.full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
-
-    // producer: warp 0 stages chunk c (harmonics of one pass for one image tile) with bulk copies
-    auto issue = [&](long c, int stage) {
-        const long tile = tile_lo + c / npt;
-        const int local = (int)(c % npt);
-        const bool src_pass = local < a.ncs;
-        const int JC = src_pass ? a.JCs : a.JCr;
-        const int j0 = (src_pass ? local : local - a.ncs) * JC;
-        const int Jp = src_pass ? a.Js_pad : a.Jr_pad;
-        const cplx *CT = (src_pass ? a.CTs : a.CTr) + ((long)blockIdx.x * Jp + j0) * LC_TF;
-        const cplx *Yg = (src_pass ? a.Ys : a.Yr) + (tile * Jp + j0) * LC_TI;
-        LcStage &S = sm.st[stage];
-        if ((tid & 31) == 0) {
-            mbar_expect_tx(&sm.full[stage], (unsigned)(JC * (LC_TF + LC_TI) * 16));
-            bulk_g2s(&S.C[0][0], CT, (unsigned)(JC * LC_TF * 16), &sm.full[stage]);
-            bulk_g2s(&S.Y[0][0], Yg, (unsigned)(JC * LC_TI * 16), &sm.full[stage]);
-        }
-    };
-
-    // per-thread frequency data
-    double kf[4], wk[4];
-    bool fvalid[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        long f = f0 + tx + 8 * q;
-        fvalid[q] = f < a.K;
-        kf[q] = fvalid[q] ? a.k[f] : 1.0;
-        wk[q] = -4.0 * 3.14159265358979323846 / (kf[q] * kf[q]);   // -4pi/k^2
+    for (int q = tid; q < LC_TF; q += LC_THREADS) {
+        long f = f0 + q;
+        double kk = f < a.K ? a.k[f] : 1.0;
+        sm.kf[q] = kk;
+        sm.wk[q] = -4.0 * 3.14159265358979323846 / (kk * kk);   // -4pi/k^2
     }
     if (fused && !flat) {
         for (int i = tid; i < 6 * LC_TF; i += LC_THREADS) {
@@ -257,13 +275,34 @@ lc_main_kernel(LcMainArgs a) {
             sm.Z[w][q] = f < a.K ? a.Z[(long)w * a.K + f] : cmake(1.0, 0.0);
         }
     }
+    __syncthreads();
 
-    cplx P[4];
+    // producer: one thread stages chunk c (JC harmonics of one pass for one image tile) with two
+    // bulk copies: the C block of this frequency tile and the Y block of the image tile
+    auto issue = [&](long c, int stage) {
+        const long tile = tile_lo + c / npt;
+        const int local = (int)(c % npt);
+        const bool src_pass = local < a.ncs;
+        const int JC = src_pass ? a.JCs : a.JCr;
+        const int j0 = (src_pass ? local : local - a.ncs) * JC;
+        const int Jp = src_pass ? a.Js_pad : a.Jr_pad;
+        const double *CT = (src_pass ? a.CTs : a.CTr) + ((long)blockIdx.x * Jp + j0) * 3 * LC_CS;
+        const double *Yg = (src_pass ? a.Ys : a.Yr) + (tile * Jp + j0) * 3 * LC_YS;
+        LcStage &S = sm.st[stage];
+        const unsigned cb = (unsigned)(JC * 3 * LC_CS * 8), yb = (unsigned)(JC * 3 * LC_YS * 8);
+        mbar_expect_tx(&sm.full[stage], cb + yb);
+        bulk_g2s(&S.C[0][0][0], CT, cb, &sm.full[stage]);
+        bulk_g2s(&S.Y[0][0][0], Yg, yb, &sm.full[stage]);
+    };
+
+    // accumulators of the three real GEMMs: [plane][m-tile][n-tile][2]
+    double T[3][2][4][2];
+    // P[freq]: this thread's 8 frequencies 2*t4 + e + 8*nt, summed over its images
+    cplx P[4][2];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) P[q] = cmake(0.0, 0.0);
-    cplx S[4][4], R[4][4];   // [freq q][image b]
+    for (int nt = 0; nt < 4; ++nt) { P[nt][0] = cmake(0.0, 0.0); P[nt][1] = cmake(0.0, 0.0); }
 
-    if (tid < 32 && total > 0) issue(0, 0);
+    if (tid == 0 && total > 0) issue(0, 0);
 
 #pragma unroll 1
     for (long c = 0; c < total; ++c) {
@@ -274,10 +313,7 @@ lc_main_kernel(LcMainArgs a) {
 
         if (local == 0) {
             // ---- new image tile: per-image records, then the factor
-            //      fac[img][freq] = -atten * 4pi/k * exp(-ikr)/k/r   (pb:314-317),
-            // computed before the contraction so that its registers are dead while the 4x4
-            // S and R accumulators are live; each thread produces exactly the 16 pairs it
-            // consumes in the epilogue.
+            //      fac[img][freq] = -atten * 4pi/k * exp(-ikr)/k/r   (pb:314-317)
             for (int i = tid; i < LC_TI; i += LC_THREADS) {
                 LcImage rec = a.img[i0 + i];
                 sm.r[i] = rec.r; sm.invr[i] = rec.inv_r;
@@ -287,26 +323,28 @@ lc_main_kernel(LcMainArgs a) {
                 sm.aflat[i] = rec.atten_flat;
             }
             __syncthreads();
+            const int tx = tid & 7, ty = tid >> 3;
 #pragma unroll 1
             for (int b = 0; b < 4; ++b) {
                 const int il = ty + 16 * b;
                 const long img = i0 + il;
                 const double r = sm.r[il], inv_r = sm.invr[il];
-#pragma unroll
+#pragma unroll 2
                 for (int q = 0; q < 4; ++q) {
+                    const int fq = tx + 8 * q;
                     double sn, cs;
-                    sincos_cw(kf[q] * r, &sn, &cs);
+                    sincos_cw(sm.kf[fq] * r, &sn, &cs);
                     cplx att;
                     if (flat) {
                         att = sm.aflat[il];
                     } else if (fused) {
-                        att = shoebox_atten(&sm.Z[0][tx + 8 * q], LC_TF, sm.cosd[0][il], sm.cosd[1][il],
+                        att = shoebox_atten(&sm.Z[0][fq], LC_TF, sm.cosd[0][il], sm.cosd[1][il],
                                             sm.cosd[2][il], sm.e[il]);
                         if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
                     } else {
-                        long f = f0 + tx + 8 * q;
+                        long f = f0 + fq;
                         att = cmake(0.0, 0.0);
-                        if (img < a.n_images && fvalid[q]) {
+                        if (img < a.n_images && f < a.K) {
                             if (a.mode == DEISM_ATTEN_C64) {
                                 float2 v = ((const float2 *)a.atten)[img * a.K + f];
                                 att = cmake((double)v.x, (double)v.y);
@@ -315,74 +353,90 @@ lc_main_kernel(LcMainArgs a) {
                             }
                         }
                     }
-                    double w = wk[q] * inv_r;
-                    sm.fac[il][tx + 8 * q] = cmul(att, cmake(cs * w, -sn * w));
+                    double w = sm.wk[fq] * inv_r;
+                    sm.fac[il][fq] = cmul(att, cmake(cs * w, -sn * w));
                 }
             }
+        }
+        if (local == 0 || local == a.ncs) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int p = 0; p < 3; ++p)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) { S[q][b] = cmake(0.0, 0.0); R[q][b] = cmake(0.0, 0.0); }
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) { T[p][mt][nt][0] = 0.0; T[p][mt][nt][1] = 0.0; }
         }
 
         // stage (c+1)&1 was released by the barrier that closed iteration c-1
-        if (tid < 32 && c + 1 < total) issue(c + 1, stage ^ 1);
+        if (tid == 0 && c + 1 < total) issue(c + 1, stage ^ 1);
         mbar_wait(&sm.full[stage], parity);
 
-        const LcStage &T = sm.st[stage];
-        if (local < a.ncs) {
-            const int jn = a.JCs;
-#pragma unroll 4
-            for (int j = 0; j < jn; ++j) {
-                cplx cq[4], yb[4];
+        const LcStage &S = sm.st[stage];
+        const int JC = local < a.ncs ? a.JCs : a.JCr;
+#pragma unroll 1
+        for (int ks = 0; ks < JC; ks += 4) {
+            double af[3][2], bf[3][4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) cq[q] = T.C[j][tx + 8 * q];
+            for (int p = 0; p < 3; ++p) {
 #pragma unroll
-                for (int b = 0; b < 4; ++b) yb[b] = T.Y[j][ty + 16 * b];
+                for (int mt = 0; mt < 2; ++mt) af[p][mt] = S.Y[ks + t4][p][warp * 16 + mt * 8 + g];
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) cfma(S[q][b], cq[q], yb[b]);
+                for (int nt = 0; nt < 4; ++nt) bf[p][nt] = S.C[ks + t4][p][nt * 8 + g];
             }
-        } else {
-            const int jn = a.JCr;
-#pragma unroll 4
-            for (int j = 0; j < jn; ++j) {
-                cplx cq[4], yb[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) cq[q] = T.C[j][tx + 8 * q];
+            for (int p = 0; p < 3; ++p)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) yb[b] = T.Y[j][ty + 16 * b];
+                for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) cfma(R[q][b], cq[q], yb[b]);
-            }
+                    for (int nt = 0; nt < 4; ++nt)
+                        dmma884(T[p][mt][nt][0], T[p][mt][nt][1], af[p][mt], bf[p][nt]);
         }
-        __syncthreads();   // every warp is done with this stage (and, on a tile's last chunk,
-                           // with the per-image arrays)
+        __syncthreads();   // every warp is done with this stage
 
+        if (local == a.ncs - 1) {
+            // ---- end of the source pass: S = (T1-T2) + i(T3-T1-T2);  park S' = fac * S.
+            // Pair ownership: image warp*16 + mt*8 + g, frequencies nt*8 + 2*t4 + {0,1}.  The
+            // factor was written by other threads: ordered by the barrier above.
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int il = warp * 16 + mt * 8 + g, fq = nt * 8 + 2 * t4 + e;
+                        double t1 = T[0][mt][nt][e], t2 = T[1][mt][nt][e], t3 = T[2][mt][nt][e];
+                        cplx s = cmake(t1 - t2, t3 - t1 - t2);
+                        sm.fac[il][fq] = cmul(sm.fac[il][fq], s);
+                    }
+        }
         if (local == npt - 1) {
-            // ---- epilogue: P += factor * S * R ----
+            // ---- end of the receiver pass: P += S' * R (same thread owns the same pairs)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int il = ty + 16 * b;
+            for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    cfma(P[q], cmul(sm.fac[il][tx + 8 * q], S[q][b]), R[q][b]);
-            }
+                for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int il = warp * 16 + mt * 8 + g, fq = nt * 8 + 2 * t4 + e;
+                        double t1 = T[0][mt][nt][e], t2 = T[1][mt][nt][e], t3 = T[2][mt][nt][e];
+                        cfma(P[nt][e], sm.fac[il][fq], cmake(t1 - t2, t3 - t1 - t2));
+                    }
+            __syncthreads();   // fac is rewritten by the next tile's factor phase
         }
     }
 
-    // ---- reduce the 16 image lanes that share a frequency, write the chunk partial ----
+    // ---- reduce over the 8 row groups x 4 warps that share a frequency (aliases the stages) ----
     __syncthreads();
+    double2 (*red)[LC_TF] = reinterpret_cast<double2 (*)[LC_TF]>(&sm.st[0]);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) sm.red[ty][tx + 8 * q] = P[q];
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) red[warp * 8 + g][nt * 8 + 2 * t4 + e] = P[nt][e];
     __syncthreads();
     if (tid < LC_TF) {
         cplx s = cmake(0.0, 0.0);
-#pragma unroll
-        for (int y = 0; y < 16; ++y) s = cadd(s, sm.red[y][tid]);
+#pragma unroll 8
+        for (int y = 0; y < 32; ++y) s = cadd(s, red[y][tid]);
         long f = f0 + tid;
         if (f < a.K) a.partial[chunk * a.K + f] = s;
     }
@@ -423,6 +477,18 @@ int validate_atten(const deism_shoebox_atten *at) {
         return set_error(DEISM_ERR_INVALID, "unknown attenuation mode %d", at->mode);
     }
     return DEISM_OK;
+}
+
+// J harmonics -> nc chunks of JC (multiple of 4, <= LC_JC): least zero padding, then fewest chunks
+static void pick_chunks(int J, int &nc, int &JC) {
+    int nc0 = (J + LC_JC - 1) / LC_JC, best = 1 << 30;
+    nc = nc0; JC = LC_JC;
+    for (int n = nc0; n <= nc0 + 6; ++n) {
+        int jc = ((J + n - 1) / n + 3) / 4 * 4;
+        if (jc > LC_JC) continue;
+        int cost = 4 * n * jc + n;   // padded FMAs dominate, one barrier per chunk breaks ties
+        if (cost < best) { best = cost; nc = n; JC = jc; }
+    }
 }
 
 int launch_z_flat(const deism_shoebox_atten *at, long K, int *flags, cudaStream_t st) {
@@ -483,11 +549,11 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
     const long n_img_tiles = (n_images + LC_TI - 1) / LC_TI;
     const long n_pad = n_img_tiles * LC_TI;
     const long n_ftiles = (K + LC_TF - 1) / LC_TF;
-    const long K_pad = n_ftiles * LC_TF;
-    // harmonics are streamed in ncs (ncr) chunks of JCs (JCr) <= LC_JC each, sized to waste
-    // as little padding as possible (J = 36 -> 3 x 12)
-    const int ncs = (Js + LC_JC - 1) / LC_JC, ncr = (Jr + LC_JC - 1) / LC_JC;
-    const int JCs = (Js + ncs - 1) / ncs, JCr = (Jr + ncr - 1) / ncr;
+    // harmonics are streamed in ncs (ncr) chunks of JCs (JCr) <= LC_JC each (multiples of 4, the
+    // DMMA k extent), sized to waste as little zero padding as possible (J = 36 -> 3 x 12)
+    int ncs, ncr, JCs, JCr;
+    pick_chunks(Js, ncs, JCs);
+    pick_chunks(Jr, ncr, JCr);
     const int Js_pad = ncs * JCs, Jr_pad = ncr * JCr;
     long n_chunks = (long)sm_count() * 2 * 8 / n_ftiles;   // ~8 waves of 2 CTAs/SM
     if (n_chunks < 1) n_chunks = 1;
@@ -497,13 +563,14 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
     n_chunks = (n_img_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
 
     LcImage *img = (LcImage *)workspace(WS_LC_IMG, (size_t)n_pad * sizeof(LcImage));
-    cplx *Ys = (cplx *)workspace(WS_LC_YS, (size_t)n_pad * Js_pad * sizeof(cplx));
-    cplx *Yr = (cplx *)workspace(WS_LC_YR, (size_t)n_pad * Jr_pad * sizeof(cplx));
-    cplx *CT = (cplx *)workspace(WS_SMALL, (size_t)(Js_pad + Jr_pad) * K_pad * sizeof(cplx));
+    double *Ys = (double *)workspace(WS_LC_YS, (size_t)n_img_tiles * Js_pad * 3 * LC_YS * sizeof(double));
+    double *Yr = (double *)workspace(WS_LC_YR, (size_t)n_img_tiles * Jr_pad * 3 * LC_YS * sizeof(double));
+    double *CT = (double *)workspace(WS_SMALL,
+                                     (size_t)n_ftiles * (Js_pad + Jr_pad) * 3 * LC_CS * sizeof(double));
     cplx *partial = (cplx *)workspace(WS_PARTIAL, (size_t)n_chunks * K * sizeof(cplx));
     int *flags = (int *)workspace(WS_FLAGS, 64);
     if (!img || !Ys || !Yr || !CT || !partial || !flags) return DEISM_ERR_NOMEM;
-    cplx *CTs = CT, *CTr = CT + (size_t)Js_pad * K_pad;
+    double *CTs = CT, *CTr = CT + (size_t)n_ftiles * Js_pad * 3 * LC_CS;
 
     rc = launch_z_flat(atten, K, flags, st);
     if (rc) return rc;
@@ -520,15 +587,15 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
     }
     lc_prep_kernel<<<(unsigned)((n_pad + 127) / 128), 128, 0, st>>>(pa, img, Ys, Yr);
     DEISM_LAUNCH_CHECK("lc_prep_kernel");
-    lc_coef_kernel<<<(unsigned)((K_pad * Js_pad + 255) / 256), 256, 0, st>>>(
-        (const float2 *)d_C_s_vec, K, Js, K_pad, Js_pad, CTs);
+    lc_coef_kernel<<<(unsigned)((n_ftiles * Js_pad * LC_CS + 255) / 256), 256, 0, st>>>(
+        (const float2 *)d_C_s_vec, K, Js, n_ftiles, Js_pad, CTs);
     DEISM_LAUNCH_CHECK("lc_coef_kernel");
-    lc_coef_kernel<<<(unsigned)((K_pad * Jr_pad + 255) / 256), 256, 0, st>>>(
-        (const float2 *)d_C_r_vec, K, Jr, K_pad, Jr_pad, CTr);
+    lc_coef_kernel<<<(unsigned)((n_ftiles * Jr_pad * LC_CS + 255) / 256), 256, 0, st>>>(
+        (const float2 *)d_C_r_vec, K, Jr, n_ftiles, Jr_pad, CTr);
     DEISM_LAUNCH_CHECK("lc_coef_kernel");
 
     LcMainArgs ma;
-    ma.n_images = n_images; ma.n_pad = n_pad; ma.K = K; ma.K_pad = K_pad;
+    ma.n_images = n_images; ma.n_pad = n_pad; ma.K = K;
     ma.Js_pad = Js_pad; ma.Jr_pad = Jr_pad; ma.ncs = ncs; ma.ncr = ncr; ma.JCs = JCs; ma.JCr = JCr;
     ma.CTs = CTs; ma.CTr = CTr; ma.Ys = Ys; ma.Yr = Yr; ma.img = img; ma.k = d_k;
     ma.mode = atten->mode; ma.atten = atten->d_atten; ma.Z = (const cplx *)atten->d_Z_S;
