@@ -161,47 +161,6 @@ lc_coef_kernel(const float2 *__restrict__ in, long K, int J, long n_ftiles, int 
     p[2 * LC_CS] = re + im;
 }
 
-// ---- mbarrier / bulk-copy (TMA) / DMMA primitives ---------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void *p) {
-    return (unsigned)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// global -> shared bulk copy (TMA, SASS UBLKCP); bytes must be a multiple of 16
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes,
-                                         unsigned long long *bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-// D(8x8) += A(8x4) * B(4x8), FP64 tensor core
-__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(d0), "+d"(d1)
-                 : "d"(a), "d"(b));
-}
-
 struct LcMainArgs {
     long n_images, n_pad, K;
     int Js_pad, Jr_pad;      // padded harmonic counts = ncs*JCs, ncr*JCr

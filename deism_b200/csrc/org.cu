@@ -123,48 +123,76 @@ __global__ void transpose_c64_kernel(const float2 *__restrict__ in, long K, int 
 }
 
 // ---------------------------------------------------------------------------------------
-// B table: grid (ceil(K/128), Lmax^2, 8 parity classes)
+// factorised path: operand-plane geometry.  Segment (l, mu) lives at row rowoff(l) + mu + l of a
+// plane set; every l block is padded to a multiple of 4 rows (the DMMA k extent) with zeros.
 // ---------------------------------------------------------------------------------------
+constexpr int ORG_TI = 32;        // images per tile
+constexpr int ORG_TF = 32;        // frequencies per tile
+constexpr int ORG_THREADS = 128;  // 2 x 2 warps, 16 images x 16 frequencies each
+constexpr int ORG_RC = 12;        // max (l,mu) rows per staged chunk
+constexpr int ORG_OS = 36;        // plane row stride in doubles (32 + 4 pad: 4 mod 16)
+constexpr int ORG_LMAX = 48;
+constexpr int ORG_MAXCHUNKS = 256;
+constexpr int SORT_THREADS = 1024;
+__constant__ int c_org_rowoff[ORG_LMAX + 1];
+__constant__ int4 c_org_chunks[ORG_MAXCHUNKS];   // row0, nrows, l, last-chunk-of-l
+
+// B planes: [8 parity][K_pad/32][R_tot][Re|Im|Re+Im][ORG_OS] doubles.
+// grid (ceil(K/128), Lmax^2 segments, 2 m'-classes); each thread evaluates the coupling
+// D = C_s*C_r of an entry ONCE and feeds the four mirror-sign variants (b, c) of its class.
 struct BtableArgs {
-    long K;
-    int nseg, nm_s, nm_r;
+    long K, n_ftiles;
+    int nseg, R_tot;
     const OrgEntry *ent[2];
     const int *seg[2];
     const cplx *CsT, *CrT;   // [nm][K]
     const double *k;
-    cplx *B;                 // [8][nseg][K]
+    double *Bp;
 };
 
 __global__ void __launch_bounds__(128) org_btable_kernel(BtableArgs a) {
     long k = (long)blockIdx.x * 128 + threadIdx.x;
-    int s = blockIdx.y, par = blockIdx.z;
-    int px = par >> 2, py = (par >> 1) & 1, pz = par & 1;
-    int cls = (px + py) & 1, b = (py + pz) & 1, c = pz;
+    const int s = blockIdx.y, cls = blockIdx.z;
     if (k >= a.K) return;
     const OrgEntry *ent = cls ? a.ent[1] : a.ent[0];
     const int *segp = cls ? a.seg[1] : a.seg[0];
-    int lo = segp[s], hi = segp[s + 1];
-    cplx acc = cmake(0.0, 0.0);
+    const int lo = segp[s], hi = segp[s + 1];
+    cplx acc[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[v] = cmake(0.0, 0.0);
     for (int j = lo; j < hi; ++j) {
         OrgEntryReg e = load_entry(ent + j);
-        int sgn = (b * e.m + c * e.n) & 1;
-        double g = sgn ? -e.G : e.G;
         cplx d = cmul(a.CsT[(long)e.idx_s * a.K + k], a.CrT[(long)e.idx_r * a.K + k]);
-        acc.x = fma(g, d.x, acc.x);
-        acc.y = fma(g, d.y, acc.y);
+        const double gx = e.G * d.x, gy = e.G * d.y;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {          // v = 2*b + c, sign (-1)^{b m + c n}
+            const int sgn = ((v >> 1) * e.m + (v & 1) * e.n) & 1;
+            acc[v].x += sgn ? -gx : gx;
+            acc[v].y += sgn ? -gy : gy;
+        }
     }
-    double ik = 1.0 / a.k[k];
-    a.B[((long)par * a.nseg + s) * a.K + k] = cmake(-acc.y * ik, acc.x * ik);   // * (i/k)
+    int l = 0;
+    while ((l + 1) * (l + 1) <= s) ++l;
+    const long row = c_org_rowoff[l] + (s - l * l);
+    const long ft = k / ORG_TF;
+    const int q = (int)(k % ORG_TF);
+    const double ik = 1.0 / a.k[k];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const int b = v >> 1, c = v & 1;
+        const int pz = c, py = b ^ c, px = cls ^ py;
+        const int par = px * 4 + py * 2 + pz;
+        const double re = -acc[v].y * ik, im = acc[v].x * ik;          // * (i/k)
+        double *p = a.Bp + (((long)par * a.n_ftiles + ft) * a.R_tot + row) * 3 * ORG_OS + q;
+        p[0] = re;
+        p[ORG_OS] = im;
+        p[2 * ORG_OS] = re + im;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
 // image grouping by parity class (stable counting sort, one CTA) and per-image tables
 // ---------------------------------------------------------------------------------------
-constexpr int ORG_TI = 32;    // images per tile
-constexpr int ORG_TF = 32;    // frequencies per tile
-constexpr int ORG_THREADS = 128;
-constexpr int SORT_THREADS = 1024;
-
 struct OrgImage {   // 80 bytes
     double r, inv_r;
     double cx, cy, cz;
@@ -252,6 +280,8 @@ struct OrgPrepArgs {
     const cplx *Z;
     long K;
     RoomGeom room;
+    double *Yp;                 // factorised path: planes [tile][R_tot][3][ORG_OS] (pre-zeroed)
+    int R_tot;
 };
 
 __global__ void __launch_bounds__(128)
@@ -268,7 +298,8 @@ org_prep_kernel(OrgPrepArgs a, OrgImage *rec_out, cplx *Y) {
     if (img < 0) {   // padding: contributes exactly zero
         rec.r = 1.0; rec.inv_r = 1.0; rec.atten_flat = cmake(0.0, 0.0);
         rec_out[pos] = rec;
-        for (int s = 0; s < a.Lmax * a.Lmax; ++s) Y[(long)s * a.n_pad_cap + pos] = cmake(0.0, 0.0);
+        if (Y)
+            for (int s = 0; s < a.Lmax * a.Lmax; ++s) Y[(long)s * a.n_pad_cap + pos] = cmake(0.0, 0.0);
         return;
     }
     double phi, theta;
@@ -298,19 +329,38 @@ org_prep_kernel(OrgPrepArgs a, OrgImage *rec_out, cplx *Y) {
     rec_out[pos] = rec;
     double st, ct;
     sincos_cw(theta, &st, &ct);
+    if (a.Yp) {
+        const long tile = pos / ORG_TI;
+        const int it = (int)(pos % ORG_TI);
+        for (int l = 0; l < a.Lmax; ++l)
+            for (int mu = -l; mu <= l; ++mu) {
+                cplx y = sph_harm_dev(mu, l, phi, ct);
+                double *p = a.Yp + ((tile * a.R_tot + c_org_rowoff[l] + mu + l) * 3) * ORG_OS + it;
+                p[0] = y.x;
+                p[ORG_OS] = y.y;
+                p[2 * ORG_OS] = y.x + y.y;
+            }
+        return;
+    }
     for (int l = 0; l < a.Lmax; ++l)
         for (int mu = -l; mu <= l; ++mu)
             Y[(long)(l * l + l + mu) * a.n_pad_cap + pos] = sph_harm_dev(mu, l, phi, ct);
 }
 
 // ---------------------------------------------------------------------------------------
-// consume kernel (factorised form)
+// consume kernel (factorised form) on the FP64 tensor cores.
+//
+// Per (l): T_l[img,k] = sum_mu Y_l^mu(img) * B[par][l,mu][k] is a complex [32 img x rows(l)] .
+// [rows(l) x 32 freq] product done as three real DMMA m8n8k4 GEMMs (3-multiplication form, see
+// lc.cu); then P[img,k] += h_l(k r_img) * T_l[img,k] with the h_l recurrence of every pair kept
+// in registers (pb:86-118, j and y carried as one complex number).  (l, mu) rows are streamed
+// in chunks of <= 12 through a two-stage TMA bulk-copy pipeline.
 // ---------------------------------------------------------------------------------------
 struct OrgConsumeArgs {
-    long K, n_pad_cap;
-    int Lmax, nseg;
-    const cplx *B;            // [8][nseg][K]
-    const cplx *Y;            // [nseg][n_pad_cap]
+    long K, n_ftiles;
+    int Lmax, R_tot, ncpt;    // chunks per tile
+    const double *Bp;         // [8][n_ftiles][R_tot][3][ORG_OS]
+    const double *Yp;         // [tiles][R_tot][3][ORG_OS]
     const OrgImage *rec;      // [n_pad]
     const long *meta;         // class starts + total
     const double *k;
@@ -322,46 +372,52 @@ struct OrgConsumeArgs {
     cplx *partial;            // [n_chunks][K]
 };
 
-// dynamic shared memory layout (sizes depend on Lmax)
-struct OrgSmemFixed {
+struct OrgStage {
+    double B[ORG_RC][3][ORG_OS];
+    double Y[ORG_RC][3][ORG_OS];
+};
+struct OrgSmem {
+    OrgStage st[2];
     double2 fac[ORG_TI][ORG_TF + 1];
-    double2 red[16][ORG_TF];
     double2 Z[6][ORG_TF];
     double2 aflat[ORG_TI];
     double r[ORG_TI], invr[ORG_TI];
     double cosd[3][ORG_TI];
+    double kf[ORG_TF], invk[ORG_TF];
     long orig[ORG_TI];
     unsigned char e[ORG_TI][8];
+    unsigned long long full[2];
 };
+static_assert(sizeof(double2) * 16 * ORG_TF <= sizeof(OrgStage) * 2, "final reduction aliases the stages");
 
 __global__ void __launch_bounds__(ORG_THREADS, 2)
 org_consume_kernel(OrgConsumeArgs a) {
-    extern __shared__ __align__(16) unsigned char org_smem_raw[];
-    OrgSmemFixed &sm = *reinterpret_cast<OrgSmemFixed *>(org_smem_raw);
-    const int MW = 2 * a.Lmax - 1;                                  // max 2l+1
-    double2 *B_sm = reinterpret_cast<double2 *>(org_smem_raw + sizeof(OrgSmemFixed));  // [MW][TF]
-    double2 *Y_sm = B_sm + (size_t)MW * ORG_TF;                     // [MW][TI]
+    extern __shared__ __align__(128) unsigned char org_smem_raw[];
+    OrgSmem &sm = *reinterpret_cast<OrgSmem *>(org_smem_raw);
 
-    const int tid = threadIdx.x;
-    const int tx = tid & 7;      // freqs f0 + tx + 8q, q < 4
-    const int ty = tid >> 3;     // images ty + 16b, b < 2
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;            // warp tile: 16 images x 16 frequencies
     const long f0 = (long)blockIdx.x * ORG_TF;
     const long n_tiles = a.meta[8] / ORG_TI;
     long tile_lo = (long)blockIdx.y * a.tiles_per_chunk;
     long tile_hi = tile_lo + a.tiles_per_chunk;
     if (tile_hi > n_tiles) tile_hi = n_tiles;
+    const long total = tile_hi > tile_lo ? (tile_hi - tile_lo) * a.ncpt : 0;
 
     const bool fused = a.mode == DEISM_ATTEN_FUSED_ROOM || a.mode == DEISM_ATTEN_FUSED_ANGLES;
     const bool flat = fused && a.flags[0] != 0;
 
-    double kf[4], invk[4];
-    bool fvalid[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        long f = f0 + tx + 8 * q;
-        fvalid[q] = f < a.K;
-        kf[q] = fvalid[q] ? a.k[f] : 1.0;
-        invk[q] = 1.0 / kf[q];
+    if (tid == 0) {
+        mbar_init(&sm.full[0], 1);
+        mbar_init(&sm.full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int q = tid; q < ORG_TF; q += ORG_THREADS) {
+        long f = f0 + q;
+        double kk = f < a.K ? a.k[f] : 1.0;
+        sm.kf[q] = kk;
+        sm.invk[q] = 1.0 / kk;
     }
     if (fused && !flat) {
         for (int i = tid; i < 6 * ORG_TF; i += ORG_THREADS) {
@@ -370,137 +426,186 @@ org_consume_kernel(OrgConsumeArgs a) {
             sm.Z[w][q] = f < a.K ? a.Z[(long)w * a.K + f] : cmake(1.0, 0.0);
         }
     }
-    cplx P[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) P[q] = cmake(0.0, 0.0);
+    __syncthreads();
 
-    for (long tile = tile_lo; tile < tile_hi; ++tile) {
+    auto issue = [&](long c, int stage) {
+        const long tile = tile_lo + c / a.ncpt;
+        const int4 ch = c_org_chunks[c % a.ncpt];
         const long p0 = tile * ORG_TI;
         int par = 0;
 #pragma unroll
-        for (int c = 1; c < 8; ++c) par += (p0 >= a.meta[c]);
-        __syncthreads();
-        for (int i = tid; i < ORG_TI; i += ORG_THREADS) {
-            OrgImage rec = a.rec[p0 + i];
-            sm.r[i] = rec.r; sm.invr[i] = rec.inv_r;
-            sm.cosd[0][i] = rec.cx; sm.cosd[1][i] = rec.cy; sm.cosd[2][i] = rec.cz;
+        for (int q = 1; q < 8; ++q) par += (p0 >= a.meta[q]);
+        const double *Bg = a.Bp + (((long)par * a.n_ftiles + blockIdx.x) * a.R_tot + ch.x) * 3 * ORG_OS;
+        const double *Yg = a.Yp + ((tile * a.R_tot + ch.x) * 3) * ORG_OS;
+        const unsigned bytes = (unsigned)(ch.y * 3 * ORG_OS * 8);
+        mbar_expect_tx(&sm.full[stage], 2 * bytes);
+        bulk_g2s(&sm.st[stage].B[0][0][0], Bg, bytes, &sm.full[stage]);
+        bulk_g2s(&sm.st[stage].Y[0][0][0], Yg, bytes, &sm.full[stage]);
+    };
+
+    double T[3][2][2][2];       // [plane][m-tile][n-tile][2]
+    cplx hm[2][2][2], hc[2][2][2], Pp[2][2][2];   // per pair [mt][nt][e]
+    cplx P[2][2];               // [nt][e], summed over this thread's images
 #pragma unroll
-            for (int b = 0; b < 8; ++b) sm.e[i][b] = rec.e[b];
-            sm.aflat[i] = rec.atten_flat;
-            sm.orig[i] = rec.orig;
-        }
-        __syncthreads();
-        // attenuation factor per pair (registers dead during the contraction)
+    for (int nt = 0; nt < 2; ++nt) { P[nt][0] = cmake(0.0, 0.0); P[nt][1] = cmake(0.0, 0.0); }
+
+    if (tid == 0 && total > 0) issue(0, 0);
+
 #pragma unroll 1
-        for (int b = 0; b < 2; ++b) {
-            const int il = ty + 16 * b;
-            const long orig = sm.orig[il];
+    for (long c = 0; c < total; ++c) {
+        const int stage = (int)(c & 1);
+        const unsigned parity = (unsigned)((c >> 1) & 1);
+        const int local = (int)(c % a.ncpt);
+        const int4 ch = c_org_chunks[local];
+        const long p0 = (tile_lo + c / a.ncpt) * ORG_TI;
+
+        if (local == 0) {
+            for (int i = tid; i < ORG_TI; i += ORG_THREADS) {
+                OrgImage rec = a.rec[p0 + i];
+                sm.r[i] = rec.r; sm.invr[i] = rec.inv_r;
+                sm.cosd[0][i] = rec.cx; sm.cosd[1][i] = rec.cy; sm.cosd[2][i] = rec.cz;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                cplx att;
-                if (orig < 0) {
-                    att = cmake(0.0, 0.0);
-                } else if (flat) {
-                    att = sm.aflat[il];
-                } else if (fused) {
-                    att = shoebox_atten(&sm.Z[0][tx + 8 * q], ORG_TF, sm.cosd[0][il], sm.cosd[1][il],
-                                        sm.cosd[2][il], sm.e[il]);
-                    if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
-                } else {
-                    long f = f0 + tx + 8 * q;
-                    att = cmake(0.0, 0.0);
-                    if (fvalid[q]) {
-                        if (a.mode == DEISM_ATTEN_C64) {
-                            float2 v = ((const float2 *)a.atten)[orig * a.K + f];
-                            att = cmake((double)v.x, (double)v.y);
+                for (int b = 0; b < 8; ++b) sm.e[i][b] = rec.e[b];
+                sm.aflat[i] = rec.atten_flat;
+                sm.orig[i] = rec.orig;
+            }
+            __syncthreads();
+            // attenuation of the tile's 32 x 32 pairs (8 per thread)
+            {
+                const int tx = tid & 7, ty = tid >> 3;
+#pragma unroll 1
+                for (int b = 0; b < 2; ++b) {
+                    const int il = ty + 16 * b;
+                    const long orig = sm.orig[il];
+#pragma unroll 2
+                    for (int q = 0; q < 4; ++q) {
+                        const int fq = tx + 8 * q;
+                        cplx att;
+                        if (orig < 0) {
+                            att = cmake(0.0, 0.0);
+                        } else if (flat) {
+                            att = sm.aflat[il];
+                        } else if (fused) {
+                            att = shoebox_atten(&sm.Z[0][fq], ORG_TF, sm.cosd[0][il], sm.cosd[1][il],
+                                                sm.cosd[2][il], sm.e[il]);
+                            if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
                         } else {
-                            att = ((const cplx *)a.atten)[orig * a.K + f];
+                            long f = f0 + fq;
+                            att = cmake(0.0, 0.0);
+                            if (f < a.K) {
+                                if (a.mode == DEISM_ATTEN_C64) {
+                                    float2 v = ((const float2 *)a.atten)[orig * a.K + f];
+                                    att = cmake((double)v.x, (double)v.y);
+                                } else {
+                                    att = ((const cplx *)a.atten)[orig * a.K + f];
+                                }
+                            }
                         }
+                        sm.fac[il][fq] = att;
                     }
                 }
-                sm.fac[il][tx + 8 * q] = att;
             }
+            // h_0, h_1 of this thread's DMMA-mapped pairs
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const int il = wm * 16 + mt * 8 + g;
+                const double r = sm.r[il], ir = sm.invr[il];
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int fq = wn * 16 + nt * 8 + 2 * t4 + e;
+                        double sn, cs;
+                        sincos_cw(sm.kf[fq] * r, &sn, &cs);
+                        const double i1 = sm.invk[fq] * ir;
+                        hm[mt][nt][e] = cmake(sn * i1, cs * i1);                                 // h_0
+                        hc[mt][nt][e] = cmake(fma(sn * i1, i1, -cs * i1), fma(cs * i1, i1, sn * i1));  // h_1
+                        Pp[mt][nt][e] = cmake(0.0, 0.0);
+                    }
+            }
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) { T[p][mt][nt][0] = 0.0; T[p][mt][nt][1] = 0.0; }
         }
 
-        // h_l(k r) recurrences, one per pair (pb:86-118 with j and y carried as one complex)
-        cplx hm[4][2], hc[4][2], Pp[4][2];
-        double ix[4][2];
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            const double r = sm.r[ty + 16 * b], ir = sm.invr[ty + 16 * b];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                double s, c;
-                sincos_cw(kf[q] * r, &s, &c);
-                double i1 = invk[q] * ir;
-                ix[q][b] = i1;
-                hm[q][b] = cmake(s * i1, c * i1);                              // h_0
-                hc[q][b] = cmake(fma(s * i1, i1, -c * i1), fma(c * i1, i1, s * i1));   // h_1
-                Pp[q][b] = cmake(0.0, 0.0);
-            }
-        }
+        if (tid == 0 && c + 1 < total) issue(c + 1, stage ^ 1);
+        mbar_wait(&sm.full[stage], parity);
 
+        const OrgStage &S = sm.st[stage];
 #pragma unroll 1
-        for (int l = 0; l < a.Lmax; ++l) {
-            const int W = 2 * l + 1;
-            __syncthreads();
-            const cplx *Bg = a.B + ((long)par * a.nseg + l * l) * a.K;
-            for (int i = tid; i < W * ORG_TF; i += ORG_THREADS) {
-                int mu = i / ORG_TF, q = i % ORG_TF;
-                long f = f0 + q;
-                B_sm[mu * ORG_TF + q] = f < a.K ? Bg[(long)mu * a.K + f] : cmake(0.0, 0.0);
-            }
-            const cplx *Yg = a.Y + (long)(l * l) * a.n_pad_cap + p0;
-            for (int i = tid; i < W * ORG_TI; i += ORG_THREADS) {
-                int mu = i / ORG_TI, ii = i % ORG_TI;
-                Y_sm[mu * ORG_TI + ii] = Yg[(long)mu * a.n_pad_cap + ii];
-            }
-            __syncthreads();
-            cplx T[4][2];
+        for (int ks = 0; ks < ch.y; ks += 4) {
+            double af[3][2], bf[3][2];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { T[q][0] = cmake(0.0, 0.0); T[q][1] = cmake(0.0, 0.0); }
-#pragma unroll 2
-            for (int mu = 0; mu < W; ++mu) {
-                cplx bq[4], yb[2];
+            for (int p = 0; p < 3; ++p) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) bq[q] = B_sm[mu * ORG_TF + tx + 8 * q];
-                yb[0] = Y_sm[mu * ORG_TI + ty];
-                yb[1] = Y_sm[mu * ORG_TI + ty + 16];
+                for (int mt = 0; mt < 2; ++mt) af[p][mt] = S.Y[ks + t4][p][wm * 16 + mt * 8 + g];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { cfma(T[q][0], bq[q], yb[0]); cfma(T[q][1], bq[q], yb[1]); }
+                for (int nt = 0; nt < 2; ++nt) bf[p][nt] = S.B[ks + t4][p][wn * 16 + nt * 8 + g];
             }
-            // advance h_l and accumulate
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+                        dmma884(T[p][mt][nt][0], T[p][mt][nt][1], af[p][mt], bf[p][nt]);
+        }
+        __syncthreads();   // stage released
+
+        if (ch.w) {
+            // ---- end of degree l: advance h_l, P_pair += h_l * T_l, reset T ----
+            const int l = ch.z;
             const double cl = (double)(2 * l - 1);
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int mt = 0; mt < 2; ++mt) {
+                const double ir = sm.invr[wm * 16 + mt * 8 + g];
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    cplx h;
-                    if (l == 0) h = hm[q][b];
-                    else if (l == 1) h = hc[q][b];
-                    else {
-                        double c = cl * ix[q][b];
-                        h = cmake(fma(c, hc[q][b].x, -hm[q][b].x), fma(c, hc[q][b].y, -hm[q][b].y));
-                        hm[q][b] = hc[q][b];
-                        hc[q][b] = h;
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        cplx h;
+                        if (l == 0) h = hm[mt][nt][e];
+                        else if (l == 1) h = hc[mt][nt][e];
+                        else {
+                            const double cf = cl * (sm.invk[wn * 16 + nt * 8 + 2 * t4 + e] * ir);
+                            h = cmake(fma(cf, hc[mt][nt][e].x, -hm[mt][nt][e].x),
+                                      fma(cf, hc[mt][nt][e].y, -hm[mt][nt][e].y));
+                            hm[mt][nt][e] = hc[mt][nt][e];
+                            hc[mt][nt][e] = h;
+                        }
+                        const double t1 = T[0][mt][nt][e], t2 = T[1][mt][nt][e], t3 = T[2][mt][nt][e];
+                        cfma(Pp[mt][nt][e], h, cmake(t1 - t2, t3 - t1 - t2));
+                        T[0][mt][nt][e] = 0.0; T[1][mt][nt][e] = 0.0; T[2][mt][nt][e] = 0.0;
                     }
-                    cfma(Pp[q][b], h, T[q][b]);
-                }
+            }
         }
+        if (local == a.ncpt - 1) {
 #pragma unroll
-        for (int b = 0; b < 2; ++b)
+            for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) cfma(P[q], sm.fac[ty + 16 * b][tx + 8 * q], Pp[q][b]);
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        cfma(P[nt][e], sm.fac[wm * 16 + mt * 8 + g][wn * 16 + nt * 8 + 2 * t4 + e],
+                             Pp[mt][nt][e]);
+            __syncthreads();   // fac and the per-image arrays are rewritten by the next tile
+        }
     }
 
     __syncthreads();
+    double2 (*red)[ORG_TF] = reinterpret_cast<double2 (*)[ORG_TF]>(&sm.st[0]);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) sm.red[ty][tx + 8 * q] = P[q];
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) red[wm * 8 + g][wn * 16 + nt * 8 + 2 * t4 + e] = P[nt][e];
     __syncthreads();
     if (tid < ORG_TF) {
         cplx s = cmake(0.0, 0.0);
 #pragma unroll
-        for (int y = 0; y < 16; ++y) s = cadd(s, sm.red[y][tid]);
+        for (int y = 0; y < 16; ++y) s = cadd(s, red[y][tid]);
         long f = f0 + tid;
         if (f < a.K) a.partial[(long)blockIdx.y * a.K + f] = s;
     }
@@ -686,6 +791,7 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
         pa.n_images = n_images; pa.n_pad_cap = n_images; pa.Lmax = Lmax; pa.perm = nullptr;
         pa.meta = nullptr; pa.R_sI_r = d_R_sI_r; pa.component_major = 0; pa.mode = atten->mode;
         pa.angdep = atten->ang_dep_flag; pa.A = d_A; pa.Z = (const cplx *)atten->d_Z_S; pa.K = K;
+        pa.Yp = nullptr; pa.R_tot = 0;
         fill_room(pa.room, atten);
         org_prep_kernel<<<(unsigned)((n_images + 127) / 128), 128, 0, st>>>(pa, rec, Y);
         DEISM_LAUNCH_CHECK("org_prep_kernel");
@@ -707,10 +813,35 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
     }
 
     // ---- factorised path ----
+    if (Lmax > ORG_LMAX) return set_error(DEISM_ERR_INVALID, "N+V+1 > %d", ORG_LMAX);
+    // plane geometry: rows(l) = roundup4(2l+1); chunks of <= ORG_RC rows
+    int rowoff[ORG_LMAX + 1];
+    int4 chunks[ORG_MAXCHUNKS];
+    int ncpt = 0, R_tot = 0;
+    for (int l = 0; l < Lmax; ++l) {
+        rowoff[l] = R_tot;
+        const int rows = (2 * l + 1 + 3) / 4 * 4;
+        for (int r0 = 0; r0 < rows; r0 += ORG_RC) {
+            if (ncpt >= ORG_MAXCHUNKS) return set_error(DEISM_ERR_INVALID, "too many (l,mu) chunks");
+            int nr = rows - r0 < ORG_RC ? rows - r0 : ORG_RC;
+            chunks[ncpt++] = make_int4(R_tot + r0, nr, l, r0 + nr >= rows ? 1 : 0);
+        }
+        R_tot += rows;
+    }
+    rowoff[Lmax] = R_tot;
+    DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_org_rowoff, rowoff, (Lmax + 1) * sizeof(int), 0,
+                                           cudaMemcpyHostToDevice, st));
+    DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_org_chunks, chunks, ncpt * sizeof(int4), 0,
+                                           cudaMemcpyHostToDevice, st));
+    DEISM_CUDA_TRY(cudaStreamSynchronize(st));   // stack tables consumed
+
+    const long n_ftiles = (K + ORG_TF - 1) / ORG_TF;
+    const size_t plane_rows = (size_t)R_tot * 3 * ORG_OS;
     cplx *CsT = (cplx *)workspace(WS_SMALL, (size_t)(NMs + NMr) * K * sizeof(cplx));
-    cplx *B = (cplx *)workspace(WS_ORG_B, (size_t)8 * nseg * K * sizeof(cplx));
-    if (!CsT || !B) return DEISM_ERR_NOMEM;
+    double *Bp = (double *)workspace(WS_ORG_B, (size_t)8 * n_ftiles * plane_rows * sizeof(double));
+    if (!CsT || !Bp) return DEISM_ERR_NOMEM;
     cplx *CrT = CsT + (size_t)NMs * K;
+    DEISM_CUDA_TRY(cudaMemsetAsync(Bp, 0, (size_t)8 * n_ftiles * plane_rows * sizeof(double), st));
     transpose_c64_kernel<<<(unsigned)(((long)K * NMs + 255) / 256), 256, 0, st>>>(
         (const float2 *)d_C_nm_s, K, NMs, CsT);
     DEISM_LAUNCH_CHECK("transpose_c64_kernel");
@@ -718,11 +849,11 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
         (const float2 *)d_C_vu_r, K, NMr, CrT);
     DEISM_LAUNCH_CHECK("transpose_c64_kernel");
     BtableArgs ba;
-    ba.K = K; ba.nseg = nseg; ba.nm_s = NMs; ba.nm_r = NMr;
+    ba.K = K; ba.n_ftiles = n_ftiles; ba.nseg = nseg; ba.R_tot = R_tot;
     for (int i = 0; i < 2; ++i) { ba.ent[i] = d_ent[i]; ba.seg[i] = d_seg[i]; }
-    ba.CsT = CsT; ba.CrT = CrT; ba.k = d_k; ba.B = B;
+    ba.CsT = CsT; ba.CrT = CrT; ba.k = d_k; ba.Bp = Bp;
     {
-        dim3 grid((unsigned)((K + 127) / 128), (unsigned)nseg, 8);
+        dim3 grid((unsigned)((K + 127) / 128), (unsigned)nseg, 2);
         prof_begin("org_btable", st);
         org_btable_kernel<<<grid, 128, 0, st>>>(ba);
         prof_end("org_btable", st);
@@ -730,10 +861,12 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
     }
 
     const long n_pad_cap = (n_images + ORG_TI - 1) / ORG_TI * ORG_TI + 8 * ORG_TI;
+    const long n_tiles_cap = n_pad_cap / ORG_TI;
     long *perm = (long *)workspace(WS_ARG_IDX, (size_t)(n_pad_cap + 16) * sizeof(long));
     OrgImage *rec = (OrgImage *)workspace(WS_ORG_IMG, (size_t)n_pad_cap * sizeof(OrgImage));
-    cplx *Y = (cplx *)workspace(WS_ORG_Y, (size_t)nseg * n_pad_cap * sizeof(cplx));
-    if (!perm || !rec || !Y) return DEISM_ERR_NOMEM;
+    double *Yp = (double *)workspace(WS_ORG_Y, (size_t)n_tiles_cap * plane_rows * sizeof(double));
+    if (!perm || !rec || !Yp) return DEISM_ERR_NOMEM;
+    DEISM_CUDA_TRY(cudaMemsetAsync(Yp, 0, (size_t)n_tiles_cap * plane_rows * sizeof(double), st));
     long *meta = perm + n_pad_cap;
     org_sort_kernel<<<1, SORT_THREADS, 0, st>>>(d_A, n_images, perm, meta, n_pad_cap);
     DEISM_LAUNCH_CHECK("org_sort_kernel");
@@ -741,13 +874,12 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
     pa.n_images = n_images; pa.n_pad_cap = n_pad_cap; pa.Lmax = Lmax; pa.perm = perm; pa.meta = meta;
     pa.R_sI_r = d_R_sI_r; pa.component_major = 0; pa.mode = atten->mode; pa.angdep = atten->ang_dep_flag;
     pa.A = d_A; pa.Z = (const cplx *)atten->d_Z_S; pa.K = K;
+    pa.Yp = Yp; pa.R_tot = R_tot;
     fill_room(pa.room, atten);
-    org_prep_kernel<<<(unsigned)((n_pad_cap + 127) / 128), 128, 0, st>>>(pa, rec, Y);
+    org_prep_kernel<<<(unsigned)((n_pad_cap + 127) / 128), 128, 0, st>>>(pa, rec, nullptr);
     DEISM_LAUNCH_CHECK("org_prep_kernel");
 
-    const long n_tiles_cap = n_pad_cap / ORG_TI;
-    const long n_ftiles = (K + ORG_TF - 1) / ORG_TF;
-    long n_chunks = (long)sm_count() * 3 * 8 / n_ftiles;
+    long n_chunks = (long)sm_count() * 2 * 8 / n_ftiles;
     if (n_chunks < 1) n_chunks = 1;
     if (n_chunks > n_tiles_cap) n_chunks = n_tiles_cap;
     if (n_chunks > 65535) n_chunks = 65535;
@@ -757,17 +889,15 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
     if (!partial) return DEISM_ERR_NOMEM;
 
     OrgConsumeArgs ca;
-    ca.K = K; ca.n_pad_cap = n_pad_cap; ca.Lmax = Lmax; ca.nseg = nseg; ca.B = B; ca.Y = Y;
-    ca.rec = rec; ca.meta = meta; ca.k = d_k; ca.mode = atten->mode; ca.atten = atten->d_atten;
-    ca.Z = (const cplx *)atten->d_Z_S; ca.flags = flags; ca.tiles_per_chunk = tiles_per_chunk;
-    ca.partial = partial;
-    const int MW = 2 * Lmax - 1;
-    size_t smem = sizeof(OrgSmemFixed) + (size_t)MW * (ORG_TF + ORG_TI) * sizeof(double2);
+    ca.K = K; ca.n_ftiles = n_ftiles; ca.Lmax = Lmax; ca.R_tot = R_tot; ca.ncpt = ncpt;
+    ca.Bp = Bp; ca.Yp = Yp; ca.rec = rec; ca.meta = meta; ca.k = d_k; ca.mode = atten->mode;
+    ca.atten = atten->d_atten; ca.Z = (const cplx *)atten->d_Z_S; ca.flags = flags;
+    ca.tiles_per_chunk = tiles_per_chunk; ca.partial = partial;
     DEISM_CUDA_TRY(cudaFuncSetAttribute(org_consume_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
+                                        (int)sizeof(OrgSmem)));
     dim3 grid((unsigned)n_ftiles, (unsigned)n_chunks);
     prof_begin("org_consume", st);
-    org_consume_kernel<<<grid, ORG_THREADS, smem, st>>>(ca);
+    org_consume_kernel<<<grid, ORG_THREADS, sizeof(OrgSmem), st>>>(ca);
     prof_end("org_consume", st);
     DEISM_LAUNCH_CHECK("org_consume_kernel");
     return launch_reduce_partials(partial, n_chunks, K, d_out, accumulate, st);
@@ -822,6 +952,7 @@ extern "C" int deism_org_arg(int64_t n_images, int64_t K, int N, int V, const fl
     pa.n_images = n_images; pa.n_pad_cap = n_images; pa.Lmax = Lmax; pa.perm = nullptr; pa.meta = nullptr;
     pa.R_sI_r = d_R_sI_r; pa.component_major = 1; pa.mode = DEISM_ATTEN_C64; pa.angdep = 0;
     pa.A = nullptr; pa.Z = nullptr; pa.K = K;
+    pa.Yp = nullptr; pa.R_tot = 0;
     for (int i = 0; i < 3; ++i) pa.room.LL[i] = pa.room.xs[i] = pa.room.xr[i] = 0.0;
     org_prep_kernel<<<(unsigned)((n_images + 127) / 128), 128, 0, st>>>(pa, rec, Y);
     DEISM_LAUNCH_CHECK("org_prep_kernel");
