@@ -115,6 +115,11 @@ def cpu_sample_params(p, target_terms):
 def run_cpu(p, steps, warmup, target_terms):
     from oracle import oracle
 
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host thread it is allowed
+    try:
+        oracle.set_num_threads(len(os.sched_getaffinity(0)))
+    except AttributeError:  # pragma: no cover
+        oracle.set_num_threads(os.cpu_count() or 1)
     q, n_img, order, t_img = cpu_sample_params(p, target_terms)
     K = len(q["waveNumbers"])
     for _ in range(max(0, min(warmup, 1))):

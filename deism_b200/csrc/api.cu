@@ -184,6 +184,41 @@ dmma_peak_kernel(int iters, double seed, double *sink) {
     if (s == 123.456) sink[0] = s;
 }
 
+// kind 2: warps 0-3 of every CTA run the DMMA loop, warps 4-7 the DFMA loop (same per-warp work as
+// kinds 1 and 0).  If the FP64 tensor path and the FP64 FMA pipe are separate units the elapsed
+// time is ~max of the two halves, not their sum.
+__global__ void __launch_bounds__(PEAK_THREADS)
+mixed_peak_kernel(int iters, double seed, double *sink) {
+    double s = 0.0;
+    if ((threadIdx.x >> 5) < PEAK_THREADS / 64) {
+        double d[PEAK_ILP][2];
+        double a = 1e-3 * (threadIdx.x & 31) + seed, b = 1e-3 + seed;
+#pragma unroll
+        for (int i = 0; i < PEAK_ILP; ++i) { d[i][0] = seed + i; d[i][1] = seed - i; }
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < PEAK_ILP; ++i) dmma_m8n8k4(d[i][0], d[i][1], a, b);
+        }
+#pragma unroll
+        for (int i = 0; i < PEAK_ILP; ++i) s += d[i][0] + d[i][1];
+    } else {
+        double a[PEAK_ILP], b = 1.0000001 + seed, c = 1e-9 + seed;
+#pragma unroll
+        for (int i = 0; i < PEAK_ILP; ++i) a[i] = seed + i + threadIdx.x * 1e-3;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int i = 0; i < PEAK_ILP; ++i) a[i] = fma(a[i], b, c);
+        }
+#pragma unroll
+        for (int i = 0; i < PEAK_ILP; ++i) s += a[i];
+    }
+    if (s == 123.456) sink[0] = s;
+}
+
 }  // namespace deism
 
 using namespace deism;
@@ -267,8 +302,10 @@ extern "C" int deism_fp64_peak(int kind, int iters, double *tflops, double *ms_o
         DEISM_CUDA_TRY(cudaEventRecord(e0, 0));
         if (kind == 0)
             dfma_peak_kernel<<<blocks, PEAK_THREADS>>>(iters, 0.0, sink);
-        else
+        else if (kind == 1)
             dmma_peak_kernel<<<blocks, PEAK_THREADS>>>(iters, 0.0, sink);
+        else
+            mixed_peak_kernel<<<blocks, PEAK_THREADS>>>(iters, 0.0, sink);
         DEISM_LAUNCH_CHECK("fp64_peak_kernel");
         DEISM_CUDA_TRY(cudaEventRecord(e1, 0));
         DEISM_CUDA_TRY(cudaEventSynchronize(e1));
@@ -279,10 +316,12 @@ extern "C" int deism_fp64_peak(int kind, int iters, double *tflops, double *ms_o
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     double fmas;
-    if (kind == 0)
-        fmas = (double)blocks * PEAK_THREADS * (double)iters * 8.0 * PEAK_ILP;
-    else   // one m8n8k4 = 8*8*4 FMAs per warp
-        fmas = (double)blocks * (PEAK_THREADS / 32) * (double)iters * 4.0 * PEAK_ILP * 256.0;
+    const double dfma_all = (double)blocks * PEAK_THREADS * (double)iters * 8.0 * PEAK_ILP;
+    // one m8n8k4 = 8*8*4 FMAs per warp
+    const double dmma_all = (double)blocks * (PEAK_THREADS / 32) * (double)iters * 4.0 * PEAK_ILP * 256.0;
+    if (kind == 0) fmas = dfma_all;
+    else if (kind == 1) fmas = dmma_all;
+    else fmas = 0.5 * (dfma_all + dmma_all);
     if (tflops) *tflops = 2.0 * fmas / ((double)best * 1e-3) / 1e12;
     if (ms_out) *ms_out = best;
     return DEISM_OK;

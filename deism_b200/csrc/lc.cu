@@ -36,7 +36,11 @@ namespace deism {
 constexpr int LC_TF = 32;        // frequencies per CTA tile
 constexpr int LC_TI = 64;        // images per tile
 constexpr int LC_JC = 12;        // max harmonics per staged chunk (multiple of 4)
-constexpr int LC_THREADS = 128;  // 4 warps x 16 images
+#ifndef LC_NT
+#define LC_NT 2                  // n-tiles (8 freqs each) per warp: 4 -> 4 warps/CTA, 2 -> 8 warps/CTA
+#endif
+constexpr int LC_WN = 4 / LC_NT;                 // warps along frequency
+constexpr int LC_THREADS = 128 * LC_WN;          // 4 (image) x LC_WN (frequency) warps
 constexpr int LC_YS = LC_TI + 4; // Y plane row stride (doubles): 68 = 4 mod 16
 constexpr int LC_CS = LC_TF + 4; // C plane row stride (doubles): 36 = 4 mod 16
 
@@ -199,12 +203,14 @@ static_assert(sizeof(double2) * 32 * LC_TF <= sizeof(LcStage) * LC_STAGES,
 
 __global__ void __launch_bounds__(LC_THREADS, 2)
 lc_main_kernel(LcMainArgs a) {
+    constexpr int NT = LC_NT;
     extern __shared__ __align__(128) unsigned char lc_smem_raw[];
     LcSmem &sm = *reinterpret_cast<LcSmem *>(lc_smem_raw);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;          // DMMA fragment coordinates
+    const int wm = warp / LC_WN, wn = warp % LC_WN;  // warp tile: images wm*16.., freqs wn*8*NT..
     const long f0 = (long)blockIdx.x * LC_TF;
     const long chunk = blockIdx.y;
     const long n_img_tiles = a.n_pad / LC_TI;
@@ -255,11 +261,11 @@ lc_main_kernel(LcMainArgs a) {
     };
 
     // accumulators of the three real GEMMs: [plane][m-tile][n-tile][2]
-    double T[3][2][4][2];
-    // P[freq]: this thread's 8 frequencies 2*t4 + e + 8*nt, summed over its images
-    cplx P[4][2];
+    double T[3][2][NT][2];
+    // P[freq]: this thread's 2*NT frequencies wn*8*NT + 8*nt + 2*t4 + e, summed over its images
+    cplx P[NT][2];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) { P[nt][0] = cmake(0.0, 0.0); P[nt][1] = cmake(0.0, 0.0); }
+    for (int nt = 0; nt < NT; ++nt) { P[nt][0] = cmake(0.0, 0.0); P[nt][1] = cmake(0.0, 0.0); }
 
     if (tid == 0 && total > 0) issue(0, 0);
 
@@ -284,8 +290,8 @@ lc_main_kernel(LcMainArgs a) {
             __syncthreads();
             const int tx = tid & 7, ty = tid >> 3;
 #pragma unroll 1
-            for (int b = 0; b < 4; ++b) {
-                const int il = ty + 16 * b;
+            for (int b = 0; b < LC_TI / (LC_THREADS / 8); ++b) {
+                const int il = ty + (LC_THREADS / 8) * b;
                 const long img = i0 + il;
                 const double r = sm.r[il], inv_r = sm.invr[il];
 #pragma unroll 2
@@ -323,7 +329,7 @@ lc_main_kernel(LcMainArgs a) {
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) { T[p][mt][nt][0] = 0.0; T[p][mt][nt][1] = 0.0; }
+                    for (int nt = 0; nt < NT; ++nt) { T[p][mt][nt][0] = 0.0; T[p][mt][nt][1] = 0.0; }
         }
 
         // stage (c+1)&1 was released by the barrier that closed iteration c-1
@@ -334,20 +340,20 @@ lc_main_kernel(LcMainArgs a) {
         const int JC = local < a.ncs ? a.JCs : a.JCr;
 #pragma unroll 1
         for (int ks = 0; ks < JC; ks += 4) {
-            double af[3][2], bf[3][4];
+            double af[3][2], bf[3][NT];
 #pragma unroll
             for (int p = 0; p < 3; ++p) {
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) af[p][mt] = S.Y[ks + t4][p][warp * 16 + mt * 8 + g];
+                for (int mt = 0; mt < 2; ++mt) af[p][mt] = S.Y[ks + t4][p][wm * 16 + mt * 8 + g];
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) bf[p][nt] = S.C[ks + t4][p][nt * 8 + g];
+                for (int nt = 0; nt < NT; ++nt) bf[p][nt] = S.C[ks + t4][p][(wn * NT + nt) * 8 + g];
             }
 #pragma unroll
             for (int p = 0; p < 3; ++p)
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt)
+                    for (int nt = 0; nt < NT; ++nt)
                         dmma884(T[p][mt][nt][0], T[p][mt][nt][1], af[p][mt], bf[p][nt]);
         }
         __syncthreads();   // every warp is done with this stage
@@ -359,10 +365,10 @@ lc_main_kernel(LcMainArgs a) {
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt)
+                for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const int il = warp * 16 + mt * 8 + g, fq = nt * 8 + 2 * t4 + e;
+                        const int il = wm * 16 + mt * 8 + g, fq = (wn * NT + nt) * 8 + 2 * t4 + e;
                         double t1 = T[0][mt][nt][e], t2 = T[1][mt][nt][e], t3 = T[2][mt][nt][e];
                         cplx s = cmake(t1 - t2, t3 - t1 - t2);
                         sm.fac[il][fq] = cmul(sm.fac[il][fq], s);
@@ -373,10 +379,10 @@ lc_main_kernel(LcMainArgs a) {
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt)
+                for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const int il = warp * 16 + mt * 8 + g, fq = nt * 8 + 2 * t4 + e;
+                        const int il = wm * 16 + mt * 8 + g, fq = (wn * NT + nt) * 8 + 2 * t4 + e;
                         double t1 = T[0][mt][nt][e], t2 = T[1][mt][nt][e], t3 = T[2][mt][nt][e];
                         cfma(P[nt][e], sm.fac[il][fq], cmake(t1 - t2, t3 - t1 - t2));
                     }
@@ -388,9 +394,9 @@ lc_main_kernel(LcMainArgs a) {
     __syncthreads();
     double2 (*red)[LC_TF] = reinterpret_cast<double2 (*)[LC_TF]>(&sm.st[0]);
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) red[warp * 8 + g][nt * 8 + 2 * t4 + e] = P[nt][e];
+        for (int e = 0; e < 2; ++e) red[wm * 8 + g][(wn * NT + nt) * 8 + 2 * t4 + e] = P[nt][e];
     __syncthreads();
     if (tid < LC_TF) {
         cplx s = cmake(0.0, 0.0);
