@@ -380,12 +380,20 @@ def main():
             units = I * Ks
         else:
             fpt, units = None, None
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+                traffic = json.load(fh).get(dom + "_kernel", {}).get(args.workload)
+            if world > 1 or args.general_impedance:
+                traffic = None      # captured at N=1 on the shipped configuration only
+        except Exception:
+            traffic = None
         if fpt:
             achieved = fpt * units / (per_launch_ms * 1e-3) / 1e12
             roofline = {"bound": "fp64", "kernel": dom + "_kernel", "achieved": round(achieved, 3),
                         "peak": peak_tf, "unit": "TFLOP/s",
                         "frac": round(achieved / peak_tf, 4) if peak_tf else None,
-                        "traffic": None,
+                        "traffic": traffic,
                         "algorithmic_flops_per_term": fpt, "terms_per_launch": units,
                         "kernel_ms_per_launch": round(per_launch_ms, 4),
                         "kernel_share_of_step": round(ms_k / steps / ms_per_step, 4),

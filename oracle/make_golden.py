@@ -121,6 +121,16 @@ def pack(d, extra=None, store_images=True, store_inputs=True):
     return out
 
 
+def rir_of(d):
+    """DEISM.get_results() (core_deism.py:675-769) without its side effect on params['RTF']."""
+    if d.mode != "RIR":
+        return None
+    keep = np.array(d.params["RTF"], copy=True)
+    p = d.get_results()
+    d.params["RTF"] = keep
+    return np.asarray(p)
+
+
 def save(name, blob):
     os.makedirs(GOLDEN, exist_ok=True)
     path = os.path.join(GOLDEN, name + ".npz")
@@ -165,6 +175,9 @@ def shoebox_case(name, mode, method, order, N=None, V=None, overrides=None, mate
           f"images {t2 - t1:.2f}s run {t3 - t2:.2f}s (cold) setup {t1 - t0:.2f}s")
     extra = {"meta/n_images": np.array(nimg), "meta/seed": np.array(seed),
              "meta/t_images_s": np.array(t2 - t1), "meta/t_run_cold_s": np.array(t3 - t2)}
+    rir = rir_of(d)
+    if rir is not None:
+        extra["RIR"] = rir
     save(name, pack(d, extra, store_images, store_inputs))
     return d
 
@@ -233,6 +246,9 @@ def convex_case(name, mode, method, order, N=None, overrides=None, store_inputs=
         extra[f"walls/{i}/reflection_matrix"] = np.asarray(lw.reflection_matrix,
                                                            dtype=np.float32)
         extra[f"walls/{i}/impedance"] = np.asarray(w.impedence_bands)
+    rir = rir_of(d)
+    if rir is not None:
+        extra["RIR"] = rir
     K = len(p["waveNumbers"])
     print(f"[{name}] convex {method} order {order}: I={extra['meta/n_images']} K={K} "
           f"T60={p['reverberationTime']:.6f} images {t2 - t1:.2f}s run {t3 - t2:.2f}s")
