@@ -49,8 +49,11 @@ def load_libroom(as_name: str = "libroom_deism"):
     path = libroom_path()
     if path is None:
         raise ImportError("oracle/_ref/libroom_deism*.so not built (make -C oracle ref)")
-    if as_name in sys.modules:
-        return sys.modules[as_name]
+    # the pybind11 types can be registered once per process: one module object, two names
+    for name in (as_name, "libroom_deism", "deism.libroom_deism"):
+        if name in sys.modules:
+            sys.modules[as_name] = sys.modules[name]
+            return sys.modules[name]
     spec = importlib.util.spec_from_file_location(as_name, path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
