@@ -66,12 +66,14 @@ _SIGNATURES = {
     "deism_shoebox_attenuation": (C.c_int, [_i64, _i64, _vp, _vp, _i32, _vp]),
     "deism_lc_shoebox": (C.c_int, [_i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                    _vp, _vp, _vp, _i32, _vp]),
+    "deism_org_plan_create": (C.c_int, [_i32, _i32, _vp, _vp, _vp]),
+    "deism_org_plan_destroy": (C.c_int, [_vp]),
     "deism_org_shoebox": (C.c_int, [_i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                    _vp, _i32, _i32, _vp]),
+                                    _vp, _i32, _i32, _vp, _vp]),
     "deism_lc_arg": (C.c_int, [_i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                _vp, _i64, _vp, _i32, _vp]),
     "deism_org_arg": (C.c_int, [_i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                _i64, _vp, _i32, _vp]),
+                                _i64, _vp, _i32, _vp, _vp]),
     "deism_wigner_tables": (C.c_int, [_i32, _i32, _vp, _vp]),
     "deism_convex_images_count": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "deism_convex_images_fill": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),

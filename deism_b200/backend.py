@@ -192,6 +192,43 @@ def _wigner_host(Wigner):
     return W1, W2
 
 
+class _OrgPlan:
+    """deism_org_plan handle (coupling lists on the device), freed with the object."""
+
+    def __init__(self, N, V, W1, W2):
+        self.ptr = C.c_void_p(0)
+        check(lib().deism_org_plan_create(N, V, W1.ctypes.data, W2.ctypes.data, C.byref(self.ptr)),
+              "deism_org_plan_create")
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().deism_org_plan_destroy(self.ptr)
+        except Exception:  # pragma: no cover  (interpreter shutdown)
+            pass
+
+
+_plan_cache = {}
+
+
+def _org_plan(Wigner, N, V):
+    """One plan per Wigner-table object (params['Wigner'] lives as long as the DEISM object); the
+    tables are scanned on the host only the first time."""
+    w2 = Wigner["W_2_all"]
+    key = (id(w2), N, V, torch.cuda.current_device())
+    hit = _plan_cache.get(key)
+    if hit is not None and hit[1] is w2:
+        return hit[0]
+    W1, W2 = _wigner_host(Wigner)
+    if W2.shape != (N + 1, V + 1, N + V + 1, 2 * N + 1, 2 * V + 1):
+        raise ValueError("Wigner tables do not match sourceOrder/receiverOrder")
+    plan = _OrgPlan(N, V, W1, W2)
+    if len(_plan_cache) >= 8:
+        _plan_cache.clear()
+    _plan_cache[key] = (plan, w2)      # keeps w2 alive so that id() stays unique
+    return plan
+
+
 def _run_org(params, images, suffix, out, accumulate, dev):
     """pb:543-591 _run_numba_org_in_batches."""
     A_all = images["A" + suffix]
@@ -207,18 +244,16 @@ def _run_org(params, images, suffix, out, accumulate, dev):
     Cr = _c64_on_device(params["C_vu_r"], dev)
     if tuple(Cs.shape) != (K, N + 1, 2 * N + 1) or tuple(Cr.shape) != (K, V + 1, 2 * V + 1):
         raise ValueError("C_nm_s / C_vu_r must be [K, N+1, 2N+1] / [K, V+1, 2V+1]")
-    W1, W2 = _wigner_host(params["Wigner"])
-    if W2.shape != (N + 1, V + 1, N + V + 1, 2 * N + 1, 2 * V + 1):
-        raise ValueError("Wigner tables do not match sourceOrder/receiverOrder")
+    plan = _org_plan(params["Wigner"], N, V)
     algo = int(params.get("b200OrgAlgo", 0))
     for lo, hi in _image_batches(params, images, suffix, n_images, K):
         A = to_device(A_all[lo:hi], torch.int32, dev)
         R = to_device(images["R_sI_r_all" + suffix][lo:hi], torch.float32, dev)
         spec = _AttenSpec(params, images, suffix, dev, lo, hi)
         rc = lib().deism_org_shoebox(
-            hi - lo, K, N, V, _ptr(Cs), _ptr(Cr), W1.ctypes.data, W2.ctypes.data, _ptr(A),
+            hi - lo, K, N, V, _ptr(Cs), _ptr(Cr), None, None, _ptr(A),
             _ptr(R), spec.ref(), _ptr(k), _ptr(out), 1 if (accumulate or lo > 0) else 0, algo,
-            _stream_ptr())
+            plan.ptr, _stream_ptr())
         check(rc, "deism_org_shoebox")
         del spec, A, R
 
@@ -296,11 +331,11 @@ def _run_arg_org(params, out, accumulate, dev, sel=None):
     Cr = _c64_on_device(params["C_vu_r"], dev)
     if tuple(Cs.shape) != (K, N + 1, 2 * N + 1, n_images):
         raise ValueError("C_nm_s_ARG must be [K, N+1, 2N+1, I]")
-    W1, W2 = _wigner_host(params["Wigner"])
+    plan = _org_plan(params["Wigner"], N, V)
     keep, n_sel, p_sel = _idx(sel)
-    rc = lib().deism_org_arg(n_images, K, N, V, _ptr(Cs), _ptr(Cr), W1.ctypes.data, W2.ctypes.data,
+    rc = lib().deism_org_arg(n_images, K, N, V, _ptr(Cs), _ptr(Cr), None, None,
                              _ptr(R), _ptr(att), _ptr(k), p_sel, n_sel, _ptr(out),
-                             1 if accumulate else 0, _stream_ptr())
+                             1 if accumulate else 0, plan.ptr, _stream_ptr())
     check(rc, "deism_org_arg")
     del keep
 

@@ -129,13 +129,14 @@ __global__ void transpose_c64_kernel(const float2 *__restrict__ in, long K, int 
 constexpr int ORG_TI = 32;        // images per tile
 constexpr int ORG_TF = 32;        // frequencies per tile
 constexpr int ORG_THREADS = 128;  // 2 x 2 warps, 16 images x 16 frequencies each
-constexpr int ORG_RC = 12;        // max (l,mu) rows per staged chunk
+constexpr int ORG_RC = 24;        // (l,mu) rows per staged chunk (chunks may span several l)
 constexpr int ORG_OS = 36;        // plane row stride in doubles (32 + 4 pad: 4 mod 16)
 constexpr int ORG_LMAX = 48;
 constexpr int ORG_MAXCHUNKS = 256;
 constexpr int SORT_THREADS = 1024;
 __constant__ int c_org_rowoff[ORG_LMAX + 1];
-__constant__ int4 c_org_chunks[ORG_MAXCHUNKS];   // row0, nrows, l, last-chunk-of-l
+__constant__ int2 c_org_chunks[ORG_MAXCHUNKS];   // row0, nrows
+__constant__ signed char c_org_ks_l[ORG_LMAX * ORG_LMAX];   // per 4-row step: l if it closes degree l, else -1
 
 // B planes: [8 parity][K_pad/32][R_tot][Re|Im|Re+Im][ORG_OS] doubles.
 // grid (ceil(K/128), Lmax^2 segments, 2 m'-classes); each thread evaluates the coupling
@@ -430,7 +431,7 @@ org_consume_kernel(OrgConsumeArgs a) {
 
     auto issue = [&](long c, int stage) {
         const long tile = tile_lo + c / a.ncpt;
-        const int4 ch = c_org_chunks[c % a.ncpt];
+        const int2 ch = c_org_chunks[c % a.ncpt];
         const long p0 = tile * ORG_TI;
         int par = 0;
 #pragma unroll
@@ -456,7 +457,7 @@ org_consume_kernel(OrgConsumeArgs a) {
         const int stage = (int)(c & 1);
         const unsigned parity = (unsigned)((c >> 1) & 1);
         const int local = (int)(c % a.ncpt);
-        const int4 ch = c_org_chunks[local];
+        const int2 ch = c_org_chunks[local];
         const long p0 = (tile_lo + c / a.ncpt) * ORG_TI;
 
         if (local == 0) {
@@ -552,36 +553,36 @@ org_consume_kernel(OrgConsumeArgs a) {
 #pragma unroll
                     for (int nt = 0; nt < 2; ++nt)
                         dmma884(T[p][mt][nt][0], T[p][mt][nt][1], af[p][mt], bf[p][nt]);
+            const int l = c_org_ks_l[(ch.x + ks) >> 2];
+            if (l >= 0) {
+                // ---- this 4-row step closes degree l: advance h_l, P_pair += h_l * T_l, reset T
+                const double cl = (double)(2 * l - 1);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const double ir = sm.invr[wm * 16 + mt * 8 + g];
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            cplx h;
+                            if (l == 0) h = hm[mt][nt][e];
+                            else if (l == 1) h = hc[mt][nt][e];
+                            else {
+                                const double cf = cl * (sm.invk[wn * 16 + nt * 8 + 2 * t4 + e] * ir);
+                                h = cmake(fma(cf, hc[mt][nt][e].x, -hm[mt][nt][e].x),
+                                          fma(cf, hc[mt][nt][e].y, -hm[mt][nt][e].y));
+                                hm[mt][nt][e] = hc[mt][nt][e];
+                                hc[mt][nt][e] = h;
+                            }
+                            const double t1 = T[0][mt][nt][e], t2 = T[1][mt][nt][e], t3 = T[2][mt][nt][e];
+                            cfma(Pp[mt][nt][e], h, cmake(t1 - t2, t3 - t1 - t2));
+                            T[0][mt][nt][e] = 0.0; T[1][mt][nt][e] = 0.0; T[2][mt][nt][e] = 0.0;
+                        }
+                }
+            }
         }
         __syncthreads();   // stage released
 
-        if (ch.w) {
-            // ---- end of degree l: advance h_l, P_pair += h_l * T_l, reset T ----
-            const int l = ch.z;
-            const double cl = (double)(2 * l - 1);
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                const double ir = sm.invr[wm * 16 + mt * 8 + g];
-#pragma unroll
-                for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        cplx h;
-                        if (l == 0) h = hm[mt][nt][e];
-                        else if (l == 1) h = hc[mt][nt][e];
-                        else {
-                            const double cf = cl * (sm.invk[wn * 16 + nt * 8 + 2 * t4 + e] * ir);
-                            h = cmake(fma(cf, hc[mt][nt][e].x, -hm[mt][nt][e].x),
-                                      fma(cf, hc[mt][nt][e].y, -hm[mt][nt][e].y));
-                            hm[mt][nt][e] = hc[mt][nt][e];
-                            hc[mt][nt][e] = h;
-                        }
-                        const double t1 = T[0][mt][nt][e], t2 = T[1][mt][nt][e], t3 = T[2][mt][nt][e];
-                        cfma(Pp[mt][nt][e], h, cmake(t1 - t2, t3 - t1 - t2));
-                        T[0][mt][nt][e] = 0.0; T[1][mt][nt][e] = 0.0; T[2][mt][nt][e] = 0.0;
-                    }
-            }
-        }
         if (local == a.ncpt - 1) {
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
@@ -710,30 +711,69 @@ __global__ void __launch_bounds__(128) org_direct_kernel(OrgDirectArgs a) {
     if (threadIdx.x == 0) a.partial[(long)blockIdx.x * a.K + kidx] = red[0];
 }
 
-// upload the two entry lists into one scratch slot; returns device pointers
-static int upload_lists(const OrgLists &L, int nseg, const OrgEntry *d_ent[2], const int *d_seg[2],
-                        cudaStream_t st) {
+}  // namespace deism
+
+// opaque to C callers (include/deism_b200.h)
+struct deism_org_plan {
+    int N, V, nseg, device;
+    void *d_block;
+    const deism::OrgEntry *d_ent[2];
+    const int *d_seg[2];
+    long nnz;
+};
+
+namespace deism {
+
+static int plan_build(int N, int V, const float *h_W1, const float *h_W2, deism_org_plan *P) {
+    const int Lmax = N + V + 1, nseg = Lmax * Lmax;
+    OrgLists L;
+    build_lists(N, V, h_W1, h_W2, L);
     size_t ent_bytes = (L.entries[0].size() + L.entries[1].size()) * sizeof(OrgEntry);
     size_t seg_bytes = 2 * (size_t)(nseg + 1) * sizeof(int);
-    unsigned char *base = (unsigned char *)workspace(WS_ORG_LIST, ent_bytes + seg_bytes + 64);
-    if (!base) return DEISM_ERR_NOMEM;
-    OrgEntry *e0 = (OrgEntry *)base;
-    OrgEntry *e1 = e0 + L.entries[0].size();
-    int *s0 = (int *)(base + ent_bytes);
-    int *s1 = s0 + nseg + 1;
-    // pageable -> device async copies are staged by the runtime before returning
+    unsigned char *base = nullptr;
+    if (cudaMalloc(&base, ent_bytes + seg_bytes + 64) != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(DEISM_ERR_NOMEM, "cudaMalloc of the coupling plan failed");
+    }
+    OrgEntry *e0 = (OrgEntry *)base, *e1 = e0 + L.entries[0].size();
+    int *s0 = (int *)(base + ent_bytes), *s1 = s0 + nseg + 1;
+    cudaError_t e = cudaSuccess;
     if (!L.entries[0].empty())
-        DEISM_CUDA_TRY(cudaMemcpyAsync(e0, L.entries[0].data(), L.entries[0].size() * sizeof(OrgEntry),
-                                       cudaMemcpyHostToDevice, st));
-    if (!L.entries[1].empty())
-        DEISM_CUDA_TRY(cudaMemcpyAsync(e1, L.entries[1].data(), L.entries[1].size() * sizeof(OrgEntry),
-                                       cudaMemcpyHostToDevice, st));
-    DEISM_CUDA_TRY(cudaMemcpyAsync(s0, L.seg[0].data(), (nseg + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-    DEISM_CUDA_TRY(cudaMemcpyAsync(s1, L.seg[1].data(), (nseg + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-    DEISM_CUDA_TRY(cudaStreamSynchronize(st));   // host vectors may die after return
-    d_ent[0] = e0; d_ent[1] = e1; d_seg[0] = s0; d_seg[1] = s1;
+        e = cudaMemcpy(e0, L.entries[0].data(), L.entries[0].size() * sizeof(OrgEntry), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !L.entries[1].empty())
+        e = cudaMemcpy(e1, L.entries[1].data(), L.entries[1].size() * sizeof(OrgEntry), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(s0, L.seg[0].data(), (nseg + 1) * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(s1, L.seg[1].data(), (nseg + 1) * sizeof(int), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(base);
+        return set_error(DEISM_ERR_CUDA, "coupling plan upload failed: %s", cudaGetErrorString(e));
+    }
+    P->N = N; P->V = V; P->nseg = nseg; P->d_block = base; P->nnz = L.nnz;
+    P->d_ent[0] = e0; P->d_ent[1] = e1; P->d_seg[0] = s0; P->d_seg[1] = s1;
+    cudaGetDevice(&P->device);
     return DEISM_OK;
 }
+
+// plan supplied by the caller, or a temporary one built from the tables (freed by the guard)
+struct PlanGuard {
+    deism_org_plan tmp = {};
+    const deism_org_plan *use = nullptr;
+    ~PlanGuard() { if (tmp.d_block) cudaFree(tmp.d_block); }   // cudaFree waits for the kernels
+    int get(const deism_org_plan *plan, int N, int V, const float *h_W1, const float *h_W2) {
+        if (plan) {
+            if (plan->N != N || plan->V != V)
+                return set_error(DEISM_ERR_INVALID, "coupling plan is for orders (%d,%d), call has (%d,%d)",
+                                 plan->N, plan->V, N, V);
+            use = plan;
+            return DEISM_OK;
+        }
+        if (!h_W1 || !h_W2) return set_error(DEISM_ERR_INVALID, "need a plan or the Wigner tables");
+        int rc = plan_build(N, V, h_W1, h_W2, &tmp);
+        if (rc) return rc;
+        use = &tmp;
+        return DEISM_OK;
+    }
+};
 
 static void fill_room(RoomGeom &room, const deism_shoebox_atten *at) {
     for (int i = 0; i < 3; ++i) {
@@ -745,11 +785,31 @@ static void fill_room(RoomGeom &room, const deism_shoebox_atten *at) {
 
 using namespace deism;
 
+extern "C" int deism_org_plan_create(int N, int V, const float *h_W1, const float *h_W2,
+                                     deism_org_plan **plan) {
+    int rc = check_device();
+    if (rc) return rc;
+    if (!plan || !h_W1 || !h_W2) return set_error(DEISM_ERR_INVALID, "null pointer");
+    if (N < 0 || V < 0 || N > 20 || V > 20) return set_error(DEISM_ERR_INVALID, "orders must be 0..20");
+    deism_org_plan *P = new deism_org_plan();
+    rc = plan_build(N, V, h_W1, h_W2, P);
+    if (rc) { delete P; return rc; }
+    *plan = P;
+    return DEISM_OK;
+}
+
+extern "C" int deism_org_plan_destroy(deism_org_plan *plan) {
+    if (!plan) return DEISM_OK;
+    if (plan->d_block) cudaFree(plan->d_block);
+    delete plan;
+    return DEISM_OK;
+}
+
 extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, const float *d_C_nm_s,
                                  const float *d_C_vu_r, const float *h_W1, const float *h_W2,
                                  const int32_t *d_A, const float *d_R_sI_r,
                                  const deism_shoebox_atten *atten, const double *d_k, double *d_out,
-                                 int accumulate, int algo, void *stream) {
+                                 int accumulate, int algo, const deism_org_plan *plan, void *stream) {
     int rc = check_device();
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -760,7 +820,7 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
         return DEISM_OK;
     }
     if (N < 0 || V < 0 || N > 20 || V > 20) return set_error(DEISM_ERR_INVALID, "orders must be 0..20");
-    if (!d_C_nm_s || !d_C_vu_r || !h_W1 || !h_W2 || !d_A || !d_R_sI_r)
+    if (!d_C_nm_s || !d_C_vu_r || !d_A || !d_R_sI_r)
         return set_error(DEISM_ERR_INVALID, "null input pointer");
     if (algo < 0 || algo > 2) return set_error(DEISM_ERR_INVALID, "algo must be 0, 1 or 2");
     rc = validate_atten(atten);
@@ -768,12 +828,11 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
 
     const int Lmax = N + V + 1, nseg = Lmax * Lmax;
     const int NMs = (N + 1) * (2 * N + 1), NMr = (V + 1) * (2 * V + 1);
-    OrgLists L;
-    build_lists(N, V, h_W1, h_W2, L);
-    const OrgEntry *d_ent[2];
-    const int *d_seg[2];
-    rc = upload_lists(L, nseg, d_ent, d_seg, st);
+    PlanGuard guard;
+    rc = guard.get(plan, N, V, h_W1, h_W2);
     if (rc) return rc;
+    const OrgEntry *d_ent[2] = {guard.use->d_ent[0], guard.use->d_ent[1]};
+    const int *d_seg[2] = {guard.use->d_seg[0], guard.use->d_seg[1]};
 
     int *flags = (int *)workspace(WS_FLAGS, 64);
     if (!flags) return DEISM_ERR_NOMEM;
@@ -816,22 +875,25 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
     if (Lmax > ORG_LMAX) return set_error(DEISM_ERR_INVALID, "N+V+1 > %d", ORG_LMAX);
     // plane geometry: rows(l) = roundup4(2l+1); chunks of <= ORG_RC rows
     int rowoff[ORG_LMAX + 1];
-    int4 chunks[ORG_MAXCHUNKS];
+    int2 chunks[ORG_MAXCHUNKS];
+    signed char ks_l[ORG_LMAX * ORG_LMAX];
     int ncpt = 0, R_tot = 0;
     for (int l = 0; l < Lmax; ++l) {
         rowoff[l] = R_tot;
         const int rows = (2 * l + 1 + 3) / 4 * 4;
-        for (int r0 = 0; r0 < rows; r0 += ORG_RC) {
-            if (ncpt >= ORG_MAXCHUNKS) return set_error(DEISM_ERR_INVALID, "too many (l,mu) chunks");
-            int nr = rows - r0 < ORG_RC ? rows - r0 : ORG_RC;
-            chunks[ncpt++] = make_int4(R_tot + r0, nr, l, r0 + nr >= rows ? 1 : 0);
-        }
+        for (int r0 = 0; r0 < rows; r0 += 4) ks_l[(R_tot + r0) >> 2] = (signed char)(r0 + 4 >= rows ? l : -1);
         R_tot += rows;
     }
     rowoff[Lmax] = R_tot;
+    for (int r0 = 0; r0 < R_tot; r0 += ORG_RC) {
+        if (ncpt >= ORG_MAXCHUNKS) return set_error(DEISM_ERR_INVALID, "too many (l,mu) chunks");
+        chunks[ncpt++] = make_int2(r0, R_tot - r0 < ORG_RC ? R_tot - r0 : ORG_RC);
+    }
     DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_org_rowoff, rowoff, (Lmax + 1) * sizeof(int), 0,
                                            cudaMemcpyHostToDevice, st));
-    DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_org_chunks, chunks, ncpt * sizeof(int4), 0,
+    DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_org_chunks, chunks, ncpt * sizeof(int2), 0,
+                                           cudaMemcpyHostToDevice, st));
+    DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_org_ks_l, ks_l, (size_t)(R_tot >> 2), 0,
                                            cudaMemcpyHostToDevice, st));
     DEISM_CUDA_TRY(cudaStreamSynchronize(st));   // stack tables consumed
 
@@ -907,7 +969,7 @@ extern "C" int deism_org_arg(int64_t n_images, int64_t K, int N, int V, const fl
                              const float *d_C_vu_r, const float *h_W1, const float *h_W2,
                              const float *d_R_sI_r, const float *d_atten, const double *d_k,
                              const int64_t *h_image_index, int64_t n_sel, double *d_out, int accumulate,
-                             void *stream) {
+                             const deism_org_plan *plan, void *stream) {
     int rc = check_device();
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -919,17 +981,16 @@ extern "C" int deism_org_arg(int64_t n_images, int64_t K, int N, int V, const fl
         return DEISM_OK;
     }
     if (N < 0 || V < 0 || N > 20 || V > 20) return set_error(DEISM_ERR_INVALID, "orders must be 0..20");
-    if (!d_C_nm_s_ARG || !d_C_vu_r || !h_W1 || !h_W2 || !d_R_sI_r || !d_atten)
+    if (!d_C_nm_s_ARG || !d_C_vu_r || !d_R_sI_r || !d_atten)
         return set_error(DEISM_ERR_INVALID, "null input pointer");
     if (K > 65535) return set_error(DEISM_ERR_INVALID, "ARG ORG supports K <= 65535");
     const int Lmax = N + V + 1, nseg = Lmax * Lmax;
     const int NMs = (N + 1) * (2 * N + 1), NMr = (V + 1) * (2 * V + 1);
-    OrgLists L;
-    build_lists(N, V, h_W1, h_W2, L);
-    const OrgEntry *d_ent[2];
-    const int *d_seg[2];
-    rc = upload_lists(L, nseg, d_ent, d_seg, st);
+    PlanGuard guard;
+    rc = guard.get(plan, N, V, h_W1, h_W2);
     if (rc) return rc;
+    const OrgEntry *d_ent[2] = {guard.use->d_ent[0], guard.use->d_ent[1]};
+    const int *d_seg[2] = {guard.use->d_seg[0], guard.use->d_seg[1]};
 
     OrgImage *rec = (OrgImage *)workspace(WS_ORG_IMG, (size_t)n_images * sizeof(OrgImage));
     cplx *Y = (cplx *)workspace(WS_ORG_Y, (size_t)nseg * n_images * sizeof(cplx));

@@ -135,17 +135,27 @@ DEISM_API int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr,
                                const deism_shoebox_atten *atten, const double *d_k,
                                double *d_out, int accumulate, void *stream);
 
+/* Coupling plan: the non-zero quintuples (n,m,v,u,l) of the Wigner tables with their real
+ * coefficients, sorted by (l, mu) and resident on the device.  Building it costs a host pass over
+ * W_2 (1.1 M entries at N=V=10); callers that run the same directivity orders repeatedly create it
+ * once (like an FFT plan) and pass it to deism_org_shoebox / deism_org_arg instead of the tables. */
+typedef struct deism_org_plan deism_org_plan;
+DEISM_API int deism_org_plan_create(int N, int V, const float *h_W1, const float *h_W2,
+                                    deism_org_plan **plan);
+DEISM_API int deism_org_plan_destroy(deism_org_plan *plan);
+
 /* Shoebox DEISM-ORG (pb:189-261 _numba_ORG_batch + batching of pb:543-591).
  * d_C_nm_s: complex64[K,N+1,2N+1], d_C_vu_r: complex64[K,V+1,2V+1] (signed m/u wrap as in
  * NumPy); h_W1: HOST complex64[N+1,V+1,N+V+1]; h_W2: HOST complex64[N+1,V+1,N+V+1,2N+1,2V+1]
- * (params["Wigner"]); d_A: int32[I,6]; d_R_sI_r: float32[I,3].
+ * (params["Wigner"]); d_A: int32[I,6]; d_R_sI_r: float32[I,3].  plan: optional (NULL = build the
+ * coupling lists from h_W1/h_W2 inside the call; non-NULL = h_W1/h_W2 are ignored).
  * algo: 0 = auto, 1 = factorised B[parity,k,l,mu] table, 2 = direct quintuple sum. */
 DEISM_API int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V,
                                 const float *d_C_nm_s, const float *d_C_vu_r,
                                 const float *h_W1, const float *h_W2, const int32_t *d_A,
                                 const float *d_R_sI_r, const deism_shoebox_atten *atten,
                                 const double *d_k, double *d_out, int accumulate, int algo,
-                                void *stream);
+                                const deism_org_plan *plan, void *stream);
 
 /* Convex DEISM-ARG LC (pb:328-385).  d_C_s_ARG_vec: complex64[K,Js,I] (image index innermost,
  * cd:1193-1217), d_C_r_vec: complex64[K,Jr], d_R_sI_r: float32[3,I] (component-major),
@@ -163,7 +173,7 @@ DEISM_API int deism_org_arg(int64_t n_images, int64_t K, int N, int V, const flo
                             const float *d_C_vu_r, const float *h_W1, const float *h_W2,
                             const float *d_R_sI_r, const float *d_atten, const double *d_k,
                             const int64_t *h_image_index, int64_t n_sel, double *d_out,
-                            int accumulate, void *stream);
+                            int accumulate, const deism_org_plan *plan, void *stream);
 
 /* ------------------------------------------------------------------------------------ */
 /* (3) Precompute — replaces cd:1842-1913 pre_calc_Wigner (sympy, 169 s at N=V=10)        */
