@@ -260,6 +260,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // global -> shared bulk copy (TMA, SASS UBLKCP); bytes must be a multiple of 16
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes,
                                          unsigned long long *bar) {

@@ -195,7 +195,8 @@ struct LcSmem {
     double cosd[3][LC_TI];
     double kf[LC_TF], wk[LC_TF];
     unsigned char e[LC_TI][8];
-    unsigned long long full[LC_STAGES];
+    unsigned long long full[LC_STAGES];    // TMA bytes landed
+    unsigned long long empty[LC_STAGES];   // all warps done reading the stage
 };
 static_assert(sizeof(LcStage) % 16 == 0, "stage must keep 16-byte alignment");
 static_assert(sizeof(double2) * 32 * LC_TF <= sizeof(LcStage) * LC_STAGES,
@@ -224,7 +225,10 @@ lc_main_kernel(LcMainArgs a) {
     const bool flat = fused && a.flags[0] != 0;
 
     if (tid == 0) {
-        for (int s = 0; s < LC_STAGES; ++s) mbar_init(&sm.full[s], 1);
+        for (int s = 0; s < LC_STAGES; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], LC_THREADS / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int q = tid; q < LC_TF; q += LC_THREADS) {
@@ -322,6 +326,7 @@ lc_main_kernel(LcMainArgs a) {
                     sm.fac[il][fq] = cmul(att, cmake(cs * w, -sn * w));
                 }
             }
+            __syncthreads();   // fac is consumed with the DMMA pair mapping (other threads' entries)
         }
         if (local == 0 || local == a.ncs) {
 #pragma unroll
@@ -332,8 +337,12 @@ lc_main_kernel(LcMainArgs a) {
                     for (int nt = 0; nt < NT; ++nt) { T[p][mt][nt][0] = 0.0; T[p][mt][nt][1] = 0.0; }
         }
 
-        // stage (c+1)&1 was released by the barrier that closed iteration c-1
-        if (tid == 0 && c + 1 < total) issue(c + 1, stage ^ 1);
+        // stage (c+1)&1 held chunk c-1: wait until every warp has released it (no CTA barrier in the
+        // chunk loop: warps drift by up to one chunk)
+        if (tid == 0 && c + 1 < total) {
+            if (c >= 1) mbar_wait(&sm.empty[stage ^ 1], (unsigned)(((c - 1) >> 1) & 1));
+            issue(c + 1, stage ^ 1);
+        }
         mbar_wait(&sm.full[stage], parity);
 
         const LcStage &S = sm.st[stage];
@@ -356,7 +365,8 @@ lc_main_kernel(LcMainArgs a) {
                     for (int nt = 0; nt < NT; ++nt)
                         dmma884(T[p][mt][nt][0], T[p][mt][nt][1], af[p][mt], bf[p][nt]);
         }
-        __syncthreads();   // every warp is done with this stage
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[stage]);   // this warp is done with the stage
 
         if (local == a.ncs - 1) {
             // ---- end of the source pass: S = (T1-T2) + i(T3-T1-T2);  park S' = fac * S.
