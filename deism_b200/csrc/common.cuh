@@ -178,14 +178,18 @@ __device__ __forceinline__ cplx cpow_uint(cplx base, unsigned e) {
 }
 // atten = bx1^e0 * bx2^e1 * by1^e2 * by2^e3 * bz1^e4 * bz2^e5   (cd:2921-2928)
 // Z points at Z_S[0][k]; zstride = K (row stride in complex elements).
+__device__ __forceinline__ bool csame(cplx a, cplx b) { return a.x == b.x && a.y == b.y; }
+// one wall pair: b1^e1 * b2^e2; when both walls carry the same impedance (the common case) the
+// two factors share one division and one power, b^(e1+e2)
+__device__ __forceinline__ cplx wall_pair(cplx z1, cplx z2, double c, unsigned e1, unsigned e2) {
+    if (csame(z1, z2)) return cpow_uint(ref_coef(c, z1), e1 + e2);
+    return cmul(cpow_uint(ref_coef(c, z1), e1), cpow_uint(ref_coef(c, z2), e2));
+}
 __device__ __forceinline__ cplx shoebox_atten(const cplx *__restrict__ Z, long zstride, double cx,
                                               double cy, double cz, const unsigned char *e) {
-    cplx a = cpow_uint(ref_coef(cx, Z[0]), e[0]);
-    a = cmul(a, cpow_uint(ref_coef(cx, Z[zstride]), e[1]));
-    a = cmul(a, cpow_uint(ref_coef(cy, Z[2 * zstride]), e[2]));
-    a = cmul(a, cpow_uint(ref_coef(cy, Z[3 * zstride]), e[3]));
-    a = cmul(a, cpow_uint(ref_coef(cz, Z[4 * zstride]), e[4]));
-    a = cmul(a, cpow_uint(ref_coef(cz, Z[5 * zstride]), e[5]));
+    cplx a = wall_pair(Z[0], Z[zstride], cx, e[0], e[1]);
+    a = cmul(a, wall_pair(Z[2 * zstride], Z[3 * zstride], cy, e[2], e[3]));
+    a = cmul(a, wall_pair(Z[4 * zstride], Z[5 * zstride], cz, e[4], e[5]));
     return a;
 }
 

@@ -90,7 +90,7 @@ def test_lc_vs_oracle_random_inputs():
     from oracle import oracle
 
     rng = np.random.default_rng(7)
-    for (I, K, N, V) in [(1, 1, 0, 0), (70, 33, 2, 1), (333, 97, 4, 3), (129, 64, 5, 5)]:
+    for (I, K, N, V) in [(1, 1, 0, 0), (70, 33, 2, 1), (333, 97, 4, 3), (129, 64, 5, 5), (65, 40, 10, 7)]:
         Js, Jr = (N + 1) ** 2, (V + 1) ** 2
         cs = (rng.standard_normal((K, N + 1, 2 * N + 1)) + 1j * rng.standard_normal((K, N + 1, 2 * N + 1))).astype(np.complex64)
         cr = (rng.standard_normal((K, V + 1, 2 * V + 1)) + 1j * rng.standard_normal((K, V + 1, 2 * V + 1))).astype(np.complex64)
@@ -201,7 +201,7 @@ def test_org_vs_oracle_random_inputs():
     from oracle import oracle
 
     rng = np.random.default_rng(11)
-    for (I, K, N, V) in [(1, 1, 0, 0), (45, 37, 2, 3), (130, 33, 4, 4), (67, 20, 6, 1)]:
+    for (I, K, N, V) in [(1, 1, 0, 0), (45, 37, 2, 3), (130, 33, 4, 4), (67, 20, 6, 1), (40, 12, 8, 9)]:
         cs = (rng.standard_normal((K, N + 1, 2 * N + 1)) + 1j * rng.standard_normal((K, N + 1, 2 * N + 1))).astype(np.complex64)
         cr = (rng.standard_normal((K, V + 1, 2 * V + 1)) + 1j * rng.standard_normal((K, V + 1, 2 * V + 1))).astype(np.complex64)
         A = rng.integers(-3, 4, size=(I, 6)).astype(np.int32)
@@ -278,3 +278,58 @@ def test_full_c3_org_order25_N10_subsampled():
 
 def test_full_c5_mix_order40_N5():
     _full_case("c5_full_N5", "MIX", 5, 5)
+
+
+def test_c_abi_argument_errors():
+    """DEISM_ERR_INVALID surfaces as ValueError with the library's message."""
+    import ctypes as C
+    import torch
+    from deism_b200._lib import ShoeboxAtten, check, lib
+
+    out = torch.zeros(4, dtype=torch.complex128, device="cuda")
+    k = torch.ones(4, dtype=torch.float64, device="cuda")
+    at = ShoeboxAtten()
+    at.mode = 7
+    n = np.zeros(1, np.int64)
+    x = torch.zeros(64, dtype=torch.float32, device="cuda")
+    with pytest.raises(ValueError, match="unknown attenuation mode"):
+        check(lib().deism_lc_shoebox(2, 4, 1, 1, n.ctypes.data, n.ctypes.data, n.ctypes.data, n.ctypes.data,
+                                     x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), C.byref(at),
+                                     k.data_ptr(), out.data_ptr(), 0, None), "deism_lc_shoebox")
+    bad = np.array([3], np.int64)      # |m| > n
+    at.mode = 0
+    at.d_atten = x.data_ptr()
+    with pytest.raises(ValueError, match="bad"):
+        check(lib().deism_lc_shoebox(2, 4, 1, 1, n.ctypes.data, bad.ctypes.data, n.ctypes.data, n.ctypes.data,
+                                     x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), C.byref(at),
+                                     k.data_ptr(), out.data_ptr(), 0, None), "deism_lc_shoebox")
+    with pytest.raises(ValueError, match="out of range"):
+        check(lib().deism_shoebox_count_images(np.ones(3).ctypes.data, np.ones(3).ctypes.data,
+                                               np.ones(3).ctypes.data, 1.0, 9999, 2, 0, x.data_ptr(),
+                                               x.data_ptr(), None), "deism_shoebox_count_images")
+
+
+def test_image_lattice_properties_at_order_60():
+    """Size-independent checks beyond the fixtures: the uncapped lattice has
+    1 + 2N(2N^2+3N+4)/3 images, every image satisfies |q-p|+|q| sums = order, the
+    distance cut only removes images, and lists are deterministic."""
+    from deism_b200 import images as im
+
+    p = {"roomSize": np.array([4.0, 3.0, 2.5]), "posSource": np.array([1.1, 1.1, 1.3]),
+         "posReceiver": np.array([2.9, 1.9, 1.3]), "soundSpeed": 343.0, "reverberationTime": 100.0,
+         "maxReflOrder": 60, "mixEarlyOrder": 2, "ifRemoveDirectPath": 0, "angDepFlag": 1,
+         "impedance": np.full((6, 2), 18.0 + 0j)}
+    a = im.merge_images(im.shoebox_images(p))
+    N = 60
+    assert len(a["A"]) == 1 + 2 * N * (2 * N * N + 3 * N + 4) // 3
+    A = a["A"].astype(np.int64)
+    order = (np.abs(A[:, 0] - A[:, 3]) + np.abs(A[:, 0]) + np.abs(A[:, 1] - A[:, 4]) + np.abs(A[:, 1])
+             + np.abs(A[:, 2] - A[:, 5]) + np.abs(A[:, 2]))
+    assert order.max() == N and order.min() == 0
+    assert len(np.unique(A, axis=0)) == len(A)
+    b = im.merge_images(im.shoebox_images(p))
+    assert all(np.array_equal(a[k], b[k]) for k in ("A", "R_sI_r_all", "R_s_rI_all", "R_r_sI_all"))
+    p["reverberationTime"] = 0.1
+    c = im.merge_images(im.shoebox_images(p))
+    assert 0 < len(c["A"]) < len(a["A"])
+    assert np.all(c["R_sI_r_all"][:, 2] <= np.float32(34.3) * (1 + 1e-6))
