@@ -311,11 +311,12 @@ def main():
     torch.cuda.synchronize()
 
     # ---- parity of this very run against the reference's frozen RTF ----
-    parity = None
+    parity, parity_worst = None, None
     if "RTF" in fixture.files and not args.general_impedance and fixture["RTF"].shape[0] == K:
         ref = fixture["RTF"]
         got = result.cpu().numpy()
         parity = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+        parity_worst = float(np.max(np.abs(got - ref) / np.abs(ref)))
 
     # ---- timed region: device-resident ----
     stop, samples = threading.Event(), []
@@ -426,6 +427,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
             "parity_rel_l2_vs_reference": parity,
+            "parity_worst_single_frequency": parity_worst,
             "wall_ms_incl_l2_flush": wall_ms,
             "extras": extras,
         }

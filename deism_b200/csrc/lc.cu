@@ -44,11 +44,12 @@ constexpr int LC_THREADS = 128 * LC_WN;          // 4 (image) x LC_WN (frequency
 constexpr int LC_YS = LC_TI + 4; // Y plane row stride (doubles): 68 = 4 mod 16
 constexpr int LC_CS = LC_TF + 4; // C plane row stride (doubles): 36 = 4 mod 16
 
-struct LcImage {        // 64 bytes per image
+struct LcImage {        // 80 bytes per image
     double r, inv_r;
     double cx, cy, cz;
     unsigned char e[8];
     double2 atten_flat;  // c64-rounded (mode ROOM) attenuation for frequency-flat impedance
+    double2 rot;         // exp(-i dk r): one frequency step on a uniform wave-number grid
 };
 
 struct LcPrepArgs {
@@ -60,6 +61,7 @@ struct LcPrepArgs {
     const float *R_sI_r;
     const cplx *Z;
     RoomGeom room;
+    const int *flags;    // flags[1]: uniform k grid, *(double *)(flags + 2) = dk
 };
 
 // n_all/m_all/v_all/u_all live in constant memory (J <= 256 each: order <= 15)
@@ -77,6 +79,24 @@ __global__ void z_flat_kernel(const cplx *__restrict__ Z, long K, int *flags) {
         if (a.x != b.x || a.y != b.y) diff = true;
     }
     if (__syncthreads_or(diff) && threadIdx.x == 0) atomicExch(flags, 0);
+}
+
+// flags[1] = 1 iff k is an arithmetic progression closely enough for the rotation recurrence of
+// the factor phase: every step k[i+1]-k[i] within 1e-12 rad/m (and 1e-6 relative) of the mean step
+// dk, so that the first-order correction for the residual d = step - dk leaves (d r)^2/2 < 1e-16
+// for r up to 1e4 m.  np.arange grids deviate by a few ulp(k) ~ 1e-13.  *(double *)(flags+2) = dk.
+__global__ void __launch_bounds__(256) k_uniform_kernel(const double *__restrict__ k, long K, int *flags) {
+    const double dk = K > 1 ? (k[K - 1] - k[0]) / (double)(K - 1) : 0.0;
+    bool bad = K < 2 || !(dk > 0.0);
+    for (long i = threadIdx.x; i + 1 < K; i += blockDim.x) {
+        double d = (k[i + 1] - k[i]) - dk;
+        if (!(fabs(d) <= 1e-12 && fabs(d) <= 1e-6 * dk)) bad = true;
+    }
+    bool any_bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) {
+        flags[1] = any_bad ? 0 : 1;
+        *reinterpret_cast<double *>(flags + 2) = dk;
+    }
 }
 
 // Y planes: [tile][j < J_pad][plane 0..2][LC_YS] doubles, plane = Re | Im | Re+Im of
@@ -105,6 +125,7 @@ lc_prep_kernel(LcPrepArgs a, LcImage *img_out, double *Ys, double *Yr) {
         for (int j = 0; j < a.Jr_pad * 3; ++j)
             Yr[tile * (long)a.Jr_pad * 3 * LC_YS + (long)j * LC_YS + LC_TI + it] = 0.0;
     }
+    rec.rot = cmake(1.0, 0.0);
     if (img >= a.n_images) {
         rec.r = 1.0; rec.inv_r = 0.0;           // weight 0: contributes exactly nothing
         rec.atten_flat = cmake(0.0, 0.0);
@@ -116,6 +137,11 @@ lc_prep_kernel(LcPrepArgs a, LcImage *img_out, double *Ys, double *Yr) {
     double phi_s = (double)a.R_s_rI[img * 3 + 0], th_s = (double)a.R_s_rI[img * 3 + 1];
     rec.r = (double)a.R_s_rI[img * 3 + 2];
     rec.inv_r = 1.0 / rec.r;
+    {
+        double sn, cs;
+        sincos_cw(*reinterpret_cast<const double *>(a.flags + 2) * rec.r, &sn, &cs);
+        rec.rot = cmake(cs, -sn);
+    }
     double phi_r = (double)a.R_r_sI[img * 3 + 0], th_r = (double)a.R_r_sI[img * 3 + 1];
     double s, ct_s, ct_r;
     sincos_cw(th_s, &s, &ct_s);
@@ -191,9 +217,11 @@ struct LcSmem {
     double2 fac[LC_TI][LC_TF + 1];   // factor[img][freq], then S' = factor * S, of the current tile
     double2 Z[6][LC_TF];
     double2 aflat[LC_TI];
+    double2 rot[LC_TI];
     double r[LC_TI], invr[LC_TI];
     double cosd[3][LC_TI];
     double kf[LC_TF], wk[LC_TF];
+    double dkd[LC_TF];               // (k[f+1] - k[f]) - dk: ulp-level deviation from the uniform step
     unsigned char e[LC_TI][8];
     unsigned long long full[LC_STAGES];    // TMA bytes landed
     unsigned long long empty[LC_STAGES];   // all warps done reading the stage
@@ -223,6 +251,7 @@ lc_main_kernel(LcMainArgs a) {
 
     const bool fused = a.mode == DEISM_ATTEN_FUSED_ROOM || a.mode == DEISM_ATTEN_FUSED_ANGLES;
     const bool flat = fused && a.flags[0] != 0;
+    const bool uniform_k = a.flags[1] != 0;
 
     if (tid == 0) {
         for (int s = 0; s < LC_STAGES; ++s) {
@@ -236,6 +265,7 @@ lc_main_kernel(LcMainArgs a) {
         double kk = f < a.K ? a.k[f] : 1.0;
         sm.kf[q] = kk;
         sm.wk[q] = -4.0 * 3.14159265358979323846 / (kk * kk);   // -4pi/k^2
+        sm.dkd[q] = f + 1 < a.K ? (a.k[f + 1] - kk) - *reinterpret_cast<const double *>(a.flags + 2) : 0.0;
     }
     if (fused && !flat) {
         for (int i = tid; i < 6 * LC_TF; i += LC_THREADS) {
@@ -290,8 +320,52 @@ lc_main_kernel(LcMainArgs a) {
 #pragma unroll
                 for (int b = 0; b < 8; ++b) sm.e[i][b] = rec.e[b];
                 sm.aflat[i] = rec.atten_flat;
+                sm.rot[i] = rec.rot;
             }
             __syncthreads();
+            if (uniform_k) {
+                // uniform grid: each thread owns RUN consecutive frequencies of one image and
+                // advances exp(-ikr) by the per-image rotation exp(-i dk r) (one sincos per run;
+                // <= RUN-1 rotations, error ~1e-16 each)
+                constexpr int RUN = LC_TI * LC_TF / LC_THREADS;
+                constexpr int GROUPS = LC_TF / RUN;
+                const int il = tid / GROUPS, fq0 = (tid % GROUPS) * RUN;
+                const long img = i0 + il;
+                const double r = sm.r[il], inv_r = sm.invr[il];
+                const cplx rot = sm.rot[il];
+                double sn, cs;
+                sincos_cw(sm.kf[fq0] * r, &sn, &cs);
+                cplx E = cmake(cs, -sn);
+#pragma unroll 2
+                for (int j = 0; j < RUN; ++j) {
+                    const int fq = fq0 + j;
+                    cplx att;
+                    if (flat) {
+                        att = sm.aflat[il];
+                    } else if (fused) {
+                        att = shoebox_atten(&sm.Z[0][fq], LC_TF, sm.cosd[0][il], sm.cosd[1][il],
+                                            sm.cosd[2][il], sm.e[il]);
+                        if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
+                    } else {
+                        long f = f0 + fq;
+                        att = cmake(0.0, 0.0);
+                        if (img < a.n_images && f < a.K) {
+                            if (a.mode == DEISM_ATTEN_C64) {
+                                float2 v = ((const float2 *)a.atten)[img * a.K + f];
+                                att = cmake((double)v.x, (double)v.y);
+                            } else {
+                                att = ((const cplx *)a.atten)[img * a.K + f];
+                            }
+                        }
+                    }
+                    const double w = sm.wk[fq] * inv_r;
+                    sm.fac[il][fq] = cmul(att, cmake(E.x * w, E.y * w));
+                    // exp(-i (dk + d) r) = rot * (1 - i d r) to first order in the ulp-level d
+                    E = cmul(E, rot);
+                    const double dr = sm.dkd[fq] * r;
+                    E = cmake(fma(E.y, dr, E.x), fma(-E.x, dr, E.y));
+                }
+            } else {
             const int tx = tid & 7, ty = tid >> 3;
 #pragma unroll 1
             for (int b = 0; b < LC_TI / (LC_THREADS / 8); ++b) {
@@ -325,6 +399,7 @@ lc_main_kernel(LcMainArgs a) {
                     double w = sm.wk[fq] * inv_r;
                     sm.fac[il][fq] = cmul(att, cmake(cs * w, -sn * w));
                 }
+            }
             }
             __syncthreads();   // fac is consumed with the DMMA pair mapping (other threads' entries)
         }
@@ -549,8 +624,11 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
 
     rc = launch_z_flat(atten, K, flags, st);
     if (rc) return rc;
+    k_uniform_kernel<<<1, 256, 0, st>>>(d_k, K, flags);
+    DEISM_LAUNCH_CHECK("k_uniform_kernel");
 
     LcPrepArgs pa;
+    pa.flags = flags;
     pa.n_images = n_images; pa.n_pad = n_pad; pa.K = K; pa.Js = Js; pa.Jr = Jr;
     pa.Js_pad = Js_pad; pa.Jr_pad = Jr_pad;
     pa.R_s_rI = d_R_s_rI; pa.R_r_sI = d_R_r_sI;

@@ -84,3 +84,11 @@ def rel_l2(a, b):
     a = np.asarray(a)
     b = np.asarray(b)
     return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def rel_max(a, b):
+    """Worst per-frequency relative error max_k |a_k - b_k| / |b_k| — stricter than rel_l2 when a
+    few frequencies dominate the norm (ORG terms reach 1e20 at small kr)."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    return float(np.max(np.abs(a - b) / np.abs(b)))

@@ -11,7 +11,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from conftest import Golden, golden_names, rel_l2
+from conftest import Golden, golden_names, rel_l2, rel_max
 
 pytestmark = pytest.mark.gpu
 RTF_TOL = 1e-9
@@ -67,6 +67,7 @@ def test_lc_reference_layout(name):
     got = backend.run_DEISM(g.params())
     assert got.dtype == np.complex128 and got.shape == g.rtf.shape
     assert rel_l2(got, g.rtf) < RTF_TOL
+    assert rel_max(got, g.rtf) < 1e-8
 
 
 @pytest.mark.parametrize("name", [n for n in SHOEBOX if "_lc_" in n])
@@ -179,6 +180,7 @@ def test_org_mix_reference_layout(name, algo):
     p["b200OrgAlgo"] = algo
     got = backend.run_DEISM(p)
     assert rel_l2(got, g.rtf) < RTF_TOL
+    assert rel_max(got, g.rtf) < 1e-8
 
 
 @pytest.mark.parametrize("name", [n for n in SHOEBOX if ("_org_" in n or "_mix_" in n) and "compact" not in n])
@@ -258,9 +260,10 @@ def _full_case(name, method, N, V):
         assert hashlib.sha256(np.ascontiguousarray(im[key]).tobytes()).hexdigest() == str(h), key
     p["images"] = im
     got = backend.run_DEISM(p)
-    err = rel_l2(got, g.rtf)
-    print(f"{name}: rel L2 error vs reference run_DEISM = {err:.3e}")
+    err, worst = rel_l2(got, g.rtf), rel_max(got, g.rtf)
+    print(f"{name}: vs reference run_DEISM rel L2 = {err:.3e}, worst single frequency = {worst:.3e}")
     assert err < RTF_TOL
+    assert worst < 1e-8      # every frequency on its own, not only the norm
     return err
 
 
