@@ -1,0 +1,40 @@
+"""CPU: host-side precompute mirrors (vectorisers, monopole coefficients) reproduce the arrays the
+reference stored in the fixtures, bit for bit."""
+import numpy as np
+import pytest
+
+from conftest import Golden, golden_names
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names("s") if "_lc_" in n or "_mix_" in n])
+def test_vectorisers_shoebox(name):
+    from deism_b200 import directivities as D
+
+    p = Golden(name).params()
+    ref = {k: p[k] for k in ("n_all", "m_all", "v_all", "u_all", "C_nm_s_vec", "C_vu_r_vec")}
+    q = {"C_nm_s": p["C_nm_s"], "C_vu_r": p["C_vu_r"], "sourceOrder": p["sourceOrder"],
+         "receiverOrder": p["receiverOrder"], "track_updated_where": True, "updated_where": {}}
+    q = D.vectorize_C_vu_r(D.vectorize_C_nm_s(q))
+    for key, val in ref.items():
+        assert np.array_equal(q[key], val) and q[key].dtype == val.dtype, key
+    assert q["updated_where"]["C_nm_s_vec"] == ["vectorize_C_nm_s"]
+
+
+def test_vectoriser_arg_and_monopoles():
+    from deism_b200 import directivities as D
+
+    p = Golden("x2_convex_rir_lc_o5_N2").params()
+    q = {"C_nm_s_ARG": p["C_nm_s_ARG"], "sourceOrder": p["sourceOrder"]}
+    q = D.vectorize_C_nm_s_ARG(q)
+    assert np.array_equal(q["C_nm_s_ARG_vec"], p["C_nm_s_ARG_vec"])
+    m = Golden("s1_shoebox_rtf_mix_o5_mono").params()
+    q = {"sourceType": "monopole", "receiverType": "monopole", "waveNumbers": m["waveNumbers"]}
+    q = D.init_receiver_directivities(D.init_source_directivities(q))
+    assert np.array_equal(q["C_nm_s"], m["C_nm_s"]) and np.array_equal(q["C_vu_r"], m["C_vu_r"])
+    assert q["sourceOrder"] == 0 and q["receiverOrder"] == 0 and q["ifReceiverNormalize"] == 0
+    x = Golden("x1_convex_rir_mix_o4_mono").params()
+    q = {"sourceType": "monopole", "waveNumbers": x["waveNumbers"], "reflection_matrix": x["reflection_matrix"]}
+    q = D.init_source_directivities_ARG(q)
+    assert np.array_equal(q["C_nm_s_ARG"], x["C_nm_s_ARG"])
+    with pytest.raises(NotImplementedError):
+        D.init_source_directivities({"sourceType": "speaker_cuboid_cyldriver_1", "waveNumbers": [1.0]})
