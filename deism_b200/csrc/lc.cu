@@ -44,13 +44,15 @@ constexpr int LC_THREADS = 128 * LC_WN;          // 4 (image) x LC_WN (frequency
 constexpr int LC_YS = LC_TI + 4; // Y plane row stride (doubles): 68 = 4 mod 16
 constexpr int LC_CS = LC_TF + 4; // C plane row stride (doubles): 36 = 4 mod 16
 
-struct LcImage {        // 80 bytes per image
+struct LcImage {        // 96 bytes per image (a tile of 64 records is one 6 KB bulk copy)
     double r, inv_r;
     double cx, cy, cz;
     unsigned char e[8];
     double2 atten_flat;  // c64-rounded (mode ROOM) attenuation for frequency-flat impedance
     double2 rot;         // exp(-i dk r): one frequency step on a uniform wave-number grid
+    double2 rot8;        // exp(-i 8 dk r)
 };
+static_assert(sizeof(LcImage) == 96, "LcImage must stay a multiple of 16 bytes");
 
 struct LcPrepArgs {
     long n_images, n_pad, K;
@@ -126,6 +128,7 @@ lc_prep_kernel(LcPrepArgs a, LcImage *img_out, double *Ys, double *Yr) {
             Yr[tile * (long)a.Jr_pad * 3 * LC_YS + (long)j * LC_YS + LC_TI + it] = 0.0;
     }
     rec.rot = cmake(1.0, 0.0);
+    rec.rot8 = cmake(1.0, 0.0);
     if (img >= a.n_images) {
         rec.r = 1.0; rec.inv_r = 0.0;           // weight 0: contributes exactly nothing
         rec.atten_flat = cmake(0.0, 0.0);
@@ -141,6 +144,8 @@ lc_prep_kernel(LcPrepArgs a, LcImage *img_out, double *Ys, double *Yr) {
         double sn, cs;
         sincos_cw(*reinterpret_cast<const double *>(a.flags + 2) * rec.r, &sn, &cs);
         rec.rot = cmake(cs, -sn);
+        sincos_cw(8.0 * *reinterpret_cast<const double *>(a.flags + 2) * rec.r, &sn, &cs);
+        rec.rot8 = cmake(cs, -sn);
     }
     double phi_r = (double)a.R_r_sI[img * 3 + 0], th_r = (double)a.R_r_sI[img * 3 + 1];
     double s, ct_s, ct_r;
@@ -214,25 +219,28 @@ struct LcStage {
 };
 struct LcSmem {
     LcStage st[LC_STAGES];
-    double2 fac[LC_TI][LC_TF + 1];   // factor[img][freq], then S' = factor * S, of the current tile
+    double2 facp[4 * LC_NT][LC_THREADS];   // thread-private factor, then S' = factor * S
+    LcImage rec[2][LC_TI];                 // per-image records of the current / next tile (TMA)
     double2 Z[6][LC_TF];
-    double2 aflat[LC_TI];
-    double2 rot[LC_TI];
-    double r[LC_TI], invr[LC_TI];
-    double cosd[3][LC_TI];
     double kf[LC_TF], wk[LC_TF];
-    double dkd[LC_TF];               // (k[f+1] - k[f]) - dk: ulp-level deviation from the uniform step
-    unsigned char e[LC_TI][8];
-    unsigned long long full[LC_STAGES];    // TMA bytes landed
-    unsigned long long empty[LC_STAGES];   // all warps done reading the stage
+    double dkd[LC_TF], dkd8[LC_TF];        // ulp-level deviations of 1 and 8 steps from the uniform grid
+    unsigned long long full[LC_STAGES];    // operand bytes landed
+    unsigned long long recfull[2];
+    int done[LC_STAGES], recdone[2];       // warps that have released a stage / a record buffer
 };
 static_assert(sizeof(LcStage) % 16 == 0, "stage must keep 16-byte alignment");
 static_assert(sizeof(double2) * 32 * LC_TF <= sizeof(LcStage) * LC_STAGES,
               "final reduction aliases the stages");
 
+// The main loop has NO CTA-wide barrier and no waiting producer: operand chunks and per-image
+// records arrive by TMA on "full" mbarriers; every warp counts itself out of a buffer when it is
+// done with it and the LAST warp out refills it (issues the next bulk copies) on the spot.  The
+// factor of a pair is computed, parked and consumed by the one thread that owns the pair in the
+// DMMA accumulator layout.  Warps of a CTA drift by up to one chunk.
 __global__ void __launch_bounds__(LC_THREADS, 2)
 lc_main_kernel(LcMainArgs a) {
     constexpr int NT = LC_NT;
+    constexpr int NWARPS = LC_THREADS / 32;
     extern __shared__ __align__(128) unsigned char lc_smem_raw[];
     LcSmem &sm = *reinterpret_cast<LcSmem *>(lc_smem_raw);
 
@@ -246,26 +254,29 @@ lc_main_kernel(LcMainArgs a) {
     long tile_lo = chunk * a.tiles_per_chunk;
     long tile_hi = tile_lo + a.tiles_per_chunk;
     if (tile_hi > n_img_tiles) tile_hi = n_img_tiles;
+    const long n_tiles = tile_hi > tile_lo ? tile_hi - tile_lo : 0;
     const int npt = a.ncs + a.ncr;                         // chunks per tile
-    const long total = tile_hi > tile_lo ? (tile_hi - tile_lo) * npt : 0;
+    const long total = n_tiles * npt;
 
     const bool fused = a.mode == DEISM_ATTEN_FUSED_ROOM || a.mode == DEISM_ATTEN_FUSED_ANGLES;
     const bool flat = fused && a.flags[0] != 0;
     const bool uniform_k = a.flags[1] != 0;
 
     if (tid == 0) {
-        for (int s = 0; s < LC_STAGES; ++s) {
-            mbar_init(&sm.full[s], 1);
-            mbar_init(&sm.empty[s], LC_THREADS / 32);
-        }
+        for (int s = 0; s < LC_STAGES; ++s) { mbar_init(&sm.full[s], 1); sm.done[s] = 0; }
+        for (int s = 0; s < 2; ++s) { mbar_init(&sm.recfull[s], 1); sm.recdone[s] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int q = tid; q < LC_TF; q += LC_THREADS) {
-        long f = f0 + q;
-        double kk = f < a.K ? a.k[f] : 1.0;
-        sm.kf[q] = kk;
-        sm.wk[q] = -4.0 * 3.14159265358979323846 / (kk * kk);   // -4pi/k^2
-        sm.dkd[q] = f + 1 < a.K ? (a.k[f + 1] - kk) - *reinterpret_cast<const double *>(a.flags + 2) : 0.0;
+    {
+        const double dk = *reinterpret_cast<const double *>(a.flags + 2);
+        for (int q = tid; q < LC_TF; q += LC_THREADS) {
+            long f = f0 + q;
+            double kk = f < a.K ? a.k[f] : 1.0;
+            sm.kf[q] = kk;
+            sm.wk[q] = -4.0 * 3.14159265358979323846 / (kk * kk);   // -4pi/k^2
+            sm.dkd[q] = f + 1 < a.K ? (a.k[f + 1] - kk) - dk : 0.0;
+            sm.dkd8[q] = f + 8 < a.K ? (a.k[f + 8] - kk) - 8.0 * dk : 0.0;
+        }
     }
     if (fused && !flat) {
         for (int i = tid; i < 6 * LC_TF; i += LC_THREADS) {
@@ -276,11 +287,9 @@ lc_main_kernel(LcMainArgs a) {
     }
     __syncthreads();
 
-    // producer: one thread stages chunk c (JC harmonics of one pass for one image tile) with two
-    // bulk copies: the C block of this frequency tile and the Y block of the image tile
-    auto issue = [&](long c, int stage) {
-        const long tile = tile_lo + c / npt;
-        const int local = (int)(c % npt);
+    // producer (thread 0): chunk c = JC harmonics of one pass for one image tile, two bulk copies
+    auto issue = [&](long tile_ord, int local, int stage) {
+        const long tile = tile_lo + tile_ord;
         const bool src_pass = local < a.ncs;
         const int JC = src_pass ? a.JCs : a.JCr;
         const int j0 = (src_pass ? local : local - a.ncs) * JC;
@@ -293,6 +302,12 @@ lc_main_kernel(LcMainArgs a) {
         bulk_g2s(&S.C[0][0][0], CT, cb, &sm.full[stage]);
         bulk_g2s(&S.Y[0][0][0], Yg, yb, &sm.full[stage]);
     };
+    auto issue_records = [&](long tt) {      // tile ordinal tt within this CTA
+        const int rb = (int)(tt & 1);
+        mbar_expect_tx(&sm.recfull[rb], (unsigned)(LC_TI * sizeof(LcImage)));
+        bulk_g2s(&sm.rec[rb][0], a.img + (tile_lo + tt) * LC_TI, (unsigned)(LC_TI * sizeof(LcImage)),
+                 &sm.recfull[rb]);
+    };
 
     // accumulators of the three real GEMMs: [plane][m-tile][n-tile][2]
     double T[3][2][NT][2];
@@ -301,107 +316,93 @@ lc_main_kernel(LcMainArgs a) {
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) { P[nt][0] = cmake(0.0, 0.0); P[nt][1] = cmake(0.0, 0.0); }
 
-    if (tid == 0 && total > 0) issue(0, 0);
+    if (tid == 0 && total > 0) {
+        issue_records(0);
+        if (n_tiles > 1) issue_records(1);
+        issue(0, 0, 0);
+        if (total > 1) issue(npt > 1 ? 0 : 1, npt > 1 ? 1 : 0, 1);
+    }
 
+    // chunk counter c = tt * npt + local, kept as (tt, local) so that no 64-bit division runs per chunk
+    int local = 0;
+    long tt = 0;
 #pragma unroll 1
-    for (long c = 0; c < total; ++c) {
+    for (long c = 0; c < total; ++c, ++local) {
+        if (local == npt) { local = 0; ++tt; }
         const int stage = (int)(c & 1);
         const unsigned parity = (unsigned)((c >> 1) & 1);
-        const int local = (int)(c % npt);
-        const long i0 = (tile_lo + c / npt) * LC_TI;
 
         if (local == 0) {
-            // ---- new image tile: per-image records, then the factor
-            //      fac[img][freq] = -atten * 4pi/k * exp(-ikr)/k/r   (pb:314-317)
-            for (int i = tid; i < LC_TI; i += LC_THREADS) {
-                LcImage rec = a.img[i0 + i];
-                sm.r[i] = rec.r; sm.invr[i] = rec.inv_r;
-                sm.cosd[0][i] = rec.cx; sm.cosd[1][i] = rec.cy; sm.cosd[2][i] = rec.cz;
+            // ---- new image tile ----
+            const int rb = (int)(tt & 1);
+            const long i0 = (tile_lo + tt) * LC_TI;
+            mbar_wait(&sm.recfull[rb], (unsigned)((tt >> 1) & 1));
+            // factor fac = -atten * 4pi/k * exp(-ikr)/k/r (pb:314-317) of the pairs this thread owns:
+            // images wm*16 + mt*8 + g, frequencies (wn*NT + nt)*8 + 2*t4 + e
+            const int fqa = wn * NT * 8 + 2 * t4;
 #pragma unroll
-                for (int b = 0; b < 8; ++b) sm.e[i][b] = rec.e[b];
-                sm.aflat[i] = rec.atten_flat;
-                sm.rot[i] = rec.rot;
-            }
-            __syncthreads();
-            if (uniform_k) {
-                // uniform grid: each thread owns RUN consecutive frequencies of one image and
-                // advances exp(-ikr) by the per-image rotation exp(-i dk r) (one sincos per run;
-                // <= RUN-1 rotations, error ~1e-16 each)
-                constexpr int RUN = LC_TI * LC_TF / LC_THREADS;
-                constexpr int GROUPS = LC_TF / RUN;
-                const int il = tid / GROUPS, fq0 = (tid % GROUPS) * RUN;
+            for (int mt = 0; mt < 2; ++mt) {
+                const int il = wm * 16 + mt * 8 + g;
+                const LcImage &rec = sm.rec[rb][il];
                 const long img = i0 + il;
-                const double r = sm.r[il], inv_r = sm.invr[il];
-                const cplx rot = sm.rot[il];
-                double sn, cs;
-                sincos_cw(sm.kf[fq0] * r, &sn, &cs);
-                cplx E = cmake(cs, -sn);
-#pragma unroll 2
-                for (int j = 0; j < RUN; ++j) {
-                    const int fq = fq0 + j;
-                    cplx att;
-                    if (flat) {
-                        att = sm.aflat[il];
-                    } else if (fused) {
-                        att = shoebox_atten(&sm.Z[0][fq], LC_TF, sm.cosd[0][il], sm.cosd[1][il],
-                                            sm.cosd[2][il], sm.e[il]);
-                        if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
-                    } else {
-                        long f = f0 + fq;
-                        att = cmake(0.0, 0.0);
-                        if (img < a.n_images && f < a.K) {
-                            if (a.mode == DEISM_ATTEN_C64) {
-                                float2 v = ((const float2 *)a.atten)[img * a.K + f];
-                                att = cmake((double)v.x, (double)v.y);
-                            } else {
-                                att = ((const cplx *)a.atten)[img * a.K + f];
-                            }
-                        }
-                    }
-                    const double w = sm.wk[fq] * inv_r;
-                    sm.fac[il][fq] = cmul(att, cmake(E.x * w, E.y * w));
-                    // exp(-i (dk + d) r) = rot * (1 - i d r) to first order in the ulp-level d
-                    E = cmul(E, rot);
-                    const double dr = sm.dkd[fq] * r;
-                    E = cmake(fma(E.y, dr, E.x), fma(-E.x, dr, E.y));
-                }
-            } else {
-            const int tx = tid & 7, ty = tid >> 3;
-#pragma unroll 1
-            for (int b = 0; b < LC_TI / (LC_THREADS / 8); ++b) {
-                const int il = ty + (LC_THREADS / 8) * b;
-                const long img = i0 + il;
-                const double r = sm.r[il], inv_r = sm.invr[il];
-#pragma unroll 2
-                for (int q = 0; q < 4; ++q) {
-                    const int fq = tx + 8 * q;
+                const double r = rec.r, inv_r = rec.inv_r;
+                cplx E0 = cmake(1.0, 0.0);
+                if (uniform_k) {
                     double sn, cs;
-                    sincos_cw(sm.kf[fq] * r, &sn, &cs);
-                    cplx att;
-                    if (flat) {
-                        att = sm.aflat[il];
-                    } else if (fused) {
-                        att = shoebox_atten(&sm.Z[0][fq], LC_TF, sm.cosd[0][il], sm.cosd[1][il],
-                                            sm.cosd[2][il], sm.e[il]);
-                        if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
-                    } else {
-                        long f = f0 + fq;
-                        att = cmake(0.0, 0.0);
-                        if (img < a.n_images && f < a.K) {
-                            if (a.mode == DEISM_ATTEN_C64) {
-                                float2 v = ((const float2 *)a.atten)[img * a.K + f];
-                                att = cmake((double)v.x, (double)v.y);
-                            } else {
-                                att = ((const cplx *)a.atten)[img * a.K + f];
+                    sincos_cw(sm.kf[fqa] * r, &sn, &cs);
+                    E0 = cmake(cs, -sn);
+                }
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    cplx E = E0;     // exp(-i k r) at frequency fqa + 8*nt
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int fq = fqa + 8 * nt + e;
+                        if (!uniform_k) {
+                            double sn, cs;
+                            sincos_cw(sm.kf[fq] * r, &sn, &cs);
+                            E = cmake(cs, -sn);
+                        }
+                        cplx att;
+                        if (flat) {
+                            att = rec.atten_flat;
+                        } else if (fused) {
+                            att = shoebox_atten(&sm.Z[0][fq], LC_TF, rec.cx, rec.cy, rec.cz, rec.e);
+                            if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
+                        } else {
+                            long f = f0 + fq;
+                            att = cmake(0.0, 0.0);
+                            if (img < a.n_images && f < a.K) {
+                                if (a.mode == DEISM_ATTEN_C64) {
+                                    float2 v = ((const float2 *)a.atten)[img * a.K + f];
+                                    att = cmake((double)v.x, (double)v.y);
+                                } else {
+                                    att = ((const cplx *)a.atten)[img * a.K + f];
+                                }
                             }
                         }
+                        const double w = sm.wk[fq] * inv_r;
+                        sm.facp[(mt * NT + nt) * 2 + e][tid] = cmul(att, cmake(E.x * w, E.y * w));
+                        if (uniform_k && e == 0) {
+                            // one step: exp(-i (dk + d) r) = rot * (1 - i d r) to first order in d
+                            E = cmul(E, rec.rot);
+                            const double dr = sm.dkd[fq] * r;
+                            E = cmake(fma(E.y, dr, E.x), fma(-E.x, dr, E.y));
+                        }
                     }
-                    double w = sm.wk[fq] * inv_r;
-                    sm.fac[il][fq] = cmul(att, cmake(cs * w, -sn * w));
+                    if (uniform_k && nt + 1 < NT) {
+                        E0 = cmul(E0, rec.rot8);                       // eight steps
+                        const double dr = sm.dkd8[fqa + 8 * nt] * r;
+                        E0 = cmake(fma(E0.y, dr, E0.x), fma(-E0.x, dr, E0.y));
+                    }
                 }
             }
+            __syncwarp();
+            if (lane == 0 && atomicAdd(&sm.recdone[rb], 1) == NWARPS - 1) {
+                // last warp out of this record buffer: refill it with the records of tile tt+2
+                sm.recdone[rb] = 0;
+                if (tt + 2 < n_tiles) issue_records(tt + 2);
             }
-            __syncthreads();   // fac is consumed with the DMMA pair mapping (other threads' entries)
         }
         if (local == 0 || local == a.ncs) {
 #pragma unroll
@@ -412,12 +413,6 @@ lc_main_kernel(LcMainArgs a) {
                     for (int nt = 0; nt < NT; ++nt) { T[p][mt][nt][0] = 0.0; T[p][mt][nt][1] = 0.0; }
         }
 
-        // stage (c+1)&1 held chunk c-1: wait until every warp has released it (no CTA barrier in the
-        // chunk loop: warps drift by up to one chunk)
-        if (tid == 0 && c + 1 < total) {
-            if (c >= 1) mbar_wait(&sm.empty[stage ^ 1], (unsigned)(((c - 1) >> 1) & 1));
-            issue(c + 1, stage ^ 1);
-        }
         mbar_wait(&sm.full[stage], parity);
 
         const LcStage &S = sm.st[stage];
@@ -441,41 +436,45 @@ lc_main_kernel(LcMainArgs a) {
                         dmma884(T[p][mt][nt][0], T[p][mt][nt][1], af[p][mt], bf[p][nt]);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[stage]);   // this warp is done with the stage
+        if (lane == 0 && atomicAdd(&sm.done[stage], 1) == NWARPS - 1) {
+            // last warp out of this stage: refill it with chunk c+2
+            sm.done[stage] = 0;
+            if (c + 2 < total) {
+                int l2 = local + 2;
+                long t2 = tt;
+                while (l2 >= npt) { l2 -= npt; ++t2; }
+                issue(t2, l2, stage);
+            }
+        }
 
         if (local == a.ncs - 1) {
-            // ---- end of the source pass: S = (T1-T2) + i(T3-T1-T2);  park S' = fac * S.
-            // Pair ownership: image warp*16 + mt*8 + g, frequencies nt*8 + 2*t4 + {0,1}.  The
-            // factor was written by other threads: ordered by the barrier above.
+            // ---- end of the source pass: S = (T1-T2) + i(T3-T1-T2);  park S' = fac * S ----
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const int il = wm * 16 + mt * 8 + g, fq = (wn * NT + nt) * 8 + 2 * t4 + e;
+                        const int j = (mt * NT + nt) * 2 + e;
                         double t1 = T[0][mt][nt][e], t2 = T[1][mt][nt][e], t3 = T[2][mt][nt][e];
-                        cplx s = cmake(t1 - t2, t3 - t1 - t2);
-                        sm.fac[il][fq] = cmul(sm.fac[il][fq], s);
+                        sm.facp[j][tid] = cmul(sm.facp[j][tid], cmake(t1 - t2, t3 - t1 - t2));
                     }
         }
         if (local == npt - 1) {
-            // ---- end of the receiver pass: P += S' * R (same thread owns the same pairs)
+            // ---- end of the receiver pass: P += S' * R ----
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const int il = wm * 16 + mt * 8 + g, fq = (wn * NT + nt) * 8 + 2 * t4 + e;
                         double t1 = T[0][mt][nt][e], t2 = T[1][mt][nt][e], t3 = T[2][mt][nt][e];
-                        cfma(P[nt][e], sm.fac[il][fq], cmake(t1 - t2, t3 - t1 - t2));
+                        cfma(P[nt][e], sm.facp[(mt * NT + nt) * 2 + e][tid], cmake(t1 - t2, t3 - t1 - t2));
                     }
-            __syncthreads();   // fac is rewritten by the next tile's factor phase
         }
     }
 
-    // ---- reduce over the 8 row groups x 4 warps that share a frequency (aliases the stages) ----
+    // ---- reduce over the 8 row groups x 4 image warps that share a frequency (aliases the stages) ----
     __syncthreads();
     double2 (*red)[LC_TF] = reinterpret_cast<double2 (*)[LC_TF]>(&sm.st[0]);
 #pragma unroll

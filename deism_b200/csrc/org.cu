@@ -429,9 +429,9 @@ org_consume_kernel(OrgConsumeArgs a) {
     }
     __syncthreads();
 
-    auto issue = [&](long c, int stage) {
-        const long tile = tile_lo + c / a.ncpt;
-        const int2 ch = c_org_chunks[c % a.ncpt];
+    auto issue = [&](long tile_ord, int local, int stage) {
+        const long tile = tile_lo + tile_ord;
+        const int2 ch = c_org_chunks[local];
         const long p0 = tile * ORG_TI;
         int par = 0;
 #pragma unroll
@@ -450,15 +450,18 @@ org_consume_kernel(OrgConsumeArgs a) {
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) { P[nt][0] = cmake(0.0, 0.0); P[nt][1] = cmake(0.0, 0.0); }
 
-    if (tid == 0 && total > 0) issue(0, 0);
+    if (tid == 0 && total > 0) issue(0, 0, 0);
 
+    // chunk counter c = tt * ncpt + local kept as (tt, local): no 64-bit division per chunk
+    int local = 0;
+    long tt = 0;
 #pragma unroll 1
-    for (long c = 0; c < total; ++c) {
+    for (long c = 0; c < total; ++c, ++local) {
+        if (local == a.ncpt) { local = 0; ++tt; }
         const int stage = (int)(c & 1);
         const unsigned parity = (unsigned)((c >> 1) & 1);
-        const int local = (int)(c % a.ncpt);
         const int2 ch = c_org_chunks[local];
-        const long p0 = (tile_lo + c / a.ncpt) * ORG_TI;
+        const long p0 = (tile_lo + tt) * ORG_TI;
 
         if (local == 0) {
             for (int i = tid; i < ORG_TI; i += ORG_THREADS) {
@@ -532,7 +535,10 @@ org_consume_kernel(OrgConsumeArgs a) {
                     for (int nt = 0; nt < 2; ++nt) { T[p][mt][nt][0] = 0.0; T[p][mt][nt][1] = 0.0; }
         }
 
-        if (tid == 0 && c + 1 < total) issue(c + 1, stage ^ 1);
+        if (tid == 0 && c + 1 < total) {
+            if (local + 1 < a.ncpt) issue(tt, local + 1, stage ^ 1);
+            else issue(tt + 1, 0, stage ^ 1);
+        }
         mbar_wait(&sm.full[stage], parity);
 
         const OrgStage &S = sm.st[stage];
