@@ -42,7 +42,7 @@ constexpr int LC_JC = 12;        // max harmonics per staged chunk (multiple of 
 constexpr int LC_WN = 4 / LC_NT;                 // warps along frequency
 constexpr int LC_THREADS = 128 * LC_WN;          // 4 (image) x LC_WN (frequency) warps
 constexpr int LC_YS = LC_TI + 4; // Y plane row stride (doubles): 68 = 4 mod 16
-constexpr int LC_CS = LC_TF + 4; // C plane row stride (doubles): 36 = 4 mod 16
+constexpr int LC_CS = LC_TF + 2; // C plane stride (doubles): harmonic row = 2 planes = 68 = 4 mod 16
 
 struct LcImage {        // 96 bytes per image (a tile of 64 records is one 6 KB bulk copy)
     double r, inv_r;
@@ -66,9 +66,28 @@ struct LcPrepArgs {
     const int *flags;    // flags[1]: uniform k grid, *(double *)(flags + 2) = dk
 };
 
-// n_all/m_all/v_all/u_all live in constant memory (J <= 256 each: order <= 15)
-constexpr int LC_JMAX = 256;
-__constant__ int c_lc_n[LC_JMAX], c_lc_m[LC_JMAX], c_lc_v[LC_JMAX], c_lc_u[LC_JMAX];
+// Real-harmonic basis of one pass (source: index 0, receiver: index 1), in constant memory.
+//
+// Y_n^{-m} = (-1)^m conj(Y_n^m), so with Y_n^{|m|} = a + i b the sum over the caller's (n_j, m_j)
+//     sum_j i^{n_j} C_j Y_{n_j}^{m_j}  =  sum_q C'_q y_q
+// runs over REAL functions y_q in {a, b} of every distinct (n, |m|) (b only for |m| > 0), with
+//     m = 0 :  C'_a += i^n C_j
+//     m > 0 :  C'_a += i^n C_j            C'_b += i^{n+1} C_j
+//     m < 0 :  C'_a += i^{n+2|m|} C_j     C'_b += i^{n+2|m|+3} C_j
+// All weights are powers of i: forming C' costs one exact sign/swap and at most one rounding per
+// entry, and the complex [I x J].[J x K] contraction becomes a REAL-by-complex one: two real
+// GEMMs instead of the three of the 3-multiplication complex form.  A complete order-N set
+// (m = -n..n) keeps its size, J' = J.
+constexpr int LC_JMAX = 256;            // caller's harmonics per pass (order <= 15)
+constexpr int LC_QMAX = 2 * LC_JMAX;    // real functions (J' <= 2 J, = J for complete sets)
+struct LcBasis {
+    int Jq;
+    unsigned char qn[LC_QMAX], qm[LC_QMAX], qim[LC_QMAX];   // y_q = (qim ? Im : Re) Y_qn^qm
+    short cptr[LC_QMAX + 1];                                // contributions of q: cptr[q]..cptr[q+1]
+    short cj[2 * LC_JMAX];                                  //   caller's column j
+    unsigned char cp[2 * LC_JMAX];                          //   weight i^cp
+};
+__constant__ LcBasis c_lc_basis[2];
 
 // flags[0] = 1 iff Z_S[w,k] == Z_S[w,0] for all w,k (frequency-flat impedance)
 __global__ void z_flat_kernel(const cplx *__restrict__ Z, long K, int *flags) {
@@ -101,14 +120,21 @@ __global__ void __launch_bounds__(256) k_uniform_kernel(const double *__restrict
     }
 }
 
-// Y planes: [tile][j < J_pad][plane 0..2][LC_YS] doubles, plane = Re | Im | Re+Im of
-// i^{n_j} Y_j(image); image index within the tile fastest.  Rows >= n_images, columns >= J and
-// the 4 pad doubles are zero, so the main kernel's bulk copies never need a bounds check.
-__device__ __forceinline__ void store_y(double *Y, long base, int j, cplx v) {
-    double *p = Y + base + (long)j * 3 * LC_YS;
-    p[0] = v.x;
-    p[LC_YS] = v.y;
-    p[2 * LC_YS] = v.x + v.y;
+// Y planes: [tile][q < J_pad][LC_YS] doubles, the real functions y_q(image); image index within
+// the tile fastest.  Rows >= n_images, functions >= J' and the 4 pad doubles are zero, so the main
+// kernel's bulk copies never need a bounds check.
+__device__ __forceinline__ void fill_y(double *Y, long base, int pass, int J_pad, double phi, double ct,
+                                       bool live) {
+    const LcBasis &B = c_lc_basis[pass];
+    cplx y = cmake(0.0, 0.0);
+    for (int q = 0; q < J_pad; ++q) {
+        double v = 0.0;
+        if (live && q < B.Jq) {
+            if (!B.qim[q]) y = sph_harm_dev(B.qm[q], B.qn[q], phi, ct);   // b follows its a
+            v = B.qim[q] ? y.y : y.x;
+        }
+        Y[base + (long)q * LC_YS] = v;
+    }
 }
 
 __global__ void __launch_bounds__(128)
@@ -119,13 +145,11 @@ lc_prep_kernel(LcPrepArgs a, LcImage *img_out, double *Ys, double *Yr) {
     rec.cx = rec.cy = rec.cz = 1.0;
     for (int i = 0; i < 8; ++i) rec.e[i] = 0;
     const long tile = img / LC_TI, it = img % LC_TI;
-    const long ys_base = tile * (long)a.Js_pad * 3 * LC_YS + it;
-    const long yr_base = tile * (long)a.Jr_pad * 3 * LC_YS + it;
+    const long ys_base = tile * (long)a.Js_pad * LC_YS + it;
+    const long yr_base = tile * (long)a.Jr_pad * LC_YS + it;
     if (it < 4) {   // the pad columns of this tile's rows
-        for (int j = 0; j < a.Js_pad * 3; ++j)
-            Ys[tile * (long)a.Js_pad * 3 * LC_YS + (long)j * LC_YS + LC_TI + it] = 0.0;
-        for (int j = 0; j < a.Jr_pad * 3; ++j)
-            Yr[tile * (long)a.Jr_pad * 3 * LC_YS + (long)j * LC_YS + LC_TI + it] = 0.0;
+        for (int j = 0; j < a.Js_pad; ++j) Ys[ys_base + (long)j * LC_YS + LC_TI] = 0.0;
+        for (int j = 0; j < a.Jr_pad; ++j) Yr[yr_base + (long)j * LC_YS + LC_TI] = 0.0;
     }
     rec.rot = cmake(1.0, 0.0);
     rec.rot8 = cmake(1.0, 0.0);
@@ -133,8 +157,8 @@ lc_prep_kernel(LcPrepArgs a, LcImage *img_out, double *Ys, double *Yr) {
         rec.r = 1.0; rec.inv_r = 0.0;           // weight 0: contributes exactly nothing
         rec.atten_flat = cmake(0.0, 0.0);
         img_out[img] = rec;
-        for (int j = 0; j < a.Js_pad; ++j) store_y(Ys, ys_base, j, cmake(0.0, 0.0));
-        for (int j = 0; j < a.Jr_pad; ++j) store_y(Yr, yr_base, j, cmake(0.0, 0.0));
+        fill_y(Ys, ys_base, 0, a.Js_pad, 0.0, 1.0, false);
+        fill_y(Yr, yr_base, 1, a.Jr_pad, 0.0, 1.0, false);
         return;
     }
     double phi_s = (double)a.R_s_rI[img * 3 + 0], th_s = (double)a.R_s_rI[img * 3 + 1];
@@ -151,12 +175,8 @@ lc_prep_kernel(LcPrepArgs a, LcImage *img_out, double *Ys, double *Yr) {
     double s, ct_s, ct_r;
     sincos_cw(th_s, &s, &ct_s);
     sincos_cw(th_r, &s, &ct_r);
-    for (int j = 0; j < a.Js_pad; ++j)
-        store_y(Ys, ys_base, j, j < a.Js
-            ? cmul_ipow(sph_harm_dev(c_lc_m[j], c_lc_n[j], phi_s, ct_s), c_lc_n[j]) : cmake(0.0, 0.0));
-    for (int j = 0; j < a.Jr_pad; ++j)
-        store_y(Yr, yr_base, j, j < a.Jr
-            ? cmul_ipow(sph_harm_dev(c_lc_u[j], c_lc_v[j], phi_r, ct_r), c_lc_v[j]) : cmake(0.0, 0.0));
+    fill_y(Ys, ys_base, 0, a.Js_pad, phi_s, ct_s, true);
+    fill_y(Yr, yr_base, 1, a.Jr_pad, phi_r, ct_r, true);
     AttenGeom g;
     g.cx = g.cy = g.cz = 1.0;
     for (int i = 0; i < 8; ++i) g.e[i] = 0;
@@ -174,34 +194,43 @@ lc_prep_kernel(LcPrepArgs a, LcImage *img_out, double *Ys, double *Yr) {
     img_out[img] = rec;
 }
 
-// C planes: complex64 [K][J] -> [K_pad/32][j < J_pad][plane 0..2][LC_CS] doubles
-// (plane = Re | Im | Re+Im, frequency within the tile fastest, zero padded)
+// C planes: complex64 [K][J] -> [K_pad/32][q < J_pad][plane 0..1][LC_CS] doubles, the real-basis
+// coefficients C'_q (plane = Re | Im, frequency within the tile fastest, zero padded)
 __global__ void __launch_bounds__(256)
-lc_coef_kernel(const float2 *__restrict__ in, long K, int J, long n_ftiles, int J_pad, double *out) {
+lc_coef_kernel(const float2 *__restrict__ in, long K, int J, long n_ftiles, int J_pad, int pass,
+               double *out) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     long total = n_ftiles * J_pad * LC_CS;
     if (i >= total) return;
-    int q = (int)(i % LC_CS);
-    int j = (int)((i / LC_CS) % J_pad);
+    const LcBasis &B = c_lc_basis[pass];
+    int col = (int)(i % LC_CS);
+    int q = (int)((i / LC_CS) % J_pad);
     long ft = i / ((long)LC_CS * J_pad);
-    long k = ft * LC_TF + q;
+    long k = ft * LC_TF + col;
     double re = 0.0, im = 0.0;
-    if (q < LC_TF && j < J && k < K) {
-        float2 c = in[k * J + j];
-        re = (double)c.x; im = (double)c.y;
+    if (col < LC_TF && q < B.Jq && k < K) {
+        for (int c = B.cptr[q]; c < B.cptr[q + 1]; ++c) {
+            float2 v = in[k * J + B.cj[c]];
+            double x = (double)v.x, y = (double)v.y;
+            switch (B.cp[c] & 3) {                 // times i^cp
+            case 0: re += x; im += y; break;
+            case 1: re -= y; im += x; break;
+            case 2: re -= x; im -= y; break;
+            default: re += y; im -= x; break;
+            }
+        }
     }
-    double *p = out + (ft * J_pad + j) * 3 * LC_CS + q;
+    double *p = out + (ft * J_pad + q) * 2 * LC_CS + col;
     p[0] = re;
     p[LC_CS] = im;
-    p[2 * LC_CS] = re + im;
 }
 
 struct LcMainArgs {
     long n_images, n_pad, K;
     int Js_pad, Jr_pad;      // padded harmonic counts = ncs*JCs, ncr*JCr
     int ncs, ncr, JCs, JCr;  // chunks per pass and harmonics per chunk (multiples of 4)
-    const double *CTs, *CTr; // [K_pad/32][J_pad][3][LC_CS]
-    const double *Ys, *Yr;   // [n_pad/64][J_pad][3][LC_YS]
+    const double *CTs, *CTr; // [K_pad/32][J_pad][2][LC_CS]
+    const double *Ys, *Yr;   // [n_pad/64][J_pad][LC_YS]
     const LcImage *img;      // [n_pad]
     const double *k;
     int mode;                // DEISM_ATTEN_*
@@ -212,10 +241,13 @@ struct LcMainArgs {
     cplx *partial;           // [n_chunks, K]
 };
 
-constexpr int LC_STAGES = 2;
+#ifndef LC_STAGES
+#define LC_STAGES 4              // operand chunks in flight per CTA (power of two)
+#endif
+static_assert((LC_STAGES & (LC_STAGES - 1)) == 0, "LC_STAGES must be a power of two");
 struct LcStage {
-    double C[LC_JC][3][LC_CS];
-    double Y[LC_JC][3][LC_YS];
+    double C[LC_JC][2][LC_CS];
+    double Y[LC_JC][LC_YS];
 };
 struct LcSmem {
     LcStage st[LC_STAGES];
@@ -294,13 +326,13 @@ lc_main_kernel(LcMainArgs a) {
         const int JC = src_pass ? a.JCs : a.JCr;
         const int j0 = (src_pass ? local : local - a.ncs) * JC;
         const int Jp = src_pass ? a.Js_pad : a.Jr_pad;
-        const double *CT = (src_pass ? a.CTs : a.CTr) + ((long)blockIdx.x * Jp + j0) * 3 * LC_CS;
-        const double *Yg = (src_pass ? a.Ys : a.Yr) + (tile * Jp + j0) * 3 * LC_YS;
+        const double *CT = (src_pass ? a.CTs : a.CTr) + ((long)blockIdx.x * Jp + j0) * 2 * LC_CS;
+        const double *Yg = (src_pass ? a.Ys : a.Yr) + (tile * Jp + j0) * LC_YS;
         LcStage &S = sm.st[stage];
-        const unsigned cb = (unsigned)(JC * 3 * LC_CS * 8), yb = (unsigned)(JC * 3 * LC_YS * 8);
+        const unsigned cb = (unsigned)(JC * 2 * LC_CS * 8), yb = (unsigned)(JC * LC_YS * 8);
         mbar_expect_tx(&sm.full[stage], cb + yb);
         bulk_g2s(&S.C[0][0][0], CT, cb, &sm.full[stage]);
-        bulk_g2s(&S.Y[0][0][0], Yg, yb, &sm.full[stage]);
+        bulk_g2s(&S.Y[0][0], Yg, yb, &sm.full[stage]);
     };
     auto issue_records = [&](long tt) {      // tile ordinal tt within this CTA
         const int rb = (int)(tt & 1);
@@ -309,8 +341,8 @@ lc_main_kernel(LcMainArgs a) {
                  &sm.recfull[rb]);
     };
 
-    // accumulators of the three real GEMMs: [plane][m-tile][n-tile][2]
-    double T[3][2][NT][2];
+    // accumulators of the two real GEMMs (Re, Im of the pass): [plane][m-tile][n-tile][2]
+    double T[2][2][NT][2];
     // P[freq]: this thread's 2*NT frequencies wn*8*NT + 8*nt + 2*t4 + e, summed over its images
     cplx P[NT][2];
 #pragma unroll
@@ -319,8 +351,12 @@ lc_main_kernel(LcMainArgs a) {
     if (tid == 0 && total > 0) {
         issue_records(0);
         if (n_tiles > 1) issue_records(1);
-        issue(0, 0, 0);
-        if (total > 1) issue(npt > 1 ? 0 : 1, npt > 1 ? 1 : 0, 1);
+        int l0 = 0;
+        long t0 = 0;
+        for (int s = 0; s < LC_STAGES && s < total; ++s) {
+            issue(t0, l0, s);
+            if (++l0 == npt) { l0 = 0; ++t0; }
+        }
     }
 
     // chunk counter c = tt * npt + local, kept as (tt, local) so that no 64-bit division runs per chunk
@@ -329,8 +365,8 @@ lc_main_kernel(LcMainArgs a) {
 #pragma unroll 1
     for (long c = 0; c < total; ++c, ++local) {
         if (local == npt) { local = 0; ++tt; }
-        const int stage = (int)(c & 1);
-        const unsigned parity = (unsigned)((c >> 1) & 1);
+        const int stage = (int)(c & (LC_STAGES - 1));
+        const unsigned parity = (unsigned)((c / LC_STAGES) & 1);
 
         if (local == 0) {
             // ---- new image tile ----
@@ -344,7 +380,6 @@ lc_main_kernel(LcMainArgs a) {
             for (int mt = 0; mt < 2; ++mt) {
                 const int il = wm * 16 + mt * 8 + g;
                 const LcImage &rec = sm.rec[rb][il];
-                const long img = i0 + il;
                 const double r = rec.r, inv_r = rec.inv_r;
                 cplx E0 = cmake(1.0, 0.0);
                 if (uniform_k) {
@@ -363,24 +398,9 @@ lc_main_kernel(LcMainArgs a) {
                             sincos_cw(sm.kf[fq] * r, &sn, &cs);
                             E = cmake(cs, -sn);
                         }
-                        cplx att;
-                        if (flat) {
-                            att = rec.atten_flat;
-                        } else if (fused) {
-                            att = shoebox_atten(&sm.Z[0][fq], LC_TF, rec.cx, rec.cy, rec.cz, rec.e);
-                            if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
-                        } else {
-                            long f = f0 + fq;
-                            att = cmake(0.0, 0.0);
-                            if (img < a.n_images && f < a.K) {
-                                if (a.mode == DEISM_ATTEN_C64) {
-                                    float2 v = ((const float2 *)a.atten)[img * a.K + f];
-                                    att = cmake((double)v.x, (double)v.y);
-                                } else {
-                                    att = ((const cplx *)a.atten)[img * a.K + f];
-                                }
-                            }
-                        }
+                        // frequency-flat impedance: one attenuation per image; otherwise the per-term
+                        // attenuation is applied by the rolled loop below (keeps this hot path small)
+                        const cplx att = flat ? rec.atten_flat : cmake(1.0, 0.0);
                         const double w = sm.wk[fq] * inv_r;
                         sm.facp[(mt * NT + nt) * 2 + e][tid] = cmul(att, cmake(E.x * w, E.y * w));
                         if (uniform_k && e == 0) {
@@ -397,6 +417,32 @@ lc_main_kernel(LcMainArgs a) {
                     }
                 }
             }
+            if (!flat) {
+                // per-term attenuation (frequency-dependent impedance or a materialised atten[I,K])
+#pragma unroll 1
+                for (int j = 0; j < 4 * NT; ++j) {
+                    const int mt = j / (2 * NT), nt = (j >> 1) % NT, e = j & 1;
+                    const int il = wm * 16 + mt * 8 + g, fq = fqa + 8 * nt + e;
+                    const LcImage &rec = sm.rec[rb][il];
+                    cplx att;
+                    if (fused) {
+                        att = shoebox_atten(&sm.Z[0][fq], LC_TF, rec.cx, rec.cy, rec.cz, rec.e);
+                        if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
+                    } else {
+                        const long img = i0 + il, f = f0 + fq;
+                        att = cmake(0.0, 0.0);
+                        if (img < a.n_images && f < a.K) {
+                            if (a.mode == DEISM_ATTEN_C64) {
+                                float2 v = ((const float2 *)a.atten)[img * a.K + f];
+                                att = cmake((double)v.x, (double)v.y);
+                            } else {
+                                att = ((const cplx *)a.atten)[img * a.K + f];
+                            }
+                        }
+                    }
+                    sm.facp[j][tid] = cmul(att, sm.facp[j][tid]);
+                }
+            }
             __syncwarp();
             if (lane == 0 && atomicAdd(&sm.recdone[rb], 1) == NWARPS - 1) {
                 // last warp out of this record buffer: refill it with the records of tile tt+2
@@ -406,7 +452,7 @@ lc_main_kernel(LcMainArgs a) {
         }
         if (local == 0 || local == a.ncs) {
 #pragma unroll
-            for (int p = 0; p < 3; ++p)
+            for (int p = 0; p < 2; ++p)
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -417,30 +463,37 @@ lc_main_kernel(LcMainArgs a) {
 
         const LcStage &S = sm.st[stage];
         const int JC = local < a.ncs ? a.JCs : a.JCr;
-#pragma unroll 1
-        for (int ks = 0; ks < JC; ks += 4) {
-            double af[3][2], bf[3][NT];
+        const double *Yw = &S.Y[t4][wm * 16 + g];
+        const double *Cw = &S.C[t4][0][wn * NT * 8 + g];
+        auto kstep = [&](int ks) {      // 4 harmonics: 2 + 2*NT fragment loads, 4*NT DMMAs
+            double af[2], bf[2][NT];
 #pragma unroll
-            for (int p = 0; p < 3; ++p) {
+            for (int mt = 0; mt < 2; ++mt) af[mt] = Yw[ks * LC_YS + mt * 8];
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) af[p][mt] = S.Y[ks + t4][p][wm * 16 + mt * 8 + g];
+            for (int p = 0; p < 2; ++p)
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) bf[p][nt] = S.C[ks + t4][p][(wn * NT + nt) * 8 + g];
-            }
+                for (int nt = 0; nt < NT; ++nt) bf[p][nt] = Cw[(ks * 2 + p) * LC_CS + nt * 8];
 #pragma unroll
-            for (int p = 0; p < 3; ++p)
+            for (int p = 0; p < 2; ++p)
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt)
-                        dmma884(T[p][mt][nt][0], T[p][mt][nt][1], af[p][mt], bf[p][nt]);
+                        dmma884(T[p][mt][nt][0], T[p][mt][nt][1], af[mt], bf[p][nt]);
+        };
+        if (JC == LC_JC) {
+#pragma unroll
+            for (int ks = 0; ks < LC_JC; ks += 4) kstep(ks);
+        } else {
+#pragma unroll 1
+            for (int ks = 0; ks < JC; ks += 4) kstep(ks);
         }
         __syncwarp();
         if (lane == 0 && atomicAdd(&sm.done[stage], 1) == NWARPS - 1) {
-            // last warp out of this stage: refill it with chunk c+2
+            // last warp out of this stage: refill it with chunk c + LC_STAGES
             sm.done[stage] = 0;
-            if (c + 2 < total) {
-                int l2 = local + 2;
+            if (c + LC_STAGES < total) {
+                int l2 = local + LC_STAGES;
                 long t2 = tt;
                 while (l2 >= npt) { l2 -= npt; ++t2; }
                 issue(t2, l2, stage);
@@ -448,7 +501,7 @@ lc_main_kernel(LcMainArgs a) {
         }
 
         if (local == a.ncs - 1) {
-            // ---- end of the source pass: S = (T1-T2) + i(T3-T1-T2);  park S' = fac * S ----
+            // ---- end of the source pass: S = T0 + i T1;  park S' = fac * S ----
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -456,8 +509,7 @@ lc_main_kernel(LcMainArgs a) {
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int j = (mt * NT + nt) * 2 + e;
-                        double t1 = T[0][mt][nt][e], t2 = T[1][mt][nt][e], t3 = T[2][mt][nt][e];
-                        sm.facp[j][tid] = cmul(sm.facp[j][tid], cmake(t1 - t2, t3 - t1 - t2));
+                        sm.facp[j][tid] = cmul(sm.facp[j][tid], cmake(T[0][mt][nt][e], T[1][mt][nt][e]));
                     }
         }
         if (local == npt - 1) {
@@ -468,8 +520,8 @@ lc_main_kernel(LcMainArgs a) {
                 for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        double t1 = T[0][mt][nt][e], t2 = T[1][mt][nt][e], t3 = T[2][mt][nt][e];
-                        cfma(P[nt][e], sm.facp[(mt * NT + nt) * 2 + e][tid], cmake(t1 - t2, t3 - t1 - t2));
+                        cfma(P[nt][e], sm.facp[(mt * NT + nt) * 2 + e][tid],
+                             cmake(T[0][mt][nt][e], T[1][mt][nt][e]));
                     }
         }
     }
@@ -540,6 +592,41 @@ static void pick_chunks(int J, int &nc, int &JC) {
     }
 }
 
+// Real-harmonic basis of the caller's (n_j, m_j) list (see LcBasis): distinct (n,|m|) in order of
+// first appearance, function a then (|m| > 0) b; repeated (n,m) entries simply add up.
+static void build_real_basis(int J, const int64_t *n, const int64_t *m, LcBasis &B) {
+    int first[LC_JMAX], cnt[LC_QMAX];
+    B.Jq = 0;
+    for (int j = 0; j < J; ++j) {
+        const int nn = (int)n[j], am = (int)llabs(m[j]);
+        int q = -1;
+        for (int t = 0; t < B.Jq; ++t)
+            if (!B.qim[t] && B.qn[t] == nn && B.qm[t] == am) { q = t; break; }
+        if (q < 0) {
+            q = B.Jq;
+            for (int part = 0; part < (am ? 2 : 1); ++part, ++B.Jq) {
+                B.qn[B.Jq] = (unsigned char)nn; B.qm[B.Jq] = (unsigned char)am;
+                B.qim[B.Jq] = (unsigned char)part; cnt[B.Jq] = 0;
+            }
+        }
+        first[j] = q;
+        cnt[q]++;
+        if (am) cnt[q + 1]++;
+    }
+    B.cptr[0] = 0;
+    for (int q = 0; q < B.Jq; ++q) { B.cptr[q + 1] = (short)(B.cptr[q] + cnt[q]); cnt[q] = 0; }
+    for (int j = 0; j < J; ++j) {
+        const int nn = (int)n[j], mm = (int)m[j], am = abs(mm), q = first[j];
+        const int pa = mm >= 0 ? nn : nn + 2 * am;          // weight of a: i^pa
+        int c = B.cptr[q] + cnt[q]++;
+        B.cj[c] = (short)j; B.cp[c] = (unsigned char)(pa & 3);
+        if (am) {
+            c = B.cptr[q + 1] + cnt[q + 1]++;
+            B.cj[c] = (short)j; B.cp[c] = (unsigned char)((pa + (mm > 0 ? 1 : 3)) & 3);
+        }
+    }
+}
+
 int launch_z_flat(const deism_shoebox_atten *at, long K, int *flags, cudaStream_t st) {
     DEISM_CUDA_TRY(cudaMemsetAsync(flags, 0, 4 * sizeof(int), st));
     if (at->mode == DEISM_ATTEN_FUSED_ROOM || at->mode == DEISM_ATTEN_FUSED_ANGLES) {
@@ -577,23 +664,21 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
     rc = validate_atten(atten);
     if (rc) return rc;
 
-    int hn[LC_JMAX], hm[LC_JMAX], hv[LC_JMAX], hu[LC_JMAX];
-    for (int j = 0; j < Js; ++j) {
-        hn[j] = (int)h_n_all[j]; hm[j] = (int)h_m_all[j];
-        if (hn[j] < 0 || hn[j] > 64 || abs(hm[j]) > hn[j])
-            return set_error(DEISM_ERR_INVALID, "bad (n,m) = (%d,%d) at j=%d", hn[j], hm[j], j);
+    // thread_local: cudaMemcpyToSymbolAsync reads the host struct at stream execution time
+    static thread_local LcBasis hb[2];
+    for (int pass = 0; pass < 2; ++pass) {
+        const int64_t *hn = pass ? h_v_all : h_n_all, *hm = pass ? h_u_all : h_m_all;
+        const int J = pass ? Jr : Js;
+        for (int j = 0; j < J; ++j)
+            if (hn[j] < 0 || hn[j] > 64 || llabs(hm[j]) > hn[j])
+                return set_error(DEISM_ERR_INVALID, "bad (%s) = (%ld,%ld) at j=%d", pass ? "v,u" : "n,m",
+                                 (long)hn[j], (long)hm[j], j);
+        build_real_basis(J, hn, hm, hb[pass]);
     }
-    for (int j = 0; j < Jr; ++j) {
-        hv[j] = (int)h_v_all[j]; hu[j] = (int)h_u_all[j];
-        if (hv[j] < 0 || hv[j] > 64 || abs(hu[j]) > hv[j])
-            return set_error(DEISM_ERR_INVALID, "bad (v,u) = (%d,%d) at j=%d", hv[j], hu[j], j);
-    }
-    DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_lc_n, hn, Js * sizeof(int), 0, cudaMemcpyHostToDevice, st));
-    DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_lc_m, hm, Js * sizeof(int), 0, cudaMemcpyHostToDevice, st));
-    DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_lc_v, hv, Jr * sizeof(int), 0, cudaMemcpyHostToDevice, st));
-    DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_lc_u, hu, Jr * sizeof(int), 0, cudaMemcpyHostToDevice, st));
-    // the host arrays above are on the stack: the copies must have been consumed before return
+    DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_lc_basis, hb, sizeof(hb), 0, cudaMemcpyHostToDevice, st));
+    // hb is rewritten by the next call on this thread: the copy must have been consumed before return
     DEISM_CUDA_TRY(cudaStreamSynchronize(st));
+    const int Jqs = hb[0].Jq, Jqr = hb[1].Jq;
 
     const long n_img_tiles = (n_images + LC_TI - 1) / LC_TI;
     const long n_pad = n_img_tiles * LC_TI;
@@ -601,10 +686,11 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
     // harmonics are streamed in ncs (ncr) chunks of JCs (JCr) <= LC_JC each (multiples of 4, the
     // DMMA k extent), sized to waste as little zero padding as possible (J = 36 -> 3 x 12)
     int ncs, ncr, JCs, JCr;
-    pick_chunks(Js, ncs, JCs);
-    pick_chunks(Jr, ncr, JCr);
+    pick_chunks(Jqs, ncs, JCs);
+    pick_chunks(Jqr, ncr, JCr);
     const int Js_pad = ncs * JCs, Jr_pad = ncr * JCr;
-    long n_chunks = (long)sm_count() * 2 * 8 / n_ftiles;   // ~8 waves of 2 CTAs/SM
+    static const int waves = getenv("DEISM_LC_WAVES") ? atoi(getenv("DEISM_LC_WAVES")) : 8;
+    long n_chunks = (long)sm_count() * 2 * waves / n_ftiles;   // ~8 waves of 2 CTAs/SM
     if (n_chunks < 1) n_chunks = 1;
     if (n_chunks > n_img_tiles) n_chunks = n_img_tiles;
     if (n_chunks > 65535) n_chunks = 65535;
@@ -612,14 +698,14 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
     n_chunks = (n_img_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
 
     LcImage *img = (LcImage *)workspace(WS_LC_IMG, (size_t)n_pad * sizeof(LcImage));
-    double *Ys = (double *)workspace(WS_LC_YS, (size_t)n_img_tiles * Js_pad * 3 * LC_YS * sizeof(double));
-    double *Yr = (double *)workspace(WS_LC_YR, (size_t)n_img_tiles * Jr_pad * 3 * LC_YS * sizeof(double));
+    double *Ys = (double *)workspace(WS_LC_YS, (size_t)n_img_tiles * Js_pad * LC_YS * sizeof(double));
+    double *Yr = (double *)workspace(WS_LC_YR, (size_t)n_img_tiles * Jr_pad * LC_YS * sizeof(double));
     double *CT = (double *)workspace(WS_SMALL,
-                                     (size_t)n_ftiles * (Js_pad + Jr_pad) * 3 * LC_CS * sizeof(double));
+                                     (size_t)n_ftiles * (Js_pad + Jr_pad) * 2 * LC_CS * sizeof(double));
     cplx *partial = (cplx *)workspace(WS_PARTIAL, (size_t)n_chunks * K * sizeof(cplx));
     int *flags = (int *)workspace(WS_FLAGS, 64);
     if (!img || !Ys || !Yr || !CT || !partial || !flags) return DEISM_ERR_NOMEM;
-    double *CTs = CT, *CTr = CT + (size_t)n_ftiles * Js_pad * 3 * LC_CS;
+    double *CTs = CT, *CTr = CT + (size_t)n_ftiles * Js_pad * 2 * LC_CS;
 
     rc = launch_z_flat(atten, K, flags, st);
     if (rc) return rc;
@@ -640,10 +726,10 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
     lc_prep_kernel<<<(unsigned)((n_pad + 127) / 128), 128, 0, st>>>(pa, img, Ys, Yr);
     DEISM_LAUNCH_CHECK("lc_prep_kernel");
     lc_coef_kernel<<<(unsigned)((n_ftiles * Js_pad * LC_CS + 255) / 256), 256, 0, st>>>(
-        (const float2 *)d_C_s_vec, K, Js, n_ftiles, Js_pad, CTs);
+        (const float2 *)d_C_s_vec, K, Js, n_ftiles, Js_pad, 0, CTs);
     DEISM_LAUNCH_CHECK("lc_coef_kernel");
     lc_coef_kernel<<<(unsigned)((n_ftiles * Jr_pad * LC_CS + 255) / 256), 256, 0, st>>>(
-        (const float2 *)d_C_r_vec, K, Jr, n_ftiles, Jr_pad, CTr);
+        (const float2 *)d_C_r_vec, K, Jr, n_ftiles, Jr_pad, 1, CTr);
     DEISM_LAUNCH_CHECK("lc_coef_kernel");
 
     LcMainArgs ma;
