@@ -48,7 +48,7 @@ struct LcImage {        // 96 bytes per image (a tile of 64 records is one 6 KB 
     double r, inv_r;
     double cx, cy, cz;
     unsigned char e[8];
-    double2 atten_flat;  // c64-rounded (mode ROOM) attenuation for frequency-flat impedance
+    double2 a_flat;      // frequency-flat impedance: c64-rounded (mode ROOM) attenuation, times 1/r
     double2 rot;         // exp(-i dk r): one frequency step on a uniform wave-number grid
     double2 rot8;        // exp(-i 8 dk r)
 };
@@ -155,7 +155,7 @@ lc_prep_kernel(LcPrepArgs a, LcImage *img_out, double *Ys, double *Yr) {
     rec.rot8 = cmake(1.0, 0.0);
     if (img >= a.n_images) {
         rec.r = 1.0; rec.inv_r = 0.0;           // weight 0: contributes exactly nothing
-        rec.atten_flat = cmake(0.0, 0.0);
+        rec.a_flat = cmake(0.0, 0.0);
         img_out[img] = rec;
         fill_y(Ys, ys_base, 0, a.Js_pad, 0.0, 1.0, false);
         fill_y(Yr, yr_base, 1, a.Jr_pad, 0.0, 1.0, false);
@@ -180,14 +180,15 @@ lc_prep_kernel(LcPrepArgs a, LcImage *img_out, double *Ys, double *Yr) {
     AttenGeom g;
     g.cx = g.cy = g.cz = 1.0;
     for (int i = 0; i < 8; ++i) g.e[i] = 0;
-    rec.atten_flat = cmake(1.0, 0.0);
+    rec.a_flat = cmake(rec.inv_r, 0.0);
     if (a.mode == DEISM_ATTEN_FUSED_ROOM || a.mode == DEISM_ATTEN_FUSED_ANGLES) {
         if (a.mode == DEISM_ATTEN_FUSED_ROOM)
             atten_geom_room(a.A + img * 6, a.room.LL, a.room.xs, a.room.xr, a.angdep, g);
         else
             atten_geom_angles(a.A + img * 6, a.R_sI_r + img * 3, a.angdep, g);
         cplx at = shoebox_atten(a.Z, a.K, g.cx, g.cy, g.cz, g.e);  // Z[:,0]
-        rec.atten_flat = a.mode == DEISM_ATTEN_FUSED_ROOM ? round_c64(at) : at;
+        if (a.mode == DEISM_ATTEN_FUSED_ROOM) at = round_c64(at);
+        rec.a_flat = cmake(at.x * rec.inv_r, at.y * rec.inv_r);
     }
     rec.cx = g.cx; rec.cy = g.cy; rec.cz = g.cz;
     for (int i = 0; i < 8; ++i) rec.e[i] = g.e[i];
@@ -197,8 +198,8 @@ lc_prep_kernel(LcPrepArgs a, LcImage *img_out, double *Ys, double *Yr) {
 // C planes: complex64 [K][J] -> [K_pad/32][q < J_pad][plane 0..1][LC_CS] doubles, the real-basis
 // coefficients C'_q (plane = Re | Im, frequency within the tile fastest, zero padded)
 __global__ void __launch_bounds__(256)
-lc_coef_kernel(const float2 *__restrict__ in, long K, int J, long n_ftiles, int J_pad, int pass,
-               double *out) {
+lc_coef_kernel(const float2 *__restrict__ in, const double *__restrict__ kvec, long K, int J,
+               long n_ftiles, int J_pad, int pass, double *out) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     long total = n_ftiles * J_pad * LC_CS;
     if (i >= total) return;
@@ -218,6 +219,10 @@ lc_coef_kernel(const float2 *__restrict__ in, long K, int J, long n_ftiles, int 
             case 2: re -= x; im -= y; break;
             default: re += y; im -= x; break;
             }
+        }
+        if (pass == 0) {     // the source planes carry the factor's -4pi/k^2 (pb:314-317)
+            const double w = -4.0 * 3.14159265358979323846 / (kvec[k] * kvec[k]);
+            re *= w; im *= w;
         }
     }
     double *p = out + (ft * J_pad + q) * 2 * LC_CS + col;
@@ -241,6 +246,9 @@ struct LcMainArgs {
     cplx *partial;           // [n_chunks, K]
 };
 
+#ifndef LC_MINB
+#define LC_MINB 2                // resident CTAs per SM the register budget is set for
+#endif
 #ifndef LC_STAGES
 #define LC_STAGES 4              // operand chunks in flight per CTA (power of two)
 #endif
@@ -254,7 +262,7 @@ struct LcSmem {
     double2 facp[4 * LC_NT][LC_THREADS];   // thread-private factor, then S' = factor * S
     LcImage rec[2][LC_TI];                 // per-image records of the current / next tile (TMA)
     double2 Z[6][LC_TF];
-    double kf[LC_TF], wk[LC_TF];
+    double kf[LC_TF];
     double dkd[LC_TF], dkd8[LC_TF];        // ulp-level deviations of 1 and 8 steps from the uniform grid
     unsigned long long full[LC_STAGES];    // operand bytes landed
     unsigned long long recfull[2];
@@ -269,7 +277,7 @@ static_assert(sizeof(double2) * 32 * LC_TF <= sizeof(LcStage) * LC_STAGES,
 // done with it and the LAST warp out refills it (issues the next bulk copies) on the spot.  The
 // factor of a pair is computed, parked and consumed by the one thread that owns the pair in the
 // DMMA accumulator layout.  Warps of a CTA drift by up to one chunk.
-__global__ void __launch_bounds__(LC_THREADS, 2)
+__global__ void __launch_bounds__(LC_THREADS, LC_MINB)
 lc_main_kernel(LcMainArgs a) {
     constexpr int NT = LC_NT;
     constexpr int NWARPS = LC_THREADS / 32;
@@ -286,9 +294,9 @@ lc_main_kernel(LcMainArgs a) {
     long tile_lo = chunk * a.tiles_per_chunk;
     long tile_hi = tile_lo + a.tiles_per_chunk;
     if (tile_hi > n_img_tiles) tile_hi = n_img_tiles;
-    const long n_tiles = tile_hi > tile_lo ? tile_hi - tile_lo : 0;
+    const int n_tiles = tile_hi > tile_lo ? (int)(tile_hi - tile_lo) : 0;
     const int npt = a.ncs + a.ncr;                         // chunks per tile
-    const long total = n_tiles * npt;
+    const int total = n_tiles * npt;                       // < 2^31: host caps tiles_per_chunk
 
     const bool fused = a.mode == DEISM_ATTEN_FUSED_ROOM || a.mode == DEISM_ATTEN_FUSED_ANGLES;
     const bool flat = fused && a.flags[0] != 0;
@@ -305,7 +313,6 @@ lc_main_kernel(LcMainArgs a) {
             long f = f0 + q;
             double kk = f < a.K ? a.k[f] : 1.0;
             sm.kf[q] = kk;
-            sm.wk[q] = -4.0 * 3.14159265358979323846 / (kk * kk);   // -4pi/k^2
             sm.dkd[q] = f + 1 < a.K ? (a.k[f + 1] - kk) - dk : 0.0;
             sm.dkd8[q] = f + 8 < a.K ? (a.k[f + 8] - kk) - 8.0 * dk : 0.0;
         }
@@ -320,7 +327,7 @@ lc_main_kernel(LcMainArgs a) {
     __syncthreads();
 
     // producer (thread 0): chunk c = JC harmonics of one pass for one image tile, two bulk copies
-    auto issue = [&](long tile_ord, int local, int stage) {
+    auto issue = [&](int tile_ord, int local, int stage) {
         const long tile = tile_lo + tile_ord;
         const bool src_pass = local < a.ncs;
         const int JC = src_pass ? a.JCs : a.JCr;
@@ -334,8 +341,8 @@ lc_main_kernel(LcMainArgs a) {
         bulk_g2s(&S.C[0][0][0], CT, cb, &sm.full[stage]);
         bulk_g2s(&S.Y[0][0], Yg, yb, &sm.full[stage]);
     };
-    auto issue_records = [&](long tt) {      // tile ordinal tt within this CTA
-        const int rb = (int)(tt & 1);
+    auto issue_records = [&](int tt) {       // tile ordinal tt within this CTA
+        const int rb = tt & 1;
         mbar_expect_tx(&sm.recfull[rb], (unsigned)(LC_TI * sizeof(LcImage)));
         bulk_g2s(&sm.rec[rb][0], a.img + (tile_lo + tt) * LC_TI, (unsigned)(LC_TI * sizeof(LcImage)),
                  &sm.recfull[rb]);
@@ -348,121 +355,26 @@ lc_main_kernel(LcMainArgs a) {
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) { P[nt][0] = cmake(0.0, 0.0); P[nt][1] = cmake(0.0, 0.0); }
 
+    // chunk ordinal c = tile * npt + local (source chunks first); (pt, pl) = the chunk LC_STAGES
+    // ahead of c, the one whose operands replace chunk c's when the last warp leaves its stage
+    int pt = LC_STAGES / npt, pl = LC_STAGES % npt;
     if (tid == 0 && total > 0) {
         issue_records(0);
         if (n_tiles > 1) issue_records(1);
-        int l0 = 0;
-        long t0 = 0;
+        int l0 = 0, t0 = 0;
         for (int s = 0; s < LC_STAGES && s < total; ++s) {
             issue(t0, l0, s);
             if (++l0 == npt) { l0 = 0; ++t0; }
         }
     }
 
-    // chunk counter c = tt * npt + local, kept as (tt, local) so that no 64-bit division runs per chunk
-    int local = 0;
-    long tt = 0;
-#pragma unroll 1
-    for (long c = 0; c < total; ++c, ++local) {
-        if (local == npt) { local = 0; ++tt; }
-        const int stage = (int)(c & (LC_STAGES - 1));
-        const unsigned parity = (unsigned)((c / LC_STAGES) & 1);
-
-        if (local == 0) {
-            // ---- new image tile ----
-            const int rb = (int)(tt & 1);
-            const long i0 = (tile_lo + tt) * LC_TI;
-            mbar_wait(&sm.recfull[rb], (unsigned)((tt >> 1) & 1));
-            // factor fac = -atten * 4pi/k * exp(-ikr)/k/r (pb:314-317) of the pairs this thread owns:
-            // images wm*16 + mt*8 + g, frequencies (wn*NT + nt)*8 + 2*t4 + e
-            const int fqa = wn * NT * 8 + 2 * t4;
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                const int il = wm * 16 + mt * 8 + g;
-                const LcImage &rec = sm.rec[rb][il];
-                const double r = rec.r, inv_r = rec.inv_r;
-                cplx E0 = cmake(1.0, 0.0);
-                if (uniform_k) {
-                    double sn, cs;
-                    sincos_cw(sm.kf[fqa] * r, &sn, &cs);
-                    E0 = cmake(cs, -sn);
-                }
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    cplx E = E0;     // exp(-i k r) at frequency fqa + 8*nt
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int fq = fqa + 8 * nt + e;
-                        if (!uniform_k) {
-                            double sn, cs;
-                            sincos_cw(sm.kf[fq] * r, &sn, &cs);
-                            E = cmake(cs, -sn);
-                        }
-                        // frequency-flat impedance: one attenuation per image; otherwise the per-term
-                        // attenuation is applied by the rolled loop below (keeps this hot path small)
-                        const cplx att = flat ? rec.atten_flat : cmake(1.0, 0.0);
-                        const double w = sm.wk[fq] * inv_r;
-                        sm.facp[(mt * NT + nt) * 2 + e][tid] = cmul(att, cmake(E.x * w, E.y * w));
-                        if (uniform_k && e == 0) {
-                            // one step: exp(-i (dk + d) r) = rot * (1 - i d r) to first order in d
-                            E = cmul(E, rec.rot);
-                            const double dr = sm.dkd[fq] * r;
-                            E = cmake(fma(E.y, dr, E.x), fma(-E.x, dr, E.y));
-                        }
-                    }
-                    if (uniform_k && nt + 1 < NT) {
-                        E0 = cmul(E0, rec.rot8);                       // eight steps
-                        const double dr = sm.dkd8[fqa + 8 * nt] * r;
-                        E0 = cmake(fma(E0.y, dr, E0.x), fma(-E0.x, dr, E0.y));
-                    }
-                }
-            }
-            if (!flat) {
-                // per-term attenuation (frequency-dependent impedance or a materialised atten[I,K])
-#pragma unroll 1
-                for (int j = 0; j < 4 * NT; ++j) {
-                    const int mt = j / (2 * NT), nt = (j >> 1) % NT, e = j & 1;
-                    const int il = wm * 16 + mt * 8 + g, fq = fqa + 8 * nt + e;
-                    const LcImage &rec = sm.rec[rb][il];
-                    cplx att;
-                    if (fused) {
-                        att = shoebox_atten(&sm.Z[0][fq], LC_TF, rec.cx, rec.cy, rec.cz, rec.e);
-                        if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
-                    } else {
-                        const long img = i0 + il, f = f0 + fq;
-                        att = cmake(0.0, 0.0);
-                        if (img < a.n_images && f < a.K) {
-                            if (a.mode == DEISM_ATTEN_C64) {
-                                float2 v = ((const float2 *)a.atten)[img * a.K + f];
-                                att = cmake((double)v.x, (double)v.y);
-                            } else {
-                                att = ((const cplx *)a.atten)[img * a.K + f];
-                            }
-                        }
-                    }
-                    sm.facp[j][tid] = cmul(att, sm.facp[j][tid]);
-                }
-            }
-            __syncwarp();
-            if (lane == 0 && atomicAdd(&sm.recdone[rb], 1) == NWARPS - 1) {
-                // last warp out of this record buffer: refill it with the records of tile tt+2
-                sm.recdone[rb] = 0;
-                if (tt + 2 < n_tiles) issue_records(tt + 2);
-            }
-        }
-        if (local == 0 || local == a.ncs) {
-#pragma unroll
-            for (int p = 0; p < 2; ++p)
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) { T[p][mt][nt][0] = 0.0; T[p][mt][nt][1] = 0.0; }
-        }
-
-        mbar_wait(&sm.full[stage], parity);
-
+    const int fqa = wn * NT * 8 + 2 * t4;     // this thread's first frequency within the tile
+    int c = 0;
+    // one operand chunk: wait for its bytes, JC/4 k-steps of DMMA, count the warp out of the stage
+    auto run_chunk = [&](const int JC) {
+        const int stage = c & (LC_STAGES - 1);
+        mbar_wait(&sm.full[stage], (unsigned)((c / LC_STAGES) & 1));
         const LcStage &S = sm.st[stage];
-        const int JC = local < a.ncs ? a.JCs : a.JCr;
         const double *Yw = &S.Y[t4][wm * 16 + g];
         const double *Cw = &S.C[t4][0][wn * NT * 8 + g];
         auto kstep = [&](int ks) {      // 4 harmonics: 2 + 2*NT fragment loads, 4*NT DMMAs
@@ -492,38 +404,121 @@ lc_main_kernel(LcMainArgs a) {
         if (lane == 0 && atomicAdd(&sm.done[stage], 1) == NWARPS - 1) {
             // last warp out of this stage: refill it with chunk c + LC_STAGES
             sm.done[stage] = 0;
-            if (c + LC_STAGES < total) {
-                int l2 = local + LC_STAGES;
-                long t2 = tt;
-                while (l2 >= npt) { l2 -= npt; ++t2; }
-                issue(t2, l2, stage);
+            if (c + LC_STAGES < total) issue(pt, pl, stage);
+        }
+        ++c;
+        if (++pl == npt) { pl = 0; ++pt; }
+    };
+    auto clear_T = [&]() {
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) { T[p][mt][nt][0] = 0.0; T[p][mt][nt][1] = 0.0; }
+    };
+    // one frequency step of the factor: exp(-i (dk + d) r) = rot * (1 - i d r) to first order in d
+    auto rot_step = [](cplx F, cplx rot, double dr) {
+        F = cmul(F, rot);
+        return cmake(fma(F.y, dr, F.x), fma(-F.x, dr, F.y));
+    };
+
+#pragma unroll 1
+    for (int tt = 0; tt < n_tiles; ++tt) {
+        const int rb = tt & 1;
+        mbar_wait(&sm.recfull[rb], (unsigned)((tt >> 1) & 1));
+        // ---- factor fac = -atten * 4pi/k * exp(-ikr)/(k r) (pb:314-317) of the pairs this thread
+        // owns (images wm*16 + mt*8 + g, frequencies fqa + 8*nt + e).  -4pi/k^2 is folded into the
+        // source coefficient planes, so here fac = (atten / r) * exp(-i k r); on a uniform wave-number
+        // grid one sincos per image starts a rotation recurrence over the thread's frequencies. ----
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const LcImage &rec = sm.rec[rb][wm * 16 + mt * 8 + g];
+            const double r = rec.r;
+            // frequency-flat impedance: one attenuation per image; otherwise the per-term
+            // attenuation is applied by the rolled loop below (keeps this hot path small)
+            const cplx A = flat ? rec.a_flat : cmake(rec.inv_r, 0.0);
+            if (uniform_k) {
+                double sn, cs;
+                sincos_cw(sm.kf[fqa] * r, &sn, &cs);
+                cplx F = cmul(A, cmake(cs, -sn));
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const int fq = fqa + 8 * nt;
+                    sm.facp[(mt * NT + nt) * 2][tid] = F;
+                    sm.facp[(mt * NT + nt) * 2 + 1][tid] = rot_step(F, rec.rot, sm.dkd[fq] * r);
+                    if (nt + 1 < NT) F = rot_step(F, rec.rot8, sm.dkd8[fq] * r);
+                }
+            } else {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        double sn, cs;
+                        sincos_cw(sm.kf[fqa + 8 * nt + e] * r, &sn, &cs);
+                        sm.facp[(mt * NT + nt) * 2 + e][tid] = cmul(A, cmake(cs, -sn));
+                    }
             }
         }
+        if (!flat) {
+            // per-term attenuation (frequency-dependent impedance or a materialised atten[I,K])
+            const long i0 = (tile_lo + tt) * LC_TI;
+#pragma unroll 1
+            for (int j = 0; j < 4 * NT; ++j) {
+                const int mt = j / (2 * NT), nt = (j >> 1) % NT, e = j & 1;
+                const int il = wm * 16 + mt * 8 + g, fq = fqa + 8 * nt + e;
+                const LcImage &rec = sm.rec[rb][il];
+                cplx att;
+                if (fused) {
+                    att = shoebox_atten(&sm.Z[0][fq], LC_TF, rec.cx, rec.cy, rec.cz, rec.e);
+                    if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
+                } else {
+                    const long img = i0 + il, f = f0 + fq;
+                    att = cmake(0.0, 0.0);
+                    if (img < a.n_images && f < a.K) {
+                        if (a.mode == DEISM_ATTEN_C64) {
+                            float2 v = ((const float2 *)a.atten)[img * a.K + f];
+                            att = cmake((double)v.x, (double)v.y);
+                        } else {
+                            att = ((const cplx *)a.atten)[img * a.K + f];
+                        }
+                    }
+                }
+                sm.facp[j][tid] = cmul(att, sm.facp[j][tid]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0 && atomicAdd(&sm.recdone[rb], 1) == NWARPS - 1) {
+            // last warp out of this record buffer: refill it with the records of tile tt+2
+            sm.recdone[rb] = 0;
+            if (tt + 2 < n_tiles) issue_records(tt + 2);
+        }
 
-        if (local == a.ncs - 1) {
-            // ---- end of the source pass: S = T0 + i T1;  park S' = fac * S ----
+        // ---- source pass: S = T0 + i T1;  park S' = fac * S ----
+        clear_T();
+#pragma unroll 1
+        for (int l = 0; l < a.ncs; ++l) run_chunk(a.JCs);
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt)
+            for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int j = (mt * NT + nt) * 2 + e;
-                        sm.facp[j][tid] = cmul(sm.facp[j][tid], cmake(T[0][mt][nt][e], T[1][mt][nt][e]));
-                    }
-        }
-        if (local == npt - 1) {
-            // ---- end of the receiver pass: P += S' * R ----
+                for (int e = 0; e < 2; ++e) {
+                    const int j = (mt * NT + nt) * 2 + e;
+                    sm.facp[j][tid] = cmul(sm.facp[j][tid], cmake(T[0][mt][nt][e], T[1][mt][nt][e]));
+                }
+        // ---- receiver pass: P += S' * R ----
+        clear_T();
+#pragma unroll 1
+        for (int l = 0; l < a.ncr; ++l) run_chunk(a.JCr);
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt)
+            for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        cfma(P[nt][e], sm.facp[(mt * NT + nt) * 2 + e][tid],
-                             cmake(T[0][mt][nt][e], T[1][mt][nt][e]));
-                    }
-        }
+                for (int e = 0; e < 2; ++e)
+                    cfma(P[nt][e], sm.facp[(mt * NT + nt) * 2 + e][tid],
+                         cmake(T[0][mt][nt][e], T[1][mt][nt][e]));
     }
 
     // ---- reduce over the 8 row groups x 4 image warps that share a frequency (aliases the stages) ----
@@ -689,11 +684,15 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
     pick_chunks(Jqs, ncs, JCs);
     pick_chunks(Jqr, ncr, JCr);
     const int Js_pad = ncs * JCs, Jr_pad = ncr * JCr;
-    static const int waves = getenv("DEISM_LC_WAVES") ? atoi(getenv("DEISM_LC_WAVES")) : 8;
-    long n_chunks = (long)sm_count() * 2 * waves / n_ftiles;   // ~8 waves of 2 CTAs/SM
+    static const int waves = getenv("DEISM_LC_WAVES") ? atoi(getenv("DEISM_LC_WAVES")) : 16;
+    long n_chunks = (long)sm_count() * 2 * waves / n_ftiles;   // ~16 waves of 2 CTAs/SM: short tail
     if (n_chunks < 1) n_chunks = 1;
     if (n_chunks > n_img_tiles) n_chunks = n_img_tiles;
     if (n_chunks > 65535) n_chunks = 65535;
+    {   // the kernel counts a CTA's operand chunks in an int
+        const long min_chunks = n_img_tiles * (ncs + ncr) / (1L << 30) + 1;
+        if (n_chunks < min_chunks) n_chunks = min_chunks;
+    }
     long tiles_per_chunk = (n_img_tiles + n_chunks - 1) / n_chunks;
     n_chunks = (n_img_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
 
@@ -726,10 +725,10 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
     lc_prep_kernel<<<(unsigned)((n_pad + 127) / 128), 128, 0, st>>>(pa, img, Ys, Yr);
     DEISM_LAUNCH_CHECK("lc_prep_kernel");
     lc_coef_kernel<<<(unsigned)((n_ftiles * Js_pad * LC_CS + 255) / 256), 256, 0, st>>>(
-        (const float2 *)d_C_s_vec, K, Js, n_ftiles, Js_pad, 0, CTs);
+        (const float2 *)d_C_s_vec, d_k, K, Js, n_ftiles, Js_pad, 0, CTs);
     DEISM_LAUNCH_CHECK("lc_coef_kernel");
     lc_coef_kernel<<<(unsigned)((n_ftiles * Jr_pad * LC_CS + 255) / 256), 256, 0, st>>>(
-        (const float2 *)d_C_r_vec, K, Jr, n_ftiles, Jr_pad, 1, CTr);
+        (const float2 *)d_C_r_vec, d_k, K, Jr, n_ftiles, Jr_pad, 1, CTr);
     DEISM_LAUNCH_CHECK("lc_coef_kernel");
 
     LcMainArgs ma;
