@@ -69,6 +69,19 @@ int sm_count() {
     return (s && s->sms > 0) ? s->sms : 148;
 }
 
+int smem_optin_bytes() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 227 * 1024;
+    if (dev != cached_dev) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || v <= 0)
+            v = 227 * 1024;
+        cached = v; cached_dev = dev;
+    }
+    return cached;
+}
+
 void *workspace(int slot, size_t bytes) {
     DeviceState *s = state();
     if (!s || slot < 0 || slot >= WS_NSLOTS) {

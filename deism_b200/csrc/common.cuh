@@ -21,6 +21,7 @@ void count_launch(int n = 1);
 int check_device();                       // DEISM_OK iff current device is sm_100
 void *workspace(int slot, size_t bytes);  // cached device scratch; nullptr on failure
 int sm_count();
+int smem_optin_bytes();   // largest dynamic shared memory a CTA may opt into
 // optional CUDA-event bracket around a named kernel (no-op unless deism_profile_enable(1))
 void prof_begin(const char *name, cudaStream_t st);
 void prof_end(const char *name, cudaStream_t st);

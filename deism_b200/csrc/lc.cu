@@ -33,16 +33,19 @@
 
 namespace deism {
 
-constexpr int LC_TF = 32;        // frequencies per CTA tile
 constexpr int LC_TI = 64;        // images per tile
 constexpr int LC_JC = 12;        // max harmonics per staged chunk (multiple of 4)
-#ifndef LC_NT
-#define LC_NT 2                  // n-tiles (8 freqs each) per warp: 4 -> 4 warps/CTA, 2 -> 8 warps/CTA
-#endif
-constexpr int LC_WN = 4 / LC_NT;                 // warps along frequency
-constexpr int LC_THREADS = 128 * LC_WN;          // 4 (image) x LC_WN (frequency) warps
-constexpr int LC_YS = LC_TI + 4; // Y plane row stride (doubles): 68 = 4 mod 16
-constexpr int LC_CS = LC_TF + 2; // C plane stride (doubles): harmonic row = 2 planes = 68 = 4 mod 16
+constexpr int LC_NT = 2;         // n-tiles (8 freqs each) per warp: warp tile = 16 images x 16 freqs
+constexpr int LC_YS = LC_TI + 4; // Y row stride (doubles): 68 = 4 mod 16 -> conflict-free fragments
+constexpr int LC_MAXST = 16;     // most ring stages
+// A CTA is 4 (image) x WN (frequency) warps: tile = 64 images x TF = 16 WN frequencies.
+//   WN = 4 (512 threads, 1 CTA/SM): the ftile's coefficient planes stay RESIDENT in shared memory
+//          for the CTA's lifetime and only the Y chunks stream through a deep ring;
+//   WN = 2 (256 threads, 2 CTAs/SM): coefficients and harmonics both stream (any number of
+//          harmonics fits).
+// C plane stride (doubles) = TF + 2, so a harmonic row (2 planes) is 4 mod 16 doubles: conflict-free.
+__host__ __device__ constexpr int lc_tf(int WN) { return 16 * WN; }
+__host__ __device__ constexpr int lc_cs(int WN) { return 16 * WN + 2; }
 
 struct LcImage {        // 96 bytes per image (a tile of 64 records is one 6 KB bulk copy)
     double r, inv_r;
@@ -195,11 +198,12 @@ lc_prep_kernel(LcPrepArgs a, LcImage *img_out, double *Ys, double *Yr) {
     img_out[img] = rec;
 }
 
-// C planes: complex64 [K][J] -> [K_pad/32][q < J_pad][plane 0..1][LC_CS] doubles, the real-basis
+// C planes: complex64 [K][J] -> [K_pad/TF][q < J_pad][plane 0..1][TF + 2] doubles, the real-basis
 // coefficients C'_q (plane = Re | Im, frequency within the tile fastest, zero padded)
 __global__ void __launch_bounds__(256)
 lc_coef_kernel(const float2 *__restrict__ in, const double *__restrict__ kvec, long K, int J,
-               long n_ftiles, int J_pad, int pass, double *out) {
+               long n_ftiles, int J_pad, int pass, int TF, double *out) {
+    const int LC_CS = TF + 2, LC_TF = TF;
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     long total = n_ftiles * J_pad * LC_CS;
     if (i >= total) return;
@@ -234,7 +238,8 @@ struct LcMainArgs {
     long n_images, n_pad, K;
     int Js_pad, Jr_pad;      // padded harmonic counts = ncs*JCs, ncr*JCr
     int ncs, ncr, JCs, JCr;  // chunks per pass and harmonics per chunk (multiples of 4)
-    const double *CTs, *CTr; // [K_pad/32][J_pad][2][LC_CS]
+    int nst;                 // ring stages (<= LC_MAXST)
+    const double *CTs, *CTr; // [K_pad/TF][J_pad][2][TF+2]
     const double *Ys, *Yr;   // [n_pad/64][J_pad][LC_YS]
     const LcImage *img;      // [n_pad]
     const double *k;
@@ -246,49 +251,46 @@ struct LcMainArgs {
     cplx *partial;           // [n_chunks, K]
 };
 
-#ifndef LC_MINB
-#define LC_MINB 2                // resident CTAs per SM the register budget is set for
-#endif
-#ifndef LC_STAGES
-#define LC_STAGES 4              // operand chunks in flight per CTA (power of two)
-#endif
-static_assert((LC_STAGES & (LC_STAGES - 1)) == 0, "LC_STAGES must be a power of two");
-struct LcStage {
-    double C[LC_JC][2][LC_CS];
-    double Y[LC_JC][LC_YS];
+// Shared-memory carve-up of lc_main_kernel<WN, CRES> (host and device use the same arithmetic).
+struct LcCarve {
+    unsigned cres, ring, stage_bytes, facp, rec, Z, kf, dkd, dkd8, bars, total;
 };
-struct LcSmem {
-    LcStage st[LC_STAGES];
-    double2 facp[4 * LC_NT][LC_THREADS];   // thread-private factor, then S' = factor * S
-    LcImage rec[2][LC_TI];                 // per-image records of the current / next tile (TMA)
-    double2 Z[6][LC_TF];
-    double kf[LC_TF];
-    double dkd[LC_TF], dkd8[LC_TF];        // ulp-level deviations of 1 and 8 steps from the uniform grid
-    unsigned long long full[LC_STAGES];    // operand bytes landed
-    unsigned long long recfull[2];
-    int done[LC_STAGES], recdone[2];       // warps that have released a stage / a record buffer
-};
-static_assert(sizeof(LcStage) % 16 == 0, "stage must keep 16-byte alignment");
-static_assert(sizeof(double2) * 32 * LC_TF <= sizeof(LcStage) * LC_STAGES,
-              "final reduction aliases the stages");
+__host__ __device__ inline LcCarve lc_carve(int WN, bool cres_on, int rows, int nst) {
+    const unsigned TF = lc_tf(WN), CS = lc_cs(WN), threads = 128 * WN;
+    LcCarve c;
+    unsigned o = 0;
+    c.cres = o;  o += cres_on ? rows * 2 * CS * 8 : 0;                      // resident C planes
+    c.stage_bytes = LC_JC * (LC_YS + (cres_on ? 0 : 2 * CS)) * 8;           // Y chunk (+ C chunk)
+    c.ring = o;  o += nst * c.stage_bytes;
+    c.facp = o;  o += 4 * LC_NT * threads * 16;     // thread-private factor, then S' = factor * S
+    c.rec = o;   o += 2 * LC_TI * (unsigned)sizeof(LcImage);                // records: this / next tile
+    c.Z = o;     o += 6 * TF * 16;
+    c.kf = o;    o += TF * 8;
+    c.dkd = o;   o += TF * 8;      // ulp-level deviations of 1 and 8 steps from the uniform grid
+    c.dkd8 = o;  o += TF * 8;
+    c.bars = o;  o += (LC_MAXST + 3) * 8 + (LC_MAXST + 2) * 4;
+    c.total = (o + 15) & ~15u;
+    return c;
+}
 
-// The main loop has NO CTA-wide barrier and no waiting producer: operand chunks and per-image
-// records arrive by TMA on "full" mbarriers; every warp counts itself out of a buffer when it is
-// done with it and the LAST warp out refills it (issues the next bulk copies) on the spot.  The
-// factor of a pair is computed, parked and consumed by the one thread that owns the pair in the
-// DMMA accumulator layout.  Warps of a CTA drift by up to one chunk.
-__global__ void __launch_bounds__(LC_THREADS, LC_MINB)
+// The main loop has NO CTA-wide barrier and no waiting producer: Y (and, when they stream, C)
+// chunks and the per-image records arrive by TMA on "full" mbarriers; every warp counts itself out
+// of a buffer when it is done with it and the LAST warp out refills it (issues the next bulk
+// copies) on the spot.  The factor of a pair is computed, parked and consumed by the one thread
+// that owns the pair in the DMMA accumulator layout.  Warps of a CTA drift by up to nst chunks.
+template <int WN, bool CRES>
+__global__ void __launch_bounds__(128 * WN, CRES ? 1 : 2)
 lc_main_kernel(LcMainArgs a) {
     constexpr int NT = LC_NT;
-    constexpr int NWARPS = LC_THREADS / 32;
+    constexpr int TF = lc_tf(WN), CS = lc_cs(WN);
+    constexpr int THREADS = 128 * WN, NWARPS = 4 * WN;
     extern __shared__ __align__(128) unsigned char lc_smem_raw[];
-    LcSmem &sm = *reinterpret_cast<LcSmem *>(lc_smem_raw);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;          // DMMA fragment coordinates
-    const int wm = warp / LC_WN, wn = warp % LC_WN;  // warp tile: images wm*16.., freqs wn*8*NT..
-    const long f0 = (long)blockIdx.x * LC_TF;
+    const int wm = warp / WN, wn = warp % WN;        // warp tile: images wm*16.., freqs wn*16..
+    const long f0 = (long)blockIdx.x * TF;
     const long chunk = blockIdx.y;
     const long n_img_tiles = a.n_pad / LC_TI;
     long tile_lo = chunk * a.tiles_per_chunk;
@@ -297,86 +299,120 @@ lc_main_kernel(LcMainArgs a) {
     const int n_tiles = tile_hi > tile_lo ? (int)(tile_hi - tile_lo) : 0;
     const int npt = a.ncs + a.ncr;                         // chunks per tile
     const int total = n_tiles * npt;                       // < 2^31: host caps tiles_per_chunk
+    const int nst = a.nst;
+
+    const LcCarve cv = lc_carve(WN, CRES, a.Js_pad + a.Jr_pad, nst);
+    double *Cres = reinterpret_cast<double *>(lc_smem_raw + cv.cres);
+    unsigned char *ring = lc_smem_raw + cv.ring;
+    double2 (*facp)[THREADS] = reinterpret_cast<double2 (*)[THREADS]>(lc_smem_raw + cv.facp);
+    LcImage (*recs)[LC_TI] = reinterpret_cast<LcImage (*)[LC_TI]>(lc_smem_raw + cv.rec);
+    double2 (*Zs)[TF] = reinterpret_cast<double2 (*)[TF]>(lc_smem_raw + cv.Z);
+    double *kf = reinterpret_cast<double *>(lc_smem_raw + cv.kf);
+    double *dkd = reinterpret_cast<double *>(lc_smem_raw + cv.dkd);
+    double *dkd8 = reinterpret_cast<double *>(lc_smem_raw + cv.dkd8);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(lc_smem_raw + cv.bars);
+    unsigned long long *recfull = full + LC_MAXST;         // [2]
+    unsigned long long *cfull = recfull + 2;               // resident C planes landed
+    int *done = reinterpret_cast<int *>(cfull + 1);        // warps that have released a stage
+    int *recdone = done + LC_MAXST;                        // ... a record buffer
 
     const bool fused = a.mode == DEISM_ATTEN_FUSED_ROOM || a.mode == DEISM_ATTEN_FUSED_ANGLES;
     const bool flat = fused && a.flags[0] != 0;
     const bool uniform_k = a.flags[1] != 0;
 
     if (tid == 0) {
-        for (int s = 0; s < LC_STAGES; ++s) { mbar_init(&sm.full[s], 1); sm.done[s] = 0; }
-        for (int s = 0; s < 2; ++s) { mbar_init(&sm.recfull[s], 1); sm.recdone[s] = 0; }
+        for (int s = 0; s < nst; ++s) { mbar_init(&full[s], 1); done[s] = 0; }
+        for (int s = 0; s < 2; ++s) { mbar_init(&recfull[s], 1); recdone[s] = 0; }
+        mbar_init(cfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
         const double dk = *reinterpret_cast<const double *>(a.flags + 2);
-        for (int q = tid; q < LC_TF; q += LC_THREADS) {
+        for (int q = tid; q < TF; q += THREADS) {
             long f = f0 + q;
             double kk = f < a.K ? a.k[f] : 1.0;
-            sm.kf[q] = kk;
-            sm.dkd[q] = f + 1 < a.K ? (a.k[f + 1] - kk) - dk : 0.0;
-            sm.dkd8[q] = f + 8 < a.K ? (a.k[f + 8] - kk) - 8.0 * dk : 0.0;
+            kf[q] = kk;
+            dkd[q] = f + 1 < a.K ? (a.k[f + 1] - kk) - dk : 0.0;
+            dkd8[q] = f + 8 < a.K ? (a.k[f + 8] - kk) - 8.0 * dk : 0.0;
         }
     }
     if (fused && !flat) {
-        for (int i = tid; i < 6 * LC_TF; i += LC_THREADS) {
-            int w = i / LC_TF, q = i % LC_TF;
+        for (int i = tid; i < 6 * TF; i += THREADS) {
+            int w = i / TF, q = i % TF;
             long f = f0 + q;
-            sm.Z[w][q] = f < a.K ? a.Z[(long)w * a.K + f] : cmake(1.0, 0.0);
+            Zs[w][q] = f < a.K ? a.Z[(long)w * a.K + f] : cmake(1.0, 0.0);
         }
     }
     __syncthreads();
 
-    // producer (thread 0): chunk c = JC harmonics of one pass for one image tile, two bulk copies
+    // producer: chunk = JC harmonics of one pass for one image tile -> one bulk copy (Y), plus the
+    // matching coefficient rows when they are not resident
     auto issue = [&](int tile_ord, int local, int stage) {
         const long tile = tile_lo + tile_ord;
         const bool src_pass = local < a.ncs;
         const int JC = src_pass ? a.JCs : a.JCr;
         const int j0 = (src_pass ? local : local - a.ncs) * JC;
         const int Jp = src_pass ? a.Js_pad : a.Jr_pad;
-        const double *CT = (src_pass ? a.CTs : a.CTr) + ((long)blockIdx.x * Jp + j0) * 2 * LC_CS;
         const double *Yg = (src_pass ? a.Ys : a.Yr) + (tile * Jp + j0) * LC_YS;
-        LcStage &S = sm.st[stage];
-        const unsigned cb = (unsigned)(JC * 2 * LC_CS * 8), yb = (unsigned)(JC * LC_YS * 8);
-        mbar_expect_tx(&sm.full[stage], cb + yb);
-        bulk_g2s(&S.C[0][0][0], CT, cb, &sm.full[stage]);
-        bulk_g2s(&S.Y[0][0], Yg, yb, &sm.full[stage]);
+        unsigned char *S = ring + (unsigned)stage * cv.stage_bytes;
+        const unsigned yb = (unsigned)(JC * LC_YS * 8);
+        if (CRES) {
+            mbar_expect_tx(&full[stage], yb);
+        } else {
+            const double *CT = (src_pass ? a.CTs : a.CTr) + ((long)blockIdx.x * Jp + j0) * 2 * CS;
+            const unsigned cb = (unsigned)(JC * 2 * CS * 8);
+            mbar_expect_tx(&full[stage], cb + yb);
+            bulk_g2s(S + LC_JC * LC_YS * 8, CT, cb, &full[stage]);
+        }
+        bulk_g2s(S, Yg, yb, &full[stage]);
     };
     auto issue_records = [&](int tt) {       // tile ordinal tt within this CTA
         const int rb = tt & 1;
-        mbar_expect_tx(&sm.recfull[rb], (unsigned)(LC_TI * sizeof(LcImage)));
-        bulk_g2s(&sm.rec[rb][0], a.img + (tile_lo + tt) * LC_TI, (unsigned)(LC_TI * sizeof(LcImage)),
-                 &sm.recfull[rb]);
+        mbar_expect_tx(&recfull[rb], (unsigned)(LC_TI * sizeof(LcImage)));
+        bulk_g2s(&recs[rb][0], a.img + (tile_lo + tt) * LC_TI, (unsigned)(LC_TI * sizeof(LcImage)),
+                 &recfull[rb]);
     };
 
     // accumulators of the two real GEMMs (Re, Im of the pass): [plane][m-tile][n-tile][2]
     double T[2][2][NT][2];
-    // P[freq]: this thread's 2*NT frequencies wn*8*NT + 8*nt + 2*t4 + e, summed over its images
+    // P[freq]: this thread's 2*NT frequencies wn*16 + 8*nt + 2*t4 + e, summed over its images
     cplx P[NT][2];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) { P[nt][0] = cmake(0.0, 0.0); P[nt][1] = cmake(0.0, 0.0); }
 
-    // chunk ordinal c = tile * npt + local (source chunks first); (pt, pl) = the chunk LC_STAGES
-    // ahead of c, the one whose operands replace chunk c's when the last warp leaves its stage
-    int pt = LC_STAGES / npt, pl = LC_STAGES % npt;
+    // chunk ordinal c = tile * npt + local (source chunks first); (pt, pl) = the chunk nst ahead of
+    // c, the one whose operands replace chunk c's when the last warp leaves its stage
+    int pt = nst / npt, pl = nst % npt;
     if (tid == 0 && total > 0) {
+        if (CRES) {     // the ftile's coefficient planes: two contiguous blocks, loaded once
+            const unsigned sb = (unsigned)(a.Js_pad * 2 * CS * 8), rbts = (unsigned)(a.Jr_pad * 2 * CS * 8);
+            mbar_expect_tx(cfull, sb + rbts);
+            bulk_g2s(Cres, a.CTs + (long)blockIdx.x * a.Js_pad * 2 * CS, sb, cfull);
+            bulk_g2s(Cres + a.Js_pad * 2 * CS, a.CTr + (long)blockIdx.x * a.Jr_pad * 2 * CS, rbts, cfull);
+        }
         issue_records(0);
         if (n_tiles > 1) issue_records(1);
         int l0 = 0, t0 = 0;
-        for (int s = 0; s < LC_STAGES && s < total; ++s) {
+        for (int s = 0; s < nst && s < total; ++s) {
             issue(t0, l0, s);
             if (++l0 == npt) { l0 = 0; ++t0; }
         }
     }
+    if (CRES && total > 0) mbar_wait(cfull, 0);
 
     const int fqa = wn * NT * 8 + 2 * t4;     // this thread's first frequency within the tile
-    int c = 0;
-    // one operand chunk: wait for its bytes, JC/4 k-steps of DMMA, count the warp out of the stage
-    auto run_chunk = [&](const int JC) {
-        const int stage = c & (LC_STAGES - 1);
-        mbar_wait(&sm.full[stage], (unsigned)((c / LC_STAGES) & 1));
-        const LcStage &S = sm.st[stage];
-        const double *Yw = &S.Y[t4][wm * 16 + g];
-        const double *Cw = &S.C[t4][0][wn * NT * 8 + g];
+    int c = 0, stage = 0;
+    unsigned phase = 0;
+    // one operand chunk: wait for its bytes, JC/4 k-steps of DMMA, count the warp out of the stage.
+    // crow = first coefficient row of the chunk within the resident planes.
+    // `side` is independent scalar work (the factor of the next pairs) placed in the same basic
+    // block as the unrolled k-steps, so that it issues in the shadow of the DMMAs' pipe occupancy.
+    auto run_chunk = [&](const int JC, const int crow, auto &&side) {
+        mbar_wait(&full[stage], phase);
+        const double *Ystage = reinterpret_cast<const double *>(ring + (unsigned)stage * cv.stage_bytes);
+        const double *Yw = Ystage + t4 * LC_YS + wm * 16 + g;
+        const double *Cw = (CRES ? Cres + (crow + t4) * 2 * CS : Ystage + LC_JC * LC_YS + t4 * 2 * CS) +
+                           wn * NT * 8 + g;
         auto kstep = [&](int ks) {      // 4 harmonics: 2 + 2*NT fragment loads, 4*NT DMMAs
             double af[2], bf[2][NT];
 #pragma unroll
@@ -384,7 +420,7 @@ lc_main_kernel(LcMainArgs a) {
 #pragma unroll
             for (int p = 0; p < 2; ++p)
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) bf[p][nt] = Cw[(ks * 2 + p) * LC_CS + nt * 8];
+                for (int nt = 0; nt < NT; ++nt) bf[p][nt] = Cw[(ks * 2 + p) * CS + nt * 8];
 #pragma unroll
             for (int p = 0; p < 2; ++p)
 #pragma unroll
@@ -394,19 +430,23 @@ lc_main_kernel(LcMainArgs a) {
                         dmma884(T[p][mt][nt][0], T[p][mt][nt][1], af[mt], bf[p][nt]);
         };
         if (JC == LC_JC) {
+            kstep(0);
+            side();
 #pragma unroll
-            for (int ks = 0; ks < LC_JC; ks += 4) kstep(ks);
+            for (int ks = 4; ks < LC_JC; ks += 4) kstep(ks);
         } else {
+            side();
 #pragma unroll 1
             for (int ks = 0; ks < JC; ks += 4) kstep(ks);
         }
         __syncwarp();
-        if (lane == 0 && atomicAdd(&sm.done[stage], 1) == NWARPS - 1) {
-            // last warp out of this stage: refill it with chunk c + LC_STAGES
-            sm.done[stage] = 0;
-            if (c + LC_STAGES < total) issue(pt, pl, stage);
+        if (lane == 0 && atomicAdd(&done[stage], 1) == NWARPS - 1) {
+            // last warp out of this stage: refill it with chunk c + nst
+            done[stage] = 0;
+            if (c + nst < total) issue(pt, pl, stage);
         }
         ++c;
+        if (++stage == nst) { stage = 0; phase ^= 1u; }
         if (++pl == npt) { pl = 0; ++pt; }
     };
     auto clear_T = [&]() {
@@ -423,81 +463,87 @@ lc_main_kernel(LcMainArgs a) {
         return cmake(fma(F.y, dr, F.x), fma(-F.x, dr, F.y));
     };
 
+    auto no_side = [] {};
+    // fast path: frequency-flat impedance on a uniform wave-number grid.  One sincos per image
+    // starts a rotation recurrence over the thread's frequencies; branch-free, so it can ride along
+    // with the first source chunks of the tile.
+    const bool fast = flat && uniform_k;
+
 #pragma unroll 1
     for (int tt = 0; tt < n_tiles; ++tt) {
         const int rb = tt & 1;
-        mbar_wait(&sm.recfull[rb], (unsigned)((tt >> 1) & 1));
+        mbar_wait(&recfull[rb], (unsigned)((tt >> 1) & 1));
         // ---- factor fac = -atten * 4pi/k * exp(-ikr)/(k r) (pb:314-317) of the pairs this thread
         // owns (images wm*16 + mt*8 + g, frequencies fqa + 8*nt + e).  -4pi/k^2 is folded into the
-        // source coefficient planes, so here fac = (atten / r) * exp(-i k r); on a uniform wave-number
-        // grid one sincos per image starts a rotation recurrence over the thread's frequencies. ----
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            const LcImage &rec = sm.rec[rb][wm * 16 + mt * 8 + g];
+        // source coefficient planes, so here fac = (atten / r) * exp(-i k r). ----
+        auto factor_fast = [&](const int mt) {
+            const LcImage &rec = recs[rb][wm * 16 + mt * 8 + g];
             const double r = rec.r;
-            // frequency-flat impedance: one attenuation per image; otherwise the per-term
-            // attenuation is applied by the rolled loop below (keeps this hot path small)
-            const cplx A = flat ? rec.a_flat : cmake(rec.inv_r, 0.0);
-            if (uniform_k) {
-                double sn, cs;
-                sincos_cw(sm.kf[fqa] * r, &sn, &cs);
-                cplx F = cmul(A, cmake(cs, -sn));
+            double sn, cs;
+            sincos_cw(kf[fqa] * r, &sn, &cs);
+            cplx F = cmul(rec.a_flat, cmake(cs, -sn));
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    const int fq = fqa + 8 * nt;
-                    sm.facp[(mt * NT + nt) * 2][tid] = F;
-                    sm.facp[(mt * NT + nt) * 2 + 1][tid] = rot_step(F, rec.rot, sm.dkd[fq] * r);
-                    if (nt + 1 < NT) F = rot_step(F, rec.rot8, sm.dkd8[fq] * r);
-                }
-            } else {
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        double sn, cs;
-                        sincos_cw(sm.kf[fqa + 8 * nt + e] * r, &sn, &cs);
-                        sm.facp[(mt * NT + nt) * 2 + e][tid] = cmul(A, cmake(cs, -sn));
-                    }
+            for (int nt = 0; nt < NT; ++nt) {
+                const int fq = fqa + 8 * nt;
+                facp[(mt * NT + nt) * 2][tid] = F;
+                facp[(mt * NT + nt) * 2 + 1][tid] = rot_step(F, rec.rot, dkd[fq] * r);
+                if (nt + 1 < NT) F = rot_step(F, rec.rot8, dkd8[fq] * r);
             }
-        }
-        if (!flat) {
-            // per-term attenuation (frequency-dependent impedance or a materialised atten[I,K])
+        };
+        clear_T();
+        if (fast) {
+            if (a.ncs == 1) {
+                run_chunk(a.JCs, 0, [&] { factor_fast(0); factor_fast(1); });
+            } else {
+                run_chunk(a.JCs, 0, [&] { factor_fast(0); });
+                run_chunk(a.JCs, a.JCs, [&] { factor_fast(1); });
+#pragma unroll 1
+                for (int l = 2; l < a.ncs; ++l) run_chunk(a.JCs, l * a.JCs, no_side);
+            }
+        } else {
+            // general path: per-term sincos off the uniform grid, per-term attenuation for a
+            // frequency-dependent impedance or a materialised atten[I,K] (rolled: rarely hot)
             const long i0 = (tile_lo + tt) * LC_TI;
 #pragma unroll 1
             for (int j = 0; j < 4 * NT; ++j) {
                 const int mt = j / (2 * NT), nt = (j >> 1) % NT, e = j & 1;
                 const int il = wm * 16 + mt * 8 + g, fq = fqa + 8 * nt + e;
-                const LcImage &rec = sm.rec[rb][il];
+                const LcImage &rec = recs[rb][il];
                 cplx att;
-                if (fused) {
-                    att = shoebox_atten(&sm.Z[0][fq], LC_TF, rec.cx, rec.cy, rec.cz, rec.e);
-                    if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
+                if (flat) {
+                    att = rec.a_flat;
                 } else {
-                    const long img = i0 + il, f = f0 + fq;
-                    att = cmake(0.0, 0.0);
-                    if (img < a.n_images && f < a.K) {
-                        if (a.mode == DEISM_ATTEN_C64) {
-                            float2 v = ((const float2 *)a.atten)[img * a.K + f];
-                            att = cmake((double)v.x, (double)v.y);
-                        } else {
-                            att = ((const cplx *)a.atten)[img * a.K + f];
+                    if (fused) {
+                        att = shoebox_atten(&Zs[0][fq], TF, rec.cx, rec.cy, rec.cz, rec.e);
+                        if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
+                    } else {
+                        const long img = i0 + il, f = f0 + fq;
+                        att = cmake(0.0, 0.0);
+                        if (img < a.n_images && f < a.K) {
+                            if (a.mode == DEISM_ATTEN_C64) {
+                                float2 v = ((const float2 *)a.atten)[img * a.K + f];
+                                att = cmake((double)v.x, (double)v.y);
+                            } else {
+                                att = ((const cplx *)a.atten)[img * a.K + f];
+                            }
                         }
                     }
+                    att = cmake(att.x * rec.inv_r, att.y * rec.inv_r);
                 }
-                sm.facp[j][tid] = cmul(att, sm.facp[j][tid]);
+                double sn, cs;
+                sincos_cw(kf[fq] * rec.r, &sn, &cs);
+                facp[j][tid] = cmul(att, cmake(cs, -sn));
             }
+#pragma unroll 1
+            for (int l = 0; l < a.ncs; ++l) run_chunk(a.JCs, l * a.JCs, no_side);
         }
         __syncwarp();
-        if (lane == 0 && atomicAdd(&sm.recdone[rb], 1) == NWARPS - 1) {
+        if (lane == 0 && atomicAdd(&recdone[rb], 1) == NWARPS - 1) {
             // last warp out of this record buffer: refill it with the records of tile tt+2
-            sm.recdone[rb] = 0;
+            recdone[rb] = 0;
             if (tt + 2 < n_tiles) issue_records(tt + 2);
         }
-
-        // ---- source pass: S = T0 + i T1;  park S' = fac * S ----
-        clear_T();
-#pragma unroll 1
-        for (int l = 0; l < a.ncs; ++l) run_chunk(a.JCs);
+        // ---- end of the source pass: S = T0 + i T1;  park S' = fac * S ----
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -505,31 +551,30 @@ lc_main_kernel(LcMainArgs a) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int j = (mt * NT + nt) * 2 + e;
-                    sm.facp[j][tid] = cmul(sm.facp[j][tid], cmake(T[0][mt][nt][e], T[1][mt][nt][e]));
+                    facp[j][tid] = cmul(facp[j][tid], cmake(T[0][mt][nt][e], T[1][mt][nt][e]));
                 }
         // ---- receiver pass: P += S' * R ----
         clear_T();
 #pragma unroll 1
-        for (int l = 0; l < a.ncr; ++l) run_chunk(a.JCr);
+        for (int l = 0; l < a.ncr; ++l) run_chunk(a.JCr, a.Js_pad + l * a.JCr, no_side);
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                 for (int e = 0; e < 2; ++e)
-                    cfma(P[nt][e], sm.facp[(mt * NT + nt) * 2 + e][tid],
-                         cmake(T[0][mt][nt][e], T[1][mt][nt][e]));
+                    cfma(P[nt][e], facp[(mt * NT + nt) * 2 + e][tid], cmake(T[0][mt][nt][e], T[1][mt][nt][e]));
     }
 
-    // ---- reduce over the 8 row groups x 4 image warps that share a frequency (aliases the stages) ----
+    // ---- reduce over the 8 row groups x 4 image warps that share a frequency (aliases facp) ----
     __syncthreads();
-    double2 (*red)[LC_TF] = reinterpret_cast<double2 (*)[LC_TF]>(&sm.st[0]);
+    double2 (*red)[TF] = reinterpret_cast<double2 (*)[TF]>(lc_smem_raw + cv.facp);
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int e = 0; e < 2; ++e) red[wm * 8 + g][(wn * NT + nt) * 8 + 2 * t4 + e] = P[nt][e];
     __syncthreads();
-    if (tid < LC_TF) {
+    if (tid < TF) {
         cplx s = cmake(0.0, 0.0);
 #pragma unroll 8
         for (int y = 0; y < 32; ++y) s = cadd(s, red[y][tid]);
@@ -677,34 +722,69 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
 
     const long n_img_tiles = (n_images + LC_TI - 1) / LC_TI;
     const long n_pad = n_img_tiles * LC_TI;
-    const long n_ftiles = (K + LC_TF - 1) / LC_TF;
     // harmonics are streamed in ncs (ncr) chunks of JCs (JCr) <= LC_JC each (multiples of 4, the
     // DMMA k extent), sized to waste as little zero padding as possible (J = 36 -> 3 x 12)
     int ncs, ncr, JCs, JCr;
     pick_chunks(Jqs, ncs, JCs);
     pick_chunks(Jqr, ncr, JCr);
     const int Js_pad = ncs * JCs, Jr_pad = ncr * JCr;
-    static const int waves = getenv("DEISM_LC_WAVES") ? atoi(getenv("DEISM_LC_WAVES")) : 16;
-    long n_chunks = (long)sm_count() * 2 * waves / n_ftiles;   // ~16 waves of 2 CTAs/SM: short tail
-    if (n_chunks < 1) n_chunks = 1;
-    if (n_chunks > n_img_tiles) n_chunks = n_img_tiles;
-    if (n_chunks > 65535) n_chunks = 65535;
-    {   // the kernel counts a CTA's operand chunks in an int
-        const long min_chunks = n_img_tiles * (ncs + ncr) / (1L << 30) + 1;
-        if (n_chunks < min_chunks) n_chunks = min_chunks;
+
+    // kernel shape: resident coefficient planes (512 threads, 64 frequencies, 1 CTA/SM) when they
+    // leave room for a ring of >= 6 Y chunks, else the streaming shape (256 threads, 32
+    // frequencies, 2 CTAs/SM, 4-stage ring of C+Y chunks)
+    const int smem_max = smem_optin_bytes();
+    static const char *force = getenv("DEISM_LC_SHAPE");     // "stream" | "resident": A/B runs
+    bool resident = false;
+    int nst = 4;
+    {
+        const LcCarve c0 = lc_carve(4, true, Js_pad + Jr_pad, 0);
+        const int room = (smem_max - (int)c0.total) / (int)c0.stage_bytes;
+        if (room >= 6) { resident = true; nst = room < LC_MAXST ? room : LC_MAXST; }
+        if (force && !strcmp(force, "stream")) { resident = false; nst = 4; }
     }
-    long tiles_per_chunk = (n_img_tiles + n_chunks - 1) / n_chunks;
-    n_chunks = (n_img_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
+    const int WN = resident ? 4 : 2, TF = lc_tf(WN), CS = lc_cs(WN);
+    const int ctas_per_sm = resident ? 1 : 2;
+    const LcCarve carve = lc_carve(WN, resident, Js_pad + Jr_pad, nst);
+    const long n_ftiles = (K + TF - 1) / TF;
+
+    // image tiles are cut into n_chunks CTAs per ftile: ~`waves` waves of CTAs over the SMs, picked
+    // so that the last wave is as full as possible
+    static const int waves = getenv("DEISM_LC_WAVES") ? atoi(getenv("DEISM_LC_WAVES")) : 16;
+    const long slots = (long)sm_count() * ctas_per_sm;
+    long n_chunks = 1, tiles_per_chunk = n_img_tiles;
+    {
+        const long min_chunks = n_img_tiles * (ncs + ncr) / (1L << 30) + 1;  // chunk counter is an int
+        long lo = slots * waves / 2 / n_ftiles, hi = slots * waves * 3 / 2 / n_ftiles;
+        if (lo < min_chunks) lo = min_chunks;
+        if (hi < lo) hi = lo;
+        if (hi > 65535) hi = 65535;
+        if (lo > hi) lo = hi;
+        double best = -1.0;
+        for (long n = lo; n <= hi; ++n) {
+            if (n > n_img_tiles) break;
+            const long tpc = (n_img_tiles + n - 1) / n, nn = (n_img_tiles + tpc - 1) / tpc;
+            const long ctas = nn * n_ftiles, rounds = (ctas + slots - 1) / slots;
+            // time ~ rounds * (tpc + fixed per-CTA cost of ~1/2 tile); useful work = n_img_tiles * n_ftiles
+            const double eff = (double)n_img_tiles * n_ftiles / ((double)rounds * slots * (tpc + 0.5));
+            if (eff > best) { best = eff; n_chunks = nn; tiles_per_chunk = tpc; }
+        }
+        if (best < 0.0) {
+            n_chunks = n_img_tiles < lo ? n_img_tiles : lo;
+            if (n_chunks < 1) n_chunks = 1;
+            tiles_per_chunk = (n_img_tiles + n_chunks - 1) / n_chunks;
+            n_chunks = (n_img_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
+        }
+    }
 
     LcImage *img = (LcImage *)workspace(WS_LC_IMG, (size_t)n_pad * sizeof(LcImage));
     double *Ys = (double *)workspace(WS_LC_YS, (size_t)n_img_tiles * Js_pad * LC_YS * sizeof(double));
     double *Yr = (double *)workspace(WS_LC_YR, (size_t)n_img_tiles * Jr_pad * LC_YS * sizeof(double));
     double *CT = (double *)workspace(WS_SMALL,
-                                     (size_t)n_ftiles * (Js_pad + Jr_pad) * 2 * LC_CS * sizeof(double));
+                                     (size_t)n_ftiles * (Js_pad + Jr_pad) * 2 * CS * sizeof(double));
     cplx *partial = (cplx *)workspace(WS_PARTIAL, (size_t)n_chunks * K * sizeof(cplx));
     int *flags = (int *)workspace(WS_FLAGS, 64);
     if (!img || !Ys || !Yr || !CT || !partial || !flags) return DEISM_ERR_NOMEM;
-    double *CTs = CT, *CTr = CT + (size_t)n_ftiles * Js_pad * 2 * LC_CS;
+    double *CTs = CT, *CTr = CT + (size_t)n_ftiles * Js_pad * 2 * CS;
 
     rc = launch_z_flat(atten, K, flags, st);
     if (rc) return rc;
@@ -724,11 +804,11 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
     }
     lc_prep_kernel<<<(unsigned)((n_pad + 127) / 128), 128, 0, st>>>(pa, img, Ys, Yr);
     DEISM_LAUNCH_CHECK("lc_prep_kernel");
-    lc_coef_kernel<<<(unsigned)((n_ftiles * Js_pad * LC_CS + 255) / 256), 256, 0, st>>>(
-        (const float2 *)d_C_s_vec, d_k, K, Js, n_ftiles, Js_pad, 0, CTs);
+    lc_coef_kernel<<<(unsigned)((n_ftiles * Js_pad * CS + 255) / 256), 256, 0, st>>>(
+        (const float2 *)d_C_s_vec, d_k, K, Js, n_ftiles, Js_pad, 0, TF, CTs);
     DEISM_LAUNCH_CHECK("lc_coef_kernel");
-    lc_coef_kernel<<<(unsigned)((n_ftiles * Jr_pad * LC_CS + 255) / 256), 256, 0, st>>>(
-        (const float2 *)d_C_r_vec, d_k, K, Jr, n_ftiles, Jr_pad, 1, CTr);
+    lc_coef_kernel<<<(unsigned)((n_ftiles * Jr_pad * CS + 255) / 256), 256, 0, st>>>(
+        (const float2 *)d_C_r_vec, d_k, K, Jr, n_ftiles, Jr_pad, 1, TF, CTr);
     DEISM_LAUNCH_CHECK("lc_coef_kernel");
 
     LcMainArgs ma;
@@ -737,11 +817,21 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
     ma.CTs = CTs; ma.CTr = CTr; ma.Ys = Ys; ma.Yr = Yr; ma.img = img; ma.k = d_k;
     ma.mode = atten->mode; ma.atten = atten->d_atten; ma.Z = (const cplx *)atten->d_Z_S;
     ma.flags = flags; ma.tiles_per_chunk = tiles_per_chunk; ma.partial = partial;
+    ma.nst = nst;
     dim3 grid((unsigned)n_ftiles, (unsigned)n_chunks);
-    DEISM_CUDA_TRY(cudaFuncSetAttribute(lc_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)sizeof(LcSmem)));
+    if ((int)carve.total > smem_max)
+        return set_error(DEISM_ERR_INVALID, "LC kernel needs %u B of shared memory, device has %d",
+                         carve.total, smem_max);
     prof_begin("lc_main", st);
-    lc_main_kernel<<<grid, LC_THREADS, sizeof(LcSmem), st>>>(ma);
+    if (resident) {
+        DEISM_CUDA_TRY(cudaFuncSetAttribute(lc_main_kernel<4, true>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)carve.total));
+        lc_main_kernel<4, true><<<grid, 512, carve.total, st>>>(ma);
+    } else {
+        DEISM_CUDA_TRY(cudaFuncSetAttribute(lc_main_kernel<2, false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)carve.total));
+        lc_main_kernel<2, false><<<grid, 256, carve.total, st>>>(ma);
+    }
     prof_end("lc_main", st);
     DEISM_LAUNCH_CHECK("lc_main_kernel");
 
