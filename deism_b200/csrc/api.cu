@@ -239,8 +239,8 @@ __global__ void __launch_bounds__(PEAK_THREADS, 2)
 dmma_fed_kernel(int iters, double seed, double *sink) {
     __shared__ double Y[12][3][68];
     __shared__ double Cc[12][3][36];
-    for (int i = threadIdx.x; i < 12 * 3 * 68; i += PEAK_THREADS) (&Y[0][0][0])[i] = seed + 1e-3 * i;
-    for (int i = threadIdx.x; i < 12 * 3 * 36; i += PEAK_THREADS) (&Cc[0][0][0])[i] = seed - 1e-3 * i;
+    for (int i = threadIdx.x; i < 12 * 3 * 68; i += blockDim.x) (&Y[0][0][0])[i] = seed + 1e-3 * i;
+    for (int i = threadIdx.x; i < 12 * 3 * 36; i += blockDim.x) (&Cc[0][0][0])[i] = seed - 1e-3 * i;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
     const int wm = warp >> 1, wn = warp & 1;
@@ -368,8 +368,12 @@ extern "C" int deism_fp64_peak(int kind, int iters, double *tflops, double *ms_o
             dmma_peak_kernel<<<blocks, PEAK_THREADS>>>(iters, 0.0, sink);
         else if (kind == 2)
             mixed_peak_kernel<<<blocks, PEAK_THREADS>>>(iters, 0.0, sink);
-        else
+        else if (kind == 3)
             dmma_fed_kernel<<<sm_count() * 2, PEAK_THREADS>>>(iters, 0.0, sink);
+        else if (kind == 4)   // one warp per SM sub-partition
+            dmma_fed_kernel<<<sm_count(), 128>>>(iters, 0.0, sink);
+        else                  // two warps per SM sub-partition
+            dmma_fed_kernel<<<sm_count(), PEAK_THREADS>>>(iters, 0.0, sink);
         DEISM_LAUNCH_CHECK("fp64_peak_kernel");
         DEISM_CUDA_TRY(cudaEventRecord(e1, 0));
         DEISM_CUDA_TRY(cudaEventSynchronize(e1));
@@ -386,7 +390,10 @@ extern "C" int deism_fp64_peak(int kind, int iters, double *tflops, double *ms_o
     if (kind == 0) fmas = dfma_all;
     else if (kind == 1) fmas = dmma_all;
     else if (kind == 2) fmas = 0.5 * (dfma_all + dmma_all);
-    else fmas = (double)sm_count() * 2 * (PEAK_THREADS / 32) * (double)iters * 36.0 * 256.0;
+    else {
+        const double warps = kind == 3 ? 2.0 * (PEAK_THREADS / 32) : kind == 4 ? 4.0 : PEAK_THREADS / 32;
+        fmas = (double)sm_count() * warps * (double)iters * 36.0 * 256.0;
+    }
     if (tflops) *tflops = 2.0 * fmas / ((double)best * 1e-3) / 1e12;
     if (ms_out) *ms_out = best;
     return DEISM_OK;

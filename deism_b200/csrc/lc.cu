@@ -34,7 +34,8 @@
 namespace deism {
 
 constexpr int LC_TI = 64;        // images per tile
-constexpr int LC_JC = 12;        // max harmonics per staged chunk (multiple of 4)
+// most harmonics per staged chunk (multiple of 4): a whole order-5 pass when only Y streams
+__host__ __device__ constexpr int lc_jcmax(bool cres_on) { return cres_on ? 36 : 12; }
 constexpr int LC_NT = 2;         // n-tiles (8 freqs each) per warp: warp tile = 16 images x 16 freqs
 constexpr int LC_YS = LC_TI + 4; // Y row stride (doubles): 68 = 4 mod 16 -> conflict-free fragments
 constexpr int LC_MAXST = 16;     // most ring stages
@@ -255,12 +256,12 @@ struct LcMainArgs {
 struct LcCarve {
     unsigned cres, ring, stage_bytes, facp, rec, Z, kf, dkd, dkd8, bars, total;
 };
-__host__ __device__ inline LcCarve lc_carve(int WN, bool cres_on, int rows, int nst) {
+__host__ __device__ inline LcCarve lc_carve(int WN, bool cres_on, int rows, int nst, int jc_rows) {
     const unsigned TF = lc_tf(WN), CS = lc_cs(WN), threads = 128 * WN;
     LcCarve c;
     unsigned o = 0;
     c.cres = o;  o += cres_on ? rows * 2 * CS * 8 : 0;                      // resident C planes
-    c.stage_bytes = LC_JC * (LC_YS + (cres_on ? 0 : 2 * CS)) * 8;           // Y chunk (+ C chunk)
+    c.stage_bytes = jc_rows * (LC_YS + (cres_on ? 0 : 2 * CS)) * 8;          // Y chunk (+ C chunk)
     c.ring = o;  o += nst * c.stage_bytes;
     c.facp = o;  o += 4 * LC_NT * threads * 16;     // thread-private factor, then S' = factor * S
     c.rec = o;   o += 2 * LC_TI * (unsigned)sizeof(LcImage);                // records: this / next tile
@@ -301,7 +302,8 @@ lc_main_kernel(LcMainArgs a) {
     const int total = n_tiles * npt;                       // < 2^31: host caps tiles_per_chunk
     const int nst = a.nst;
 
-    const LcCarve cv = lc_carve(WN, CRES, a.Js_pad + a.Jr_pad, nst);
+    const int jc_rows = a.JCs > a.JCr ? a.JCs : a.JCr;    // harmonics a ring stage holds
+    const LcCarve cv = lc_carve(WN, CRES, a.Js_pad + a.Jr_pad, nst, jc_rows);
     double *Cres = reinterpret_cast<double *>(lc_smem_raw + cv.cres);
     unsigned char *ring = lc_smem_raw + cv.ring;
     double2 (*facp)[THREADS] = reinterpret_cast<double2 (*)[THREADS]>(lc_smem_raw + cv.facp);
@@ -362,7 +364,7 @@ lc_main_kernel(LcMainArgs a) {
             const double *CT = (src_pass ? a.CTs : a.CTr) + ((long)blockIdx.x * Jp + j0) * 2 * CS;
             const unsigned cb = (unsigned)(JC * 2 * CS * 8);
             mbar_expect_tx(&full[stage], cb + yb);
-            bulk_g2s(S + LC_JC * LC_YS * 8, CT, cb, &full[stage]);
+            bulk_g2s(S + jc_rows * LC_YS * 8, CT, cb, &full[stage]);
         }
         bulk_g2s(S, Yg, yb, &full[stage]);
     };
@@ -407,20 +409,24 @@ lc_main_kernel(LcMainArgs a) {
     // crow = first coefficient row of the chunk within the resident planes.
     // `side` is independent scalar work (the factor of the next pairs) placed in the same basic
     // block as the unrolled k-steps, so that it issues in the shadow of the DMMAs' pipe occupancy.
-    auto run_chunk = [&](const int JC, const int crow, auto &&side) {
+    // `pre` (the previous pass's epilogue, which ends by clearing T) runs after the wait so that it,
+    // too, shares a basic block with the first k-step.
+    auto run_chunk = [&](const int JC, const int crow, auto &&pre, auto &&side0, auto &&side1) {
         mbar_wait(&full[stage], phase);
         const double *Ystage = reinterpret_cast<const double *>(ring + (unsigned)stage * cv.stage_bytes);
         const double *Yw = Ystage + t4 * LC_YS + wm * 16 + g;
-        const double *Cw = (CRES ? Cres + (crow + t4) * 2 * CS : Ystage + LC_JC * LC_YS + t4 * 2 * CS) +
-                           wn * NT * 8 + g;
-        auto kstep = [&](int ks) {      // 4 harmonics: 2 + 2*NT fragment loads, 4*NT DMMAs
-            double af[2], bf[2][NT];
+        const double *Cw = (CRES ? Cres + (crow + t4) * 2 * CS
+                                 : Ystage + jc_rows * LC_YS + t4 * 2 * CS) + wn * NT * 8 + g;
+        // a k-step = 4 harmonics: 2 + 2*NT fragment loads, 4*NT DMMAs
+        auto load_frag = [&](int ks, double (&af)[2], double (&bf)[2][NT]) {
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) af[mt] = Yw[ks * LC_YS + mt * 8];
 #pragma unroll
             for (int p = 0; p < 2; ++p)
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) bf[p][nt] = Cw[(ks * 2 + p) * CS + nt * 8];
+        };
+        auto mma_frag = [&](const double (&af)[2], const double (&bf)[2][NT]) {
 #pragma unroll
             for (int p = 0; p < 2; ++p)
 #pragma unroll
@@ -429,15 +435,34 @@ lc_main_kernel(LcMainArgs a) {
                     for (int nt = 0; nt < NT; ++nt)
                         dmma884(T[p][mt][nt][0], T[p][mt][nt][1], af[mt], bf[p][nt]);
         };
-        if (JC == LC_JC) {
-            kstep(0);
-            side();
-#pragma unroll
-            for (int ks = 4; ks < LC_JC; ks += 4) kstep(ks);
-        } else {
-            side();
+        double af[2], bf[2][NT];
+        pre();
+        load_frag(0, af, bf);
+        mma_frag(af, bf);
+        side0();
+        if (JC > 4) {
+            load_frag(4, af, bf);
+            mma_frag(af, bf);
+            side1();
+            if (JC > 8) {
+                // remaining k-steps: fragments of step ks+4 are in flight while step ks multiplies
+                load_frag(8, af, bf);
 #pragma unroll 1
-            for (int ks = 0; ks < JC; ks += 4) kstep(ks);
+                for (int ks = 12; ks < JC; ks += 4) {
+                    double an[2], bn[2][NT];
+                    load_frag(ks, an, bn);
+                    mma_frag(af, bf);
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) af[mt] = an[mt];
+#pragma unroll
+                    for (int p = 0; p < 2; ++p)
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) bf[p][nt] = bn[p][nt];
+                }
+                mma_frag(af, bf);
+            }
+        } else {
+            side1();
         }
         __syncwarp();
         if (lane == 0 && atomicAdd(&done[stage], 1) == NWARPS - 1) {
@@ -464,6 +489,33 @@ lc_main_kernel(LcMainArgs a) {
     };
 
     auto no_side = [] {};
+    // end of a source pass: S = T0 + i T1;  park S' = fac * S
+    auto epi_S = [&] {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = (mt * NT + nt) * 2 + e;
+                    facp[j][tid] = cmul(facp[j][tid], cmake(T[0][mt][nt][e], T[1][mt][nt][e]));
+                }
+        clear_T();
+    };
+    // end of a receiver pass: P += S' * R  (a no-op before the first tile: T = 0, facp = 0)
+    auto epi_P = [&] {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    cfma(P[nt][e], facp[(mt * NT + nt) * 2 + e][tid], cmake(T[0][mt][nt][e], T[1][mt][nt][e]));
+        clear_T();
+    };
+#pragma unroll
+    for (int j = 0; j < 4 * NT; ++j) facp[j][tid] = cmake(0.0, 0.0);
+    clear_T();
     // fast path: frequency-flat impedance on a uniform wave-number grid.  One sincos per image
     // starts a rotation recurrence over the thread's frequencies; branch-free, so it can ride along
     // with the first source chunks of the tile.
@@ -490,19 +542,14 @@ lc_main_kernel(LcMainArgs a) {
                 if (nt + 1 < NT) F = rot_step(F, rec.rot8, dkd8[fq] * r);
             }
         };
-        clear_T();
         if (fast) {
-            if (a.ncs == 1) {
-                run_chunk(a.JCs, 0, [&] { factor_fast(0); factor_fast(1); });
-            } else {
-                run_chunk(a.JCs, 0, [&] { factor_fast(0); });
-                run_chunk(a.JCs, a.JCs, [&] { factor_fast(1); });
+            run_chunk(a.JCs, 0, epi_P, [&] { factor_fast(0); }, [&] { factor_fast(1); });
 #pragma unroll 1
-                for (int l = 2; l < a.ncs; ++l) run_chunk(a.JCs, l * a.JCs, no_side);
-            }
+            for (int l = 1; l < a.ncs; ++l) run_chunk(a.JCs, l * a.JCs, no_side, no_side, no_side);
         } else {
             // general path: per-term sincos off the uniform grid, per-term attenuation for a
             // frequency-dependent impedance or a materialised atten[I,K] (rolled: rarely hot)
+            epi_P();
             const long i0 = (tile_lo + tt) * LC_TI;
 #pragma unroll 1
             for (int j = 0; j < 4 * NT; ++j) {
@@ -535,7 +582,7 @@ lc_main_kernel(LcMainArgs a) {
                 facp[j][tid] = cmul(att, cmake(cs, -sn));
             }
 #pragma unroll 1
-            for (int l = 0; l < a.ncs; ++l) run_chunk(a.JCs, l * a.JCs, no_side);
+            for (int l = 0; l < a.ncs; ++l) run_chunk(a.JCs, l * a.JCs, no_side, no_side, no_side);
         }
         __syncwarp();
         if (lane == 0 && atomicAdd(&recdone[rb], 1) == NWARPS - 1) {
@@ -543,28 +590,12 @@ lc_main_kernel(LcMainArgs a) {
             recdone[rb] = 0;
             if (tt + 2 < n_tiles) issue_records(tt + 2);
         }
-        // ---- end of the source pass: S = T0 + i T1;  park S' = fac * S ----
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int j = (mt * NT + nt) * 2 + e;
-                    facp[j][tid] = cmul(facp[j][tid], cmake(T[0][mt][nt][e], T[1][mt][nt][e]));
-                }
-        // ---- receiver pass: P += S' * R ----
-        clear_T();
+        // ---- receiver pass; its first chunk carries the source pass's epilogue ----
+        run_chunk(a.JCr, a.Js_pad, epi_S, no_side, no_side);
 #pragma unroll 1
-        for (int l = 0; l < a.ncr; ++l) run_chunk(a.JCr, a.Js_pad + l * a.JCr, no_side);
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                for (int e = 0; e < 2; ++e)
-                    cfma(P[nt][e], facp[(mt * NT + nt) * 2 + e][tid], cmake(T[0][mt][nt][e], T[1][mt][nt][e]));
+        for (int l = 1; l < a.ncr; ++l) run_chunk(a.JCr, a.Js_pad + l * a.JCr, no_side, no_side, no_side);
     }
+    epi_P();
 
     // ---- reduce over the 8 row groups x 4 image warps that share a frequency (aliases facp) ----
     __syncthreads();
@@ -620,8 +651,9 @@ int validate_atten(const deism_shoebox_atten *at) {
     return DEISM_OK;
 }
 
-// J harmonics -> nc chunks of JC (multiple of 4, <= LC_JC): least zero padding, then fewest chunks
-static void pick_chunks(int J, int &nc, int &JC) {
+// J harmonics -> nc chunks of JC (multiple of 4, <= jcmax): least zero padding, then fewest chunks
+static void pick_chunks(int J, int jcmax, int &nc, int &JC) {
+    const int LC_JC = jcmax;
     int nc0 = (J + LC_JC - 1) / LC_JC, best = 1 << 30;
     nc = nc0; JC = LC_JC;
     for (int n = nc0; n <= nc0 + 6; ++n) {
@@ -722,29 +754,32 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
 
     const long n_img_tiles = (n_images + LC_TI - 1) / LC_TI;
     const long n_pad = n_img_tiles * LC_TI;
-    // harmonics are streamed in ncs (ncr) chunks of JCs (JCr) <= LC_JC each (multiples of 4, the
-    // DMMA k extent), sized to waste as little zero padding as possible (J = 36 -> 3 x 12)
-    int ncs, ncr, JCs, JCr;
-    pick_chunks(Jqs, ncs, JCs);
-    pick_chunks(Jqr, ncr, JCr);
-    const int Js_pad = ncs * JCs, Jr_pad = ncr * JCr;
-
-    // kernel shape: resident coefficient planes (512 threads, 64 frequencies, 1 CTA/SM) when they
-    // leave room for a ring of >= 6 Y chunks, else the streaming shape (256 threads, 32
-    // frequencies, 2 CTAs/SM, 4-stage ring of C+Y chunks)
+    // kernel shape: resident coefficient planes (512 threads, 64 frequencies, 1 CTA/SM, Y chunks of
+    // up to 36 harmonics) when they leave room for a ring of >= 2 such chunks, else the streaming
+    // shape (256 threads, 32 frequencies, 2 CTAs/SM, 4-stage ring of C+Y chunks of <= 12 harmonics).
+    // Harmonics go in ncs (ncr) chunks of JCs (JCr) each (multiples of 4, the DMMA k extent), sized
+    // to waste as little zero padding as possible.
     const int smem_max = smem_optin_bytes();
-    static const char *force = getenv("DEISM_LC_SHAPE");     // "stream" | "resident": A/B runs
-    bool resident = false;
-    int nst = 4;
-    {
-        const LcCarve c0 = lc_carve(4, true, Js_pad + Jr_pad, 0);
-        const int room = (smem_max - (int)c0.total) / (int)c0.stage_bytes;
-        if (room >= 6) { resident = true; nst = room < LC_MAXST ? room : LC_MAXST; }
-        if (force && !strcmp(force, "stream")) { resident = false; nst = 4; }
+    static const char *force = getenv("DEISM_LC_SHAPE");     // "stream": A/B runs
+    bool resident = !(force && !strcmp(force, "stream"));
+    int nst = 4, ncs, ncr, JCs, JCr;
+    if (resident) {
+        pick_chunks(Jqs, lc_jcmax(true), ncs, JCs);
+        pick_chunks(Jqr, lc_jcmax(true), ncr, JCr);
+        const LcCarve c0 = lc_carve(4, true, ncs * JCs + ncr * JCr, 0, JCs > JCr ? JCs : JCr);
+        const int room = smem_max > (int)c0.total ? (smem_max - (int)c0.total) / (int)c0.stage_bytes : 0;
+        if (room >= 2) nst = room < LC_MAXST ? room : LC_MAXST;
+        else resident = false;
     }
+    if (!resident) {
+        pick_chunks(Jqs, lc_jcmax(false), ncs, JCs);
+        pick_chunks(Jqr, lc_jcmax(false), ncr, JCr);
+        nst = 4;
+    }
+    const int Js_pad = ncs * JCs, Jr_pad = ncr * JCr;
     const int WN = resident ? 4 : 2, TF = lc_tf(WN), CS = lc_cs(WN);
     const int ctas_per_sm = resident ? 1 : 2;
-    const LcCarve carve = lc_carve(WN, resident, Js_pad + Jr_pad, nst);
+    const LcCarve carve = lc_carve(WN, resident, Js_pad + Jr_pad, nst, JCs > JCr ? JCs : JCr);
     const long n_ftiles = (K + TF - 1) / TF;
 
     // image tiles are cut into n_chunks CTAs per ftile: ~`waves` waves of CTAs over the SMs, picked

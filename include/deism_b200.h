@@ -215,7 +215,9 @@ DEISM_API int deism_convex_images_fill(const deism_convex_walls *walls, int64_t 
 /* (5) Micro-benchmarks used by bench.py to measure the FP64 roofline denominators         */
 /* ------------------------------------------------------------------------------------ */
 /* Runs a register-resident DFMA (kind 0) or DMMA m8n8k4 (kind 1) loop on every SM and returns
- * the achieved TFLOP/s (2 flops per FMA) in *tflops, timed with CUDA events. */
+ * the achieved TFLOP/s (2 flops per FMA) in *tflops, timed with CUDA events.  kind 2: half the
+ * warps DMMA, half DFMA (the two share one datapath); kinds 3/4/5: DMMA fed by shared-memory
+ * fragment loads at 16 / 4 / 8 warps per SM. */
 DEISM_API int deism_fp64_peak(int kind, int iters, double *tflops, double *ms);
 
 #ifdef __cplusplus
