@@ -130,7 +130,8 @@ constexpr int ORG_TI = 32;        // images per tile
 constexpr int ORG_TF = 32;        // frequencies per tile
 constexpr int ORG_THREADS = 128;  // 2 x 2 warps, 16 images x 16 frequencies each
 constexpr int ORG_RC = 24;        // (l,mu) rows per staged chunk (chunks may span several l)
-constexpr int ORG_OS = 36;        // plane row stride in doubles (32 + 4 pad: 4 mod 16)
+constexpr int ORG_OS = 36;        // Y row stride in doubles (32 images + 4 pad: 4 mod 16)
+constexpr int ORG_BS = 34;        // B plane stride: a row of 2 planes is 68 = 4 mod 16 doubles
 constexpr int ORG_LMAX = 48;
 constexpr int ORG_MAXCHUNKS = 256;
 constexpr int SORT_THREADS = 1024;
@@ -138,9 +139,15 @@ __constant__ int c_org_rowoff[ORG_LMAX + 1];
 __constant__ int2 c_org_chunks[ORG_MAXCHUNKS];   // row0, nrows
 __constant__ signed char c_org_ks_l[ORG_LMAX * ORG_LMAX];   // per 4-row step: l if it closes degree l, else -1
 
-// B planes: [8 parity][K_pad/32][R_tot][Re|Im|Re+Im][ORG_OS] doubles.
-// grid (ceil(K/128), Lmax^2 segments, 2 m'-classes); each thread evaluates the coupling
-// D = C_s*C_r of an entry ONCE and feeds the four mirror-sign variants (b, c) of its class.
+// Real-harmonic rows.  Y_l^{-mu} = (-1)^mu conj(Y_l^mu), so with Y_l^mu = a + i b (mu > 0)
+//     sum_mu Y_l^mu B[l,mu]  =  a_0 B[l,0] + sum_{mu>0} a_mu (B[l,mu] + (-1)^mu B[l,-mu])
+//                                          + b_mu i (B[l,mu] - (-1)^mu B[l,-mu])
+// is a REAL-by-complex contraction: two real GEMMs instead of the three of the 3-multiplication
+// complex form.  Row order inside the block of degree l: a_0, a_1, b_1, a_2, b_2, ...
+//
+// B planes: [8 parity][K_pad/32][R_tot][Re|Im][ORG_BS] doubles.
+// grid (ceil(K/128), Lmax(Lmax+1)/2 pairs (l, mu >= 0), 2 m'-classes); each thread evaluates the
+// coupling D = C_s*C_r of an entry ONCE and feeds the four mirror-sign variants (b, c) of its class.
 struct BtableArgs {
     long K, n_ftiles;
     int nseg, R_tot;
@@ -153,41 +160,56 @@ struct BtableArgs {
 
 __global__ void __launch_bounds__(128) org_btable_kernel(BtableArgs a) {
     long k = (long)blockIdx.x * 128 + threadIdx.x;
-    const int s = blockIdx.y, cls = blockIdx.z;
+    const int cls = blockIdx.z;
     if (k >= a.K) return;
+    int l = 0;
+    while ((l + 1) * (l + 2) / 2 <= (int)blockIdx.y) ++l;
+    const int am = (int)blockIdx.y - l * (l + 1) / 2;        // |mu|
     const OrgEntry *ent = cls ? a.ent[1] : a.ent[0];
     const int *segp = cls ? a.seg[1] : a.seg[0];
-    const int lo = segp[s], hi = segp[s + 1];
-    cplx acc[4];
+    cplx acc[2][4];     // [mu sign][mirror variant]
 #pragma unroll
-    for (int v = 0; v < 4; ++v) acc[v] = cmake(0.0, 0.0);
-    for (int j = lo; j < hi; ++j) {
-        OrgEntryReg e = load_entry(ent + j);
-        cplx d = cmul(a.CsT[(long)e.idx_s * a.K + k], a.CrT[(long)e.idx_r * a.K + k]);
-        const double gx = e.G * d.x, gy = e.G * d.y;
+    for (int sg = 0; sg < 2; ++sg)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {          // v = 2*b + c, sign (-1)^{b m + c n}
-            const int sgn = ((v >> 1) * e.m + (v & 1) * e.n) & 1;
-            acc[v].x += sgn ? -gx : gx;
-            acc[v].y += sgn ? -gy : gy;
+        for (int v = 0; v < 4; ++v) acc[sg][v] = cmake(0.0, 0.0);
+#pragma unroll
+    for (int sg = 0; sg < 2; ++sg) {
+        if (sg == 1 && am == 0) break;
+        const int s = l * l + l + (sg ? -am : am);
+        const int lo = segp[s], hi = segp[s + 1];
+        for (int j = lo; j < hi; ++j) {
+            OrgEntryReg e = load_entry(ent + j);
+            cplx d = cmul(a.CsT[(long)e.idx_s * a.K + k], a.CrT[(long)e.idx_r * a.K + k]);
+            const double gx = e.G * d.x, gy = e.G * d.y;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {          // v = 2*b + c, sign (-1)^{b m + c n}
+                const int sgn = ((v >> 1) * e.m + (v & 1) * e.n) & 1;
+                acc[sg][v].x += sgn ? -gx : gx;
+                acc[sg][v].y += sgn ? -gy : gy;
+            }
         }
     }
-    int l = 0;
-    while ((l + 1) * (l + 1) <= s) ++l;
-    const long row = c_org_rowoff[l] + (s - l * l);
+    const long row_a = c_org_rowoff[l] + (am ? 2 * am - 1 : 0);
     const long ft = k / ORG_TF;
     const int q = (int)(k % ORG_TF);
     const double ik = 1.0 / a.k[k];
+    const double sm = (am & 1) ? -1.0 : 1.0;
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
         const int b = v >> 1, c = v & 1;
         const int pz = c, py = b ^ c, px = cls ^ py;
         const int par = px * 4 + py * 2 + pz;
-        const double re = -acc[v].y * ik, im = acc[v].x * ik;          // * (i/k)
-        double *p = a.Bp + (((long)par * a.n_ftiles + ft) * a.R_tot + row) * 3 * ORG_OS + q;
-        p[0] = re;
-        p[ORG_OS] = im;
-        p[2 * ORG_OS] = re + im;
+        // B = (i/k) acc;  a-row: B+ + (-1)^mu B-;  b-row: i (B+ - (-1)^mu B-)
+        const double sx = acc[0][v].x + sm * acc[1][v].x, sy = acc[0][v].y + sm * acc[1][v].y;
+        const double dx = acc[0][v].x - sm * acc[1][v].x, dy = acc[0][v].y - sm * acc[1][v].y;
+        double *p = a.Bp + (((long)par * a.n_ftiles + ft) * a.R_tot + row_a) * 2 * ORG_BS + q;
+        p[0] = -sy * ik;            // (i/k)(sx + i sy) = (-sy + i sx)/k
+        p[ORG_BS] = sx * ik;
+        if (am) {
+            p += 2 * ORG_BS;        // i (i/k)(dx + i dy) = (-dx - i dy)/k
+            p[0] = -dx * ik;
+            p[ORG_BS] = -dy * ik;
+        }
     }
 }
 
@@ -281,7 +303,7 @@ struct OrgPrepArgs {
     const cplx *Z;
     long K;
     RoomGeom room;
-    double *Yp;                 // factorised path: planes [tile][R_tot][3][ORG_OS] (pre-zeroed)
+    double *Yp;                 // factorised path: real rows [tile][R_tot][ORG_OS] (pre-zeroed)
     int R_tot;
 };
 
@@ -334,12 +356,11 @@ org_prep_kernel(OrgPrepArgs a, OrgImage *rec_out, cplx *Y) {
         const long tile = pos / ORG_TI;
         const int it = (int)(pos % ORG_TI);
         for (int l = 0; l < a.Lmax; ++l)
-            for (int mu = -l; mu <= l; ++mu) {
-                cplx y = sph_harm_dev(mu, l, phi, ct);
-                double *p = a.Yp + ((tile * a.R_tot + c_org_rowoff[l] + mu + l) * 3) * ORG_OS + it;
+            for (int am = 0; am <= l; ++am) {      // rows a_0, a_1, b_1, a_2, b_2, ...
+                cplx y = sph_harm_dev(am, l, phi, ct);
+                double *p = a.Yp + (tile * a.R_tot + c_org_rowoff[l] + (am ? 2 * am - 1 : 0)) * ORG_OS + it;
                 p[0] = y.x;
-                p[ORG_OS] = y.y;
-                p[2 * ORG_OS] = y.x + y.y;
+                if (am) p[ORG_OS] = y.y;
             }
         return;
     }
@@ -351,17 +372,17 @@ org_prep_kernel(OrgPrepArgs a, OrgImage *rec_out, cplx *Y) {
 // ---------------------------------------------------------------------------------------
 // consume kernel (factorised form) on the FP64 tensor cores.
 //
-// Per (l): T_l[img,k] = sum_mu Y_l^mu(img) * B[par][l,mu][k] is a complex [32 img x rows(l)] .
-// [rows(l) x 32 freq] product done as three real DMMA m8n8k4 GEMMs (3-multiplication form, see
-// lc.cu); then P[img,k] += h_l(k r_img) * T_l[img,k] with the h_l recurrence of every pair kept
+// Per (l): T_l[img,k] = sum_mu Y_l^mu(img) * B[par][l,mu][k], in the real-harmonic row basis a
+// real [32 img x rows(l)] by complex [rows(l) x 32 freq] product = two real DMMA m8n8k4 GEMMs;
+// then P[img,k] += h_l(k r_img) * T_l[img,k] with the h_l recurrence of every pair kept
 // in registers (pb:86-118, j and y carried as one complex number).  (l, mu) rows are streamed
 // in chunks of <= 12 through a two-stage TMA bulk-copy pipeline.
 // ---------------------------------------------------------------------------------------
 struct OrgConsumeArgs {
     long K, n_ftiles;
     int Lmax, R_tot, ncpt;    // chunks per tile
-    const double *Bp;         // [8][n_ftiles][R_tot][3][ORG_OS]
-    const double *Yp;         // [tiles][R_tot][3][ORG_OS]
+    const double *Bp;         // [8][n_ftiles][R_tot][2][ORG_BS]
+    const double *Yp;         // [tiles][R_tot][ORG_OS]
     const OrgImage *rec;      // [n_pad]
     const long *meta;         // class starts + total
     const double *k;
@@ -374,8 +395,8 @@ struct OrgConsumeArgs {
 };
 
 struct OrgStage {
-    double B[ORG_RC][3][ORG_OS];
-    double Y[ORG_RC][3][ORG_OS];
+    double B[ORG_RC][2][ORG_BS];
+    double Y[ORG_RC][ORG_OS];
 };
 struct OrgSmem {
     OrgStage st[2];
@@ -436,15 +457,15 @@ org_consume_kernel(OrgConsumeArgs a) {
         int par = 0;
 #pragma unroll
         for (int q = 1; q < 8; ++q) par += (p0 >= a.meta[q]);
-        const double *Bg = a.Bp + (((long)par * a.n_ftiles + blockIdx.x) * a.R_tot + ch.x) * 3 * ORG_OS;
-        const double *Yg = a.Yp + ((tile * a.R_tot + ch.x) * 3) * ORG_OS;
-        const unsigned bytes = (unsigned)(ch.y * 3 * ORG_OS * 8);
-        mbar_expect_tx(&sm.full[stage], 2 * bytes);
-        bulk_g2s(&sm.st[stage].B[0][0][0], Bg, bytes, &sm.full[stage]);
-        bulk_g2s(&sm.st[stage].Y[0][0][0], Yg, bytes, &sm.full[stage]);
+        const double *Bg = a.Bp + (((long)par * a.n_ftiles + blockIdx.x) * a.R_tot + ch.x) * 2 * ORG_BS;
+        const double *Yg = a.Yp + (tile * a.R_tot + ch.x) * ORG_OS;
+        const unsigned bb = (unsigned)(ch.y * 2 * ORG_BS * 8), yb = (unsigned)(ch.y * ORG_OS * 8);
+        mbar_expect_tx(&sm.full[stage], bb + yb);
+        bulk_g2s(&sm.st[stage].B[0][0][0], Bg, bb, &sm.full[stage]);
+        bulk_g2s(&sm.st[stage].Y[0][0], Yg, yb, &sm.full[stage]);
     };
 
-    double T[3][2][2][2];       // [plane][m-tile][n-tile][2]
+    double T[2][2][2][2];       // [Re|Im][m-tile][n-tile][2]
     cplx hm[2][2][2], hc[2][2][2], Pp[2][2][2];   // per pair [mt][nt][e]
     cplx P[2][2];               // [nt][e], summed over this thread's images
 #pragma unroll
@@ -528,7 +549,7 @@ org_consume_kernel(OrgConsumeArgs a) {
                     }
             }
 #pragma unroll
-            for (int p = 0; p < 3; ++p)
+            for (int p = 0; p < 2; ++p)
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -544,21 +565,20 @@ org_consume_kernel(OrgConsumeArgs a) {
         const OrgStage &S = sm.st[stage];
 #pragma unroll 1
         for (int ks = 0; ks < ch.y; ks += 4) {
-            double af[3][2], bf[3][2];
+            double af[2], bf[2][2];
 #pragma unroll
-            for (int p = 0; p < 3; ++p) {
+            for (int mt = 0; mt < 2; ++mt) af[mt] = S.Y[ks + t4][wm * 16 + mt * 8 + g];
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) af[p][mt] = S.Y[ks + t4][p][wm * 16 + mt * 8 + g];
+            for (int p = 0; p < 2; ++p)
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) bf[p][nt] = S.B[ks + t4][p][wn * 16 + nt * 8 + g];
-            }
 #pragma unroll
-            for (int p = 0; p < 3; ++p)
+            for (int p = 0; p < 2; ++p)
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
                     for (int nt = 0; nt < 2; ++nt)
-                        dmma884(T[p][mt][nt][0], T[p][mt][nt][1], af[p][mt], bf[p][nt]);
+                        dmma884(T[p][mt][nt][0], T[p][mt][nt][1], af[mt], bf[p][nt]);
             const int l = c_org_ks_l[(ch.x + ks) >> 2];
             if (l >= 0) {
                 // ---- this 4-row step closes degree l: advance h_l, P_pair += h_l * T_l, reset T
@@ -580,9 +600,8 @@ org_consume_kernel(OrgConsumeArgs a) {
                                 hm[mt][nt][e] = hc[mt][nt][e];
                                 hc[mt][nt][e] = h;
                             }
-                            const double t1 = T[0][mt][nt][e], t2 = T[1][mt][nt][e], t3 = T[2][mt][nt][e];
-                            cfma(Pp[mt][nt][e], h, cmake(t1 - t2, t3 - t1 - t2));
-                            T[0][mt][nt][e] = 0.0; T[1][mt][nt][e] = 0.0; T[2][mt][nt][e] = 0.0;
+                            cfma(Pp[mt][nt][e], h, cmake(T[0][mt][nt][e], T[1][mt][nt][e]));
+                            T[0][mt][nt][e] = 0.0; T[1][mt][nt][e] = 0.0;
                         }
                 }
             }
@@ -904,12 +923,12 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
     DEISM_CUDA_TRY(cudaStreamSynchronize(st));   // stack tables consumed
 
     const long n_ftiles = (K + ORG_TF - 1) / ORG_TF;
-    const size_t plane_rows = (size_t)R_tot * 3 * ORG_OS;
+    const size_t b_rows = (size_t)R_tot * 2 * ORG_BS, y_rows = (size_t)R_tot * ORG_OS;
     cplx *CsT = (cplx *)workspace(WS_SMALL, (size_t)(NMs + NMr) * K * sizeof(cplx));
-    double *Bp = (double *)workspace(WS_ORG_B, (size_t)8 * n_ftiles * plane_rows * sizeof(double));
+    double *Bp = (double *)workspace(WS_ORG_B, (size_t)8 * n_ftiles * b_rows * sizeof(double));
     if (!CsT || !Bp) return DEISM_ERR_NOMEM;
     cplx *CrT = CsT + (size_t)NMs * K;
-    DEISM_CUDA_TRY(cudaMemsetAsync(Bp, 0, (size_t)8 * n_ftiles * plane_rows * sizeof(double), st));
+    DEISM_CUDA_TRY(cudaMemsetAsync(Bp, 0, (size_t)8 * n_ftiles * b_rows * sizeof(double), st));
     transpose_c64_kernel<<<(unsigned)(((long)K * NMs + 255) / 256), 256, 0, st>>>(
         (const float2 *)d_C_nm_s, K, NMs, CsT);
     DEISM_LAUNCH_CHECK("transpose_c64_kernel");
@@ -921,7 +940,7 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
     for (int i = 0; i < 2; ++i) { ba.ent[i] = d_ent[i]; ba.seg[i] = d_seg[i]; }
     ba.CsT = CsT; ba.CrT = CrT; ba.k = d_k; ba.Bp = Bp;
     {
-        dim3 grid((unsigned)((K + 127) / 128), (unsigned)nseg, 2);
+        dim3 grid((unsigned)((K + 127) / 128), (unsigned)(Lmax * (Lmax + 1) / 2), 2);
         prof_begin("org_btable", st);
         org_btable_kernel<<<grid, 128, 0, st>>>(ba);
         prof_end("org_btable", st);
@@ -932,9 +951,9 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
     const long n_tiles_cap = n_pad_cap / ORG_TI;
     long *perm = (long *)workspace(WS_ARG_IDX, (size_t)(n_pad_cap + 16) * sizeof(long));
     OrgImage *rec = (OrgImage *)workspace(WS_ORG_IMG, (size_t)n_pad_cap * sizeof(OrgImage));
-    double *Yp = (double *)workspace(WS_ORG_Y, (size_t)n_tiles_cap * plane_rows * sizeof(double));
+    double *Yp = (double *)workspace(WS_ORG_Y, (size_t)n_tiles_cap * y_rows * sizeof(double));
     if (!perm || !rec || !Yp) return DEISM_ERR_NOMEM;
-    DEISM_CUDA_TRY(cudaMemsetAsync(Yp, 0, (size_t)n_tiles_cap * plane_rows * sizeof(double), st));
+    DEISM_CUDA_TRY(cudaMemsetAsync(Yp, 0, (size_t)n_tiles_cap * y_rows * sizeof(double), st));
     long *meta = perm + n_pad_cap;
     org_sort_kernel<<<1, SORT_THREADS, 0, st>>>(d_A, n_images, perm, meta, n_pad_cap);
     DEISM_LAUNCH_CHECK("org_sort_kernel");
