@@ -37,10 +37,13 @@ sys.path.insert(0, ROOT)
 
 # --------------------------------------------------------------------------------------
 # algorithmic work per term (SURVEY.md §8d conventions:
-# complex MAC = 8 flops, complex mul = 6, complex x real = 2)
+# complex MAC = 8 flops, complex mul = 6, complex x real = 2).  The directivity contractions are
+# counted in the real-harmonic basis the kernels use (Y_n^-m = (-1)^m conj Y_n^m makes them
+# real x complex: 4 flops per harmonic and term instead of 8), i.e. the cheapest formulation known
+# to us, not the reference's complex x complex loop.
 # --------------------------------------------------------------------------------------
 def lc_flops_per_term(Js, Jr, fused_per_term, mean_order):
-    f = 8 * (Js + Jr) + 52
+    f = 4 * (Js + Jr) + 52
     if fused_per_term:
         f += 140 + 6 * mean_order
     return f
@@ -48,7 +51,7 @@ def lc_flops_per_term(Js, Jr, fused_per_term, mean_order):
 
 def org_consume_flops_per_term(N, V):
     L = N + V + 1
-    return 8 * L * L + 14 * L + 40      # contraction + h_l recurrence/accumulate + sincos
+    return 4 * L * L + 14 * L + 40      # contraction + h_l recurrence/accumulate + sincos
 
 
 def clocks_sampler(stop, out, gpu_index):

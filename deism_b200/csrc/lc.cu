@@ -551,6 +551,8 @@ lc_main_kernel(LcMainArgs a) {
             // frequency-dependent impedance or a materialised atten[I,K] (rolled: rarely hot)
             epi_P();
             const long i0 = (tile_lo + tt) * LC_TI;
+            cplx E = cmake(1.0, 0.0), E0 = E;
+            static_assert(NT == 2, "rotation order below assumes two n-tiles per warp");
 #pragma unroll 1
             for (int j = 0; j < 4 * NT; ++j) {
                 const int mt = j / (2 * NT), nt = (j >> 1) % NT, e = j & 1;
@@ -577,9 +579,19 @@ lc_main_kernel(LcMainArgs a) {
                     }
                     att = cmake(att.x * rec.inv_r, att.y * rec.inv_r);
                 }
-                double sn, cs;
-                sincos_cw(kf[fq] * rec.r, &sn, &cs);
-                facp[j][tid] = cmul(att, cmake(cs, -sn));
+                // exp(-i k r): per-term sincos, or on a uniform grid one sincos per image and the
+                // rotation recurrence (base, +1, +8, +9 steps for nt = 0,0,1,1 / e = 0,1,0,1)
+                if (!uniform_k || (j & 3) == 0) {
+                    double sn, cs;
+                    sincos_cw(kf[fq] * rec.r, &sn, &cs);
+                    E = cmake(cs, -sn);
+                    E0 = E;
+                } else if ((j & 3) == 2) {
+                    E = rot_step(E0, rec.rot8, dkd8[fq - 8] * rec.r);
+                } else {
+                    E = rot_step(E, rec.rot, dkd[fq - 1] * rec.r);
+                }
+                facp[j][tid] = cmul(att, E);
             }
 #pragma unroll 1
             for (int l = 0; l < a.ncs; ++l) run_chunk(a.JCs, l * a.JCs, no_side, no_side, no_side);
