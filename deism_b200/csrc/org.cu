@@ -128,16 +128,19 @@ __global__ void transpose_c64_kernel(const float2 *__restrict__ in, long K, int 
 // ---------------------------------------------------------------------------------------
 constexpr int ORG_TI = 32;        // images per tile
 constexpr int ORG_TF = 32;        // frequencies per tile
-constexpr int ORG_THREADS = 128;  // 2 x 2 warps, 16 images x 16 frequencies each
-constexpr int ORG_RC = 24;        // (l,mu) rows per staged chunk (chunks may span several l)
+#ifndef ORG_NT
+#define ORG_NT 1                  // n-tiles (8 freqs) per warp: 1 -> 2x4 warps of 16x8, 2 -> 2x2 warps of 16x16
+#endif
+constexpr int ORG_WN = 4 / ORG_NT;             // warps along frequency
+constexpr int ORG_THREADS = 64 * ORG_WN;       // 2 (image) x ORG_WN (frequency) warps
+constexpr int ORG_RC = 48;        // (l,mu) rows per staged chunk (whole degrees; grows to the widest degree)
 constexpr int ORG_OS = 36;        // Y row stride in doubles (32 images + 4 pad: 4 mod 16)
 constexpr int ORG_BS = 34;        // B plane stride: a row of 2 planes is 68 = 4 mod 16 doubles
 constexpr int ORG_LMAX = 48;
 constexpr int ORG_MAXCHUNKS = 256;
 constexpr int SORT_THREADS = 1024;
 __constant__ int c_org_rowoff[ORG_LMAX + 1];
-__constant__ int2 c_org_chunks[ORG_MAXCHUNKS];   // row0, nrows
-__constant__ signed char c_org_ks_l[ORG_LMAX * ORG_LMAX];   // per 4-row step: l if it closes degree l, else -1
+__constant__ int4 c_org_chunks[ORG_MAXCHUNKS];   // row0, nrows, first degree, one past the last degree
 
 // Real-harmonic rows.  Y_l^{-mu} = (-1)^mu conj(Y_l^mu), so with Y_l^mu = a + i b (mu > 0)
 //     sum_mu Y_l^mu B[l,mu]  =  a_0 B[l,0] + sum_{mu>0} a_mu (B[l,mu] + (-1)^mu B[l,-mu])
@@ -381,6 +384,7 @@ org_prep_kernel(OrgPrepArgs a, OrgImage *rec_out, cplx *Y) {
 struct OrgConsumeArgs {
     long K, n_ftiles;
     int Lmax, R_tot, ncpt;    // chunks per tile
+    int rc;                   // rows a stage holds
     const double *Bp;         // [8][n_ftiles][R_tot][2][ORG_BS]
     const double *Yp;         // [tiles][R_tot][ORG_OS]
     const OrgImage *rec;      // [n_pad]
@@ -394,12 +398,9 @@ struct OrgConsumeArgs {
     cplx *partial;            // [n_chunks][K]
 };
 
-struct OrgStage {
-    double B[ORG_RC][2][ORG_BS];
-    double Y[ORG_RC][ORG_OS];
-};
+// fixed part of the shared memory; the two operand stages (rc rows of B then rc rows of Y each)
+// follow it
 struct OrgSmem {
-    OrgStage st[2];
     double2 fac[ORG_TI][ORG_TF + 1];
     double2 Z[6][ORG_TF];
     double2 aflat[ORG_TI];
@@ -409,23 +410,38 @@ struct OrgSmem {
     long orig[ORG_TI];
     unsigned char e[ORG_TI][8];
     unsigned long long full[2];
+    int done[2];
 };
-static_assert(sizeof(double2) * 16 * ORG_TF <= sizeof(OrgStage) * 2, "final reduction aliases the stages");
+static_assert(sizeof(OrgSmem) % 16 == 0, "stages must stay 16-byte aligned");
+static_assert(sizeof(double2) * 16 * ORG_TF <= sizeof(double2) * ORG_TI * (ORG_TF + 1),
+              "final reduction aliases fac");
 
+// Degrees are whole inside a chunk.  Per degree l the first k-step shares a basic block with the
+// accumulation of degree l-1 (P_pair += h_{l-1} T_{l-1}, reads T before the DMMAs overwrite it) and
+// with the h_l recurrence (independent of T), so that scalar FP64 work issues in the shadow of the
+// DMMAs; the remaining k-steps run in a loop that keeps the next fragments in flight.  Operand
+// chunks arrive by TMA; the last warp out of a stage refills it.  CTA-wide barriers only frame the
+// cooperative per-tile staging.
 __global__ void __launch_bounds__(ORG_THREADS, 2)
 org_consume_kernel(OrgConsumeArgs a) {
+    constexpr int NT = ORG_NT;
+    constexpr int NWARPS = ORG_THREADS / 32;
     extern __shared__ __align__(128) unsigned char org_smem_raw[];
     OrgSmem &sm = *reinterpret_cast<OrgSmem *>(org_smem_raw);
+    const unsigned stage_bytes = (unsigned)a.rc * (2 * ORG_BS + ORG_OS) * 8;
+    unsigned char *stages = org_smem_raw + sizeof(OrgSmem);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;
-    const int wm = warp >> 1, wn = warp & 1;            // warp tile: 16 images x 16 frequencies
+    const int wm = warp / ORG_WN, wn = warp % ORG_WN;   // warp tile: 16 images x 8*NT frequencies
     const long f0 = (long)blockIdx.x * ORG_TF;
-    const long n_tiles = a.meta[8] / ORG_TI;
+    const long n_tiles_all = a.meta[8] / ORG_TI;
     long tile_lo = (long)blockIdx.y * a.tiles_per_chunk;
     long tile_hi = tile_lo + a.tiles_per_chunk;
-    if (tile_hi > n_tiles) tile_hi = n_tiles;
-    const long total = tile_hi > tile_lo ? (tile_hi - tile_lo) * a.ncpt : 0;
+    if (tile_hi > n_tiles_all) tile_hi = n_tiles_all;
+    const int n_tiles = tile_hi > tile_lo ? (int)(tile_hi - tile_lo) : 0;
+    const int ncpt = a.ncpt;
+    const int total = n_tiles * ncpt;
 
     const bool fused = a.mode == DEISM_ATTEN_FUSED_ROOM || a.mode == DEISM_ATTEN_FUSED_ANGLES;
     const bool flat = fused && a.flags[0] != 0;
@@ -433,6 +449,7 @@ org_consume_kernel(OrgConsumeArgs a) {
     if (tid == 0) {
         mbar_init(&sm.full[0], 1);
         mbar_init(&sm.full[1], 1);
+        sm.done[0] = 0; sm.done[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int q = tid; q < ORG_TF; q += ORG_THREADS) {
@@ -450,9 +467,9 @@ org_consume_kernel(OrgConsumeArgs a) {
     }
     __syncthreads();
 
-    auto issue = [&](long tile_ord, int local, int stage) {
+    auto issue = [&](int tile_ord, int local, int stage) {
         const long tile = tile_lo + tile_ord;
-        const int2 ch = c_org_chunks[local];
+        const int4 ch = c_org_chunks[local];
         const long p0 = tile * ORG_TI;
         int par = 0;
 #pragma unroll
@@ -460,173 +477,212 @@ org_consume_kernel(OrgConsumeArgs a) {
         const double *Bg = a.Bp + (((long)par * a.n_ftiles + blockIdx.x) * a.R_tot + ch.x) * 2 * ORG_BS;
         const double *Yg = a.Yp + (tile * a.R_tot + ch.x) * ORG_OS;
         const unsigned bb = (unsigned)(ch.y * 2 * ORG_BS * 8), yb = (unsigned)(ch.y * ORG_OS * 8);
+        unsigned char *S = stages + (unsigned)stage * stage_bytes;
         mbar_expect_tx(&sm.full[stage], bb + yb);
-        bulk_g2s(&sm.st[stage].B[0][0][0], Bg, bb, &sm.full[stage]);
-        bulk_g2s(&sm.st[stage].Y[0][0], Yg, yb, &sm.full[stage]);
+        bulk_g2s(S, Bg, bb, &sm.full[stage]);
+        bulk_g2s(S + (unsigned)a.rc * 2 * ORG_BS * 8, Yg, yb, &sm.full[stage]);
     };
 
-    double T[2][2][2][2];       // [Re|Im][m-tile][n-tile][2]
-    cplx hm[2][2][2], hc[2][2][2], Pp[2][2][2];   // per pair [mt][nt][e]
-    cplx P[2][2];               // [nt][e], summed over this thread's images
+    double T[2][2][NT][2];      // [Re|Im][m-tile][n-tile][2]
+    cplx hm[2][NT][2], hc[2][NT][2], Pp[2][NT][2];   // per pair [mt][nt][e]: h_{l-1}, h_l, sum_l h_l T_l
+    double xinv[2][NT][2];      // 1 / (k r) of the pair
+    cplx P[NT][2];              // [nt][e], summed over this thread's images
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt) { P[nt][0] = cmake(0.0, 0.0); P[nt][1] = cmake(0.0, 0.0); }
+    for (int nt = 0; nt < NT; ++nt) { P[nt][0] = cmake(0.0, 0.0); P[nt][1] = cmake(0.0, 0.0); }
 
-    if (tid == 0 && total > 0) issue(0, 0, 0);
+    if (tid == 0 && total > 0) {
+        issue(0, 0, 0);
+        if (total > 1) issue(ncpt > 1 ? 0 : 1, ncpt > 1 ? 1 : 0, 1);
+    }
+    // (pt, pl): the chunk two ahead of the current one
+    int pt = 2 / ncpt, pl = 2 % ncpt;
+    int c = 0;
 
-    // chunk counter c = tt * ncpt + local kept as (tt, local): no 64-bit division per chunk
-    int local = 0;
-    long tt = 0;
+    // P_pair += h * T, T = 0: closes the degree whose h the recurrence reached last
+    auto accumulate = [&]() {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    cfma(Pp[mt][nt][e], hc[mt][nt][e], cmake(T[0][mt][nt][e], T[1][mt][nt][e]));
+                    T[0][mt][nt][e] = 0.0; T[1][mt][nt][e] = 0.0;
+                }
+    };
+
 #pragma unroll 1
-    for (long c = 0; c < total; ++c, ++local) {
-        if (local == a.ncpt) { local = 0; ++tt; }
-        const int stage = (int)(c & 1);
-        const unsigned parity = (unsigned)((c >> 1) & 1);
-        const int2 ch = c_org_chunks[local];
+    for (int tt = 0; tt < n_tiles; ++tt) {
         const long p0 = (tile_lo + tt) * ORG_TI;
-
-        if (local == 0) {
-            for (int i = tid; i < ORG_TI; i += ORG_THREADS) {
-                OrgImage rec = a.rec[p0 + i];
-                sm.r[i] = rec.r; sm.invr[i] = rec.inv_r;
-                sm.cosd[0][i] = rec.cx; sm.cosd[1][i] = rec.cy; sm.cosd[2][i] = rec.cz;
+        // ---- cooperative staging of the tile's image records and attenuation ----
+        for (int i = tid; i < ORG_TI; i += ORG_THREADS) {
+            OrgImage rec = a.rec[p0 + i];
+            sm.r[i] = rec.r; sm.invr[i] = rec.inv_r;
+            sm.cosd[0][i] = rec.cx; sm.cosd[1][i] = rec.cy; sm.cosd[2][i] = rec.cz;
 #pragma unroll
-                for (int b = 0; b < 8; ++b) sm.e[i][b] = rec.e[b];
-                sm.aflat[i] = rec.atten_flat;
-                sm.orig[i] = rec.orig;
-            }
-            __syncthreads();
-            // attenuation of the tile's 32 x 32 pairs (8 per thread)
-            {
-                const int tx = tid & 7, ty = tid >> 3;
+            for (int b = 0; b < 8; ++b) sm.e[i][b] = rec.e[b];
+            sm.aflat[i] = rec.atten_flat;
+            sm.orig[i] = rec.orig;
+        }
+        __syncthreads();
+        {   // attenuation of the tile's 32 x 32 pairs (1024 / ORG_THREADS per thread)
+            const int tx = tid & 7, ty = tid >> 3;
 #pragma unroll 1
-                for (int b = 0; b < 2; ++b) {
-                    const int il = ty + 16 * b;
-                    const long orig = sm.orig[il];
+            for (int b = 0; b < ORG_TI / (ORG_THREADS / 8); ++b) {
+                const int il = ty + (ORG_THREADS / 8) * b;
+                const long orig = sm.orig[il];
 #pragma unroll 2
-                    for (int q = 0; q < 4; ++q) {
-                        const int fq = tx + 8 * q;
-                        cplx att;
-                        if (orig < 0) {
-                            att = cmake(0.0, 0.0);
-                        } else if (flat) {
-                            att = sm.aflat[il];
-                        } else if (fused) {
-                            att = shoebox_atten(&sm.Z[0][fq], ORG_TF, sm.cosd[0][il], sm.cosd[1][il],
-                                                sm.cosd[2][il], sm.e[il]);
-                            if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
-                        } else {
-                            long f = f0 + fq;
-                            att = cmake(0.0, 0.0);
-                            if (f < a.K) {
-                                if (a.mode == DEISM_ATTEN_C64) {
-                                    float2 v = ((const float2 *)a.atten)[orig * a.K + f];
-                                    att = cmake((double)v.x, (double)v.y);
-                                } else {
-                                    att = ((const cplx *)a.atten)[orig * a.K + f];
-                                }
+                for (int q = 0; q < 4; ++q) {
+                    const int fq = tx + 8 * q;
+                    cplx att;
+                    if (orig < 0) {
+                        att = cmake(0.0, 0.0);
+                    } else if (flat) {
+                        att = sm.aflat[il];
+                    } else if (fused) {
+                        att = shoebox_atten(&sm.Z[0][fq], ORG_TF, sm.cosd[0][il], sm.cosd[1][il],
+                                            sm.cosd[2][il], sm.e[il]);
+                        if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
+                    } else {
+                        long f = f0 + fq;
+                        att = cmake(0.0, 0.0);
+                        if (f < a.K) {
+                            if (a.mode == DEISM_ATTEN_C64) {
+                                float2 v = ((const float2 *)a.atten)[orig * a.K + f];
+                                att = cmake((double)v.x, (double)v.y);
+                            } else {
+                                att = ((const cplx *)a.atten)[orig * a.K + f];
                             }
                         }
-                        sm.fac[il][fq] = att;
                     }
+                    sm.fac[il][fq] = att;
                 }
             }
-            // h_0, h_1 of this thread's DMMA-mapped pairs
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                const int il = wm * 16 + mt * 8 + g;
-                const double r = sm.r[il], ir = sm.invr[il];
-#pragma unroll
-                for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int fq = wn * 16 + nt * 8 + 2 * t4 + e;
-                        double sn, cs;
-                        sincos_cw(sm.kf[fq] * r, &sn, &cs);
-                        const double i1 = sm.invk[fq] * ir;
-                        hm[mt][nt][e] = cmake(sn * i1, cs * i1);                                 // h_0
-                        hc[mt][nt][e] = cmake(fma(sn * i1, i1, -cs * i1), fma(cs * i1, i1, sn * i1));  // h_1
-                        Pp[mt][nt][e] = cmake(0.0, 0.0);
-                    }
-            }
-#pragma unroll
-            for (int p = 0; p < 2; ++p)
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                    for (int nt = 0; nt < 2; ++nt) { T[p][mt][nt][0] = 0.0; T[p][mt][nt][1] = 0.0; }
         }
-
-        if (tid == 0 && c + 1 < total) {
-            if (local + 1 < a.ncpt) issue(tt, local + 1, stage ^ 1);
-            else issue(tt + 1, 0, stage ^ 1);
+        // Spherical Hankel recurrence of this thread's DMMA-mapped pairs (pb:86-118), h = (j, -y).
+        // It is started two orders early, from h_{-2} and h_{-1} (j_{-1} = cos x / x, y_{-1} =
+        // sin x / x, f_{l-2} = (2l-1)/x f_{l-1} - f_l), so that every degree, 0 and 1 included,
+        // takes the same branch-free step h_l = (2l-1)/x h_{l-1} - h_{l-2}.
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int il = wm * 16 + mt * 8 + g;
+            const double r = sm.r[il], ir = sm.invr[il];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int fq = wn * 8 * NT + nt * 8 + 2 * t4 + e;
+                    double sn, cs;
+                    sincos_cw(sm.kf[fq] * r, &sn, &cs);
+                    const double i1 = sm.invk[fq] * ir;
+                    xinv[mt][nt][e] = i1;
+                    const double ci = cs * i1, si = sn * i1;
+                    hc[mt][nt][e] = cmake(ci, -si);                                   // h_{-1}
+                    hm[mt][nt][e] = cmake(fma(-ci, i1, -si), fma(si, i1, -ci));       // h_{-2}
+                    Pp[mt][nt][e] = cmake(0.0, 0.0);
+                    T[0][mt][nt][e] = 0.0; T[1][mt][nt][e] = 0.0;
+                }
         }
-        mbar_wait(&sm.full[stage], parity);
-
-        const OrgStage &S = sm.st[stage];
+        __syncthreads();   // fac is complete before any warp reaches the end of the tile
+        // (T = 0 at the start of a tile: the first accumulate adds nothing)
 #pragma unroll 1
-        for (int ks = 0; ks < ch.y; ks += 4) {
-            double af[2], bf[2][2];
+        for (int local = 0; local < ncpt; ++local) {
+            const int stage = c & 1;
+            const int4 ch = c_org_chunks[local];
+            mbar_wait(&sm.full[stage], (unsigned)((c >> 1) & 1));
+            const double *Bs = reinterpret_cast<const double *>(stages + (unsigned)stage * stage_bytes);
+            const double *Ys = Bs + a.rc * 2 * ORG_BS;
+#pragma unroll 1
+            for (int l = ch.z; l < ch.w; ++l) {
+                const int row = c_org_rowoff[l] - ch.x;
+                const int ksn = (c_org_rowoff[l + 1] - c_org_rowoff[l]) >> 2;    // k-steps of degree l
+                const double *Yw = Ys + (row + t4) * ORG_OS + wm * 16 + g;
+                const double *Bw = Bs + (row + t4) * 2 * ORG_BS + wn * 8 * NT + g;
+                auto load_frag = [&](int ks, double (&af)[2], double (&bf)[2][NT]) {
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) af[mt] = S.Y[ks + t4][wm * 16 + mt * 8 + g];
+                    for (int mt = 0; mt < 2; ++mt) af[mt] = Yw[ks * 4 * ORG_OS + mt * 8];
 #pragma unroll
-            for (int p = 0; p < 2; ++p)
+                    for (int p = 0; p < 2; ++p)
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt) bf[p][nt] = S.B[ks + t4][p][wn * 16 + nt * 8 + g];
+                        for (int nt = 0; nt < NT; ++nt) bf[p][nt] = Bw[(ks * 8 + p) * ORG_BS + nt * 8];
+                };
+                auto mma_frag = [&](const double (&af)[2], const double (&bf)[2][NT]) {
 #pragma unroll
-            for (int p = 0; p < 2; ++p)
+                    for (int p = 0; p < 2; ++p)
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
+                        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                    for (int nt = 0; nt < 2; ++nt)
-                        dmma884(T[p][mt][nt][0], T[p][mt][nt][1], af[mt], bf[p][nt]);
-            const int l = c_org_ks_l[(ch.x + ks) >> 2];
-            if (l >= 0) {
-                // ---- this 4-row step closes degree l: advance h_l, P_pair += h_l * T_l, reset T
-                const double cl = (double)(2 * l - 1);
+                            for (int nt = 0; nt < NT; ++nt)
+                                dmma884(T[p][mt][nt][0], T[p][mt][nt][1], af[mt], bf[p][nt]);
+                };
+                double af[2], bf[2][NT];
+                accumulate();
+                load_frag(0, af, bf);
+                mma_frag(af, bf);
+                {   // advance the recurrence to degree l: h_l = (2l-1)/(kr) h_{l-1} - h_{l-2}
+                    const double cl = (double)(2 * l - 1);
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    const double ir = sm.invr[wm * 16 + mt * 8 + g];
+                    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                    for (int nt = 0; nt < 2; ++nt)
+                        for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            cplx h;
-                            if (l == 0) h = hm[mt][nt][e];
-                            else if (l == 1) h = hc[mt][nt][e];
-                            else {
-                                const double cf = cl * (sm.invk[wn * 16 + nt * 8 + 2 * t4 + e] * ir);
-                                h = cmake(fma(cf, hc[mt][nt][e].x, -hm[mt][nt][e].x),
-                                          fma(cf, hc[mt][nt][e].y, -hm[mt][nt][e].y));
+                            for (int e = 0; e < 2; ++e) {
+                                const double cf = cl * xinv[mt][nt][e];
+                                const cplx hn = cmake(fma(cf, hc[mt][nt][e].x, -hm[mt][nt][e].x),
+                                                      fma(cf, hc[mt][nt][e].y, -hm[mt][nt][e].y));
                                 hm[mt][nt][e] = hc[mt][nt][e];
-                                hc[mt][nt][e] = h;
+                                hc[mt][nt][e] = hn;
                             }
-                            cfma(Pp[mt][nt][e], h, cmake(T[0][mt][nt][e], T[1][mt][nt][e]));
-                            T[0][mt][nt][e] = 0.0; T[1][mt][nt][e] = 0.0;
-                        }
+                }
+                // remaining k-steps, two per trip with ping-pong fragment registers: the loads of one
+                // step are in flight while the other multiplies
+                if (ksn > 1) {
+                    double a2[2], b2[2][NT];
+                    load_frag(1, af, bf);
+                    int ks = 2;
+#pragma unroll 1
+                    for (; ks + 1 < ksn; ks += 2) {
+                        load_frag(ks, a2, b2);
+                        mma_frag(af, bf);
+                        load_frag(ks + 1, af, bf);
+                        mma_frag(a2, b2);
+                    }
+                    if (ks < ksn) {
+                        load_frag(ks, a2, b2);
+                        mma_frag(af, bf);
+                        mma_frag(a2, b2);
+                    } else {
+                        mma_frag(af, bf);
+                    }
                 }
             }
+            __syncwarp();
+            if (lane == 0 && atomicAdd(&sm.done[stage], 1) == NWARPS - 1) {
+                // last warp out of this stage: refill it with the chunk two ahead
+                sm.done[stage] = 0;
+                if (c + 2 < total) issue(pt, pl, stage);
+            }
+            ++c;
+            if (++pl == ncpt) { pl = 0; ++pt; }
         }
-        __syncthreads();   // stage released
-
-        if (local == a.ncpt - 1) {
+        accumulate();
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt)
+            for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e)
-                        cfma(P[nt][e], sm.fac[wm * 16 + mt * 8 + g][wn * 16 + nt * 8 + 2 * t4 + e],
-                             Pp[mt][nt][e]);
-            __syncthreads();   // fac and the per-image arrays are rewritten by the next tile
-        }
+                for (int e = 0; e < 2; ++e)
+                    cfma(P[nt][e], sm.fac[wm * 16 + mt * 8 + g][wn * 8 * NT + nt * 8 + 2 * t4 + e],
+                         Pp[mt][nt][e]);
+        __syncthreads();   // fac and the per-image arrays are rewritten by the next tile
     }
 
     __syncthreads();
-    double2 (*red)[ORG_TF] = reinterpret_cast<double2 (*)[ORG_TF]>(&sm.st[0]);
+    double2 (*red)[ORG_TF] = reinterpret_cast<double2 (*)[ORG_TF]>(&sm.fac[0][0]);
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
+    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) red[wm * 8 + g][wn * 16 + nt * 8 + 2 * t4 + e] = P[nt][e];
+        for (int e = 0; e < 2; ++e) red[wm * 8 + g][wn * 8 * NT + nt * 8 + 2 * t4 + e] = P[nt][e];
     __syncthreads();
     if (tid < ORG_TF) {
         cplx s = cmake(0.0, 0.0);
@@ -898,27 +954,27 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
 
     // ---- factorised path ----
     if (Lmax > ORG_LMAX) return set_error(DEISM_ERR_INVALID, "N+V+1 > %d", ORG_LMAX);
-    // plane geometry: rows(l) = roundup4(2l+1); chunks of <= ORG_RC rows
+    // plane geometry: rows(l) = roundup4(2l+1); chunks hold whole degrees, <= rc rows each
     int rowoff[ORG_LMAX + 1];
-    int2 chunks[ORG_MAXCHUNKS];
-    signed char ks_l[ORG_LMAX * ORG_LMAX];
-    int ncpt = 0, R_tot = 0;
+    int4 chunks[ORG_MAXCHUNKS];
+    int ncpt = 0, R_tot = 0, rc_rows = ORG_RC;
     for (int l = 0; l < Lmax; ++l) {
         rowoff[l] = R_tot;
         const int rows = (2 * l + 1 + 3) / 4 * 4;
-        for (int r0 = 0; r0 < rows; r0 += 4) ks_l[(R_tot + r0) >> 2] = (signed char)(r0 + 4 >= rows ? l : -1);
+        if (rows > rc_rows) rc_rows = rows;
         R_tot += rows;
     }
     rowoff[Lmax] = R_tot;
-    for (int r0 = 0; r0 < R_tot; r0 += ORG_RC) {
+    for (int l = 0; l < Lmax;) {
         if (ncpt >= ORG_MAXCHUNKS) return set_error(DEISM_ERR_INVALID, "too many (l,mu) chunks");
-        chunks[ncpt++] = make_int2(r0, R_tot - r0 < ORG_RC ? R_tot - r0 : ORG_RC);
+        int l1 = l + 1;
+        while (l1 < Lmax && rowoff[l1 + 1] - rowoff[l] <= rc_rows) ++l1;
+        chunks[ncpt++] = make_int4(rowoff[l], rowoff[l1] - rowoff[l], l, l1);
+        l = l1;
     }
     DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_org_rowoff, rowoff, (Lmax + 1) * sizeof(int), 0,
                                            cudaMemcpyHostToDevice, st));
-    DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_org_chunks, chunks, ncpt * sizeof(int2), 0,
-                                           cudaMemcpyHostToDevice, st));
-    DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_org_ks_l, ks_l, (size_t)(R_tot >> 2), 0,
+    DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_org_chunks, chunks, ncpt * sizeof(int4), 0,
                                            cudaMemcpyHostToDevice, st));
     DEISM_CUDA_TRY(cudaStreamSynchronize(st));   // stack tables consumed
 
@@ -976,15 +1032,18 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
     if (!partial) return DEISM_ERR_NOMEM;
 
     OrgConsumeArgs ca;
-    ca.K = K; ca.n_ftiles = n_ftiles; ca.Lmax = Lmax; ca.R_tot = R_tot; ca.ncpt = ncpt;
+    ca.K = K; ca.n_ftiles = n_ftiles; ca.Lmax = Lmax; ca.R_tot = R_tot; ca.ncpt = ncpt; ca.rc = rc_rows;
     ca.Bp = Bp; ca.Yp = Yp; ca.rec = rec; ca.meta = meta; ca.k = d_k; ca.mode = atten->mode;
     ca.atten = atten->d_atten; ca.Z = (const cplx *)atten->d_Z_S; ca.flags = flags;
     ca.tiles_per_chunk = tiles_per_chunk; ca.partial = partial;
+    const size_t consume_smem = sizeof(OrgSmem) + (size_t)2 * rc_rows * (2 * ORG_BS + ORG_OS) * 8;
+    if ((int)consume_smem > smem_optin_bytes())
+        return set_error(DEISM_ERR_INVALID, "ORG consume kernel needs %zu B of shared memory", consume_smem);
     DEISM_CUDA_TRY(cudaFuncSetAttribute(org_consume_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)sizeof(OrgSmem)));
+                                        (int)consume_smem));
     dim3 grid((unsigned)n_ftiles, (unsigned)n_chunks);
     prof_begin("org_consume", st);
-    org_consume_kernel<<<grid, ORG_THREADS, sizeof(OrgSmem), st>>>(ca);
+    org_consume_kernel<<<grid, ORG_THREADS, consume_smem, st>>>(ca);
     prof_end("org_consume", st);
     DEISM_LAUNCH_CHECK("org_consume_kernel");
     return launch_reduce_partials(partial, n_chunks, K, d_out, accumulate, st);
