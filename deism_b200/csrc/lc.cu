@@ -7,27 +7,25 @@
 //   S[img,k] = sum_j i^{n_j} C_s[k,j] Y_{n_j}^{m_j}(theta_s,phi_s)       (source->receiver image)
 //   R[img,k] = sum_j i^{v_j} C_r[k,j] Y_{v_j}^{u_j}(theta_r,phi_r)       (receiver->source image)
 //
-// S and R are dense complex contractions [I x J] . [J x K] whose [I x K] result must never reach
-// memory (22 GB for the order-40 / 16k-frequency config), so they are computed tile by tile on
-// the FP64 tensor cores and consumed in registers:
+// S and R are dense contractions [I x J] . [J x K] whose [I x K] result must never reach memory
+// (22 GB for the order-40 / 16k-frequency config), so they are computed tile by tile on the FP64
+// tensor cores and consumed in registers.  In the real-harmonic basis (LcBasis below) Y is REAL,
+// so each pass is two real GEMMs (Re and Im of the coefficients), issued as mma.sync m8n8k4 f64.
 //
-//   lc_prep_kernel   one thread per image: phase-folded harmonics Y'[img,j] (i^n folded in),
-//                    r, 1/r, direction cosines + wall exponents, flat-impedance attenuation.
-//   lc_coef_kernel   C[k,j] complex64 -> FP64 operand planes.
-//   lc_main_kernel   CTA tile = 64 images x 32 frequencies, 4 warps (16 images each).
-//                    The complex product uses the 3-multiplication form
-//                        T1 = Yr.Cr   T2 = Yi.Ci   T3 = (Yr+Yi).(Cr+Ci)
-//                        S = (T1 - T2) + i (T3 - T1 - T2)
-//                    i.e. three REAL GEMMs per pass, each issued as mma.sync m8n8k4 f64 (DMMA):
-//                    25 % fewer FP64 FMAs than the 4-multiplication form, error ~1e-16 relative.
-//                    Operand planes (Yr | Yi | Yr+Yi and Cr | Ci | Cr+Ci) are laid out in global
-//                    memory exactly as the kernel wants them in shared memory (row stride
-//                    = 4 mod 16 doubles -> conflict-free fragment loads), so one harmonic chunk of
-//                    one tile is ONE contiguous block staged by a single TMA bulk copy
-//                    (cp.async.bulk -> UBLKCP) per operand, double buffered on mbarriers.
-//                    Epilogue in registers: fac = -atten * 4pi/k^2/r * exp(-ikr) (computed per
-//                    tile before the contraction), S' = fac*S parked in shared memory, then
-//                    P[k] += S'*R accumulated over the CTA's image chunk.
+//   lc_prep_kernel   one thread per image: real harmonic rows y_q(img), r, 1/r, atten/r,
+//                    rotation steps exp(-i dk r), direction cosines + wall exponents.
+//   lc_coef_kernel   C[k,j] complex64 -> real-basis FP64 planes (Re | Im), i^n and (source pass)
+//                    -4pi/k^2 folded in.
+//   lc_main_kernel   <4,true>: CTA tile 64 images x 64 frequencies, 16 warps of 16x16; the
+//                    frequency tile's coefficient planes are resident in shared memory, Y rows
+//                    stream as whole-pass chunks through a TMA (cp.async.bulk -> UBLKCP) ring on
+//                    mbarriers, refilled by the last warp out of a stage; <2,false>: 64 x 32,
+//                    8 warps, C and Y both stream.  Operand rows are laid out in global memory as
+//                    the kernel wants them in shared memory (row stride = 4 mod 16 doubles ->
+//                    conflict-free fragment loads).  Per tile: fac = (atten/r) exp(-ikr) by one
+//                    sincos per image and a rotation recurrence (computed in the shadow of the
+//                    source pass's DMMAs), S' = fac*S parked thread-privately in shared memory,
+//                    P[k] += S'*R accumulated in registers over the CTA's image chunk.
 //   reduce_partials  deterministic sum of the per-chunk partials into out[K].
 #include "common.cuh"
 

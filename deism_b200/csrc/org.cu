@@ -19,8 +19,9 @@
 // Kernels:
 //   org_btable_kernel   B for the 8 parity classes (image independent)          [algo 1]
 //   org_sort/prep       images grouped by parity class, Y_l^mu(img) table, attenuation geometry
-//   org_consume_kernel  32 freq x 32 image CTA tile, 4x2 register tile; per l: a (2l+1)-long
-//                       complex contraction from shared memory, h_l recurrence in registers
+//   org_consume_kernel  32 freq x 32 image CTA tile on the FP64 tensor cores; per l: a (2l+1)-row
+//                       real x complex contraction (real-harmonic rows) from TMA-staged shared
+//                       memory, h_l recurrence in registers
 //   org_direct_kernel   the quintuple sum done per (image, frequency) pair with per-image
 //                       source coefficients: the ARG form (pb:388-460) and the shoebox
 //                       cross-check [algo 2]
