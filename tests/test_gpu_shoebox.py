@@ -111,6 +111,41 @@ def test_lc_vs_oracle_random_inputs():
         assert rel_l2(got, want) < RTF_TOL, (I, K, N, V)
 
 
+def test_lc_arbitrary_harmonic_lists():
+    """The LC entry point takes ANY (n_all, m_all) / (v_all, u_all) lists (pb:264-325 just loops
+    over them): shuffled order, missing +-m partners, only negative m, repeated entries.  The
+    kernels regroup them into real harmonics; the result must not depend on that."""
+    from deism_b200 import backend
+    from oracle import oracle
+
+    rng = np.random.default_rng(11)
+    I, K = 150, 70
+    cases = [
+        ([(0, 0)], [(3, -2)]),                                          # single terms
+        ([(2, -2), (2, -1), (1, -1)], [(4, 3), (4, -3), (0, 0)]),          # only negative m / a +-pair
+        ([(n, m) for n in range(4) for m in range(-n, n + 1)][::-1],      # complete, reversed
+         [(n, m) for n in range(3) for m in range(-n, n + 1) if m >= 0]), # m >= 0 only
+        ([(1, 1), (1, 1), (1, -1), (2, 0), (1, 1)], [(2, 1), (5, -4), (2, 1)]),   # duplicates
+        (list(map(tuple, rng.permutation([(n, m) for n in range(6) for m in range(-n, n + 1)])[:23])),
+         list(map(tuple, rng.permutation([(n, m) for n in range(5) for m in range(-n, n + 1)])[:17]))),
+    ]
+    R = lambda: np.stack([rng.uniform(-np.pi, np.pi, I), rng.uniform(0.05, 3.0, I),
+                          rng.uniform(0.5, 300.0, I)], axis=1).astype(np.float32)
+    for src, rec in cases:
+        cplx = lambda J: (rng.standard_normal((K, J)) + 1j * rng.standard_normal((K, J))).astype(np.complex64)
+        atten = (rng.standard_normal((I, K)) + 1j * rng.standard_normal((I, K))).astype(np.complex64)
+        params = {"DEISM_method": "LC", "waveNumbers": np.linspace(0.3, 350.0, K),
+                  "n_all": np.array([a for a, _ in src]), "m_all": np.array([b for _, b in src]),
+                  "v_all": np.array([a for a, _ in rec]), "u_all": np.array([b for _, b in rec]),
+                  "C_nm_s_vec": cplx(len(src)), "C_vu_r_vec": cplx(len(rec)), "silentMode": 1,
+                  "angDepFlag": 1, "numParaImages": 64,
+                  "images": {"A": np.zeros((I, 6), np.int32), "R_sI_r_all": R(), "R_s_rI_all": R(),
+                             "R_r_sI_all": R(), "atten_all": atten}}
+        want = oracle.run_DEISM(params)
+        got = backend.run_DEISM(params)
+        assert rel_l2(got, want) < RTF_TOL, (src, rec)
+
+
 def test_zero_images_gives_zeros():
     from deism_b200 import backend
 
