@@ -5,9 +5,15 @@ contract as the reference:
     monopole branches of init_{source,receiver}_directivities[_ARG] ~ core_deism.py:1254-1263,
                                                        1323-1338, 1623-1640, 1730-1745
 
+    cal_C_nm_s_new (+ SHCs_from_pressure_LS, vectorize_C_nm_s_ARG fused)   ~ core_deism.py:1545-1605,
+                                                       1481-1509, 1193-1217   [GPU: deism_arg_refit]
+    rotation_matrix_ZXZ                                                  ~ shared_utils.py:9-26
+
 Sampled (non-monopole) directivities need the .mat data sets that are absent from the reference
-tree (.MISSING_LARGE_BLOBS); callers inject ``C_nm_s`` / ``C_vu_r`` (complex64 [K, N+1, 2N+1],
-signed m indexed NumPy-style) and call the vectorisers.
+tree (.MISSING_LARGE_BLOBS); shoebox callers inject ``C_nm_s`` / ``C_vu_r`` (complex64
+[K, N+1, 2N+1], signed m indexed NumPy-style) and call the vectorisers; convex (ARG) callers inject
+the sampled field as ``params["sampledSource"] = {"freqs", "Psh", "Dir_all", "r0"}`` (what
+``load_directive_pressure`` returns, data_loader.py:1099-1145).
 """
 from __future__ import annotations
 
@@ -80,9 +86,90 @@ def init_receiver_directivities(params):
     return params
 
 
+def rotation_matrix_ZXZ(alpha, beta, gamma):
+    """COMSOL's Z-X-Z Euler rotation (shared_utils.py:9-26)."""
+    ca, sa, cb, sb, cg, sg = np.cos(alpha), np.sin(alpha), np.cos(beta), np.sin(beta), np.cos(gamma), np.sin(gamma)
+    return np.array([[ca * cg - sa * cb * sg, -ca * sg - sa * cb * cg, sb * sa],
+                     [sa * cg + ca * cb * sg, -sa * sg + ca * cb * cg, -sb * ca],
+                     [sb * sg, sb * cg, cb]])
+
+
+def cal_C_nm_s_ARG_vec_device(reflection_matrix, Psh_source, src_Psh_coords, params, device=None):
+    """Reflected source directivity coefficients of every image, vectorised: complex64 torch tensor
+    [K, (N+1)^2, I] on the GPU (= ``C_nm_s_ARG_vec`` of cd:1193-1217 fed by cd:1545-1605).
+
+    reflection_matrix: [3, 3, I] (reference layout) or a torch/NumPy [I, 3, 3] float32 array;
+    Psh_source: [>=K, n_dir] complex; src_Psh_coords: [3, n_dir] Cartesian sampling points."""
+    import ctypes as C
+
+    import torch
+
+    from . import _lib
+    from .backend import to_device
+
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    k = np.asarray(params["waveNumbers"], dtype=np.float64)
+    K, N = int(k.size), int(params["sourceOrder"])
+    # [3, 3, I] is the reference's layout (also assumed for the ambiguous 3 x 3 x 3); [I, 3, 3] the engine's
+    R = reflection_matrix
+    engine_layout = tuple(R.shape[-2:]) == (3, 3) and R.shape[0] != 3
+    if isinstance(R, torch.Tensor):
+        R = R.to(dev, torch.float32)
+        R = R if engine_layout else R.permute(2, 0, 1)
+    else:
+        R = np.asarray(R, dtype=np.float32)
+        R = to_device(np.ascontiguousarray(R if engine_layout else np.transpose(R, (2, 0, 1))), torch.float32, dev)
+    R = R.contiguous()
+    n_img = int(R.shape[0])
+    X = to_device(np.ascontiguousarray(np.asarray(src_Psh_coords, dtype=np.float64)), torch.float64, dev)
+    n_dir = int(X.shape[1])
+    P = np.asarray(Psh_source)[:K, :] if not isinstance(Psh_source, torch.Tensor) else Psh_source[:K, :]
+    if tuple(P.shape) != (K, n_dir):
+        raise ValueError(f"Psh_source must provide [{K}, {n_dir}] samples, got {tuple(P.shape)}")
+    P = to_device(np.ascontiguousarray(P, dtype=np.complex128) if not isinstance(P, torch.Tensor) else P,
+                  torch.complex128, dev).contiguous()
+    kd = to_device(k, torch.float64, dev)
+    out = torch.empty((K, (N + 1) ** 2, n_img), dtype=torch.complex64, device=dev)
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.lib().deism_arg_refit(n_img, K, N, n_dir, R.data_ptr(), X.data_ptr(), P.data_ptr(),
+                                             kd.data_ptr(), float(params["radiusSource"]), out.data_ptr(),
+                                             C.c_void_p(st)), "deism_arg_refit")
+    return out
+
+
+def cal_C_nm_s_new(reflection_matrix, Psh_source, src_Psh_coords, params):
+    """cd:1545-1605 with the reference's output layout [K, N+1, 2N+1, I] (signed m wraps NumPy-style).
+    Values are the complex64 the reference rounds to right after the call (cd:1708)."""
+    vec = cal_C_nm_s_ARG_vec_device(reflection_matrix, Psh_source, src_Psh_coords, params).cpu().numpy()
+    N = int(params["sourceOrder"])
+    out = np.zeros((vec.shape[0], N + 1, 2 * N + 1, vec.shape[2]), dtype=np.complex64)
+    for n in range(N + 1):
+        for m in range(-n, n + 1):
+            out[:, n, m, :] = vec[:, n * n + n + m, :]
+    return out
+
+
 def init_source_directivities_ARG(params):
     if params["sourceType"] != "monopole":
-        raise NotImplementedError("sampled source directivities need the absent .mat data")
+        # cd:1641-1712: sampled field -> rotated sampling points -> per-image refit (on the GPU)
+        smp = params.get("sampledSource")
+        if smp is None:
+            raise FileNotFoundError("sampled source directivities: the .mat data sets are absent from the "
+                                    "reference tree; provide params['sampledSource']")
+        if not np.allclose(smp["freqs"], params["freqs"]):
+            raise ValueError("The frequencies in the directivity data are not the same as the ones "
+                             "defined in params['freqs']")
+        Dir = np.asarray(smp["Dir_all"], dtype=np.float64)
+        el = np.pi / 2 - Dir[:, 1]
+        xyz = np.vstack((np.cos(el) * np.cos(Dir[:, 0]), np.cos(el) * np.sin(Dir[:, 0]), np.sin(el)))
+        Rm = rotation_matrix_ZXZ(*[float(a) for a in params["orientSource"][:3]])
+        if params.get("ifRotateRoom") == 1:
+            rr = np.asarray(params["roomRotation"], dtype=np.float64) * np.pi / 180
+            Rm = rotation_matrix_ZXZ(rr[0], rr[1], rr[2]) @ Rm
+        params["C_nm_s_ARG"] = cal_C_nm_s_new(params["reflection_matrix"], smp["Psh"], Rm @ xyz, params)
+        _track(params, ("C_nm_s_ARG",), "init_source_directivities")
+        return params
     n_img = params["reflection_matrix"].shape[2]
     c = _monopole(params["waveNumbers"])[..., None, None, None].astype(np.complex64)
     params["C_nm_s_ARG"] = c * np.ones((1, 1, 1, n_img)).astype(np.complex64)

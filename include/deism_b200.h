@@ -212,6 +212,24 @@ DEISM_API int deism_convex_images_fill(const deism_convex_walls *walls, int64_t 
                                        float *d_attenuations, float *d_reflection, void *stream);
 
 /* ------------------------------------------------------------------------------------ */
+/* (4b) DEISM-ARG source directivity of every image source                    */
+/* ------------------------------------------------------------------------------------ */
+/* Replaces cal_C_nm_s_new (deism/core_deism.py:1545-1605), its per-image least-squares fit
+ * SHCs_from_pressure_LS (core_deism.py:1481-1509) and vectorize_C_nm_s_ARG
+ * (core_deism.py:1193-1217).  For every image the sampling directions are mirrored by the
+ * image's reflection matrix, order-N spherical-harmonic coefficients are fitted to the sampled
+ * pressures and divided by h_n^(2)(k r0).
+ *   d_reflection : float32[I,3,3]  (deism_convex_images_fill's d_reflection)
+ *   d_coords     : float64[3,n_dir] Cartesian sampling directions (already rotated, cd:1676-1699)
+ *   d_Psh        : complex128[K,n_dir] sampled pressures
+ *   d_C_vec      : out, complex64[K,(N+1)^2,I], image index innermost (= C_nm_s_ARG_vec)
+ * N <= 7.  DEISM_ERR_INVALID if the directions do not determine the fit. */
+DEISM_API int deism_arg_refit(int64_t n_images, int64_t K, int N, int64_t n_dir,
+                              const float *d_reflection, const double *d_coords,
+                              const double *d_Psh, const double *d_k, double r0, float *d_C_vec,
+                              void *stream);
+
+/* ------------------------------------------------------------------------------------ */
 /* (5) Micro-benchmarks used by bench.py to measure the FP64 roofline denominators         */
 /* ------------------------------------------------------------------------------------ */
 /* Runs a register-resident DFMA (kind 0) or DMMA m8n8k4 (kind 1) loop on every SM and returns

@@ -335,13 +335,48 @@ def augment_full():
         print("  augmented", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def refit_case(name="r1_arg_refit_N3", n_img=40, N=3, n_dir=50, seed=3):
+    """the reference's cal_C_nm_s_new (cd:1545-1605) + vectorize_C_nm_s_ARG
+    (cd:1193-1217) on the reflection matrices of the x2 convex fixture and a synthetic sampled
+    source field (the directivity .mat data sets are absent from the reference tree)."""
+    ref_import.import_reference()
+    from deism.core_deism import cal_C_nm_s_new, vectorize_C_nm_s_ARG
+
+    x2 = np.load(os.path.join(GOLDEN, "x2_convex_rir_lc_o5_N2.npz"), allow_pickle=True)
+    rng = np.random.default_rng(seed)
+    R = np.ascontiguousarray(x2["params/reflection_matrix"][:, :, :n_img])
+    k, freqs = x2["params/waveNumbers"], x2["params/freqs"]
+    # quasi-uniform sampling sphere (Fibonacci lattice), rotated by a fixed ZXZ rotation
+    i = np.arange(n_dir) + 0.5
+    pol, az = np.arccos(1 - 2 * i / n_dir), np.pi * (1 + 5 ** 0.5) * i
+    X = np.vstack((np.sin(pol) * np.cos(az), np.sin(pol) * np.sin(az), np.cos(pol)))
+    from deism.core_deism import rotation_matrix_ZXZ
+    X = rotation_matrix_ZXZ(0.3, 0.9, -1.1) @ X
+    Psh = rng.standard_normal((len(k), n_dir)) + 1j * rng.standard_normal((len(k), n_dir))
+    params = {"waveNumbers": k, "sourceOrder": N, "radiusSource": 0.4, "freqs": freqs,
+              "track_updated_where": False}
+    C4 = cal_C_nm_s_new(R, Psh, X, params)
+    params["C_nm_s_ARG"] = C4.astype(np.complex64)                      # cd:1708
+    params["images"] = {"R_sI_r_all": np.zeros((3, n_img), np.float32)}
+    params = vectorize_C_nm_s_ARG(params)
+    path = os.path.join(GOLDEN, name + ".npz")
+    np.savez_compressed(path, reflection_matrix=R, waveNumbers=k, freqs=freqs, coords=X, Psh=Psh,
+                        radiusSource=0.4, sourceOrder=N, C_nm_s_ARG=params["C_nm_s_ARG"],
+                        C_nm_s_ARG_vec=params["C_nm_s_ARG_vec"])
+    print("  wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", nargs="*", default=None,
                     help="full-size configs to mint (c1 c2 c3 c4 c5); no value = all")
     ap.add_argument("--skip-small", action="store_true")
     ap.add_argument("--augment", action="store_true")
+    ap.add_argument("--refit", action="store_true", help="mint only the ARG refit fixture (f2)")
     args = ap.parse_args()
+    if args.refit:
+        refit_case()
+        sys.exit(0)
     if args.augment:
         augment_full()
         sys.exit(0)

@@ -524,3 +524,41 @@ def cosf(x):
     L = lib()
     L.oracle_cosf.restype = C.c_float
     return float(L.oracle_cosf(C.c_float(x)))
+
+
+# ------------------------------------------------------------------------------------------
+# ARG source directivity refit per image (NumPy restatement; test infrastructure)
+# ------------------------------------------------------------------------------------------
+def SHCs_from_pressure_LS(Psh, Dir_all, order):
+    """core_deism.py:1481-1509: fnm = pinv(Y) @ Psh.T with Y[s, n^2+n+m] = Y_n^m(az_s, polar_s).
+    Returns fnm [J, K] (the reference reshapes it to [K, n, m+n])."""
+    from scipy import special as sps
+
+    J = (order + 1) ** 2
+    Y = np.zeros((len(Dir_all), J), dtype=complex)
+    for n in range(order + 1):
+        for m in range(-n, n + 1):
+            Y[:, n * n + n + m] = sps.sph_harm_y(n, m, Dir_all[:, 1], Dir_all[:, 0])
+    return np.linalg.pinv(Y) @ np.asarray(Psh).T
+
+
+def cal_C_nm_s_ARG_vec(reflection_matrix, Psh_source, src_Psh_coords, k, order, r0):
+    """core_deism.py:1545-1605 followed by 1193-1217: complex64 [K, J, I].
+    reflection_matrix [3, 3, I]; Psh_source [K, n_dir]; src_Psh_coords [3, n_dir]."""
+    from scipy import special as sps
+
+    k = np.asarray(k, dtype=np.float64)
+    n_img = reflection_matrix.shape[2]
+    J = (order + 1) ** 2
+    out = np.zeros((k.size, J, n_img), dtype=complex)
+    hn = np.stack([sps.spherical_jn(n, k * r0) - 1j * sps.spherical_yn(n, k * r0) for n in range(order + 1)])
+    for i in range(n_img):
+        xyz = reflection_matrix[:, :, i] @ src_Psh_coords                    # cd:1577
+        hxy = np.hypot(xyz[0], xyz[1])
+        az, el = np.arctan2(xyz[1], xyz[0]), np.arctan2(xyz[2], hxy)         # utilities.py:95-102
+        fnm = SHCs_from_pressure_LS(Psh_source[: k.size], np.stack((az, np.pi / 2 - el), axis=1), order)
+        for n in range(order + 1):
+            for m in range(-n, n + 1):
+                j = n * n + n + m
+                out[:, j, i] = fnm[j] / hn[n]                                 # cd:1597-1604
+    return out.astype(np.complex64)

@@ -38,3 +38,42 @@ def test_vectoriser_arg_and_monopoles():
     assert np.array_equal(q["C_nm_s_ARG"], x["C_nm_s_ARG"])
     with pytest.raises(NotImplementedError):
         D.init_source_directivities({"sourceType": "speaker_cuboid_cyldriver_1", "waveNumbers": [1.0]})
+
+
+def _refit_fixture():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "r1_arg_refit_N3.npz"))
+
+
+def test_refit_oracle_matches_reference_fixture():
+    """the NumPy restatement of cal_C_nm_s_new + vectorize_C_nm_s_ARG reproduces the
+    reference's complex64 output (identical up to rounding flips of values that agree to ~1e-13)."""
+    from oracle import oracle
+
+    f = _refit_fixture()
+    got = oracle.cal_C_nm_s_ARG_vec(f["reflection_matrix"], f["Psh"], f["coords"], f["waveNumbers"],
+                                    int(f["sourceOrder"]), float(f["radiusSource"]))
+    want = f["C_nm_s_ARG_vec"]
+    assert got.shape == want.shape and got.dtype == want.dtype == np.complex64
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-8
+    assert np.mean(got != want) < 1e-3
+    # the 4-D layout the reference keeps next to it: signed m wraps NumPy-style
+    N = int(f["sourceOrder"])
+    for n in range(N + 1):
+        for m in range(-n, n + 1):
+            assert np.array_equal(f["C_nm_s_ARG"][:, n, m, :], want[:, n * n + n + m, :])
+
+
+def test_rotation_matrix_zxz():
+    from deism_b200 import directivities as D
+
+    R = D.rotation_matrix_ZXZ(0.3, 0.9, -1.1)
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-15) and np.isclose(np.linalg.det(R), 1.0)
+    assert np.allclose(D.rotation_matrix_ZXZ(0.0, 0.0, 0.0), np.eye(3))
+    # the fixture's sampling points were rotated with the reference's own implementation
+    f = _refit_fixture()
+    n_dir = f["coords"].shape[1]
+    i = np.arange(n_dir) + 0.5
+    pol, az = np.arccos(1 - 2 * i / n_dir), np.pi * (1 + 5 ** 0.5) * i
+    X = np.vstack((np.sin(pol) * np.cos(az), np.sin(pol) * np.sin(az), np.cos(pol)))
+    assert np.allclose(R @ X, f["coords"], atol=1e-15)

@@ -88,3 +88,69 @@ def test_convex_end_to_end_monopole(name):
     err = rel_l2(got, g.rtf)
     print(f"{name}: convex end-to-end rel L2 = {err:.3e}")
     assert err < RTF_TOL
+
+
+def _c64_close(got, want):
+    """complex64 arrays computed from values that agree to ~1e-13: equal up to rare 1-ulp flips."""
+    assert got.shape == want.shape and got.dtype == want.dtype == np.complex64
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-8
+    assert np.mean(got != want) < 2e-3
+    assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-30)) < 3e-7
+
+
+def test_arg_refit_reference_fixture():
+    """deism_arg_refit against the reference's cal_C_nm_s_new + vectorize_C_nm_s_ARG."""
+    import os
+
+    from deism_b200 import directivities as D
+
+    f = np.load(os.path.join(os.path.dirname(__file__), "golden", "r1_arg_refit_N3.npz"))
+    params = {"waveNumbers": f["waveNumbers"], "sourceOrder": int(f["sourceOrder"]),
+              "radiusSource": float(f["radiusSource"]), "freqs": f["freqs"]}
+    got = D.cal_C_nm_s_ARG_vec_device(f["reflection_matrix"], f["Psh"], f["coords"], params).cpu().numpy()
+    _c64_close(got, f["C_nm_s_ARG_vec"])
+    # engine layout [I,3,3] gives the same, and the 4-D mirror matches the reference's array
+    got2 = D.cal_C_nm_s_ARG_vec_device(np.ascontiguousarray(np.transpose(f["reflection_matrix"], (2, 0, 1))),
+                                       f["Psh"], f["coords"], params).cpu().numpy()
+    assert np.array_equal(got, got2)
+    _c64_close(D.cal_C_nm_s_new(f["reflection_matrix"], f["Psh"], f["coords"], params), f["C_nm_s_ARG"])
+
+
+@pytest.mark.parametrize("I,K,N,n_dir", [(1, 1, 0, 1), (5, 3, 1, 4), (130, 37, 2, 31), (77, 20, 5, 200),
+                                         (9, 33, 7, 150)])
+def test_arg_refit_vs_oracle(I, K, N, n_dir):
+    """Ragged sizes, orders 0..7, proper and improper orthogonal matrices (float32), against the
+    NumPy restatement (pinv per image)."""
+    from deism_b200 import directivities as D
+    from oracle import oracle
+
+    rng = np.random.default_rng(100 + I)
+    Q = np.linalg.qr(rng.standard_normal((I, 3, 3)))[0]
+    Q[::2] *= -1.0                                                   # mix reflections and rotations
+    R = np.ascontiguousarray(np.transpose(Q, (1, 2, 0)).astype(np.float32))
+    X = rng.standard_normal((3, n_dir))
+    X /= np.linalg.norm(X, axis=0)
+    if n_dir == 1:
+        X[:] = [[0.3], [0.4], [0.5]]
+    Psh = rng.standard_normal((K, n_dir)) + 1j * rng.standard_normal((K, n_dir))
+    k = np.sort(rng.uniform(0.05, 300.0, K))
+    params = {"waveNumbers": k, "sourceOrder": N, "radiusSource": 0.35}
+    got = D.cal_C_nm_s_ARG_vec_device(R, Psh, X, params).cpu().numpy()
+    want = oracle.cal_C_nm_s_ARG_vec(R, Psh, X, k, N, 0.35)
+    _c64_close(got, want)
+
+
+def test_arg_refit_errors():
+    from deism_b200 import directivities as D
+
+    X = np.random.default_rng(0).standard_normal((3, 10))
+    P = np.ones((2, 10), complex)
+    base = {"waveNumbers": np.array([1.0, 2.0]), "radiusSource": 0.4}
+    with pytest.raises(ValueError):          # 10 directions cannot determine 16 coefficients
+        D.cal_C_nm_s_ARG_vec_device(np.eye(3, dtype=np.float32)[None], P, X, dict(base, sourceOrder=3))
+    with pytest.raises(ValueError):          # order above the kernel's budget
+        D.cal_C_nm_s_ARG_vec_device(np.eye(3, dtype=np.float32)[None], np.ones((2, 100), complex),
+                                    np.random.default_rng(0).standard_normal((3, 100)), dict(base, sourceOrder=8))
+    with pytest.raises(ValueError):          # all directions identical: rank-deficient fit
+        D.cal_C_nm_s_ARG_vec_device(np.eye(3, dtype=np.float32)[None], P, np.tile([[0.], [0.], [1.]], (1, 10)),
+                                    dict(base, sourceOrder=1))
