@@ -75,6 +75,7 @@ _SIGNATURES = {
     "deism_org_arg": (C.c_int, [_i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _i64, _vp, _i32, _vp, _vp]),
     "deism_wigner_tables": (C.c_int, [_i32, _i32, _vp, _vp]),
+    "deism_pchip_interp": (C.c_int, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
     "deism_arg_refit": (C.c_int, [_i64, _i64, _i32, _i64, _vp, _vp, _vp, _vp, C.c_double, _vp, _vp]),
     "deism_convex_images_count": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "deism_convex_images_fill": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -9,6 +9,8 @@ After that the UNMODIFIED reference class ``deism.core_deism.DEISM`` drives this
   * ``deism.core_deism.pre_calc_images_src_rec_optimized_nofs_v2_numba`` / ``merge_images``
     (core_deism.py:136-139, 161-162)                       -> deism_b200.images
   * ``deism.core_deism.pre_calc_Wigner`` (core_deism.py:490) -> deism_b200.wigner
+  * ``deism.core_deism.cal_C_nm_s_new`` (called by init_source_directivities_ARG,
+    core_deism.py:1702)                                    -> deism_b200.directivities
   * ``deism.core_deism_arg.Room_deism_cpp._init_room``'s engine (core_deism_arg.py:906-933)
                                                            -> deism_b200.convex.Room_deism
 
@@ -19,7 +21,7 @@ from __future__ import annotations
 _saved = {}
 
 
-def install(images: bool = True, wigner: bool = True, convex: bool = True):
+def install(images: bool = True, wigner: bool = True, convex: bool = True, directivities: bool = True):
     import deism.core_deism as cd
     import deism.parallel_backends as pb
 
@@ -37,6 +39,10 @@ def install(images: bool = True, wigner: bool = True, convex: bool = True):
         swap(cd, "merge_images", gimages.merge_images)
     if wigner:
         swap(cd, "pre_calc_Wigner", gwigner.pre_calc_Wigner)
+    if directivities:
+        from . import directivities as gdir
+
+        swap(cd, "cal_C_nm_s_new", gdir.cal_C_nm_s_new)
     if convex:
         import deism.core_deism_arg as cda
 

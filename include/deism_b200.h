@@ -230,6 +230,17 @@ DEISM_API int deism_arg_refit(int64_t n_images, int64_t K, int N, int64_t n_dir,
                               void *stream);
 
 /* ------------------------------------------------------------------------------------ */
+/* (4c) Wall material data on the dense frequency grid                        */
+/* ------------------------------------------------------------------------------------ */
+/* Replaces interpolate_functions (deism/core_deism.py:1126-1163): PCHIP interpolation of the real
+ * and imaginary parts of d_data complex128[rows, n_bands] (sampled at d_sparse_freqs, strictly
+ * increasing) at d_dense_freqs[K], end values held outside the band, a single band broadcast.
+ * d_out: complex128[rows, K] — e.g. the Z_S[6, K] of deism_shoebox_atten.  n_bands <= 64. */
+DEISM_API int deism_pchip_interp(int rows, int n_bands, int64_t K, const double *d_sparse_freqs,
+                                 const double *d_data, const double *d_dense_freqs, double *d_out,
+                                 void *stream);
+
+/* ------------------------------------------------------------------------------------ */
 /* (5) Micro-benchmarks used by bench.py to measure the FP64 roofline denominators         */
 /* ------------------------------------------------------------------------------------ */
 /* Runs a register-resident DFMA (kind 0) or DMMA m8n8k4 (kind 1) loop on every SM and returns

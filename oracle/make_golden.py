@@ -366,6 +366,45 @@ def refit_case(name="r1_arg_refit_N3", n_img=40, N=3, n_dir=50, seed=3):
     print("  wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def materials_case(name="m1_materials"):
+    """the reference's material conversions (cd:807-1123) and interpolate_functions
+    (cd:1126-1163) on a 4 x 3 x 2.5 m room."""
+    ref_import.import_reference()
+    from deism.core_deism import convert_imp_abs_t60_shoebox, interpolate_functions
+
+    rng = np.random.default_rng(5)
+    V, A, c = 30.0, np.array([7.5, 7.5, 10.0, 10.0, 12.0, 12.0]), 343.0
+    out = {"V": V, "A": A, "c": c}
+    Z = (rng.uniform(5, 40, (6, 3)) + 1j * rng.uniform(-8, 8, (6, 3)))
+    out["imp_in"] = Z
+    i, a, t = convert_imp_abs_t60_shoebox(V, A, c, Z, "impedance")
+    out["imp_abs"], out["imp_t60"] = a, t
+    absn = np.tile(np.array([0.6, 0.69, 0.71, 0.7, 0.63]), (6, 1)) * rng.uniform(0.5, 1.0, (6, 1))
+    out["abs_in"] = absn
+    i, a, t = convert_imp_abs_t60_shoebox(V, A, c, absn, "absorption")
+    out["abs_imp"], out["abs_t60"] = i, t
+    for key, T in (("t1", 1.0 / 3.0), ("t2", 2.0 / 3.0), ("t3", 0.184515)):
+        i, a, t = convert_imp_abs_t60_shoebox(V, A, c, T, "reverberationTime")
+        out[key + "_in"], out[key + "_imp"], out[key + "_abs"] = T, i, a
+    dense = np.concatenate(([2.0, 100.0], np.linspace(125.0, 4000.0, 57), [4000.0, 6000.0, 24000.0]))
+    out["dense"] = dense
+    for key, bands, data in (
+            ("i3", np.array([250.0, 1000.0, 4000.0]), Z),
+            ("i5", np.array([125.0, 250.0, 500.0, 1000.0, 2000.0]), absn.astype(complex)),
+            ("i2", np.array([500.0, 2000.0]), Z[:, :2]),
+            ("i1", np.array([1000.0]), Z[:, :1]),
+            ("i7", np.array([125.0, 250.0, 500.0, 1000.0, 2000.0, 3000.0, 4000.0]),
+             np.array([[1, 1, 2, 2, 1.5, 3, 3], [5, 4, 3, 2, 1, 0, -1], [0, 0, 0, 1, 0, 0, 0],
+                       [1, -1, 1, -1, 1, -1, 1]], dtype=float)
+             + 1j * np.array([[0, 1, 0, 2, 0, 3, 0], [1, 1, 1, 1, 1, 1, 1], [3, 2, 2, 2, 5, 5, 9],
+                              [0, 0.1, 0.4, 0.9, 1.6, 2.5, 3.6]]))):
+        out[key + "_bands"], out[key + "_data"] = bands, data
+        out[key + "_out"] = interpolate_functions(data, bands, dense)
+    path = os.path.join(GOLDEN, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("  wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", nargs="*", default=None,
@@ -373,9 +412,13 @@ if __name__ == "__main__":
     ap.add_argument("--skip-small", action="store_true")
     ap.add_argument("--augment", action="store_true")
     ap.add_argument("--refit", action="store_true", help="mint only the ARG refit fixture (f2)")
+    ap.add_argument("--materials", action="store_true", help="mint only the materials fixture (f4)")
     args = ap.parse_args()
     if args.refit:
         refit_case()
+        sys.exit(0)
+    if args.materials:
+        materials_case()
         sys.exit(0)
     if args.augment:
         augment_full()

@@ -16,7 +16,8 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 n_dir = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 cpu_images = int(sys.argv[3]) if len(sys.argv) > 3 else 6
 g = Golden("c4_full"); p = g.params()
-R = np.asarray(p["reflection_matrix"], np.float32)          # [3,3,I]
+raw = np.load(os.path.join(ROOT, "tests", "golden", "c4_full.npz"), allow_pickle=True)
+R = np.ascontiguousarray(np.transpose(raw["engine/reflection_matrix"], (1, 2, 0)).astype(np.float32))  # [3,3,I]
 k = np.asarray(p["waveNumbers"]); K, I = k.size, R.shape[2]
 rng = np.random.default_rng(0)
 i = np.arange(n_dir) + 0.5

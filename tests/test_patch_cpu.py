@@ -21,7 +21,7 @@ def test_install_swaps_plug_points_and_routes_calls():
     orig = (pb.run_DEISM, cd.pre_calc_Wigner)
     names = patch.install()
     try:
-        assert {"run_DEISM", "run_DEISM_ARG", "pre_calc_Wigner", "merge_images", "_init_room",
+        assert {"run_DEISM", "run_DEISM_ARG", "pre_calc_Wigner", "merge_images", "_init_room", "cal_C_nm_s_new",
                 "pre_calc_images_src_rec_optimized_nofs_v2_numba"} <= set(names)
         assert pb.run_DEISM is backend.run_DEISM and pb.run_DEISM_ARG is backend.run_DEISM_ARG
         assert cd.pre_calc_Wigner is wigner.pre_calc_Wigner
