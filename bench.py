@@ -339,6 +339,7 @@ def main():
         if n.value:
             prof[name] = (ms.value, n.value)
     lib.deism_profile_enable(0)
+    kernel_ms = {name: round(ms / n, 4) for name, (ms, n) in prof.items()}
     dev_ms = max_over_ranks(dev_ms)
     ms_per_step = dev_ms / steps
 
@@ -432,6 +433,7 @@ def main():
             "parity_rel_l2_vs_reference": parity,
             "parity_worst_single_frequency": parity_worst,
             "wall_ms_incl_l2_flush": wall_ms,
+            "kernel_ms_per_launch": kernel_ms,
             "extras": extras,
         }
         print(json.dumps(line))

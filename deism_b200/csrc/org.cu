@@ -112,15 +112,15 @@ static void build_lists(int N, int V, const float *W1, const float *W2, OrgLists
 }
 
 // ---------------------------------------------------------------------------------------
-// coefficient transposes: complex64 [K][J] -> complex128 [J][K]
+// coefficient transposes: complex64 [K][J] -> complex64 [J][K] (the B-table build streams them
+// once per coupling entry: keeping them at 8 bytes halves its L2 traffic)
 // ---------------------------------------------------------------------------------------
-__global__ void transpose_c64_kernel(const float2 *__restrict__ in, long K, int J, cplx *out) {
+__global__ void transpose_c64_kernel(const float2 *__restrict__ in, long K, int J, float2 *out) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= K * J) return;
     long k = i / J;
     int j = (int)(i % J);
-    float2 v = in[i];
-    out[(long)j * K + k] = cmake((double)v.x, (double)v.y);
+    out[(long)j * K + k] = in[i];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -157,7 +157,7 @@ struct BtableArgs {
     int nseg, R_tot;
     const OrgEntry *ent[2];
     const int *seg[2];
-    const cplx *CsT, *CrT;   // [nm][K]
+    const float2 *CsT, *CrT; // [nm][K] complex64
     const double *k;
     double *Bp;
 };
@@ -181,15 +181,20 @@ __global__ void __launch_bounds__(128) org_btable_kernel(BtableArgs a) {
         if (sg == 1 && am == 0) break;
         const int s = l * l + l + (sg ? -am : am);
         const int lo = segp[s], hi = segp[s + 1];
+#pragma unroll 4
         for (int j = lo; j < hi; ++j) {
             OrgEntryReg e = load_entry(ent + j);
-            cplx d = cmul(a.CsT[(long)e.idx_s * a.K + k], a.CrT[(long)e.idx_r * a.K + k]);
-            const double gx = e.G * d.x, gy = e.G * d.y;
+            const float2 cs = __ldg(&a.CsT[(long)e.idx_s * a.K + k]), cr = __ldg(&a.CrT[(long)e.idx_r * a.K + k]);
+            cplx d = cmul(cmake((double)cs.x, (double)cs.y), cmake((double)cr.x, (double)cr.y));
+            // mirror variants v = 2*b + c carry the sign (-1)^{b m + c n}: flip G's sign bit
+            const int ghi = __double2hiint(e.G), glo = __double2loint(e.G);
+            const int sn = (e.n & 1) << 31, sm_ = (e.m & 1) << 31;
+            const double Gv[4] = {e.G, __hiloint2double(ghi ^ sn, glo), __hiloint2double(ghi ^ sm_, glo),
+                                  __hiloint2double(ghi ^ sn ^ sm_, glo)};
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {          // v = 2*b + c, sign (-1)^{b m + c n}
-                const int sgn = ((v >> 1) * e.m + (v & 1) * e.n) & 1;
-                acc[sg][v].x += sgn ? -gx : gx;
-                acc[sg][v].y += sgn ? -gy : gy;
+            for (int v = 0; v < 4; ++v) {
+                acc[sg][v].x = fma(Gv[v], d.x, acc[sg][v].x);
+                acc[sg][v].y = fma(Gv[v], d.y, acc[sg][v].y);
             }
         }
     }
@@ -359,13 +364,32 @@ org_prep_kernel(OrgPrepArgs a, OrgImage *rec_out, cplx *Y) {
     if (a.Yp) {
         const long tile = pos / ORG_TI;
         const int it = (int)(pos % ORG_TI);
-        for (int l = 0; l < a.Lmax; ++l)
-            for (int am = 0; am <= l; ++am) {      // rows a_0, a_1, b_1, a_2, b_2, ...
-                cplx y = sph_harm_dev(am, l, phi, ct);
+        // Y_l^{|mu|} for all l >= |mu| in one upward pass of the Legendre recurrence per |mu| (the
+        // same recurrence, normalisation and operation order as sph_harm_dev, pb:40-83, which
+        // restarts it for every (l, mu))
+        const double somx2 = sqrt(fma(-ct, ct, 1.0));
+        double pmm = 1.0, fact = 1.0;
+        for (int am = 0; am < a.Lmax; ++am) {      // rows a_0, a_1, b_1, a_2, b_2, ...
+            if (am > 0) { pmm *= -fact * somx2; fact += 2.0; }
+            double sn, cs;
+            sincos_cw((double)am * phi, &sn, &cs);
+            double p0 = pmm, p1 = ct * (double)(2 * am + 1) * pmm;     // P_am^am, P_{am+1}^am
+            for (int l = am; l < a.Lmax; ++l) {
+                double p_val;
+                if (l == am) p_val = p0;
+                else if (l == am + 1) p_val = p1;
+                else {
+                    p_val = (ct * (double)(2 * l - 1) * p1 - (double)(l + am - 1) * p0) / (double)(l - am);
+                    p0 = p1; p1 = p_val;
+                }
+                double ratio = 1.0;
+                for (int i = l - am + 1; i <= l + am; ++i) ratio *= (double)i;
+                const double np_ = sqrt((double)(2 * l + 1) / (4.0 * 3.14159265358979323846) / ratio) * p_val;
                 double *p = a.Yp + (tile * a.R_tot + c_org_rowoff[l] + (am ? 2 * am - 1 : 0)) * ORG_OS + it;
-                p[0] = y.x;
-                if (am) p[ORG_OS] = y.y;
+                p[0] = np_ * cs;
+                if (am) p[ORG_OS] = np_ * sn;
             }
+        }
         return;
     }
     for (int l = 0; l < a.Lmax; ++l)
@@ -981,10 +1005,10 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
 
     const long n_ftiles = (K + ORG_TF - 1) / ORG_TF;
     const size_t b_rows = (size_t)R_tot * 2 * ORG_BS, y_rows = (size_t)R_tot * ORG_OS;
-    cplx *CsT = (cplx *)workspace(WS_SMALL, (size_t)(NMs + NMr) * K * sizeof(cplx));
+    float2 *CsT = (float2 *)workspace(WS_SMALL, (size_t)(NMs + NMr) * K * sizeof(float2));
     double *Bp = (double *)workspace(WS_ORG_B, (size_t)8 * n_ftiles * b_rows * sizeof(double));
     if (!CsT || !Bp) return DEISM_ERR_NOMEM;
-    cplx *CrT = CsT + (size_t)NMs * K;
+    float2 *CrT = CsT + (size_t)NMs * K;
     DEISM_CUDA_TRY(cudaMemsetAsync(Bp, 0, (size_t)8 * n_ftiles * b_rows * sizeof(double), st));
     transpose_c64_kernel<<<(unsigned)(((long)K * NMs + 255) / 256), 256, 0, st>>>(
         (const float2 *)d_C_nm_s, K, NMs, CsT);
