@@ -26,6 +26,7 @@
 //                       source coefficients: the ARG form (pb:388-460) and the shoebox
 //                       cross-check [algo 2]
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -997,11 +998,22 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
         chunks[ncpt++] = make_int4(rowoff[l], rowoff[l1] - rowoff[l], l, l1);
         l = l1;
     }
-    DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_org_rowoff, rowoff, (Lmax + 1) * sizeof(int), 0,
-                                           cudaMemcpyHostToDevice, st));
-    DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_org_chunks, chunks, ncpt * sizeof(int4), 0,
-                                           cudaMemcpyHostToDevice, st));
-    DEISM_CUDA_TRY(cudaStreamSynchronize(st));   // stack tables consumed
+    {   // the tables depend on Lmax only: upload (and synchronise on the stack copies) once per change
+        static std::mutex geom_mu;
+        static int uploaded_dev = -1, uploaded_lmax = -1;
+        int dev = -1;
+        DEISM_CUDA_TRY(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lk(geom_mu);
+        if (dev != uploaded_dev || Lmax != uploaded_lmax) {
+            uploaded_dev = -1;
+            DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_org_rowoff, rowoff, (Lmax + 1) * sizeof(int), 0,
+                                                   cudaMemcpyHostToDevice, st));
+            DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_org_chunks, chunks, ncpt * sizeof(int4), 0,
+                                                   cudaMemcpyHostToDevice, st));
+            DEISM_CUDA_TRY(cudaStreamSynchronize(st));   // stack tables consumed
+            uploaded_dev = dev; uploaded_lmax = Lmax;
+        }
+    }
 
     const long n_ftiles = (K + ORG_TF - 1) / ORG_TF;
     const size_t b_rows = (size_t)R_tot * 2 * ORG_BS, y_rows = (size_t)R_tot * ORG_OS;
