@@ -427,27 +427,23 @@ struct OrgConsumeArgs {
 // fixed part of the shared memory; the two operand stages (rc rows of B then rc rows of Y each)
 // follow it
 struct OrgSmem {
-    double2 fac[ORG_TI][ORG_TF + 1];
+    double2 red[16][ORG_TF];           // final reduction over the row groups that share a frequency
+    OrgImage rec[2][ORG_TI];           // per-image records of the current / next tile (TMA)
     double2 Z[6][ORG_TF];
-    double2 aflat[ORG_TI];
-    double r[ORG_TI], invr[ORG_TI];
-    double cosd[3][ORG_TI];
     double kf[ORG_TF], invk[ORG_TF];
-    long orig[ORG_TI];
-    unsigned char e[ORG_TI][8];
-    unsigned long long full[2];
-    int done[2];
+    unsigned long long full[2], recfull[2];
+    int done[2], recdone[2];
 };
 static_assert(sizeof(OrgSmem) % 16 == 0, "stages must stay 16-byte aligned");
-static_assert(sizeof(double2) * 16 * ORG_TF <= sizeof(double2) * ORG_TI * (ORG_TF + 1),
-              "final reduction aliases fac");
+static_assert(sizeof(OrgImage) % 16 == 0, "records are moved by bulk copies");
 
 // Degrees are whole inside a chunk.  Per degree l the first k-step shares a basic block with the
 // accumulation of degree l-1 (P_pair += h_{l-1} T_{l-1}, reads T before the DMMAs overwrite it) and
 // with the h_l recurrence (independent of T), so that scalar FP64 work issues in the shadow of the
 // DMMAs; the remaining k-steps run in a loop that keeps the next fragments in flight.  Operand
-// chunks arrive by TMA; the last warp out of a stage refills it.  CTA-wide barriers only frame the
-// cooperative per-tile staging.
+// chunks and the per-image records arrive by TMA; the last warp out of a buffer refills it; the
+// attenuation of a pair is applied by the thread that owns the pair: no CTA-wide barrier in the
+// tile loop.
 __global__ void __launch_bounds__(ORG_THREADS, 2)
 org_consume_kernel(OrgConsumeArgs a) {
     constexpr int NT = ORG_NT;
@@ -473,9 +469,11 @@ org_consume_kernel(OrgConsumeArgs a) {
     const bool flat = fused && a.flags[0] != 0;
 
     if (tid == 0) {
-        mbar_init(&sm.full[0], 1);
-        mbar_init(&sm.full[1], 1);
-        sm.done[0] = 0; sm.done[1] = 0;
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&sm.full[b], 1);
+            mbar_init(&sm.recfull[b], 1);
+            sm.done[b] = 0; sm.recdone[b] = 0;
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int q = tid; q < ORG_TF; q += ORG_THREADS) {
@@ -516,7 +514,15 @@ org_consume_kernel(OrgConsumeArgs a) {
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) { P[nt][0] = cmake(0.0, 0.0); P[nt][1] = cmake(0.0, 0.0); }
 
+    auto issue_records = [&](int tile_ord) {
+        const int rb = tile_ord & 1;
+        mbar_expect_tx(&sm.recfull[rb], (unsigned)(ORG_TI * sizeof(OrgImage)));
+        bulk_g2s(&sm.rec[rb][0], a.rec + (tile_lo + tile_ord) * ORG_TI, (unsigned)(ORG_TI * sizeof(OrgImage)),
+                 &sm.recfull[rb]);
+    };
     if (tid == 0 && total > 0) {
+        issue_records(0);
+        if (n_tiles > 1) issue_records(1);
         issue(0, 0, 0);
         if (total > 1) issue(ncpt > 1 ? 0 : 1, ncpt > 1 ? 1 : 0, 1);
     }
@@ -539,60 +545,16 @@ org_consume_kernel(OrgConsumeArgs a) {
 
 #pragma unroll 1
     for (int tt = 0; tt < n_tiles; ++tt) {
-        const long p0 = (tile_lo + tt) * ORG_TI;
-        // ---- cooperative staging of the tile's image records and attenuation ----
-        for (int i = tid; i < ORG_TI; i += ORG_THREADS) {
-            OrgImage rec = a.rec[p0 + i];
-            sm.r[i] = rec.r; sm.invr[i] = rec.inv_r;
-            sm.cosd[0][i] = rec.cx; sm.cosd[1][i] = rec.cy; sm.cosd[2][i] = rec.cz;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) sm.e[i][b] = rec.e[b];
-            sm.aflat[i] = rec.atten_flat;
-            sm.orig[i] = rec.orig;
-        }
-        __syncthreads();
-        {   // attenuation of the tile's 32 x 32 pairs (1024 / ORG_THREADS per thread)
-            const int tx = tid & 7, ty = tid >> 3;
-#pragma unroll 1
-            for (int b = 0; b < ORG_TI / (ORG_THREADS / 8); ++b) {
-                const int il = ty + (ORG_THREADS / 8) * b;
-                const long orig = sm.orig[il];
-#pragma unroll 2
-                for (int q = 0; q < 4; ++q) {
-                    const int fq = tx + 8 * q;
-                    cplx att;
-                    if (orig < 0) {
-                        att = cmake(0.0, 0.0);
-                    } else if (flat) {
-                        att = sm.aflat[il];
-                    } else if (fused) {
-                        att = shoebox_atten(&sm.Z[0][fq], ORG_TF, sm.cosd[0][il], sm.cosd[1][il],
-                                            sm.cosd[2][il], sm.e[il]);
-                        if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
-                    } else {
-                        long f = f0 + fq;
-                        att = cmake(0.0, 0.0);
-                        if (f < a.K) {
-                            if (a.mode == DEISM_ATTEN_C64) {
-                                float2 v = ((const float2 *)a.atten)[orig * a.K + f];
-                                att = cmake((double)v.x, (double)v.y);
-                            } else {
-                                att = ((const cplx *)a.atten)[orig * a.K + f];
-                            }
-                        }
-                    }
-                    sm.fac[il][fq] = att;
-                }
-            }
-        }
+        const int rb = tt & 1;
+        mbar_wait(&sm.recfull[rb], (unsigned)((tt >> 1) & 1));
         // Spherical Hankel recurrence of this thread's DMMA-mapped pairs (pb:86-118), h = (j, -y).
         // It is started two orders early, from h_{-2} and h_{-1} (j_{-1} = cos x / x, y_{-1} =
         // sin x / x, f_{l-2} = (2l-1)/x f_{l-1} - f_l), so that every degree, 0 and 1 included,
         // takes the same branch-free step h_l = (2l-1)/x h_{l-1} - h_{l-2}.
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
-            const int il = wm * 16 + mt * 8 + g;
-            const double r = sm.r[il], ir = sm.invr[il];
+            const OrgImage &rec = sm.rec[rb][wm * 16 + mt * 8 + g];
+            const double r = rec.r, ir = rec.inv_r;
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
@@ -609,7 +571,6 @@ org_consume_kernel(OrgConsumeArgs a) {
                     T[0][mt][nt][e] = 0.0; T[1][mt][nt][e] = 0.0;
                 }
         }
-        __syncthreads();   // fac is complete before any warp reaches the end of the tile
         // (T = 0 at the start of a tile: the first accumulate adds nothing)
 #pragma unroll 1
         for (int local = 0; local < ncpt; ++local) {
@@ -692,19 +653,47 @@ org_consume_kernel(OrgConsumeArgs a) {
             if (++pl == ncpt) { pl = 0; ++pt; }
         }
         accumulate();
+        // ---- P += atten * P_pair, the attenuation taken by the thread that owns the pair ----
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < 2; ++mt) {
+            const OrgImage &rec = sm.rec[rb][wm * 16 + mt * 8 + g];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                for (int e = 0; e < 2; ++e)
-                    cfma(P[nt][e], sm.fac[wm * 16 + mt * 8 + g][wn * 8 * NT + nt * 8 + 2 * t4 + e],
-                         Pp[mt][nt][e]);
-        __syncthreads();   // fac and the per-image arrays are rewritten by the next tile
+                for (int e = 0; e < 2; ++e) {
+                    const int fq = wn * 8 * NT + nt * 8 + 2 * t4 + e;
+                    cplx att;
+                    if (rec.orig < 0) {
+                        att = cmake(0.0, 0.0);
+                    } else if (flat) {
+                        att = rec.atten_flat;
+                    } else if (fused) {
+                        att = shoebox_atten(&sm.Z[0][fq], ORG_TF, rec.cx, rec.cy, rec.cz, rec.e);
+                        if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
+                    } else {
+                        const long f = f0 + fq;
+                        att = cmake(0.0, 0.0);
+                        if (f < a.K) {
+                            if (a.mode == DEISM_ATTEN_C64) {
+                                float2 v = ((const float2 *)a.atten)[rec.orig * a.K + f];
+                                att = cmake((double)v.x, (double)v.y);
+                            } else {
+                                att = ((const cplx *)a.atten)[rec.orig * a.K + f];
+                            }
+                        }
+                    }
+                    cfma(P[nt][e], att, Pp[mt][nt][e]);
+                }
+        }
+        __syncwarp();
+        if (lane == 0 && atomicAdd(&sm.recdone[rb], 1) == NWARPS - 1) {
+            // last warp out of this record buffer: refill it with the records of tile tt+2
+            sm.recdone[rb] = 0;
+            if (tt + 2 < n_tiles) issue_records(tt + 2);
+        }
     }
 
-    __syncthreads();
-    double2 (*red)[ORG_TF] = reinterpret_cast<double2 (*)[ORG_TF]>(&sm.fac[0][0]);
+    double2 (*red)[ORG_TF] = sm.red;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
