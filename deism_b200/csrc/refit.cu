@@ -15,10 +15,12 @@
 //     the real basis span the same space, so the least-squares fit is the same one) — the normal
 //     matrix G_i = Yr_i^T Yr_i is real symmetric [J x J] and is Cholesky-factorised per image;
 //   * refit_pinv_kernel (one CTA per image) writes W_i = G_i^-1 Yr_i^T, the real [J x n_dir]
-//     pseudo-inverse, image index innermost;
-//   * refit_apply_kernel contracts W with the sampled pressures (real x complex, thread = image,
-//     16 frequencies per thread), maps real-basis coefficients back to (n, +-m), divides by the
-//     spherical Hankel function and stores complex64 coalesced along the image axis.
+//     pseudo-inverse, in the operand layout of the contraction below;
+//   * refit_apply_kernel contracts W with the sampled pressures on the FP64 tensor cores: a real
+//     [64 images x n_dir] by complex [n_dir x 32 frequencies] product per (real-function pair,
+//     image tile, frequency tile) as DMMA m8n8k4 GEMMs fed by a TMA ring, then maps real-basis
+//     coefficients back to (n, +-m), divides by the spherical Hankel function and stores
+//     complex64 along the image axis.
 //
 // R_i is the float32 matrix the reflection-tree engine produced; it is applied in double, as
 // numpy's float32 @ float64 product does (cd:1577).
@@ -30,8 +32,11 @@ constexpr int RF_NMAX = 7;                        // source order supported by t
 constexpr int RF_JMAX = (RF_NMAX + 1) * (RF_NMAX + 1);
 constexpr int RF_CH = 128;                        // samples per chunk
 constexpr int RF_THREADS = 256;
-constexpr int RF_KT = 16;                         // frequencies per thread in the apply kernel
-constexpr int RF_SC = 64;                         // samples staged per step in the apply kernel
+constexpr int RF_TI = 64, RF_TF = 32;             // apply kernel CTA tile: images x frequencies
+constexpr int RF_SC = 24;                         // samples per staged chunk (multiple of 4)
+constexpr int RF_WS = RF_TI + 2;                  // W row (doubles); a sample = 2 rows = 132 = 4 mod 16
+constexpr int RF_PS = RF_TF + 2;                  // P plane (doubles); a sample = 2 planes = 68 = 4 mod 16
+constexpr int RF_APPLY_THREADS = 256;             // 4 (image) x 2 (frequency) warps of 16 x 16
 
 // Real functions are ordered pairs first — (a_m, b_m) for n = 1..N, m = 1..n at q = 2p, 2p+1 with
 // p = n(n-1)/2 + m - 1 — then a_0 of n = 0..N at q = N(N+1) + n: pairs stay 16-byte aligned.
@@ -70,11 +75,12 @@ struct RefitSmem {
     double y[RF_CH][RF_JMAX + 1];            // real harmonics of a chunk of samples, one row per thread
 };
 
-// W layout: pairs   W2[p][s][I_pad] double2   (p < npairs)
-//           singles W1[n][s][I_pad] double    (n <= N)
+// W layout: [group][image tile][sample < n_dir_pad][a|b][RF_WS] doubles, image within the tile
+// fastest; group g < npairs is the pair (a_m, b_m), g >= npairs the single a_0 of n = g - npairs
+// (its b row stays zero).  Pre-zeroed: padded samples, images and rows contribute nothing.
 __global__ void __launch_bounds__(RF_THREADS)
-refit_pinv_kernel(long n_images, long I_pad, int N, long n_dir, const float *__restrict__ refl,
-                  const double *__restrict__ X, double2 *W2, double *W1, int *status) {
+refit_pinv_kernel(long n_images, long n_itiles, int N, long n_dir, long n_dir_pad,
+                  const float *__restrict__ refl, const double *__restrict__ X, double *W, int *status) {
     extern __shared__ __align__(16) unsigned char rf_smem_raw[];
     RefitSmem &sm = *reinterpret_cast<RefitSmem *>(rf_smem_raw);
     const long img = blockIdx.x;
@@ -143,9 +149,13 @@ refit_pinv_kernel(long n_images, long I_pad, int N, long n_dir, const float *__r
                 y[r] = v / sm.G[r][r];
             }
             const long s = s0 + tid;
-            for (int p = 0; p < npairs; ++p)
-                W2[((long)p * n_dir + s) * I_pad + img] = make_double2(y[2 * p], y[2 * p + 1]);
-            for (int n = 0; n <= N; ++n) W1[((long)n * n_dir + s) * I_pad + img] = y[2 * npairs + n];
+            const long itile = img / RF_TI;
+            const int it = (int)(img % RF_TI);
+            for (int gq = 0; gq < npairs + N + 1; ++gq) {
+                double *w = W + ((((long)gq * n_itiles + itile) * n_dir_pad + s) * 2) * RF_WS + it;
+                if (gq < npairs) { w[0] = y[2 * gq]; w[RF_WS] = y[2 * gq + 1]; }
+                else w[0] = y[2 * npairs + (gq - npairs)];
+            }
         }
         __syncthreads();
     }
@@ -174,80 +184,140 @@ __global__ void refit_hankel_kernel(long K, int N, const double *__restrict__ k,
     }
 }
 
-// blockIdx.y: group g < npairs -> pair (n, m) of real functions, else single a_0 of n = g - npairs
-__global__ void __launch_bounds__(128)
-refit_apply_kernel(long n_images, long I_pad, long K, int N, long n_dir, const double2 *__restrict__ W2,
-                   const double *__restrict__ W1, const cplx *__restrict__ Psh,
+// sampled pressures complex128 [K][n_dir] -> planes [K_pad/32][sample < n_dir_pad][Re|Im][RF_PS]
+__global__ void __launch_bounds__(256)
+refit_planes_kernel(long K, long n_dir, long n_dir_pad, long n_ktiles, const cplx *__restrict__ Psh,
+                    double *PB) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = n_ktiles * n_dir_pad * RF_PS;
+    if (i >= total) return;
+    const int col = (int)(i % RF_PS);
+    const long s = (i / RF_PS) % n_dir_pad, kt = i / (RF_PS * n_dir_pad);
+    const long k = kt * RF_TF + col;
+    cplx v = cmake(0.0, 0.0);
+    if (col < RF_TF && k < K && s < n_dir) v = Psh[k * n_dir + s];
+    double *p = PB + ((kt * n_dir_pad + s) * 2) * RF_PS + col;
+    p[0] = v.x;
+    p[RF_PS] = v.y;
+}
+
+struct RefitStage {
+    double W[RF_SC][2][RF_WS];
+    double P[RF_SC][2][RF_PS];
+};
+struct RefitApplySmem {
+    RefitStage st[2];
+    unsigned long long full[2];
+    int done[2];
+};
+
+// grid (image tiles, frequency tiles, groups).  c_a[img,k] = sum_s W_a[img,s] P[k,s] (and c_b):
+// per k-step of 4 samples 4 + 4 fragment loads feed 16 DMMAs; operand chunks arrive by TMA bulk
+// copies, the last warp out of a stage refills it (no CTA barrier in the loop).
+__global__ void __launch_bounds__(RF_APPLY_THREADS, 2)
+refit_apply_kernel(long n_images, long n_itiles, long K, int N, long n_dir_pad, long n_ktiles,
+                   const double *__restrict__ W, const double *__restrict__ PB,
                    const cplx *__restrict__ Hinv, float2 *out) {
-    __shared__ double2 Ps[RF_SC][RF_KT];
-    const long img = (long)blockIdx.x * 128 + threadIdx.x;
-    const int g = blockIdx.y;
-    const long k0 = (long)blockIdx.z * RF_KT;
+    extern __shared__ __align__(128) unsigned char rfa_smem_raw[];
+    RefitApplySmem &sm = *reinterpret_cast<RefitApplySmem *>(rfa_smem_raw);
+    constexpr int NWARPS = RF_APPLY_THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3, wm = warp >> 1, wn = warp & 1;
+    const long itile = blockIdx.x, kt = blockIdx.y;
+    const int grp = blockIdx.z;
     const int npairs = N * (N + 1) / 2, J = (N + 1) * (N + 1);
-    const bool pair = g < npairs;
-    cplx ca[RF_KT], cb[RF_KT];
+    const int n_chunks = (int)(n_dir_pad / RF_SC);
+    const double *Wg = W + (((long)grp * n_itiles + itile) * n_dir_pad) * 2 * RF_WS;
+    const double *Pg = PB + (kt * n_dir_pad) * 2 * RF_PS;
+
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) { mbar_init(&sm.full[b], 1); sm.done[b] = 0; }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int c, int stage) {
+        const unsigned wb = RF_SC * 2 * RF_WS * 8, pb = RF_SC * 2 * RF_PS * 8;
+        mbar_expect_tx(&sm.full[stage], wb + pb);
+        bulk_g2s(&sm.st[stage].W[0][0][0], Wg + (long)c * RF_SC * 2 * RF_WS, wb, &sm.full[stage]);
+        bulk_g2s(&sm.st[stage].P[0][0][0], Pg + (long)c * RF_SC * 2 * RF_PS, pb, &sm.full[stage]);
+    };
+    if (tid == 0) {
+        issue(0, 0);
+        if (n_chunks > 1) issue(1, 1);
+    }
+    double T[2][2][2][2][2];      // [a|b][Re|Im][m-tile][n-tile][2]
 #pragma unroll
-    for (int q = 0; q < RF_KT; ++q) { ca[q] = cmake(0.0, 0.0); cb[q] = cmake(0.0, 0.0); }
-    for (long s0 = 0; s0 < n_dir; s0 += RF_SC) {
-        __syncthreads();
-        for (int e = threadIdx.x; e < RF_SC * RF_KT; e += 128) {
-            const int kk = e / RF_SC, sl = e % RF_SC;           // consecutive threads: consecutive samples
-            const long kq = k0 + kk, s = s0 + sl;
-            Ps[sl][kk] = (kq < K && s < n_dir) ? Psh[kq * n_dir + s] : cmake(0.0, 0.0);
+    for (int i = 0; i < 32; ++i) (&T[0][0][0][0][0])[i] = 0.0;
+
+#pragma unroll 1
+    for (int c = 0; c < n_chunks; ++c) {
+        const int stage = c & 1;
+        mbar_wait(&sm.full[stage], (unsigned)((c >> 1) & 1));
+        const double *Ww = &sm.st[stage].W[t4][0][wm * 16 + g];
+        const double *Pw = &sm.st[stage].P[t4][0][wn * 16 + g];
+#pragma unroll
+        for (int ks = 0; ks < RF_SC; ks += 4) {
+            double af[2][2], bf[2][2];
+#pragma unroll
+            for (int ab = 0; ab < 2; ++ab)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) af[ab][mt] = Ww[(ks * 2 + ab) * RF_WS + mt * 8];
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) bf[p][nt] = Pw[(ks * 2 + p) * RF_PS + nt * 8];
+#pragma unroll
+            for (int ab = 0; ab < 2; ++ab)
+#pragma unroll
+                for (int p = 0; p < 2; ++p)
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt)
+                            dmma884(T[ab][p][mt][nt][0], T[ab][p][mt][nt][1], af[ab][mt], bf[p][nt]);
         }
-        __syncthreads();
-        const int ns = (int)(n_dir - s0 < RF_SC ? n_dir - s0 : RF_SC);
-        if (pair) {
-            const double2 *w = W2 + ((long)g * n_dir + s0) * I_pad + img;
-#pragma unroll 2
-            for (int sl = 0; sl < ns; ++sl) {
-                const double2 wv = w[(long)sl * I_pad];
-#pragma unroll
-                for (int q = 0; q < RF_KT; ++q) {
-                    const double2 pv = Ps[sl][q];
-                    ca[q].x = fma(wv.x, pv.x, ca[q].x); ca[q].y = fma(wv.x, pv.y, ca[q].y);
-                    cb[q].x = fma(wv.y, pv.x, cb[q].x); cb[q].y = fma(wv.y, pv.y, cb[q].y);
-                }
-            }
-        } else {
-            const double *w = W1 + ((long)(g - npairs) * n_dir + s0) * I_pad + img;
-#pragma unroll 2
-            for (int sl = 0; sl < ns; ++sl) {
-                const double wv = w[(long)sl * I_pad];
-#pragma unroll
-                for (int q = 0; q < RF_KT; ++q) {
-                    const double2 pv = Ps[sl][q];
-                    ca[q].x = fma(wv, pv.x, ca[q].x); ca[q].y = fma(wv, pv.y, ca[q].y);
-                }
-            }
+        __syncwarp();
+        if (lane == 0 && atomicAdd(&sm.done[stage], 1) == NWARPS - 1) {
+            sm.done[stage] = 0;
+            if (c + 2 < n_chunks) issue(c + 2, stage);
         }
     }
-    if (img >= n_images) return;
+
+    // ---- epilogue: real-basis coefficients -> (n, +-m), / h_n, complex64 ----
     int n, m;
-    if (pair) {
+    if (grp < npairs) {
         n = 1;
-        while (n * (n + 1) / 2 <= g) ++n;
-        m = g - n * (n - 1) / 2 + 1;
+        while (n * (n + 1) / 2 <= grp) ++n;
+        m = grp - n * (n - 1) / 2 + 1;
     } else {
-        n = g - npairs; m = 0;
+        n = grp - npairs; m = 0;
     }
+    const double sg = (m & 1) ? -0.5 : 0.5;
 #pragma unroll
-    for (int q = 0; q < RF_KT; ++q) {
-        const long kq = k0 + q;
-        if (kq >= K) break;
-        const cplx hi = Hinv[(long)n * K + kq];
-        if (m == 0) {
-            const cplx c = cmul(ca[q], hi);
-            out[(kq * J + (long)(n * n + n)) * n_images + img] = make_float2((float)c.x, (float)c.y);
-        } else {
-            // C_m = (c_a - i c_b)/2,   C_-m = (-1)^m (c_a + i c_b)/2
-            const cplx cp = cmake(0.5 * (ca[q].x + cb[q].y), 0.5 * (ca[q].y - cb[q].x));
-            const double sg = (m & 1) ? -0.5 : 0.5;
-            const cplx cm = cmake(sg * (ca[q].x - cb[q].y), sg * (ca[q].y + cb[q].x));
-            const cplx a = cmul(cp, hi), b = cmul(cm, hi);
-            out[(kq * J + (long)(n * n + n + m)) * n_images + img] = make_float2((float)a.x, (float)a.y);
-            out[(kq * J + (long)(n * n + n - m)) * n_images + img] = make_float2((float)b.x, (float)b.y);
-        }
+    for (int mt = 0; mt < 2; ++mt) {
+        const long img = itile * RF_TI + wm * 16 + mt * 8 + g;
+        if (img >= n_images) continue;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const long kq = kt * RF_TF + wn * 16 + nt * 8 + 2 * t4 + e;
+                if (kq >= K) continue;
+                const cplx hi = Hinv[(long)n * K + kq];
+                const cplx ca = cmake(T[0][0][mt][nt][e], T[0][1][mt][nt][e]);
+                const cplx cb = cmake(T[1][0][mt][nt][e], T[1][1][mt][nt][e]);
+                if (m == 0) {
+                    const cplx v = cmul(ca, hi);
+                    out[(kq * J + (long)(n * n + n)) * n_images + img] = make_float2((float)v.x, (float)v.y);
+                } else {
+                    // C_m = (c_a - i c_b)/2,   C_-m = (-1)^m (c_a + i c_b)/2
+                    const cplx cp = cmake(0.5 * (ca.x + cb.y), 0.5 * (ca.y - cb.x));
+                    const cplx cm = cmake(sg * (ca.x - cb.y), sg * (ca.y + cb.x));
+                    const cplx va = cmul(cp, hi), vb = cmul(cm, hi);
+                    out[(kq * J + (long)(n * n + n + m)) * n_images + img] = make_float2((float)va.x, (float)va.y);
+                    out[(kq * J + (long)(n * n + n - m)) * n_images + img] = make_float2((float)vb.x, (float)vb.y);
+                }
+            }
     }
 }
 
@@ -272,32 +342,40 @@ extern "C" int deism_arg_refit(int64_t n_images, int64_t K, int N, int64_t n_dir
         return set_error(DEISM_ERR_INVALID, "null input pointer");
     if (!(r0 > 0.0)) return set_error(DEISM_ERR_INVALID, "radius r0 must be positive");
 
-    const long I_pad = (n_images + 127) / 128 * 128;
-    const size_t w2_bytes = (size_t)(npairs > 0 ? npairs : 1) * n_dir * I_pad * sizeof(double2);
-    const size_t w1_bytes = (size_t)(N + 1) * n_dir * I_pad * sizeof(double);
-    double2 *W2 = (double2 *)workspace(WS_ORG_B, w2_bytes);
-    double *W1 = (double *)workspace(WS_ORG_Y, w1_bytes);
+    const long n_itiles = (n_images + RF_TI - 1) / RF_TI, n_ktiles = (K + RF_TF - 1) / RF_TF;
+    const long n_dir_pad = (n_dir + RF_SC - 1) / RF_SC * RF_SC;
+    const int n_groups = npairs + N + 1;
+    const size_t w_bytes = (size_t)n_groups * n_itiles * n_dir_pad * 2 * RF_WS * sizeof(double);
+    const size_t p_bytes = (size_t)n_ktiles * n_dir_pad * 2 * RF_PS * sizeof(double);
+    double *W = (double *)workspace(WS_ORG_B, w_bytes);
+    double *PB = (double *)workspace(WS_ORG_Y, p_bytes);
     cplx *Hinv = (cplx *)workspace(WS_SMALL, (size_t)(N + 1) * K * sizeof(cplx));
     int *status = (int *)workspace(WS_FLAGS, 64);
-    if (!W2 || !W1 || !Hinv || !status) return DEISM_ERR_NOMEM;
-    // padded image columns are read by the apply kernel: keep them finite
-    DEISM_CUDA_TRY(cudaMemsetAsync(W2, 0, w2_bytes, st));
-    DEISM_CUDA_TRY(cudaMemsetAsync(W1, 0, w1_bytes, st));
+    if (!W || !PB || !Hinv || !status) return DEISM_ERR_NOMEM;
+    // padded samples / images / the b row of the single groups must read as zero
+    DEISM_CUDA_TRY(cudaMemsetAsync(W, 0, w_bytes, st));
     DEISM_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int), st));
 
     DEISM_CUDA_TRY(cudaFuncSetAttribute(refit_pinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)sizeof(RefitSmem)));
     prof_begin("refit_pinv", st);
     refit_pinv_kernel<<<(unsigned)n_images, RF_THREADS, sizeof(RefitSmem), st>>>(
-        n_images, I_pad, N, n_dir, d_reflection, d_coords, W2, W1, status);
+        n_images, n_itiles, N, n_dir, n_dir_pad, d_reflection, d_coords, W, status);
     prof_end("refit_pinv", st);
     DEISM_LAUNCH_CHECK("refit_pinv_kernel");
     refit_hankel_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(K, N, d_k, r0, Hinv);
     DEISM_LAUNCH_CHECK("refit_hankel_kernel");
-    dim3 grid((unsigned)(I_pad / 128), (unsigned)(npairs + N + 1), (unsigned)((K + RF_KT - 1) / RF_KT));
+    refit_planes_kernel<<<(unsigned)((n_ktiles * n_dir_pad * RF_PS + 255) / 256), 256, 0, st>>>(
+        K, n_dir, n_dir_pad, n_ktiles, (const cplx *)d_Psh, PB);
+    DEISM_LAUNCH_CHECK("refit_planes_kernel");
+    if (n_ktiles > 65535 || n_groups > 65535)
+        return set_error(DEISM_ERR_INVALID, "too many frequency tiles (%ld) for one launch", n_ktiles);
+    dim3 grid((unsigned)n_itiles, (unsigned)n_ktiles, (unsigned)n_groups);
+    DEISM_CUDA_TRY(cudaFuncSetAttribute(refit_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sizeof(RefitApplySmem)));
     prof_begin("refit_apply", st);
-    refit_apply_kernel<<<grid, 128, 0, st>>>(n_images, I_pad, K, N, n_dir, W2, W1, (const cplx *)d_Psh,
-                                             Hinv, (float2 *)d_C_vec);
+    refit_apply_kernel<<<grid, RF_APPLY_THREADS, sizeof(RefitApplySmem), st>>>(
+        n_images, n_itiles, K, N, n_dir_pad, n_ktiles, W, PB, Hinv, (float2 *)d_C_vec);
     prof_end("refit_apply", st);
     DEISM_LAUNCH_CHECK("refit_apply_kernel");
     int h_status = 0;
