@@ -85,12 +85,25 @@ class Room_deism:
         self.sound_speed = float(sound_speed)
         self.ism_order = int(ism_order)
         self.n_bands = int(self._tables["impedance"].shape[1])
-        self.sources = np.zeros((3, 0), np.float32)
-        self.orders = np.zeros(0, np.int32)
-        self.gen_walls = np.zeros(0, np.int32)
-        self.attenuations = np.zeros((self.n_bands, 0), np.float32)
-        self.reflection_matrix = []
+        # results stay on the GPU (self.device_arrays); the reference's readonly NumPy attributes
+        # (libroom.cpp:101-127) are copied to the host the first time they are read
+        self.device_arrays = None
+        self._host = {"sources": np.zeros((3, 0), np.float32), "orders": np.zeros(0, np.int32),
+                      "gen_walls": np.zeros(0, np.int32),
+                      "attenuations": np.zeros((self.n_bands, 0), np.float32), "reflection_matrix": []}
         self.visible_mics = np.zeros((0, 0), bool)
+
+    def _lazy(self, name):
+        if name not in self._host:
+            t = self.device_arrays[name].cpu().numpy()
+            self._host[name] = list(t) if name == "reflection_matrix" else t
+        return self._host[name]
+
+    sources = property(lambda self: self._lazy("sources"))
+    orders = property(lambda self: self._lazy("orders"))
+    gen_walls = property(lambda self: self._lazy("gen_walls"))
+    attenuations = property(lambda self: self._lazy("attenuations"))
+    reflection_matrix = property(lambda self: self._lazy("reflection_matrix"))
 
     def add_mic(self, loc):
         """room.hpp:330-336.  (The reference's wrapper pushes a new microphone on every
@@ -124,11 +137,9 @@ class Room_deism:
         check(lib().deism_convex_images_fill(C.byref(ws), K, _ptr(sources), _ptr(orders),
                                              _ptr(gen_walls), _ptr(atten), _ptr(refl), st),
               "deism_convex_images_fill")
-        self.sources = sources.cpu().numpy()
-        self.orders = orders.cpu().numpy()
-        self.gen_walls = gen_walls.cpu().numpy()
-        self.attenuations = atten.cpu().numpy()
-        self.reflection_matrix = list(refl.cpu().numpy())
+        self.device_arrays = {"sources": sources, "orders": orders, "gen_walls": gen_walls,
+                              "attenuations": atten, "reflection_matrix": refl}
+        self._host = {}
         self.visible_mics = np.ones((1, I), dtype=bool)
         return I
 
@@ -171,4 +182,35 @@ def get_ref_paths_ARG(params, room_engine):
                   "atten_all": atten_all}
     params["images"] = images
     params["reflection_matrix"] = reflection_matrix
+    return params
+
+
+def get_ref_paths_ARG_device(params, room_engine):
+    """get_ref_paths_ARG (core_deism_arg.py:1204-1262) without leaving the GPU: the image
+    geometry, attenuations and reflection matrices the tree enumeration left in
+    ``room_engine.device_arrays`` become the torch tensors ``run_DEISM_ARG`` consumes.  Only the
+    reflection orders (4 bytes per image) visit the host, to split early / late images.
+    ``params['reflection_matrix']`` keeps the engine's [I, 3, 3] layout (what
+    ``directivities.cal_C_nm_s_ARG_vec_device`` takes)."""
+    d = room_engine.device_arrays
+    if d is None:
+        raise RuntimeError("image_source_model() has not run on this engine")
+    src = d["sources"].to(torch.float64)
+    rcv = torch.as_tensor(np.asarray(params["posReceiver"], dtype=np.float64), device=src.device)
+    R = rcv[:, None] - src
+    hxy = torch.hypot(R[0], R[1])
+    geom = torch.stack((torch.atan2(R[1], R[0]), np.pi / 2 - torch.atan2(R[2], hxy),
+                        torch.hypot(hxy, R[2]))).to(torch.float32)
+    atten = d["attenuations"].to(torch.complex64)
+    refl = d["reflection_matrix"]
+    if params["ifRemoveDirectPath"]:
+        geom, atten, refl = geom[:, 1:], atten[:, 1:], refl[1:]
+    images = {"R_sI_r_all": geom.contiguous(), "atten_all": atten.contiguous()}
+    if params["DEISM_method"] == "MIX":
+        orders = room_engine.orders          # un-sliced, as the reference does (cda:1222-1233)
+        early = np.where(orders <= params["mixEarlyOrder"])[0]
+        images["early_indices"] = early
+        images["late_indices"] = np.setdiff1d(np.arange(geom.shape[1]), early)
+    params["images"] = images
+    params["reflection_matrix"] = refl.contiguous()
     return params

@@ -29,16 +29,22 @@ def _track(params, keys, who):
 
 
 def _flatten(C, order):
-    """j = n^2 + n + m over the first axes [K, n, m(, I)]; negative m wraps like NumPy."""
+    """j = n^2 + n + m over the first axes [K, n, m(, I)]; negative m wraps like NumPy.  Torch
+    tensors (device-resident coefficients) stay torch tensors on their device."""
     J = (order + 1) ** 2
     n_all = np.zeros(J, dtype="int")
     m_all = np.zeros(J, dtype="int")
-    vec = np.zeros((C.shape[0], J) + C.shape[3:], dtype="complex")
     for n in range(order + 1):
         for m in range(-n, n + 1):
-            j = n * n + n + m
-            n_all[j], m_all[j] = n, m
-            vec[:, j] = C[:, n, m]
+            n_all[n * n + n + m], m_all[n * n + n + m] = n, m
+    if hasattr(C, "device") and not isinstance(C, np.ndarray):
+        import torch
+
+        vec = torch.stack([C[:, int(n), int(m)] for n, m in zip(n_all, m_all)], dim=1)
+        return n_all, m_all, vec.to(torch.complex64).contiguous()
+    vec = np.zeros((C.shape[0], J) + C.shape[3:], dtype="complex")
+    for j in range(J):
+        vec[:, j] = C[:, n_all[j], m_all[j]]
     return n_all, m_all, vec.astype(np.complex64)
 
 
@@ -170,9 +176,17 @@ def init_source_directivities_ARG(params):
         params["C_nm_s_ARG"] = cal_C_nm_s_new(params["reflection_matrix"], smp["Psh"], Rm @ xyz, params)
         _track(params, ("C_nm_s_ARG",), "init_source_directivities")
         return params
-    n_img = params["reflection_matrix"].shape[2]
+    refl = params["reflection_matrix"]
     c = _monopole(params["waveNumbers"])[..., None, None, None].astype(np.complex64)
-    params["C_nm_s_ARG"] = c * np.ones((1, 1, 1, n_img)).astype(np.complex64)
+    if hasattr(refl, "device") and not isinstance(refl, np.ndarray):
+        # device-resident pipeline (convex.get_ref_paths_ARG_device): [I, 3, 3] torch tensor
+        import torch
+
+        n_img = int(refl.shape[0])
+        params["C_nm_s_ARG"] = torch.from_numpy(c).to(refl.device).expand(-1, 1, 1, n_img).contiguous()
+    else:
+        n_img = refl.shape[2]
+        params["C_nm_s_ARG"] = c * np.ones((1, 1, 1, n_img)).astype(np.complex64)
     params["sourceOrder"] = 0
     _track(params, ("C_nm_s_ARG", "sourceOrder"), "init_source_directivities")
     return params

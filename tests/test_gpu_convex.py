@@ -154,3 +154,50 @@ def test_arg_refit_errors():
     with pytest.raises(ValueError):          # all directions identical: rank-deficient fit
         D.cal_C_nm_s_ARG_vec_device(np.eye(3, dtype=np.float32)[None], P, np.tile([[0.], [0.], [1.]], (1, 10)),
                                     dict(base, sourceOrder=1))
+
+
+@pytest.mark.parametrize("name", ["x1_convex_rir_mix_o4_mono", "c4_full"])
+def test_device_resident_convex_pipeline(name):
+    """Tree enumeration -> geometry -> monopole coefficients -> accumulation with every array left
+    on the GPU (get_ref_paths_ARG_device) gives the reference's RTF; the lazily copied host
+    attributes are still the reference's arrays."""
+    import os
+
+    from deism_b200 import backend, convex, directivities as D, wigner, workloads
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+
+    class W:
+        pass
+
+    walls = []
+    for i in range(int(z["walls/n"])):
+        w = W()
+        w.normal, w.origin = z[f"walls/{i}/normal"], z[f"walls/{i}/origin"]
+        w.basis, w.flat_corners = z[f"walls/{i}/basis"], z[f"walls/{i}/flat_corners"]
+        w.reflection_matrix, w.impedence_bands = z[f"walls/{i}/reflection_matrix"], z[f"walls/{i}/impedance"]
+        walls.append(w)
+    room = convex.Room_deism(walls, [], [], 343.0, int(z["params/maxReflOrder"]))
+    room.add_mic(z["params/posReceiver"].astype(np.float32))
+    n = room.image_source_model(z["params/posSource"].astype(np.float32))
+    k = z["params/waveNumbers"]
+    mono = workloads.monopole_coeffs(k)
+    q = {"DEISM_method": "MIX", "silentMode": 1, "waveNumbers": k, "posReceiver": z["params/posReceiver"],
+         "ifRemoveDirectPath": int(z["params/ifRemoveDirectPath"]), "mixEarlyOrder": int(z["params/mixEarlyOrder"]),
+         "sourceOrder": 0, "receiverOrder": 0, "sourceType": "monopole", "C_vu_r": mono}
+    q["v_all"], q["u_all"], q["C_vu_r_vec"] = workloads.vectorize(mono, 0)
+    q = wigner.pre_calc_Wigner(q)
+    q = convex.get_ref_paths_ARG_device(q, room)
+    assert q["images"]["atten_all"].is_cuda and q["images"]["R_sI_r_all"].is_cuda
+    q = D.vectorize_C_nm_s_ARG(D.init_source_directivities_ARG(q))
+    assert q["C_nm_s_ARG_vec"].is_cuda and tuple(q["C_nm_s_ARG_vec"].shape) == (len(k), 1, q["images"]["R_sI_r_all"].shape[1])
+    got = backend.run_DEISM_ARG(q)
+    assert rel_l2(got, z["RTF"]) < RTF_TOL
+    # geometry computed on the GPU equals the host formula bit for bit; lazy attributes match
+    host = convex.get_ref_paths_ARG({"DEISM_method": "MIX", "posReceiver": z["params/posReceiver"],
+                                     "ifRemoveDirectPath": int(z["params/ifRemoveDirectPath"]),
+                                     "mixEarlyOrder": int(z["params/mixEarlyOrder"])}, room)
+    assert np.array_equal(host["images"]["R_sI_r_all"].view(np.uint32),
+                          q["images"]["R_sI_r_all"].cpu().numpy().view(np.uint32))
+    assert np.array_equal(host["images"]["late_indices"], q["images"]["late_indices"])
+    assert np.array_equal(room.orders, z["engine/orders"]) and n == len(room.orders)
