@@ -627,6 +627,143 @@ lc_main_kernel(LcMainArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Monopole source and receiver (J = 1 each; BASELINE C1 and the monopole run of C2): S and R do
+// not depend on the image, so
+//     P[k] = -C_s[k] C_r[k] Y_00^2 4pi/k^2 * sum_img (atten/r) exp(-i k r)
+// and the contraction disappears.  Thread = one image x 16 consecutive frequencies: one sincos,
+// then 15 steps of the rotation recurrence; 64 images x 64 frequencies per CTA pass; partial sums
+// over the CTA's images stay in registers and are reduced once at the end.
+// ---------------------------------------------------------------------------------------
+constexpr int LM_TF = 64, LM_FPT = 16, LM_THREADS = 256;
+
+struct LcMonoArgs {
+    long n_images, n_pad, K;
+    const LcImage *img;
+    const double *k;
+    const float2 *Cs, *Cr;   // [K][1]
+    int mode;
+    const void *atten;
+    const cplx *Z;
+    const int *flags;
+    long tiles_per_chunk;
+    cplx *partial;
+};
+
+__global__ void __launch_bounds__(LM_THREADS, 2)
+lc_mono_kernel(LcMonoArgs a) {
+    __shared__ double kf[LM_TF], dkd[LM_TF];
+    __shared__ double2 Zs[6][LM_TF];
+    __shared__ double2 red[LM_THREADS / 32][LM_FPT];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int il = tid & (LC_TI - 1), fg = tid / LC_TI;          // image lane, frequency group
+    const long f0 = (long)blockIdx.x * LM_TF;
+    const long n_img_tiles = a.n_pad / LC_TI;
+    long tile_lo = (long)blockIdx.y * a.tiles_per_chunk;
+    long tile_hi = tile_lo + a.tiles_per_chunk;
+    if (tile_hi > n_img_tiles) tile_hi = n_img_tiles;
+    const bool fused = a.mode == DEISM_ATTEN_FUSED_ROOM || a.mode == DEISM_ATTEN_FUSED_ANGLES;
+    const bool flat = fused && a.flags[0] != 0;
+    const bool uniform_k = a.flags[1] != 0;
+    {
+        const double dk = *reinterpret_cast<const double *>(a.flags + 2);
+        for (int q = tid; q < LM_TF; q += LM_THREADS) {
+            const long f = f0 + q;
+            const double kk = f < a.K ? a.k[f] : 1.0;
+            kf[q] = kk;
+            dkd[q] = f + 1 < a.K ? (a.k[f + 1] - kk) - dk : 0.0;
+        }
+        if (fused && !flat)
+            for (int i = tid; i < 6 * LM_TF; i += LM_THREADS) {
+                const int w = i / LM_TF, q = i % LM_TF;
+                const long f = f0 + q;
+                Zs[w][q] = f < a.K ? a.Z[(long)w * a.K + f] : cmake(1.0, 0.0);
+            }
+    }
+    __syncthreads();
+    const int q0 = fg * LM_FPT;
+    cplx P[LM_FPT];
+#pragma unroll
+    for (int q = 0; q < LM_FPT; ++q) P[q] = cmake(0.0, 0.0);
+
+#pragma unroll 1
+    for (long tile = tile_lo; tile < tile_hi; ++tile) {
+        const long img = tile * LC_TI + il;
+        const LcImage rec = a.img[img];
+        const double r = rec.r;
+        if (flat && uniform_k) {
+            double sn, cs;
+            sincos_cw(kf[q0] * r, &sn, &cs);
+            cplx F = cmul(rec.a_flat, cmake(cs, -sn));
+#pragma unroll
+            for (int q = 0; q < LM_FPT; ++q) {
+                P[q] = cadd(P[q], F);
+                if (q + 1 < LM_FPT) {
+                    F = cmul(F, rec.rot);                      // exp(-i (dk + d) r) ~ rot (1 - i d r)
+                    const double dr = dkd[q0 + q] * r;
+                    F = cmake(fma(F.y, dr, F.x), fma(-F.x, dr, F.y));
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int q = 0; q < LM_FPT; ++q) {
+                const long f = f0 + q0 + q;
+                cplx att;
+                if (flat) {
+                    att = rec.a_flat;
+                } else {
+                    if (fused) {
+                        att = shoebox_atten(&Zs[0][q0 + q], LM_TF, rec.cx, rec.cy, rec.cz, rec.e);
+                        if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
+                    } else {
+                        att = cmake(0.0, 0.0);
+                        if (img < a.n_images && f < a.K) {
+                            if (a.mode == DEISM_ATTEN_C64) {
+                                float2 v = ((const float2 *)a.atten)[img * a.K + f];
+                                att = cmake((double)v.x, (double)v.y);
+                            } else {
+                                att = ((const cplx *)a.atten)[img * a.K + f];
+                            }
+                        }
+                    }
+                    att = cmake(att.x * rec.inv_r, att.y * rec.inv_r);
+                }
+                double sn, cs;
+                sincos_cw(kf[q0 + q] * r, &sn, &cs);
+                const cplx v = cmul(att, cmake(cs, -sn));
+#pragma unroll
+                for (int qq = 0; qq < LM_FPT; ++qq)      // P stays in registers: no dynamic index
+                    if (qq == q) P[qq] = cadd(P[qq], v);
+            }
+        }
+    }
+    // ---- sum over the 64 image lanes of each frequency group: shuffles, then two warps per group ----
+#pragma unroll
+    for (int q = 0; q < LM_FPT; ++q) {
+        double x = P[q].x, y = P[q].y;
+        for (int o = 16; o > 0; o >>= 1) {
+            x += __shfl_down_sync(0xffffffffu, x, o);
+            y += __shfl_down_sync(0xffffffffu, y, o);
+        }
+        if (lane == 0) red[warp][q] = cmake(x, y);
+    }
+    __syncthreads();
+    if (tid < LM_TF) {
+        const int g = tid / LM_FPT, q = tid % LM_FPT;
+        const cplx s = cadd(red[2 * g][q], red[2 * g + 1][q]);
+        const long f = f0 + tid;
+        if (f < a.K) {
+            // S R (-4pi/k^2):  C_s Y_00 * C_r Y_00, Y_00 = 1/(2 sqrt(pi))
+            const float2 cs = a.Cs[f], cr = a.Cr[f];
+            const double y00 = sph_harm_dev(0, 0, 0.0, 1.0).x;
+            const cplx SR = cmul(cmake((double)cs.x * y00, (double)cs.y * y00),
+                                 cmake((double)cr.x * y00, (double)cr.y * y00));
+            const double w = -4.0 * 3.14159265358979323846 / (kf[tid] * kf[tid]);
+            a.partial[(long)blockIdx.y * a.K + f] = cmul(cmake(SR.x * w, SR.y * w), s);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const cplx *__restrict__ partial, long n_chunks, long K, cplx *out,
                        int accumulate) {
@@ -779,6 +916,9 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
         }
     }
     const int Jqs = hb[0].Jq, Jqr = hb[1].Jq;
+    // monopole source and receiver: dedicated kernel (no contraction)
+    const bool monopole = Js == 1 && Jr == 1 && h_n_all[0] == 0 && h_m_all[0] == 0 && h_v_all[0] == 0 &&
+                          h_u_all[0] == 0 && !getenv("DEISM_LC_NO_MONO");
 
     const long n_img_tiles = (n_images + LC_TI - 1) / LC_TI;
     const long n_pad = n_img_tiles * LC_TI;
@@ -853,6 +993,40 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
     if (rc) return rc;
     k_uniform_kernel<<<1, 256, 0, st>>>(d_k, K, flags);
     DEISM_LAUNCH_CHECK("k_uniform_kernel");
+
+    if (monopole) {
+        LcPrepArgs mp;
+        mp.flags = flags;
+        mp.n_images = n_images; mp.n_pad = n_pad; mp.K = K; mp.Js = 1; mp.Jr = 1;
+        mp.Js_pad = 0; mp.Jr_pad = 0;                       // records only, no harmonic rows
+        mp.R_s_rI = d_R_s_rI; mp.R_r_sI = d_R_r_sI;
+        mp.mode = atten->mode; mp.angdep = atten->ang_dep_flag;
+        mp.A = atten->d_A; mp.R_sI_r = atten->d_R_sI_r; mp.Z = (const cplx *)atten->d_Z_S;
+        for (int i = 0; i < 3; ++i) {
+            mp.room.LL[i] = atten->room_size[i]; mp.room.xs[i] = atten->pos_source[i];
+            mp.room.xr[i] = atten->pos_receiver[i];
+        }
+        lc_prep_kernel<<<(unsigned)((n_pad + 127) / 128), 128, 0, st>>>(mp, img, Ys, Yr);
+        DEISM_LAUNCH_CHECK("lc_prep_kernel");
+        const long m_ftiles = (K + LM_TF - 1) / LM_TF;
+        long m_chunks = (long)sm_count() * 8 * 4 / m_ftiles;          // ~4 waves of 8 CTAs/SM
+        if (m_chunks < 1) m_chunks = 1;
+        if (m_chunks > n_img_tiles) m_chunks = n_img_tiles;
+        if (m_chunks > n_chunks) m_chunks = n_chunks;                 // partial[] was sized for n_chunks
+        const long m_tpc = (n_img_tiles + m_chunks - 1) / m_chunks;
+        m_chunks = (n_img_tiles + m_tpc - 1) / m_tpc;
+        LcMonoArgs mo;
+        mo.n_images = n_images; mo.n_pad = n_pad; mo.K = K; mo.img = img; mo.k = d_k;
+        mo.Cs = (const float2 *)d_C_s_vec; mo.Cr = (const float2 *)d_C_r_vec;
+        mo.mode = atten->mode; mo.atten = atten->d_atten; mo.Z = (const cplx *)atten->d_Z_S;
+        mo.flags = flags; mo.tiles_per_chunk = m_tpc; mo.partial = partial;
+        dim3 mgrid((unsigned)m_ftiles, (unsigned)m_chunks);
+        prof_begin("lc_main", st);
+        lc_mono_kernel<<<mgrid, LM_THREADS, 0, st>>>(mo);
+        prof_end("lc_main", st);
+        DEISM_LAUNCH_CHECK("lc_mono_kernel");
+        return launch_reduce_partials(partial, m_chunks, K, d_out, accumulate, st);
+    }
 
     LcPrepArgs pa;
     pa.flags = flags;
