@@ -43,7 +43,12 @@ sys.path.insert(0, ROOT)
 # to us, not the reference's complex x complex loop.
 # --------------------------------------------------------------------------------------
 def lc_flops_per_term(Js, Jr, fused_per_term, mean_order):
-    f = 4 * (Js + Jr) + 52
+    if Js == 1 and Jr == 1:
+        # monopole kernel: no contraction; per term one step of the rotation recurrence (complex
+        # mul 6 + first-order grid correction 5), the accumulate (2) and 1/16 of a sincos
+        f = 6 + 5 + 2 + 3
+    else:
+        f = 4 * (Js + Jr) + 52
     if fused_per_term:
         f += 140 + 6 * mean_order
     return f
@@ -380,6 +385,9 @@ def main():
             Js, Jr = (N + 1) ** 2, (V + 1) ** 2
             fpt = lc_flops_per_term(Js, Jr, args.general_impedance, 0.75 * p["maxReflOrder"])
             units = n_late * Ks
+            if Js == 1 and Jr == 1 and extras.get("fp64_peak_dfma_tflops"):
+                # lc_mono_kernel issues no DMMA: its roofline is the FP64 FMA pipe
+                peak_tf, peak_kind = extras["fp64_peak_dfma_tflops"], "dfma"
         elif dom == "org_consume":
             fpt = org_consume_flops_per_term(N, V)
             units = I * Ks

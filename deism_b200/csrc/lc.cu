@@ -37,7 +37,9 @@ namespace deism {
 constexpr int LC_TI = 64;        // images per tile
 // most harmonics per staged chunk (multiple of 4): a whole order-5 pass when only Y streams
 __host__ __device__ constexpr int lc_jcmax(bool cres_on) { return cres_on ? 36 : 12; }
-constexpr int LC_NT = 2;         // n-tiles (8 freqs each) per warp: warp tile = 16 images x 16 freqs
+#ifndef LC_NT
+#define LC_NT 2                  // n-tiles (8 freqs each) per warp: warp tile = 16 images x 8*LC_NT freqs
+#endif
 constexpr int LC_YS = LC_TI + 4; // Y row stride (doubles): 68 = 4 mod 16 -> conflict-free fragments
 constexpr int LC_MAXST = 16;     // most ring stages
 // A CTA is 4 (image) x WN (frequency) warps: tile = 64 images x TF = 16 WN frequencies.
@@ -46,8 +48,10 @@ constexpr int LC_MAXST = 16;     // most ring stages
 //   WN = 2 (256 threads, 2 CTAs/SM): coefficients and harmonics both stream (any number of
 //          harmonics fits).
 // C plane stride (doubles) = TF + 2, so a harmonic row (2 planes) is 4 mod 16 doubles: conflict-free.
-__host__ __device__ constexpr int lc_tf(int WN) { return 16 * WN; }
-__host__ __device__ constexpr int lc_cs(int WN) { return 16 * WN + 2; }
+constexpr int LC_WN_RES = 8 / LC_NT;     // warps along frequency: resident shape (64 frequencies)
+constexpr int LC_WN_STR = 4 / LC_NT;     //                            streaming shape (32 frequencies)
+__host__ __device__ constexpr int lc_tf(int WN) { return 8 * LC_NT * WN; }
+__host__ __device__ constexpr int lc_cs(int WN) { return 8 * LC_NT * WN + 2; }
 
 struct LcImage {        // 96 bytes per image (a tile of 64 records is one 6 KB bulk copy)
     double r, inv_r;
@@ -553,7 +557,7 @@ lc_main_kernel(LcMainArgs a) {
             epi_P();
             const long i0 = (tile_lo + tt) * LC_TI;
             cplx E = cmake(1.0, 0.0), E0 = E;
-            static_assert(NT == 2, "rotation order below assumes two n-tiles per warp");
+            static_assert(NT == 1 || NT == 2, "rotation order below assumes one or two n-tiles per warp");
 #pragma unroll 1
             for (int j = 0; j < 4 * NT; ++j) {
                 const int mt = j / (2 * NT), nt = (j >> 1) % NT, e = j & 1;
@@ -582,12 +586,13 @@ lc_main_kernel(LcMainArgs a) {
                 }
                 // exp(-i k r): per-term sincos, or on a uniform grid one sincos per image and the
                 // rotation recurrence (base, +1, +8, +9 steps for nt = 0,0,1,1 / e = 0,1,0,1)
-                if (!uniform_k || (j & 3) == 0) {
+                const int jj = j % (2 * NT);
+                if (!uniform_k || jj == 0) {
                     double sn, cs;
                     sincos_cw(kf[fq] * rec.r, &sn, &cs);
                     E = cmake(cs, -sn);
                     E0 = E;
-                } else if ((j & 3) == 2) {
+                } else if (NT == 2 && jj == 2) {
                     E = rot_step(E0, rec.rot8, dkd8[fq - 8] * rec.r);
                 } else {
                     E = rot_step(E, rec.rot, dkd[fq - 1] * rec.r);
@@ -934,7 +939,7 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
     if (resident) {
         pick_chunks(Jqs, lc_jcmax(true), ncs, JCs);
         pick_chunks(Jqr, lc_jcmax(true), ncr, JCr);
-        const LcCarve c0 = lc_carve(4, true, ncs * JCs + ncr * JCr, 0, JCs > JCr ? JCs : JCr);
+        const LcCarve c0 = lc_carve(LC_WN_RES, true, ncs * JCs + ncr * JCr, 0, JCs > JCr ? JCs : JCr);
         const int room = smem_max > (int)c0.total ? (smem_max - (int)c0.total) / (int)c0.stage_bytes : 0;
         if (room >= 2) nst = room < LC_MAXST ? room : LC_MAXST;
         else resident = false;
@@ -945,7 +950,7 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
         nst = 4;
     }
     const int Js_pad = ncs * JCs, Jr_pad = ncr * JCr;
-    const int WN = resident ? 4 : 2, TF = lc_tf(WN), CS = lc_cs(WN);
+    const int WN = resident ? LC_WN_RES : LC_WN_STR, TF = lc_tf(WN), CS = lc_cs(WN);
     const int ctas_per_sm = resident ? 1 : 2;
     const LcCarve carve = lc_carve(WN, resident, Js_pad + Jr_pad, nst, JCs > JCr ? JCs : JCr);
     const long n_ftiles = (K + TF - 1) / TF;
@@ -1061,13 +1066,13 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
                          carve.total, smem_max);
     prof_begin("lc_main", st);
     if (resident) {
-        DEISM_CUDA_TRY(cudaFuncSetAttribute(lc_main_kernel<4, true>,
+        DEISM_CUDA_TRY(cudaFuncSetAttribute(lc_main_kernel<LC_WN_RES, true>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)carve.total));
-        lc_main_kernel<4, true><<<grid, 512, carve.total, st>>>(ma);
+        lc_main_kernel<LC_WN_RES, true><<<grid, 128 * LC_WN_RES, carve.total, st>>>(ma);
     } else {
-        DEISM_CUDA_TRY(cudaFuncSetAttribute(lc_main_kernel<2, false>,
+        DEISM_CUDA_TRY(cudaFuncSetAttribute(lc_main_kernel<LC_WN_STR, false>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)carve.total));
-        lc_main_kernel<2, false><<<grid, 256, carve.total, st>>>(ma);
+        lc_main_kernel<LC_WN_STR, false><<<grid, 128 * LC_WN_STR, carve.total, st>>>(ma);
     }
     prof_end("lc_main", st);
     DEISM_LAUNCH_CHECK("lc_main_kernel");
