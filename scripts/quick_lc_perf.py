@@ -5,19 +5,19 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import numpy as np, torch
 from conftest import Golden
 from deism_b200 import backend, images as im
-from oracle import oracle
+from deism_b200 import workloads
 
 def run(name, N, V, flatZ=True):
     g = Golden(name); p = g.params(); p["ifRemoveDirectPath"] = 0
     k = p["waveNumbers"]; K = len(k)
     rng = np.random.default_rng(0)
     if N == 0:
-        cs = oracle.monopole_coefficients(k); cr = oracle.monopole_coefficients(k)
+        cs = workloads.monopole_coeffs(k); cr = workloads.monopole_coeffs(k)
     else:
         cs = (rng.standard_normal((K, N+1, 2*N+1)) + 1j*rng.standard_normal((K, N+1, 2*N+1))).astype(np.complex64)
         cr = (rng.standard_normal((K, V+1, 2*V+1)) + 1j*rng.standard_normal((K, V+1, 2*V+1))).astype(np.complex64)
-    p["n_all"], p["m_all"], p["C_nm_s_vec"] = oracle.vectorize(cs, N)
-    p["v_all"], p["u_all"], p["C_vu_r_vec"] = oracle.vectorize(cr, V)
+    p["n_all"], p["m_all"], p["C_nm_s_vec"] = workloads.vectorize(cs, N)
+    p["v_all"], p["u_all"], p["C_vu_r_vec"] = workloads.vectorize(cr, V)
     p["DEISM_method"] = "LC"
     if not flatZ:
         Z = np.array(p["impedance"]); Z = Z * (1 + 0.1*np.linspace(0, 1, K))[None, :]; p["impedance"] = Z
