@@ -343,7 +343,8 @@ def _run_arg_org(params, out, accumulate, dev, sel=None):
 def run_DEISM_ARG_device(params, dev=None):
     dev = dev or _device()
     method = params["DEISM_method"]
-    K = int(np.asarray(params["waveNumbers"]).shape[0])
+    wn = params["waveNumbers"]
+    K = int(wn.shape[0]) if isinstance(wn, torch.Tensor) else int(np.asarray(wn).shape[0])
     out = torch.zeros(K, dtype=torch.complex128, device=dev)
     if method == "LC":
         _run_arg_lc(params, out, False, dev)

@@ -11,6 +11,9 @@
 // is used once, so the kernel is bound by streaming C_s (8 B per (k,j,img)) from HBM.
 // Mapping: thread = image (lanes run along the innermost, contiguous image axis -> coalesced
 // 128-byte loads), blockIdx.y = frequency; Y tables [J][I] stay in L2.
+#include <cstring>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace deism {
@@ -57,41 +60,77 @@ struct ArgMainArgs {
     cplx *partial;        // [gridDim.x][K]
 };
 
-__global__ void __launch_bounds__(128) arg_lc_kernel(ArgMainArgs a) {
-    __shared__ double2 red[128];
-    __shared__ double2 cr_sm[ARG_JMAX];
-    const long kidx = blockIdx.y;
-    for (int j = threadIdx.x; j < a.Jr; j += 128) {
-        float2 c = a.Cr[kidx * a.Jr + j];
-        cr_sm[j] = cmake((double)c.x, (double)c.y);
+// thread = image, blockIdx.y = a tile of ARG_KT frequencies: the image's harmonics Y_j are read
+// once per tile and reused from registers for every frequency of the tile (re-reading them per
+// frequency cost twice the traffic of the C_s stream itself), ARG_KT independent C_s loads are in
+// flight per harmonic.
+constexpr int ARG_KT = 8;
+
+__global__ void __launch_bounds__(128, 4) arg_lc_kernel(ArgMainArgs a) {
+    __shared__ double2 red[4][ARG_KT];
+    __shared__ double2 cr_sm[ARG_KT][ARG_JMAX];
+    const long k0 = (long)blockIdx.y * ARG_KT;
+    for (int e = threadIdx.x; e < ARG_KT * a.Jr; e += 128) {
+        const int q = e / a.Jr, j = e % a.Jr;
+        float2 c = k0 + q < a.K ? a.Cr[(k0 + q) * a.Jr + j] : make_float2(0.f, 0.f);
+        cr_sm[q][j] = cmake((double)c.x, (double)c.y);
     }
     __syncthreads();
     const long s = (long)blockIdx.x * 128 + threadIdx.x;
-    cplx P = cmake(0.0, 0.0);
+    cplx P[ARG_KT];
+#pragma unroll
+    for (int q = 0; q < ARG_KT; ++q) P[q] = cmake(0.0, 0.0);
     if (s < a.n_sel) {
         const long img = a.sel ? a.sel[s] : s;
-        const double kk = a.k[kidx], r = a.r[img];
-        cplx S = cmake(0.0, 0.0), R = cmake(0.0, 0.0);
-        const float2 *Cs = a.Cs + kidx * a.Js * a.n_images + img;
+        const double r = a.r[img];
+        cplx S[ARG_KT], R[ARG_KT];
+#pragma unroll
+        for (int q = 0; q < ARG_KT; ++q) { S[q] = cmake(0.0, 0.0); R[q] = cmake(0.0, 0.0); }
+        const long kstride = (long)a.Js * a.n_images;
+        const float2 *Cs = a.Cs + k0 * kstride + img;
+#pragma unroll 2
         for (int j = 0; j < a.Js; ++j) {
-            float2 c = Cs[(long)j * a.n_images];
-            cfma(S, cmake((double)c.x, (double)c.y), a.Ys[(long)j * a.n_images + img]);
+            const cplx y = a.Ys[(long)j * a.n_images + img];
+            float2 c[ARG_KT];
+#pragma unroll
+            for (int q = 0; q < ARG_KT; ++q)
+                c[q] = k0 + q < a.K ? __ldcs(&Cs[q * kstride + (long)j * a.n_images]) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < ARG_KT; ++q) cfma(S[q], cmake((double)c[q].x, (double)c[q].y), y);
         }
-        for (int j = 0; j < a.Jr; ++j) cfma(R, cr_sm[j], a.Yr[(long)j * a.n_images + img]);
-        double sn, cs;
-        sincos_cw(kk * r, &sn, &cs);
-        float2 at = a.atten[kidx * a.n_images + img];
-        double w = -4.0 * 3.14159265358979323846 / (kk * kk * r);
-        cplx fac = cmul(cmake((double)at.x, (double)at.y), cmake(cs * w, -sn * w));
-        P = cmul(cmul(fac, S), R);
+        for (int j = 0; j < a.Jr; ++j) {
+            const cplx y = a.Yr[(long)j * a.n_images + img];
+#pragma unroll
+            for (int q = 0; q < ARG_KT; ++q) cfma(R[q], cr_sm[q][j], y);
+        }
+#pragma unroll
+        for (int q = 0; q < ARG_KT; ++q) {
+            if (k0 + q >= a.K) break;
+            const double kk = a.k[k0 + q];
+            double sn, cs;
+            sincos_cw(kk * r, &sn, &cs);
+            const float2 at = a.atten[(k0 + q) * a.n_images + img];
+            const double w = -4.0 * 3.14159265358979323846 / (kk * kk * r);
+            const cplx fac = cmul(cmake((double)at.x, (double)at.y), cmake(cs * w, -sn * w));
+            P[q] = cmul(cmul(fac, S[q]), R[q]);
+        }
     }
-    red[threadIdx.x] = P;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < ARG_KT; ++q) {
+        double x = P[q].x, y = P[q].y;
+        for (int o = 16; o > 0; o >>= 1) {
+            x += __shfl_down_sync(0xffffffffu, x, o);
+            y += __shfl_down_sync(0xffffffffu, y, o);
+        }
+        if (lane == 0) red[warp][q] = cmake(x, y);
+    }
     __syncthreads();
-    for (int st = 64; st > 0; st >>= 1) {
-        if (threadIdx.x < st) red[threadIdx.x] = cadd(red[threadIdx.x], red[threadIdx.x + st]);
-        __syncthreads();
+    if (threadIdx.x < ARG_KT && k0 + threadIdx.x < a.K) {
+        const int q = threadIdx.x;
+        a.partial[(long)blockIdx.x * a.K + k0 + q] =
+            cadd(cadd(red[0][q], red[1][q]), cadd(red[2][q], red[3][q]));
     }
-    if (threadIdx.x == 0) a.partial[(long)blockIdx.x * a.K + kidx] = red[0];
 }
 
 }  // namespace deism
@@ -130,10 +169,27 @@ extern "C" int deism_lc_arg(int64_t n_images, int64_t K, int Js, int Jr, const i
         if (hv[j] < 0 || hv[j] > 64 || abs(hu[j]) > hv[j])
             return set_error(DEISM_ERR_INVALID, "bad (v,u) at j=%d", j);
     }
-    DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_arg_n, hn, Js * sizeof(int), 0, cudaMemcpyHostToDevice, st));
-    DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_arg_m, hm, Js * sizeof(int), 0, cudaMemcpyHostToDevice, st));
-    DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_arg_v, hv, Jr * sizeof(int), 0, cudaMemcpyHostToDevice, st));
-    DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_arg_u, hu, Jr * sizeof(int), 0, cudaMemcpyHostToDevice, st));
+    bool tables_uploaded = false;
+    {   // (n,m,v,u) live in constant memory: upload only when they change (no host sync otherwise)
+        static std::mutex mu;
+        static int last[4][ARG_JMAX], last_js = -1, last_jr = -1, last_dev = -1;
+        int dev = -1;
+        DEISM_CUDA_TRY(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev != last_dev || Js != last_js || Jr != last_jr || memcmp(last[0], hn, Js * sizeof(int)) ||
+            memcmp(last[1], hm, Js * sizeof(int)) || memcmp(last[2], hv, Jr * sizeof(int)) ||
+            memcmp(last[3], hu, Jr * sizeof(int))) {
+            last_dev = -1;
+            DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_arg_n, hn, Js * sizeof(int), 0, cudaMemcpyHostToDevice, st));
+            DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_arg_m, hm, Js * sizeof(int), 0, cudaMemcpyHostToDevice, st));
+            DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_arg_v, hv, Jr * sizeof(int), 0, cudaMemcpyHostToDevice, st));
+            DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_arg_u, hu, Jr * sizeof(int), 0, cudaMemcpyHostToDevice, st));
+            memcpy(last[0], hn, Js * sizeof(int)); memcpy(last[1], hm, Js * sizeof(int));
+            memcpy(last[2], hv, Jr * sizeof(int)); memcpy(last[3], hu, Jr * sizeof(int));
+            last_js = Js; last_jr = Jr; last_dev = dev;
+            tables_uploaded = true;
+        }
+    }
 
     cplx *Ys = (cplx *)workspace(WS_LC_YS, (size_t)n_images * Js * sizeof(cplx));
     cplx *Yr = (cplx *)workspace(WS_LC_YR, (size_t)n_images * Jr * sizeof(cplx));
@@ -151,7 +207,8 @@ extern "C" int deism_lc_arg(int64_t n_images, int64_t K, int Js, int Jr, const i
         DEISM_CUDA_TRY(cudaMemcpyAsync(sel, h_image_index, (size_t)n_sel * sizeof(long),
                                        cudaMemcpyHostToDevice, st));
     }
-    DEISM_CUDA_TRY(cudaStreamSynchronize(st));   // stack / caller host buffers consumed
+    if (tables_uploaded || sel)
+        DEISM_CUDA_TRY(cudaStreamSynchronize(st));   // stack / caller host buffers consumed
     if (!Ys || !Yr || !r || !partial) return DEISM_ERR_NOMEM;
 
     ArgPrepArgs pa;
@@ -162,7 +219,7 @@ extern "C" int deism_lc_arg(int64_t n_images, int64_t K, int Js, int Jr, const i
     ma.n_sel = n_sel; ma.n_images = n_images; ma.K = K; ma.Js = Js; ma.Jr = Jr;
     ma.Cs = (const float2 *)d_C_s_ARG_vec; ma.Cr = (const float2 *)d_C_r_vec; ma.Ys = Ys; ma.Yr = Yr;
     ma.r = r; ma.atten = (const float2 *)d_atten; ma.k = d_k; ma.sel = sel; ma.partial = partial;
-    dim3 grid((unsigned)nblk, (unsigned)K);
+    dim3 grid((unsigned)nblk, (unsigned)((K + ARG_KT - 1) / ARG_KT));
     prof_begin("arg_lc", st);
     arg_lc_kernel<<<grid, 128, 0, st>>>(ma);
     prof_end("arg_lc", st);
