@@ -272,11 +272,51 @@ def run_DEISM_device(params, dev=None):
         _run_lc(params, images, "", out, False, dev)
     elif method == "MIX":
         # pb:725-777: early images -> ORG, late images -> LC, results added
-        _run_org(params, images, "_early", out, False, dev)
-        _run_lc(params, images, "_late", out, True, dev)
+        if isinstance(params.get("C_nm_s"), torch.Tensor) or len(images["A_late"]) == 0:
+            _run_org(params, images, "_early", out, False, dev)
+            _run_lc(params, images, "_late", out, True, dev)
+        else:
+            _run_mix_from_host(params, images, out, dev)
     else:
         raise ValueError(f"Unknown DEISM method: {method}")
     return out
+
+
+_copy_streams = {}
+
+
+def _run_mix_from_host(params, images, out, dev):
+    """MIX with host-resident inputs: the (long) LC part starts as soon as ITS inputs are on the
+    device; the ORG part's inputs — the [K, N+1, 2N+1] coefficient tables are the largest arrays
+    of the call — travel on a copy stream underneath it and the ORG kernels follow.  Same two
+    partial sums, added in the other order."""
+    p = dict(params)
+    p["waveNumbers"] = to_device(params["waveNumbers"], torch.float64, dev)        # shared: once
+    if params.get("impedance") is not None:
+        Z = params["impedance"]
+        p["impedance"] = to_device(Z if isinstance(Z, torch.Tensor) else np.asarray(Z, dtype=np.complex128),
+                                   torch.complex128, dev)
+    main = torch.cuda.current_stream(dev)
+    _run_lc(p, images, "_late", out, False, dev)
+    side = _copy_streams.get(dev.index)
+    if side is None:
+        side = _copy_streams[dev.index] = torch.cuda.Stream(dev)
+    staged = []
+    with torch.cuda.stream(side):
+        for key in ("C_nm_s", "C_vu_r"):
+            p[key] = _c64_on_device(params[key], dev)
+            staged.append(p[key])
+        early = dict(images)
+        for key, dt in (("A_early", torch.int32), ("R_sI_r_all_early", torch.float32)):
+            if key in images:
+                early[key] = to_device(images[key], dt, dev)
+                staged.append(early[key])
+        done = torch.cuda.Event()
+        done.record(side)
+    main.wait_event(done)
+    for t in staged:
+        t.record_stream(main)
+    _run_org(p, early, "_early", out, True, dev)
 
 
 def run_DEISM(params):
