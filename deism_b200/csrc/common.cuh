@@ -29,7 +29,10 @@ void prof_end(const char *name, cudaStream_t st);
 enum WsSlot {
     WS_LC_IMG = 0, WS_LC_YS, WS_LC_YR, WS_PARTIAL, WS_FLAGS, WS_SMALL, WS_ORG_B, WS_ORG_IMG,
     WS_ORG_Y, WS_ORG_LIST, WS_ARG_IDX, WS_CONVEX_A, WS_CONVEX_B, WS_CONVEX_C, WS_CONVEX_D,
-    WS_CONVEX_E, WS_BENCH, WS_NSLOTS
+    WS_CONVEX_E, WS_BENCH,
+    // the ORG entry points own their scratch: the ORG and LC parts of a MIX run may execute
+    // concurrently on two streams
+    WS_ORG_SMALL, WS_ORG_PARTIAL, WS_ORG_FLAGS, WS_NSLOTS
 };
 
 #define DEISM_CUDA_TRY(expr)                                                                  \

@@ -930,7 +930,7 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
     const OrgEntry *d_ent[2] = {guard.use->d_ent[0], guard.use->d_ent[1]};
     const int *d_seg[2] = {guard.use->d_seg[0], guard.use->d_seg[1]};
 
-    int *flags = (int *)workspace(WS_FLAGS, 64);
+    int *flags = (int *)workspace(WS_ORG_FLAGS, 64);
     if (!flags) return DEISM_ERR_NOMEM;
     rc = launch_z_flat(atten, K, flags, st);
     if (rc) return rc;
@@ -940,7 +940,7 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
         OrgImage *rec = (OrgImage *)workspace(WS_ORG_IMG, (size_t)n_images * sizeof(OrgImage));
         cplx *Y = (cplx *)workspace(WS_ORG_Y, (size_t)nseg * n_images * sizeof(cplx));
         long nblk = (n_images + 127) / 128;
-        cplx *partial = (cplx *)workspace(WS_PARTIAL, (size_t)nblk * K * sizeof(cplx));
+        cplx *partial = (cplx *)workspace(WS_ORG_PARTIAL, (size_t)nblk * K * sizeof(cplx));
         if (!rec || !Y || !partial) return DEISM_ERR_NOMEM;
         OrgPrepArgs pa;
         pa.n_images = n_images; pa.n_pad_cap = n_images; pa.Lmax = Lmax; pa.perm = nullptr;
@@ -1006,7 +1006,7 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
 
     const long n_ftiles = (K + ORG_TF - 1) / ORG_TF;
     const size_t b_rows = (size_t)R_tot * 2 * ORG_BS, y_rows = (size_t)R_tot * ORG_OS;
-    float2 *CsT = (float2 *)workspace(WS_SMALL, (size_t)(NMs + NMr) * K * sizeof(float2));
+    float2 *CsT = (float2 *)workspace(WS_ORG_SMALL, (size_t)(NMs + NMr) * K * sizeof(float2));
     double *Bp = (double *)workspace(WS_ORG_B, (size_t)8 * n_ftiles * b_rows * sizeof(double));
     if (!CsT || !Bp) return DEISM_ERR_NOMEM;
     float2 *CrT = CsT + (size_t)NMs * K;
@@ -1054,7 +1054,7 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
     if (n_chunks > 65535) n_chunks = 65535;
     long tiles_per_chunk = (n_tiles_cap + n_chunks - 1) / n_chunks;
     n_chunks = (n_tiles_cap + tiles_per_chunk - 1) / tiles_per_chunk;
-    cplx *partial = (cplx *)workspace(WS_PARTIAL, (size_t)n_chunks * K * sizeof(cplx));
+    cplx *partial = (cplx *)workspace(WS_ORG_PARTIAL, (size_t)n_chunks * K * sizeof(cplx));
     if (!partial) return DEISM_ERR_NOMEM;
 
     OrgConsumeArgs ca;
@@ -1105,7 +1105,7 @@ extern "C" int deism_org_arg(int64_t n_images, int64_t K, int N, int V, const fl
     OrgImage *rec = (OrgImage *)workspace(WS_ORG_IMG, (size_t)n_images * sizeof(OrgImage));
     cplx *Y = (cplx *)workspace(WS_ORG_Y, (size_t)nseg * n_images * sizeof(cplx));
     long nblk = (n_sel + 127) / 128;
-    cplx *partial = (cplx *)workspace(WS_PARTIAL, (size_t)nblk * K * sizeof(cplx));
+    cplx *partial = (cplx *)workspace(WS_ORG_PARTIAL, (size_t)nblk * K * sizeof(cplx));
     long *sel = nullptr;
     if (h_image_index) {
         for (int64_t i = 0; i < n_sel; ++i)
