@@ -84,6 +84,37 @@ def test_lc_fused(name):
     assert rel_l2(got, g.rtf) < RTF_TOL
 
 
+@pytest.mark.parametrize("name", ["s5_shoebox_rtf_lc_o7_mono_noang", "s1_shoebox_rtf_mix_o5_mono",
+                                  "s4_shoebox_rir_mix_o9_N2", "s2_shoebox_rtf_lc_o6_N3"])
+def test_frequency_dependent_impedance_fused_vs_materialised(name):
+    """Impedance that varies with frequency (complex, different per wall): the in-kernel per-term
+    attenuation (monopole, tensor-core and ORG kernels) against the same run fed with the
+    attenuation array materialised by the image generator and against the CPU oracle on it."""
+    from deism_b200 import backend, images as im
+    from oracle import oracle
+
+    p = Golden(name).params()
+    p.pop("images")
+    K = len(p["waveNumbers"])
+    ramp = 1.0 + 0.3 * np.linspace(0.0, 1.0, K)
+    Z = np.asarray(p["impedance"], dtype=np.complex128) * ramp[None, :]
+    Z = Z * (1.0 + 0.1 * np.arange(6))[:, None] + 1j * (2.0 - 3.0 * np.linspace(0, 1, K))[None, :]
+    p["impedance"] = Z
+    method = p["DEISM_method"]
+    fused = im.pre_calc_images_src_rec_optimized_nofs_v2_numba(p)
+    mat = im.pre_calc_images_src_rec_optimized_nofs_v2_numba(p, materialize=True)
+    if method in ("ORG", "LC"):
+        fused, mat = im.merge_images(fused), im.merge_images(mat)
+    assert fused["storage"] == "fused" and mat["storage"] == "materialized"
+    p["images"] = fused
+    got = backend.run_DEISM(p)
+    p["images"] = mat
+    via_array = backend.run_DEISM(p)
+    want = oracle.run_DEISM(p)
+    assert rel_l2(via_array, want) < RTF_TOL
+    assert rel_l2(got, want) < RTF_TOL
+
+
 def test_lc_vs_oracle_random_inputs():
     """Seeded random geometry / coefficients / complex frequency-dependent impedance, ragged
     sizes (K and I not multiples of the tile sizes), against the CPU oracle."""
@@ -91,7 +122,10 @@ def test_lc_vs_oracle_random_inputs():
     from oracle import oracle
 
     rng = np.random.default_rng(7)
-    for (I, K, N, V) in [(1, 1, 0, 0), (70, 33, 2, 1), (333, 97, 4, 3), (129, 64, 5, 5), (65, 40, 10, 7)]:
+    # covers the monopole kernel (0,0), the resident-coefficient shape with one / several chunks per
+    # pass (5,5), (5,6), (7,2), the streaming shape (6,6), (10,7) and a monopole receiver (3,0)
+    for (I, K, N, V) in [(1, 1, 0, 0), (70, 33, 2, 1), (333, 97, 4, 3), (129, 64, 5, 5), (65, 40, 10, 7),
+                         (200, 130, 5, 6), (90, 70, 6, 6), (150, 65, 7, 2), (64, 64, 3, 0), (300, 200, 0, 0)]:
         Js, Jr = (N + 1) ** 2, (V + 1) ** 2
         cs = (rng.standard_normal((K, N + 1, 2 * N + 1)) + 1j * rng.standard_normal((K, N + 1, 2 * N + 1))).astype(np.complex64)
         cr = (rng.standard_normal((K, V + 1, 2 * V + 1)) + 1j * rng.standard_normal((K, V + 1, 2 * V + 1))).astype(np.complex64)
@@ -238,7 +272,8 @@ def test_org_vs_oracle_random_inputs():
     from oracle import oracle
 
     rng = np.random.default_rng(11)
-    for (I, K, N, V) in [(1, 1, 0, 0), (45, 37, 2, 3), (130, 33, 4, 4), (67, 20, 6, 1), (40, 12, 8, 9)]:
+    for (I, K, N, V) in [(1, 1, 0, 0), (45, 37, 2, 3), (130, 33, 4, 4), (67, 20, 6, 1), (40, 12, 8, 9),
+                         (33, 65, 10, 10), (97, 31, 0, 5)]:
         cs = (rng.standard_normal((K, N + 1, 2 * N + 1)) + 1j * rng.standard_normal((K, N + 1, 2 * N + 1))).astype(np.complex64)
         cr = (rng.standard_normal((K, V + 1, 2 * V + 1)) + 1j * rng.standard_normal((K, V + 1, 2 * V + 1))).astype(np.complex64)
         A = rng.integers(-3, 4, size=(I, 6)).astype(np.int32)
