@@ -349,6 +349,46 @@ def test_full_c3_org_order25_N10_subsampled():
     _full_case("c3_sub100", "ORG", 10, 10)
 
 
+def test_full_c3_all_2000_frequencies_properties():
+    """C3 at its full size (20 586 images x 2 000 frequencies, N = V = 10).  The reference could
+    only be afforded on every 20th frequency (fixture c3_sub100); the full grid is checked through
+    size-independent properties: (a) frequencies are independent, so the 100 reference frequencies
+    inside the full run reproduce the reference; (b) additivity over a split of the image list;
+    (c) linearity in the source coefficients."""
+    from deism_b200 import backend, wigner
+
+    g = Golden("c3_sub100")
+    p = _full_params(g)
+    f_ref = np.asarray(p["freqs"], dtype=np.float64)
+    freqs = np.arange(2.0, 4002.0, 2.0)
+    idx = np.searchsorted(freqs, f_ref)
+    assert np.array_equal(freqs[idx], f_ref)
+    K, N, V = len(freqs), 10, 10
+    cs_ref, cr_ref = _synth(len(f_ref), N, V)               # what the reference run used
+    cs, cr = _synth(K, N, V, seed=1)
+    cs[idx], cr[idx] = cs_ref, cr_ref
+    Z = np.repeat(np.asarray(p["impedance"])[:, :1], K, axis=1)
+    p.update({"DEISM_method": "ORG", "freqs": freqs, "waveNumbers": 2 * np.pi * freqs / p["soundSpeed"],
+              "impedance": Z, "C_nm_s": cs, "C_vu_r": cr, "sourceOrder": N, "receiverOrder": V})
+    p = wigner.pre_calc_Wigner(p)
+    im = _images_from_params(p, "ORG")
+    p["images"] = im
+    full = backend.run_DEISM(p)
+    assert full.shape == (K,) and np.all(np.isfinite(full.view(np.float64)))
+    assert rel_l2(full[idx], g.rtf) < RTF_TOL and rel_max(full[idx], g.rtf) < 1e-8        # (a)
+    n = len(im["A"])
+    cut = n // 3 + 5                                          # ragged split, not a tile multiple
+    parts = []
+    for sl in (slice(0, cut), slice(cut, n)):
+        q = dict(p)
+        q["images"] = {k: (v[sl] if isinstance(v, np.ndarray) and len(v) == n else v) for k, v in im.items()}
+        parts.append(backend.run_DEISM(q))
+    assert rel_l2(parts[0] + parts[1], full) < 1e-12                                     # (b)
+    q = dict(p)
+    q["C_nm_s"] = (-2.0 * cs).astype(np.complex64)            # a power of two: exact in complex64
+    assert rel_l2(backend.run_DEISM(q), -2.0 * full) < 1e-13                             # (c)
+
+
 def test_full_c5_mix_order40_N5():
     _full_case("c5_full_N5", "MIX", 5, 5)
 
