@@ -40,11 +40,17 @@ def run(name, N, V, flatZ=True):
     t0 = time.time(); out_h = backend.run_DEISM(p); t_e2e = time.time() - t0
     J = (N+1)**2 + (V+1)**2
     print(f"{name} N={N} flatZ={flatZ}: I={I} K={K} terms={I*K:.3e} kernel {ms:.3f} ms -> {I*K/ms*1e3:.3e} terms/s, "
-          f"contraction {8*J*I*K/ms*1e3/1e12:.2f} TFLOP/s; e2e {t_e2e*1e3:.1f} ms; images {t_img*1e3:.1f} ms", flush=True)
+          f"contraction {4*J*I*K/ms*1e3/1e12:.2f} TFLOP/s (real-basis count); e2e {t_e2e*1e3:.1f} ms; images {t_img*1e3:.1f} ms", flush=True)
 
-run("c2_full_mono", 0, 0)
-run("c2_full_N5", 5, 5)
-run("c2_full_N5", 5, 5, flatZ=False)
-run("c5_full_N5", 5, 5)
-run("c5_full_N5", 5, 5, flatZ=False)
-run("c5_full_N5", 0, 0)
+if __name__ == "__main__":
+    if len(sys.argv) > 1:          # python scripts/quick_lc_perf.py c2_full_N5 3,3 6,6 10,10
+        for nv in sys.argv[2:]:
+            n, v = (int(t) for t in nv.split(","))
+            run(sys.argv[1], n, v)
+    else:
+        run("c2_full_mono", 0, 0)
+        run("c2_full_N5", 5, 5)
+        run("c2_full_N5", 5, 5, flatZ=False)
+        run("c5_full_N5", 5, 5)
+        run("c5_full_N5", 5, 5, flatZ=False)
+        run("c5_full_N5", 0, 0)
