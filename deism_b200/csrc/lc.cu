@@ -36,7 +36,13 @@ namespace deism {
 
 constexpr int LC_TI = 64;        // images per tile
 // most harmonics per staged chunk (multiple of 4): a whole order-5 pass when only Y streams
-__host__ __device__ constexpr int lc_jcmax(bool cres_on) { return cres_on ? 36 : 12; }
+#ifndef LC_STREAM_JC
+#define LC_STREAM_JC 12
+#endif
+#ifndef LC_STREAM_NST
+#define LC_STREAM_NST 4
+#endif
+__host__ __device__ constexpr int lc_jcmax(bool cres_on) { return cres_on ? 36 : LC_STREAM_JC; }
 #ifndef LC_NT
 #define LC_NT 2                  // n-tiles (8 freqs each) per warp: warp tile = 16 images x 8*LC_NT freqs
 #endif
@@ -242,7 +248,7 @@ lc_coef_kernel(const float2 *__restrict__ in, const double *__restrict__ kvec, l
 
 struct LcMainArgs {
     long n_images, n_pad, K;
-    int Js_pad, Jr_pad;      // padded harmonic counts = ncs*JCs, ncr*JCr
+    int Js_pad, Jr_pad;      // harmonic counts padded to the DMMA k extent (multiples of 4)
     int ncs, ncr, JCs, JCr;  // chunks per pass and harmonics per chunk (multiples of 4)
     int nst;                 // ring stages (<= LC_MAXST)
     const double *CTs, *CTr; // [K_pad/TF][J_pad][2][TF+2]
@@ -357,9 +363,10 @@ lc_main_kernel(LcMainArgs a) {
     auto issue = [&](int tile_ord, int local, int stage) {
         const long tile = tile_lo + tile_ord;
         const bool src_pass = local < a.ncs;
-        const int JC = src_pass ? a.JCs : a.JCr;
-        const int j0 = (src_pass ? local : local - a.ncs) * JC;
+        const int JCfull = src_pass ? a.JCs : a.JCr;
+        const int j0 = (src_pass ? local : local - a.ncs) * JCfull;
         const int Jp = src_pass ? a.Js_pad : a.Jr_pad;
+        const int JC = Jp - j0 < JCfull ? Jp - j0 : JCfull;       // the last chunk of a pass may be short
         const double *Yg = (src_pass ? a.Ys : a.Yr) + (tile * Jp + j0) * LC_YS;
         unsigned char *S = ring + (unsigned)stage * cv.stage_bytes;
         const unsigned yb = (unsigned)(JC * LC_YS * 8);
@@ -494,6 +501,7 @@ lc_main_kernel(LcMainArgs a) {
     };
 
     auto no_side = [] {};
+    auto chunk_rows = [](int Jpad, int JC, int l) { return Jpad - l * JC < JC ? Jpad - l * JC : JC; };
     // end of a source pass: S = T0 + i T1;  park S' = fac * S
     auto epi_S = [&] {
 #pragma unroll
@@ -548,9 +556,10 @@ lc_main_kernel(LcMainArgs a) {
             }
         };
         if (fast) {
-            run_chunk(a.JCs, 0, epi_P, [&] { factor_fast(0); }, [&] { factor_fast(1); });
+            run_chunk(chunk_rows(a.Js_pad, a.JCs, 0), 0, epi_P, [&] { factor_fast(0); }, [&] { factor_fast(1); });
 #pragma unroll 1
-            for (int l = 1; l < a.ncs; ++l) run_chunk(a.JCs, l * a.JCs, no_side, no_side, no_side);
+            for (int l = 1; l < a.ncs; ++l)
+                run_chunk(chunk_rows(a.Js_pad, a.JCs, l), l * a.JCs, no_side, no_side, no_side);
         } else {
             // general path: per-term sincos off the uniform grid, per-term attenuation for a
             // frequency-dependent impedance or a materialised atten[I,K] (rolled: rarely hot)
@@ -600,7 +609,8 @@ lc_main_kernel(LcMainArgs a) {
                 facp[j][tid] = cmul(att, E);
             }
 #pragma unroll 1
-            for (int l = 0; l < a.ncs; ++l) run_chunk(a.JCs, l * a.JCs, no_side, no_side, no_side);
+            for (int l = 0; l < a.ncs; ++l)
+                run_chunk(chunk_rows(a.Js_pad, a.JCs, l), l * a.JCs, no_side, no_side, no_side);
         }
         __syncwarp();
         if (lane == 0 && atomicAdd(&recdone[rb], 1) == NWARPS - 1) {
@@ -609,9 +619,10 @@ lc_main_kernel(LcMainArgs a) {
             if (tt + 2 < n_tiles) issue_records(tt + 2);
         }
         // ---- receiver pass; its first chunk carries the source pass's epilogue ----
-        run_chunk(a.JCr, a.Js_pad, epi_S, no_side, no_side);
+        run_chunk(chunk_rows(a.Jr_pad, a.JCr, 0), a.Js_pad, epi_S, no_side, no_side);
 #pragma unroll 1
-        for (int l = 1; l < a.ncr; ++l) run_chunk(a.JCr, a.Js_pad + l * a.JCr, no_side, no_side, no_side);
+        for (int l = 1; l < a.ncr; ++l)
+            run_chunk(chunk_rows(a.Jr_pad, a.JCr, l), a.Js_pad + l * a.JCr, no_side, no_side, no_side);
     }
     epi_P();
 
@@ -806,17 +817,12 @@ int validate_atten(const deism_shoebox_atten *at) {
     return DEISM_OK;
 }
 
-// J harmonics -> nc chunks of JC (multiple of 4, <= jcmax): least zero padding, then fewest chunks
-static void pick_chunks(int J, int jcmax, int &nc, int &JC) {
-    const int LC_JC = jcmax;
-    int nc0 = (J + LC_JC - 1) / LC_JC, best = 1 << 30;
-    nc = nc0; JC = LC_JC;
-    for (int n = nc0; n <= nc0 + 6; ++n) {
-        int jc = ((J + n - 1) / n + 3) / 4 * 4;
-        if (jc > LC_JC) continue;
-        int cost = 4 * n * jc + n;   // padded FMAs dominate, one barrier per chunk breaks ties
-        if (cost < best) { best = cost; nc = n; JC = jc; }
-    }
+// J harmonics (padded to Jpad, a multiple of 4) -> nc chunks of JC rows (multiple of 4, <= jcmax);
+// the last chunk holds what is left.  Fewest chunks, near-equal sizes.
+static void pick_chunks(int J, int jcmax, int &nc, int &JC, int &Jpad) {
+    Jpad = (J + 3) / 4 * 4;
+    nc = (Jpad + jcmax - 1) / jcmax;
+    JC = ((Jpad / 4 + nc - 1) / nc) * 4;
 }
 
 // Real-harmonic basis of the caller's (n_j, m_j) list (see LcBasis): distinct (n,|m|) in order of
@@ -935,21 +941,20 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
     const int smem_max = smem_optin_bytes();
     static const char *force = getenv("DEISM_LC_SHAPE");     // "stream": A/B runs
     bool resident = !(force && !strcmp(force, "stream"));
-    int nst = 4, ncs, ncr, JCs, JCr;
+    int nst = 4, ncs, ncr, JCs, JCr, Js_pad, Jr_pad;
     if (resident) {
-        pick_chunks(Jqs, lc_jcmax(true), ncs, JCs);
-        pick_chunks(Jqr, lc_jcmax(true), ncr, JCr);
-        const LcCarve c0 = lc_carve(LC_WN_RES, true, ncs * JCs + ncr * JCr, 0, JCs > JCr ? JCs : JCr);
+        pick_chunks(Jqs, lc_jcmax(true), ncs, JCs, Js_pad);
+        pick_chunks(Jqr, lc_jcmax(true), ncr, JCr, Jr_pad);
+        const LcCarve c0 = lc_carve(LC_WN_RES, true, Js_pad + Jr_pad, 0, JCs > JCr ? JCs : JCr);
         const int room = smem_max > (int)c0.total ? (smem_max - (int)c0.total) / (int)c0.stage_bytes : 0;
         if (room >= 2) nst = room < LC_MAXST ? room : LC_MAXST;
         else resident = false;
     }
     if (!resident) {
-        pick_chunks(Jqs, lc_jcmax(false), ncs, JCs);
-        pick_chunks(Jqr, lc_jcmax(false), ncr, JCr);
-        nst = 4;
+        pick_chunks(Jqs, lc_jcmax(false), ncs, JCs, Js_pad);
+        pick_chunks(Jqr, lc_jcmax(false), ncr, JCr, Jr_pad);
+        nst = LC_STREAM_NST;
     }
-    const int Js_pad = ncs * JCs, Jr_pad = ncr * JCr;
     const int WN = resident ? LC_WN_RES : LC_WN_STR, TF = lc_tf(WN), CS = lc_cs(WN);
     const int ctas_per_sm = resident ? 1 : 2;
     const LcCarve carve = lc_carve(WN, resident, Js_pad + Jr_pad, nst, JCs > JCr ? JCs : JCr);
