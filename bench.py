@@ -378,6 +378,7 @@ def main():
     roofline = None
     if rank == 0 and prof:
         dom = max(prof, key=lambda n: prof[n][0])
+        dom_kernel = dom + "_kernel"
         ms_k, n_k = prof[dom]
         per_launch_ms = ms_k / n_k
         if dom == "lc_main":
@@ -385,9 +386,11 @@ def main():
             Js, Jr = (N + 1) ** 2, (V + 1) ** 2
             fpt = lc_flops_per_term(Js, Jr, args.general_impedance, 0.75 * p["maxReflOrder"])
             units = n_late * Ks
-            if Js == 1 and Jr == 1 and extras.get("fp64_peak_dfma_tflops"):
-                # lc_mono_kernel issues no DMMA: its roofline is the FP64 FMA pipe
-                peak_tf, peak_kind = extras["fp64_peak_dfma_tflops"], "dfma"
+            if Js == 1 and Jr == 1:
+                dom_kernel = "lc_mono_kernel"      # what deism_lc_shoebox launches for monopoles
+                if extras.get("fp64_peak_dfma_tflops"):
+                    # no DMMA in it: its roofline is the FP64 FMA pipe
+                    peak_tf, peak_kind = extras["fp64_peak_dfma_tflops"], "dfma"
         elif dom == "org_consume":
             fpt = org_consume_flops_per_term(N, V)
             units = I * Ks
@@ -396,14 +399,14 @@ def main():
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
-                traffic = json.load(fh).get(dom + "_kernel", {}).get(args.workload)
+                traffic = json.load(fh).get(dom_kernel, {}).get(args.workload)
             if world > 1 or args.general_impedance:
                 traffic = None      # captured at N=1 on the shipped configuration only
         except Exception:
             traffic = None
         if fpt:
             achieved = fpt * units / (per_launch_ms * 1e-3) / 1e12
-            roofline = {"bound": "fp64", "kernel": dom + "_kernel", "achieved": round(achieved, 3),
+            roofline = {"bound": "fp64", "kernel": dom_kernel, "achieved": round(achieved, 3),
                         "peak": peak_tf, "unit": "TFLOP/s",
                         "frac": round(achieved / peak_tf, 4) if peak_tf else None,
                         "traffic": traffic,
