@@ -67,3 +67,38 @@ def test_device_impedance_feeds_run_deism():
     p["impedance"] = dense_from_three
     want = backend.run_DEISM(p)
     assert rel_l2(got, want) < 1e-12
+
+
+def test_update_freqs_keeps_impedance_on_device():
+    """update_wall_materials -> update_freqs(device_impedance=True): Z_S[6, K] is a CUDA tensor equal
+    to the host pipeline's array; a five-band absorption table goes through the same route."""
+    import torch
+
+    from deism_b200 import materials as M
+
+    base = {"roomVolumn": 30.0, "roomAreas": np.array([7.5, 7.5, 10.0, 10.0, 12.0, 12.0]), "soundSpeed": 343.0,
+            "roomSize": np.array([4.0, 3.0, 2.5]), "mode": "RTF", "startFreq": 20, "endFreq": 4000, "freqStep": 4,
+            "ifReceiverNormalize": 0}
+    Z = (np.random.default_rng(3).uniform(5, 30, (6, 4)) + 1j * np.random.default_rng(4).uniform(-5, 5, (6, 4)))
+    bands = np.array([125.0, 500.0, 1000.0, 2000.0])
+    host = M.update_freqs(M.update_wall_materials(dict(base), Z, bands, "impedance"))
+    devp = M.update_freqs(M.update_wall_materials(dict(base), Z, bands, "impedance"), device_impedance=True)
+    assert isinstance(devp["impedance"], torch.Tensor) and devp["impedance"].is_cuda
+    assert tuple(devp["impedance"].shape) == host["impedance"].shape == (6, len(host["freqs"]))
+    assert np.max(np.abs(devp["impedance"].cpu().numpy() - host["impedance"])) <= 1e-13 * np.max(np.abs(host["impedance"]))
+
+
+def test_empty_inputs_are_accepted():
+    import ctypes as C
+
+    import torch
+
+    from deism_b200 import _lib
+
+    lib = _lib.lib()
+    x = torch.zeros(16, dtype=torch.float64, device="cuda")
+    assert lib.deism_pchip_interp(0, 3, 10, x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), None) == 0
+    assert lib.deism_pchip_interp(6, 3, 0, x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), None) == 0
+    assert lib.deism_arg_refit(0, 5, 2, 20, None, None, None, None, C.c_double(0.4), None, None) == 0
+    assert lib.deism_arg_refit(5, 0, 2, 20, None, None, None, None, C.c_double(0.4), None, None) == 0
+    assert lib.deism_arg_refit(5, 5, 2, 20, None, None, None, None, C.c_double(0.4), None, None) != 0   # null pointers
