@@ -5,15 +5,18 @@ contract as the reference:
     monopole branches of init_{source,receiver}_directivities[_ARG] ~ core_deism.py:1254-1263,
                                                        1323-1338, 1623-1640, 1730-1745
 
+    sampled (non-monopole) init_{source,receiver}_directivities: rotate_directions,
+    SHCs_from_pressure_LS, get_directivity_coefs                    ~ core_deism.py:1264-1308, 1340-1397,
+                                                       1481-1542 (one least-squares fit: host NumPy)
     cal_C_nm_s_new (+ SHCs_from_pressure_LS, vectorize_C_nm_s_ARG fused)   ~ core_deism.py:1545-1605,
                                                        1481-1509, 1193-1217   [GPU: deism_arg_refit]
     rotation_matrix_ZXZ                                                  ~ shared_utils.py:9-26
 
 Sampled (non-monopole) directivities need the .mat data sets that are absent from the reference
-tree (.MISSING_LARGE_BLOBS); shoebox callers inject ``C_nm_s`` / ``C_vu_r`` (complex64
-[K, N+1, 2N+1], signed m indexed NumPy-style) and call the vectorisers; convex (ARG) callers inject
-the sampled field as ``params["sampledSource"] = {"freqs", "Psh", "Dir_all", "r0"}`` (what
-``load_directive_pressure`` returns, data_loader.py:1099-1145).
+tree (.MISSING_LARGE_BLOBS); callers inject the sampled field as ``params["sampledSource"]`` /
+``params["sampledReceiver"]`` = ``{"freqs", "Psh", "Dir_all", "r0"}`` (what
+``load_directive_pressure`` returns, data_loader.py:1099-1145), or ready coefficients ``C_nm_s`` /
+``C_vu_r`` (complex64 [K, N+1, 2N+1], signed m indexed NumPy-style) and call the vectorisers.
 """
 from __future__ import annotations
 
@@ -71,10 +74,71 @@ def _monopole(k):
     return (-1j * np.asarray(k, dtype=np.float64) * 1.0 * _Y00)
 
 
+def rotate_directions(Dir_all, facing):
+    """Sampling directions [azimuth, inclination] after rotating +x to the facing direction given as
+    ZXZ Euler angles in degrees (cd:1512-1531)."""
+    alpha, beta, gamma = np.asarray(facing, dtype=float) * np.pi / 180
+    el = np.pi / 2 - Dir_all[:, 1]
+    xyz = np.vstack((np.cos(el) * np.cos(Dir_all[:, 0]), np.cos(el) * np.sin(Dir_all[:, 0]), np.sin(el)))
+    r = rotation_matrix_ZXZ(alpha, beta, gamma) @ xyz
+    hxy = np.hypot(r[0], r[1])
+    return np.hstack((np.arctan2(r[1], r[0])[:, None], (np.pi / 2 - np.arctan2(r[2], hxy))[:, None]))
+
+
+def SHCs_from_pressure_LS(Psh, Dir_all, sph_order_FEM, freqs_all):
+    """Least-squares spherical-harmonic coefficients of a field sampled on a sphere (cd:1481-1509):
+    [K, N+1, 2N+1] with mode m stored at index m + n."""
+    from scipy import special as sps
+
+    N = int(sph_order_FEM)
+    Y = np.zeros((len(Dir_all), (N + 1) ** 2), dtype=complex)
+    for n in range(N + 1):
+        for m in range(-n, n + 1):
+            Y[:, n * n + n + m] = sps.sph_harm_y(n, m, Dir_all[:, 1], Dir_all[:, 0])
+    fnm = np.linalg.pinv(Y) @ np.asarray(Psh).T
+    out = np.zeros((np.asarray(freqs_all).size, N + 1, 2 * N + 1), dtype=complex)
+    for n in range(N + 1):
+        for m in range(-n, n + 1):
+            out[:, n, m + n] = fnm[n * n + n + m, :]
+    return out
+
+
+def get_directivity_coefs(k, maxSHorder, Pmnr0, r0):
+    """C[k, n, m] = P_mn(r0) / h_n^(2)(k r0), signed m wrapping NumPy-style (cd:1534-1542)."""
+    from scipy import special as sps
+
+    k = np.asarray(k, dtype=float)
+    C_ = np.zeros((k.size, maxSHorder + 1, 2 * maxSHorder + 1), dtype=complex)
+    for n in range(maxSHorder + 1):
+        hn = sps.spherical_jn(n, k * r0) - 1j * sps.spherical_yn(n, k * r0)
+        for m in range(-n, n + 1):
+            C_[:, n, m] = Pmnr0[:, n, m + n] / hn
+    return C_
+
+
+def _sampled(params, which):
+    """The tuple load_directive_pressure returns (data_loader.py:1099-1145), injected by the caller
+    as params['sampledSource' | 'sampledReceiver'] = {freqs, Psh, Dir_all, r0}: the reference's
+    .mat data sets are absent from its tree."""
+    smp = params.get("sampled" + which)
+    if smp is None:
+        raise FileNotFoundError(f"sampled {which.lower()} directivities: the .mat data sets are absent from "
+                                f"the reference tree; provide params['sampled{which}']")
+    if not np.allclose(smp["freqs"], params["freqs"]):
+        raise ValueError("The frequencies in the directivity data are not the same as the ones "
+                         "defined in params['freqs']")
+    return np.asarray(smp["Psh"]), np.asarray(smp["Dir_all"], dtype=float)
+
+
 def init_source_directivities(params):
-    if params["sourceType"] != "monopole":
-        raise NotImplementedError("sampled source directivities need the absent .mat data; inject "
-                                  "params['C_nm_s'] instead")
+    if params["sourceType"] != "monopole":                                   # cd:1264-1308
+        Psh, Dir_all = _sampled(params, "Source")
+        P = SHCs_from_pressure_LS(Psh, rotate_directions(Dir_all, params["orientSource"]),
+                                  params["sourceOrder"], params["freqs"])
+        params["C_nm_s"] = get_directivity_coefs(params["waveNumbers"], params["sourceOrder"], P,
+                                                 params["radiusSource"]).astype(np.complex64)
+        _track(params, ("C_nm_s",), "init_source_directivities")
+        return params
     params["C_nm_s"] = _monopole(params["waveNumbers"])[..., None, None].astype(np.complex64)
     params["sourceOrder"] = 0
     _track(params, ("C_nm_s", "sourceOrder"), "init_source_directivities")
@@ -82,9 +146,16 @@ def init_source_directivities(params):
 
 
 def init_receiver_directivities(params):
-    if params["receiverType"] != "monopole":
-        raise NotImplementedError("sampled receiver directivities need the absent .mat data; inject "
-                                  "params['C_vu_r'] instead")
+    if params["receiverType"] != "monopole":                                 # cd:1340-1397
+        Psh, Dir_all = _sampled(params, "Receiver")
+        if params["ifReceiverNormalize"]:
+            Psh = Psh / np.asarray(params["pointSrcStrength"])[..., None]
+        P = SHCs_from_pressure_LS(Psh, rotate_directions(Dir_all, params["orientReceiver"]),
+                                  params["receiverOrder"], params["freqs"])
+        params["C_vu_r"] = get_directivity_coefs(params["waveNumbers"], params["receiverOrder"], P,
+                                                 params["radiusReceiver"]).astype(np.complex64)
+        _track(params, ("C_vu_r",), "init_receiver_directivities")
+        return params
     params["C_vu_r"] = _monopole(params["waveNumbers"])[..., None, None].astype(np.complex64)
     params["receiverOrder"] = 0
     params["ifReceiverNormalize"] = 0
@@ -159,21 +230,14 @@ def cal_C_nm_s_new(reflection_matrix, Psh_source, src_Psh_coords, params):
 def init_source_directivities_ARG(params):
     if params["sourceType"] != "monopole":
         # cd:1641-1712: sampled field -> rotated sampling points -> per-image refit (on the GPU)
-        smp = params.get("sampledSource")
-        if smp is None:
-            raise FileNotFoundError("sampled source directivities: the .mat data sets are absent from the "
-                                    "reference tree; provide params['sampledSource']")
-        if not np.allclose(smp["freqs"], params["freqs"]):
-            raise ValueError("The frequencies in the directivity data are not the same as the ones "
-                             "defined in params['freqs']")
-        Dir = np.asarray(smp["Dir_all"], dtype=np.float64)
+        Psh_src, Dir = _sampled(params, "Source")
         el = np.pi / 2 - Dir[:, 1]
         xyz = np.vstack((np.cos(el) * np.cos(Dir[:, 0]), np.cos(el) * np.sin(Dir[:, 0]), np.sin(el)))
         Rm = rotation_matrix_ZXZ(*[float(a) for a in params["orientSource"][:3]])
         if params.get("ifRotateRoom") == 1:
             rr = np.asarray(params["roomRotation"], dtype=np.float64) * np.pi / 180
             Rm = rotation_matrix_ZXZ(rr[0], rr[1], rr[2]) @ Rm
-        params["C_nm_s_ARG"] = cal_C_nm_s_new(params["reflection_matrix"], smp["Psh"], Rm @ xyz, params)
+        params["C_nm_s_ARG"] = cal_C_nm_s_new(params["reflection_matrix"], Psh_src, Rm @ xyz, params)
         _track(params, ("C_nm_s_ARG",), "init_source_directivities")
         return params
     refl = params["reflection_matrix"]

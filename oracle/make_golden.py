@@ -366,6 +366,39 @@ def refit_case(name="r1_arg_refit_N3", n_img=40, N=3, n_dir=50, seed=3):
     print("  wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def sampled_directivity_case(name="d1_sampled_directivities", N=3, V=2, n_dir=40, seed=9):
+    """The reference's init_source_directivities / init_receiver_directivities (cd:1245-1397) on a
+    synthetic sampled field (its loader is patched: the .mat data sets are absent from the tree)."""
+    ref_import.import_reference()
+    import deism.core_deism as cd
+
+    rng = np.random.default_rng(seed)
+    freqs = np.arange(50.0, 550.0, 50.0)
+    k = 2 * np.pi * freqs / 343.0
+    i = np.arange(n_dir) + 0.5
+    Dir = np.stack(((np.pi * (1 + 5 ** 0.5) * i) % (2 * np.pi), np.arccos(1 - 2 * i / n_dir)), axis=1)
+    Ps = rng.standard_normal((len(k), n_dir)) + 1j * rng.standard_normal((len(k), n_dir))
+    Pr = rng.standard_normal((len(k), n_dir)) + 1j * rng.standard_normal((len(k), n_dir))
+    data = {"source": (freqs, Ps, Dir, 0.4), "receiver": (freqs, Pr, Dir, 0.5)}
+    keep = cd.load_directive_pressure
+    cd.load_directive_pressure = lambda silent, which, name_: data[which]
+    try:
+        p = {"silentMode": 1, "sourceType": "synthetic", "receiverType": "synthetic", "freqs": freqs,
+             "waveNumbers": k, "sourceOrder": N, "receiverOrder": V, "radiusSource": 0.4, "radiusReceiver": 0.5,
+             "orientSource": np.array([30.0, 20.0, -10.0]), "orientReceiver": np.array([-75.0, 5.0, 40.0]),
+             "ifReceiverNormalize": 1, "pointSrcStrength": 1j * k * 343.0 * 1.2 * 0.001,
+             "track_updated_where": False}
+        p = cd.init_receiver_directivities(cd.init_source_directivities(p))
+    finally:
+        cd.load_directive_pressure = keep
+    path = os.path.join(GOLDEN, name + ".npz")
+    np.savez_compressed(path, freqs=freqs, waveNumbers=k, Dir_all=Dir, Psh_source=Ps, Psh_receiver=Pr,
+                        orientSource=p["orientSource"], orientReceiver=p["orientReceiver"],
+                        pointSrcStrength=p["pointSrcStrength"], sourceOrder=N, receiverOrder=V,
+                        C_nm_s=p["C_nm_s"], C_vu_r=p["C_vu_r"])
+    print("  wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 def materials_case(name="m1_materials"):
     """the reference's material conversions (cd:807-1123) and interpolate_functions
     (cd:1126-1163) on a 4 x 3 x 2.5 m room."""
@@ -413,12 +446,16 @@ if __name__ == "__main__":
     ap.add_argument("--augment", action="store_true")
     ap.add_argument("--refit", action="store_true", help="mint only the ARG refit fixture (f2)")
     ap.add_argument("--materials", action="store_true", help="mint only the materials fixture (f4)")
+    ap.add_argument("--directivities", action="store_true", help="mint only the sampled-directivity fixture")
     args = ap.parse_args()
     if args.refit:
         refit_case()
         sys.exit(0)
     if args.materials:
         materials_case()
+        sys.exit(0)
+    if args.directivities:
+        sampled_directivity_case()
         sys.exit(0)
     if args.augment:
         augment_full()

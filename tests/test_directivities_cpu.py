@@ -36,7 +36,7 @@ def test_vectoriser_arg_and_monopoles():
     q = {"sourceType": "monopole", "waveNumbers": x["waveNumbers"], "reflection_matrix": x["reflection_matrix"]}
     q = D.init_source_directivities_ARG(q)
     assert np.array_equal(q["C_nm_s_ARG"], x["C_nm_s_ARG"])
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(FileNotFoundError):      # what the reference's loader raises without its .mat file
         D.init_source_directivities({"sourceType": "speaker_cuboid_cyldriver_1", "waveNumbers": [1.0]})
 
 
@@ -77,3 +77,28 @@ def test_rotation_matrix_zxz():
     pol, az = np.arccos(1 - 2 * i / n_dir), np.pi * (1 + 5 ** 0.5) * i
     X = np.vstack((np.sin(pol) * np.cos(az), np.sin(pol) * np.sin(az), np.cos(pol)))
     assert np.allclose(R @ X, f["coords"], atol=1e-15)
+
+
+def test_sampled_directivities_match_reference_fixture():
+    """Non-monopole init_source_directivities / init_receiver_directivities (rotation of the sampling
+    directions, least-squares fit, division by h_n, receiver normalisation) against the arrays the
+    reference produced for the same injected field (fixture d1_sampled_directivities)."""
+    import os
+
+    from deism_b200 import directivities as D
+
+    f = np.load(os.path.join(os.path.dirname(__file__), "golden", "d1_sampled_directivities.npz"))
+    p = {"sourceType": "synthetic", "receiverType": "synthetic", "freqs": f["freqs"], "waveNumbers": f["waveNumbers"],
+         "sourceOrder": int(f["sourceOrder"]), "receiverOrder": int(f["receiverOrder"]), "radiusSource": 0.4,
+         "radiusReceiver": 0.5, "orientSource": f["orientSource"], "orientReceiver": f["orientReceiver"],
+         "ifReceiverNormalize": 1, "pointSrcStrength": f["pointSrcStrength"],
+         "sampledSource": {"freqs": f["freqs"], "Psh": f["Psh_source"], "Dir_all": f["Dir_all"], "r0": 0.4},
+         "sampledReceiver": {"freqs": f["freqs"], "Psh": f["Psh_receiver"], "Dir_all": f["Dir_all"], "r0": 0.5}}
+    p = D.init_receiver_directivities(D.init_source_directivities(p))
+    for key in ("C_nm_s", "C_vu_r"):
+        got, want = p[key], f[key]
+        assert got.dtype == want.dtype == np.complex64 and got.shape == want.shape
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-7 and np.mean(got != want) < 5e-3, key
+    bad = dict(p, freqs=f["freqs"] + 1.0)
+    with pytest.raises(ValueError):
+        D.init_source_directivities(bad)
