@@ -389,6 +389,37 @@ def test_full_c3_all_2000_frequencies_properties():
     assert rel_l2(backend.run_DEISM(q), -2.0 * full) < 1e-13                             # (c)
 
 
+def test_c1_from_the_yaml_scalars_through_every_stage():
+    """BASELINE C1 without borrowing any derived array from the fixture: the scalars of
+    examples/configSingleParam_RTF.yml -> materials (impedance 18 -> T60) -> frequency grid ->
+    GPU image lattice -> monopole directivities -> Wigner tables -> MIX accumulation.  Every
+    intermediate the fixture also holds must be bit-equal, the RTF must be the reference's."""
+    from deism_b200 import backend, directivities as D, images as im, materials as M, wigner
+
+    g = Golden("c1_full")
+    ref = g.params()
+    p = {"soundSpeed": 343.0, "roomSize": np.array([4.0, 3.0, 2.5]), "roomVolumn": 30.0,
+         "roomAreas": np.array([7.5, 7.5, 10.0, 10.0, 12.0, 12.0]), "posSource": np.array([1.1, 1.1, 1.3]),
+         "posReceiver": np.array([2.9, 1.9, 1.3]), "impedance": [18, 18, 18, 18, 18, 18],
+         "givenMaterials": ["impedance"], "mode": "RTF", "startFreq": 2, "endFreq": 24000, "freqStep": 2,
+         "angDepFlag": 1, "maxReflOrder": 25, "mixEarlyOrder": 2, "ifRemoveDirectPath": 0, "numParaImages": 1000,
+         "DEISM_method": "MIX", "sourceType": "monopole", "receiverType": "monopole", "ifReceiverNormalize": 0,
+         "silentMode": 1, "track_updated_where": False}
+    p = M.update_freqs(M.update_wall_materials(p))
+    assert p["reverberationTime"] == float(ref["reverberationTime"])
+    assert np.array_equal(p["waveNumbers"], ref["waveNumbers"]) and np.array_equal(p["freqs"], ref["freqs"])
+    assert np.asarray(p["impedance"]).shape == (6, 12000) and np.all(np.asarray(p["impedance"]) == 18)
+    p["images"] = im.pre_calc_images_src_rec_optimized_nofs_v2_numba(p)
+    for key, h in g.group("imagehash").items():
+        if not key.startswith("atten"):
+            assert hashlib.sha256(np.ascontiguousarray(p["images"][key]).tobytes()).hexdigest() == str(h), key
+    p = D.init_receiver_directivities(D.init_source_directivities(p))
+    p = D.vectorize_C_vu_r(D.vectorize_C_nm_s(p))
+    p = wigner.pre_calc_Wigner(p)
+    got = backend.run_DEISM(p)
+    assert rel_l2(got, g.rtf) < RTF_TOL and rel_max(got, g.rtf) < 1e-8
+
+
 def test_full_c5_mix_order40_N5():
     _full_case("c5_full_N5", "MIX", 5, 5)
 
