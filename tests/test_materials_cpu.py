@@ -62,6 +62,11 @@ def test_params_drivers_shipped_c2_c5_values():
         p = M.update_freqs(M.update_wall_materials(p, T, None, "reverberationTime"))
         assert p["givenMaterials"] == ["reverberationTime"] and p["freqs_bands"].tolist() == [1000]
         assert p["impedance"].shape == (6, K) and abs(p["impedance"][0, 0].real - z_want) < 5e-5
+        # ... and to the last bit what the reference's own run stored (fixtures c2_full_N5 / c5_full_N5)
+        fx = np.load(os.path.join(HERE, "golden", "c2_full_N5.npz" if K == 8000 else "c5_full_N5.npz"))
+        assert np.array_equal(p["impedance"][:, 0], fx["params/impedance_col0"])
+        assert np.array_equal(p["waveNumbers"], fx["params/waveNumbers"])
+        assert p["reverberationTime"] == float(fx["params/reverberationTime"])
         assert p["impedance"][3, 17].imag == 1e-16 and np.all(p["impedance"] == p["impedance"][0, 0])
         assert (p["n1"], p["n2"], p["n3"]) == tuple(int(np.floor(343.0 * T / L / 2)) for L in (4.0, 3.0, 2.5))
         assert np.allclose(p["waveNumbers"], 2 * np.pi * p["freqs"] / 343.0)
