@@ -197,6 +197,58 @@ __device__ __forceinline__ cplx shoebox_atten(const cplx *__restrict__ Z, long z
     return a;
 }
 
+// The same product for NQ frequencies of ONE image at once: the exponents (and with them the
+// control flow of the powers) are shared, so the NQ chains advance in one loop with NQ-way
+// instruction-level parallelism.  Element for element the operations are those of shoebox_atten.
+template <int NQ>
+__device__ __forceinline__ void cpow_uint_n(cplx (&base)[NQ], unsigned e, cplx (&out)[NQ]) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) out[q] = cmake(1.0, 0.0);
+    while (e) {
+        if (e & 1u) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) out[q] = cmul(out[q], base[q]);
+        }
+        e >>= 1;
+        if (e) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) base[q] = cmul(base[q], base[q]);
+        }
+    }
+}
+template <int NQ>
+__device__ __forceinline__ void shoebox_atten_n(const cplx *__restrict__ Z, long zstride, const int (&fq)[NQ],
+                                                double cx, double cy, double cz, const unsigned char *e,
+                                                cplx (&out)[NQ]) {
+    const double c3[3] = {cx, cy, cz};
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+        cplx b1[NQ], z2[NQ], p[NQ];
+        bool same = true;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const cplx z1 = Z[(2 * w) * zstride + fq[q]];
+            z2[q] = Z[(2 * w + 1) * zstride + fq[q]];
+            same = same && csame(z1, z2[q]);
+            b1[q] = ref_coef(c3[w], z1);
+        }
+        const unsigned e1 = e[2 * w], e2 = e[2 * w + 1];
+        if (same) {
+            cpow_uint_n<NQ>(b1, e1 + e2, p);
+        } else {
+            cplx b2[NQ], p2[NQ];
+            cpow_uint_n<NQ>(b1, e1, p);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) b2[q] = ref_coef(c3[w], z2[q]);
+            cpow_uint_n<NQ>(b2, e2, p2);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) p[q] = cmul(p[q], p2[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) out[q] = w == 0 ? p[q] : cmul(out[q], p[q]);
+    }
+}
+
 // Per-image attenuation geometry shared by images.cu / lc.cu / org.cu
 struct AttenGeom {
     double cx, cy, cz;

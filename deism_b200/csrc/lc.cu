@@ -285,12 +285,51 @@ __host__ __device__ inline LcCarve lc_carve(int WN, bool cres_on, int rows, int 
     return c;
 }
 
+// Factors (atten/r) exp(-ikr) of ONE image at the four frequencies a thread owns, for an impedance
+// that varies with frequency: the wall exponents are shared by the four, so their attenuations are
+// built together (shoebox_atten_n).  Only the general instantiation of the main kernel carries it.
+__device__ __forceinline__ void lc_general_factors(const cplx *Zs, int TF, const double *kf, const double *dkd,
+                                                const double *dkd8, const LcImage *recp, int fqa,
+                                                bool round_to_c64, bool uniform_k, double2 *fac, int stride) {
+    constexpr int NQ = 2 * LC_NT;
+    static_assert(LC_NT == 2, "frequency offsets below assume two n-tiles per warp");
+    const LcImage &rec = *recp;
+    const int fqs[NQ] = {fqa, fqa + 1, fqa + 8, fqa + 9};
+    cplx att[NQ], Eq[NQ];
+    shoebox_atten_n<NQ>(Zs, TF, fqs, rec.cx, rec.cy, rec.cz, rec.e, att);
+    auto rot_step = [](cplx F, cplx rot, double dr) {
+        F = cmul(F, rot);
+        return cmake(fma(F.y, dr, F.x), fma(-F.x, dr, F.y));
+    };
+    if (uniform_k) {
+        double sn, cs;
+        sincos_cw(kf[fqa] * rec.r, &sn, &cs);
+        Eq[0] = cmake(cs, -sn);
+        Eq[1] = rot_step(Eq[0], rec.rot, dkd[fqa] * rec.r);
+        Eq[2] = rot_step(Eq[0], rec.rot8, dkd8[fqa] * rec.r);
+        Eq[3] = rot_step(Eq[2], rec.rot, dkd[fqa + 8] * rec.r);
+    } else {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            double sn, cs;
+            sincos_cw(kf[fqs[q]] * rec.r, &sn, &cs);
+            Eq[q] = cmake(cs, -sn);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        cplx a_ = round_to_c64 ? round_c64(att[q]) : att[q];
+        a_ = cmake(a_.x * rec.inv_r, a_.y * rec.inv_r);
+        fac[(long)q * stride] = cmul(a_, Eq[q]);
+    }
+}
+
 // The main loop has NO CTA-wide barrier and no waiting producer: Y (and, when they stream, C)
 // chunks and the per-image records arrive by TMA on "full" mbarriers; every warp counts itself out
 // of a buffer when it is done with it and the LAST warp out refills it (issues the next bulk
 // copies) on the spot.  The factor of a pair is computed, parked and consumed by the one thread
 // that owns the pair in the DMMA accumulator layout.  Warps of a CTA drift by up to nst chunks.
-template <int WN, bool CRES>
+template <int WN, bool CRES, bool FAST>
 __global__ void __launch_bounds__(128 * WN, CRES ? 1 : 2)
 lc_main_kernel(LcMainArgs a) {
     constexpr int NT = LC_NT;
@@ -332,6 +371,11 @@ lc_main_kernel(LcMainArgs a) {
     const bool fused = a.mode == DEISM_ATTEN_FUSED_ROOM || a.mode == DEISM_ATTEN_FUSED_ANGLES;
     const bool flat = fused && a.flags[0] != 0;
     const bool uniform_k = a.flags[1] != 0;
+    // Two instantiations are launched back to back: FAST carries only the frequency-flat /
+    // uniform-grid factor code, the other one only the general code.  Which case applies is decided
+    // on the device (flags), so the instantiation it does not belong to returns at once — the hot
+    // path keeps its registers to itself and the host never has to read the flags.
+    if ((flat && uniform_k) != FAST) return;
 
     if (tid == 0) {
         for (int s = 0; s < nst; ++s) { mbar_init(&full[s], 1); done[s] = 0; }
@@ -532,7 +576,7 @@ lc_main_kernel(LcMainArgs a) {
     // fast path: frequency-flat impedance on a uniform wave-number grid.  One sincos per image
     // starts a rotation recurrence over the thread's frequencies; branch-free, so it can ride along
     // with the first source chunks of the tile.
-    const bool fast = flat && uniform_k;
+    constexpr bool fast = FAST;
 
 #pragma unroll 1
     for (int tt = 0; tt < n_tiles; ++tt) {
@@ -565,6 +609,13 @@ lc_main_kernel(LcMainArgs a) {
             // frequency-dependent impedance or a materialised atten[I,K] (rolled: rarely hot)
             epi_P();
             const long i0 = (tile_lo + tt) * LC_TI;
+            if (fused && !flat) {
+#pragma unroll 1
+                for (int mt = 0; mt < 2; ++mt)
+                    lc_general_factors(&Zs[0][0], TF, kf, dkd, dkd8, &recs[rb][wm * 16 + mt * 8 + g], fqa,
+                                       a.mode == DEISM_ATTEN_FUSED_ROOM, uniform_k,
+                                       &facp[mt * 2 * NT][tid], THREADS);
+            } else {
             cplx E = cmake(1.0, 0.0), E0 = E;
             static_assert(NT == 1 || NT == 2, "rotation order below assumes one or two n-tiles per warp");
 #pragma unroll 1
@@ -607,6 +658,7 @@ lc_main_kernel(LcMainArgs a) {
                     E = rot_step(E, rec.rot, dkd[fq - 1] * rec.r);
                 }
                 facp[j][tid] = cmul(att, E);
+            }
             }
 #pragma unroll 1
             for (int l = 0; l < a.ncs; ++l)
@@ -1071,13 +1123,19 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
                          carve.total, smem_max);
     prof_begin("lc_main", st);
     if (resident) {
-        DEISM_CUDA_TRY(cudaFuncSetAttribute(lc_main_kernel<LC_WN_RES, true>,
+        DEISM_CUDA_TRY(cudaFuncSetAttribute(lc_main_kernel<LC_WN_RES, true, true>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)carve.total));
-        lc_main_kernel<LC_WN_RES, true><<<grid, 128 * LC_WN_RES, carve.total, st>>>(ma);
+        DEISM_CUDA_TRY(cudaFuncSetAttribute(lc_main_kernel<LC_WN_RES, true, false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)carve.total));
+        lc_main_kernel<LC_WN_RES, true, true><<<grid, 128 * LC_WN_RES, carve.total, st>>>(ma);
+        lc_main_kernel<LC_WN_RES, true, false><<<grid, 128 * LC_WN_RES, carve.total, st>>>(ma);
     } else {
-        DEISM_CUDA_TRY(cudaFuncSetAttribute(lc_main_kernel<LC_WN_STR, false>,
+        DEISM_CUDA_TRY(cudaFuncSetAttribute(lc_main_kernel<LC_WN_STR, false, true>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)carve.total));
-        lc_main_kernel<LC_WN_STR, false><<<grid, 128 * LC_WN_STR, carve.total, st>>>(ma);
+        DEISM_CUDA_TRY(cudaFuncSetAttribute(lc_main_kernel<LC_WN_STR, false, false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)carve.total));
+        lc_main_kernel<LC_WN_STR, false, true><<<grid, 128 * LC_WN_STR, carve.total, st>>>(ma);
+        lc_main_kernel<LC_WN_STR, false, false><<<grid, 128 * LC_WN_STR, carve.total, st>>>(ma);
     }
     prof_end("lc_main", st);
     DEISM_LAUNCH_CHECK("lc_main_kernel");
