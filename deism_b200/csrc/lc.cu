@@ -1138,6 +1138,7 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
         lc_main_kernel<LC_WN_STR, false, false><<<grid, 128 * LC_WN_STR, carve.total, st>>>(ma);
     }
     prof_end("lc_main", st);
+    count_launch();                          // two instantiations went out
     DEISM_LAUNCH_CHECK("lc_main_kernel");
 
     return launch_reduce_partials(partial, n_chunks, K, d_out, accumulate, st);
