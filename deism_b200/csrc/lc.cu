@@ -703,7 +703,9 @@ lc_main_kernel(LcMainArgs a) {
 // then 15 steps of the rotation recurrence; 64 images x 64 frequencies per CTA pass; partial sums
 // over the CTA's images stay in registers and are reduced once at the end.
 // ---------------------------------------------------------------------------------------
-constexpr int LM_TF = 64, LM_FPT = 16, LM_THREADS = 256;
+constexpr int LM_THREADS = 256;          // 64 image lanes x 4 frequency groups
+constexpr int LM_FPT_FAST = 16;          // frequencies per thread: rotation recurrence (flat impedance, uniform grid)
+constexpr int LM_FPT_GEN = 4;            //                         per-term attenuation / arbitrary grid
 
 struct LcMonoArgs {
     long n_images, n_pad, K;
@@ -715,17 +717,24 @@ struct LcMonoArgs {
     const cplx *Z;
     const int *flags;
     long tiles_per_chunk;
+    long partial_rows;       // rows of partial[] the reduction will read (>= gridDim.y)
     cplx *partial;
 };
 
+// Like the main kernel, two instantiations go out back to back and the one the device-side flags
+// do not select returns at once.  FAST: 16 frequencies per thread, one sincos + 15 rotation steps.
+// General: 4 frequencies per thread; the four share the image's wall exponents, so their
+// attenuations are built together (shoebox_atten_n), and the grid may be non-uniform.
+template <int FPT, bool FAST>
 __global__ void __launch_bounds__(LM_THREADS, 2)
 lc_mono_kernel(LcMonoArgs a) {
-    __shared__ double kf[LM_TF], dkd[LM_TF];
-    __shared__ double2 Zs[6][LM_TF];
-    __shared__ double2 red[LM_THREADS / 32][LM_FPT];
+    constexpr int TF = 4 * FPT;
+    __shared__ double kf[TF], dkd[TF];
+    __shared__ double2 Zs[6][TF];
+    __shared__ double2 red[LM_THREADS / 32][FPT];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int il = tid & (LC_TI - 1), fg = tid / LC_TI;          // image lane, frequency group
-    const long f0 = (long)blockIdx.x * LM_TF;
+    const long f0 = (long)blockIdx.x * TF;
     const long n_img_tiles = a.n_pad / LC_TI;
     long tile_lo = (long)blockIdx.y * a.tiles_per_chunk;
     long tile_hi = tile_lo + a.tiles_per_chunk;
@@ -733,81 +742,104 @@ lc_mono_kernel(LcMonoArgs a) {
     const bool fused = a.mode == DEISM_ATTEN_FUSED_ROOM || a.mode == DEISM_ATTEN_FUSED_ANGLES;
     const bool flat = fused && a.flags[0] != 0;
     const bool uniform_k = a.flags[1] != 0;
+    if ((flat && uniform_k) != FAST) return;
     {
         const double dk = *reinterpret_cast<const double *>(a.flags + 2);
-        for (int q = tid; q < LM_TF; q += LM_THREADS) {
+        for (int q = tid; q < TF; q += LM_THREADS) {
             const long f = f0 + q;
             const double kk = f < a.K ? a.k[f] : 1.0;
             kf[q] = kk;
             dkd[q] = f + 1 < a.K ? (a.k[f + 1] - kk) - dk : 0.0;
         }
         if (fused && !flat)
-            for (int i = tid; i < 6 * LM_TF; i += LM_THREADS) {
-                const int w = i / LM_TF, q = i % LM_TF;
+            for (int i = tid; i < 6 * TF; i += LM_THREADS) {
+                const int w = i / TF, q = i % TF;
                 const long f = f0 + q;
                 Zs[w][q] = f < a.K ? a.Z[(long)w * a.K + f] : cmake(1.0, 0.0);
             }
     }
     __syncthreads();
-    const int q0 = fg * LM_FPT;
-    cplx P[LM_FPT];
+    const int q0 = fg * FPT;
+    cplx P[FPT];
 #pragma unroll
-    for (int q = 0; q < LM_FPT; ++q) P[q] = cmake(0.0, 0.0);
+    for (int q = 0; q < FPT; ++q) P[q] = cmake(0.0, 0.0);
 
 #pragma unroll 1
     for (long tile = tile_lo; tile < tile_hi; ++tile) {
         const long img = tile * LC_TI + il;
         const LcImage rec = a.img[img];
         const double r = rec.r;
-        if (flat && uniform_k) {
+        if (FAST) {
             double sn, cs;
             sincos_cw(kf[q0] * r, &sn, &cs);
             cplx F = cmul(rec.a_flat, cmake(cs, -sn));
 #pragma unroll
-            for (int q = 0; q < LM_FPT; ++q) {
+            for (int q = 0; q < FPT; ++q) {
                 P[q] = cadd(P[q], F);
-                if (q + 1 < LM_FPT) {
+                if (q + 1 < FPT) {
                     F = cmul(F, rec.rot);                      // exp(-i (dk + d) r) ~ rot (1 - i d r)
                     const double dr = dkd[q0 + q] * r;
                     F = cmake(fma(F.y, dr, F.x), fma(-F.x, dr, F.y));
                 }
             }
         } else {
-#pragma unroll 1
-            for (int q = 0; q < LM_FPT; ++q) {
-                const long f = f0 + q0 + q;
-                cplx att;
-                if (flat) {
-                    att = rec.a_flat;
+            cplx att[FPT], E[FPT];
+            if (flat) {
+#pragma unroll
+                for (int q = 0; q < FPT; ++q) att[q] = rec.a_flat;
+            } else {
+                if (fused) {
+                    int fqs[FPT];
+#pragma unroll
+                    for (int q = 0; q < FPT; ++q) fqs[q] = q0 + q;
+                    shoebox_atten_n<FPT>(&Zs[0][0], TF, fqs, rec.cx, rec.cy, rec.cz, rec.e, att);
+                    if (a.mode == DEISM_ATTEN_FUSED_ROOM) {
+#pragma unroll
+                        for (int q = 0; q < FPT; ++q) att[q] = round_c64(att[q]);
+                    }
                 } else {
-                    if (fused) {
-                        att = shoebox_atten(&Zs[0][q0 + q], LM_TF, rec.cx, rec.cy, rec.cz, rec.e);
-                        if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
-                    } else {
-                        att = cmake(0.0, 0.0);
+#pragma unroll
+                    for (int q = 0; q < FPT; ++q) {
+                        const long f = f0 + q0 + q;
+                        att[q] = cmake(0.0, 0.0);
                         if (img < a.n_images && f < a.K) {
                             if (a.mode == DEISM_ATTEN_C64) {
                                 float2 v = ((const float2 *)a.atten)[img * a.K + f];
-                                att = cmake((double)v.x, (double)v.y);
+                                att[q] = cmake((double)v.x, (double)v.y);
                             } else {
-                                att = ((const cplx *)a.atten)[img * a.K + f];
+                                att[q] = ((const cplx *)a.atten)[img * a.K + f];
                             }
                         }
                     }
-                    att = cmake(att.x * rec.inv_r, att.y * rec.inv_r);
                 }
-                double sn, cs;
-                sincos_cw(kf[q0 + q] * r, &sn, &cs);
-                const cplx v = cmul(att, cmake(cs, -sn));
 #pragma unroll
-                for (int qq = 0; qq < LM_FPT; ++qq)      // P stays in registers: no dynamic index
-                    if (qq == q) P[qq] = cadd(P[qq], v);
+                for (int q = 0; q < FPT; ++q) att[q] = cmake(att[q].x * rec.inv_r, att[q].y * rec.inv_r);
             }
+            if (uniform_k) {
+                double sn, cs;
+                sincos_cw(kf[q0] * r, &sn, &cs);
+                E[0] = cmake(cs, -sn);
+#pragma unroll
+                for (int q = 1; q < FPT; ++q) {
+                    const cplx F = cmul(E[q - 1], rec.rot);
+                    const double dr = dkd[q0 + q - 1] * r;
+                    E[q] = cmake(fma(F.y, dr, F.x), fma(-F.x, dr, F.y));
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < FPT; ++q) {
+                    double sn, cs;
+                    sincos_cw(kf[q0 + q] * r, &sn, &cs);
+                    E[q] = cmake(cs, -sn);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < FPT; ++q) cfma(P[q], att[q], E[q]);
         }
     }
     // ---- sum over the 64 image lanes of each frequency group: shuffles, then two warps per group ----
 #pragma unroll
-    for (int q = 0; q < LM_FPT; ++q) {
+    for (int q = 0; q < FPT; ++q) {
         double x = P[q].x, y = P[q].y;
         for (int o = 16; o > 0; o >>= 1) {
             x += __shfl_down_sync(0xffffffffu, x, o);
@@ -816,8 +848,8 @@ lc_mono_kernel(LcMonoArgs a) {
         if (lane == 0) red[warp][q] = cmake(x, y);
     }
     __syncthreads();
-    if (tid < LM_TF) {
-        const int g = tid / LM_FPT, q = tid % LM_FPT;
+    if (tid < TF) {
+        const int g = tid / FPT, q = tid % FPT;
         const cplx s = cadd(red[2 * g][q], red[2 * g + 1][q]);
         const long f = f0 + tid;
         if (f < a.K) {
@@ -828,6 +860,9 @@ lc_mono_kernel(LcMonoArgs a) {
                                  cmake((double)cr.x * y00, (double)cr.y * y00));
             const double w = -4.0 * 3.14159265358979323846 / (kf[tid] * kf[tid]);
             a.partial[(long)blockIdx.y * a.K + f] = cmul(cmake(SR.x * w, SR.y * w), s);
+            // this instantiation may run with fewer image chunks than partial[] has rows
+            for (long row = blockIdx.y + gridDim.y; row < a.partial_rows; row += gridDim.y)
+                a.partial[row * a.K + f] = cmake(0.0, 0.0);
         }
     }
 }
@@ -1070,7 +1105,7 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
         }
         lc_prep_kernel<<<(unsigned)((n_pad + 127) / 128), 128, 0, st>>>(mp, img, Ys, Yr);
         DEISM_LAUNCH_CHECK("lc_prep_kernel");
-        const long m_ftiles = (K + LM_TF - 1) / LM_TF;
+        const long m_ftiles = (K + 4 * LM_FPT_FAST - 1) / (4 * LM_FPT_FAST);
         long m_chunks = (long)sm_count() * 8 * 4 / m_ftiles;          // ~4 waves of 8 CTAs/SM
         if (m_chunks < 1) m_chunks = 1;
         if (m_chunks > n_img_tiles) m_chunks = n_img_tiles;
@@ -1081,11 +1116,21 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
         mo.n_images = n_images; mo.n_pad = n_pad; mo.K = K; mo.img = img; mo.k = d_k;
         mo.Cs = (const float2 *)d_C_s_vec; mo.Cr = (const float2 *)d_C_r_vec;
         mo.mode = atten->mode; mo.atten = atten->d_atten; mo.Z = (const cplx *)atten->d_Z_S;
-        mo.flags = flags; mo.tiles_per_chunk = m_tpc; mo.partial = partial;
-        dim3 mgrid((unsigned)m_ftiles, (unsigned)m_chunks);
+        mo.flags = flags; mo.tiles_per_chunk = m_tpc; mo.partial = partial; mo.partial_rows = m_chunks;
+        // the general instantiation has 4x the frequency tiles: give it 1/4 of the image chunks so
+        // that, when it does not apply, its empty grid costs no more than the fast one's
+        const long g_ftiles = (K + 4 * LM_FPT_GEN - 1) / (4 * LM_FPT_GEN);
+        long g_chunks = m_chunks / 4 > 0 ? m_chunks / 4 : 1;
+        const long g_tpc = (n_img_tiles + g_chunks - 1) / g_chunks;
+        g_chunks = (n_img_tiles + g_tpc - 1) / g_tpc;
+        if (g_ftiles > 2147483647L) return set_error(DEISM_ERR_INVALID, "too many frequencies");
         prof_begin("lc_main", st);
-        lc_mono_kernel<<<mgrid, LM_THREADS, 0, st>>>(mo);
+        lc_mono_kernel<LM_FPT_FAST, true><<<dim3((unsigned)m_ftiles, (unsigned)m_chunks), LM_THREADS, 0, st>>>(mo);
+        LcMonoArgs mg = mo;
+        mg.tiles_per_chunk = g_tpc;
+        lc_mono_kernel<LM_FPT_GEN, false><<<dim3((unsigned)g_ftiles, (unsigned)g_chunks), LM_THREADS, 0, st>>>(mg);
         prof_end("lc_main", st);
+        count_launch();
         DEISM_LAUNCH_CHECK("lc_mono_kernel");
         return launch_reduce_partials(partial, m_chunks, K, d_out, accumulate, st);
     }
