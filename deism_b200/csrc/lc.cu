@@ -501,21 +501,25 @@ lc_main_kernel(LcMainArgs a) {
             mma_frag(af, bf);
             side1();
             if (JC > 8) {
-                // remaining k-steps: fragments of step ks+4 are in flight while step ks multiplies
+                // remaining k-steps, two per trip with ping-pong fragment registers: the loads of one
+                // step are in flight while the other multiplies
+                double a2[2], b2[2][NT];
                 load_frag(8, af, bf);
+                int ks = 12;
 #pragma unroll 1
-                for (int ks = 12; ks < JC; ks += 4) {
-                    double an[2], bn[2][NT];
-                    load_frag(ks, an, bn);
+                for (; ks + 4 < JC; ks += 8) {
+                    load_frag(ks, a2, b2);
                     mma_frag(af, bf);
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) af[mt] = an[mt];
-#pragma unroll
-                    for (int p = 0; p < 2; ++p)
-#pragma unroll
-                        for (int nt = 0; nt < NT; ++nt) bf[p][nt] = bn[p][nt];
+                    load_frag(ks + 4, af, bf);
+                    mma_frag(a2, b2);
                 }
-                mma_frag(af, bf);
+                if (ks < JC) {
+                    load_frag(ks, a2, b2);
+                    mma_frag(af, bf);
+                    mma_frag(a2, b2);
+                } else {
+                    mma_frag(af, bf);
+                }
             }
         } else {
             side1();
