@@ -505,6 +505,16 @@ lc_main_kernel(LcMainArgs a) {
                 // step are in flight while the other multiplies
                 double a2[2], b2[2][NT];
                 load_frag(8, af, bf);
+                if (JC == 36) {          // a whole order-5 pass: straight-line code
+#pragma unroll
+                    for (int kq = 12; kq + 4 < 36; kq += 8) {
+                        load_frag(kq, a2, b2);
+                        mma_frag(af, bf);
+                        load_frag(kq + 4, af, bf);
+                        mma_frag(a2, b2);
+                    }
+                    mma_frag(af, bf);
+                } else {
                 int ks = 12;
 #pragma unroll 1
                 for (; ks + 4 < JC; ks += 8) {
@@ -519,6 +529,7 @@ lc_main_kernel(LcMainArgs a) {
                     mma_frag(a2, b2);
                 } else {
                     mma_frag(af, bf);
+                }
                 }
             }
         } else {
