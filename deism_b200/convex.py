@@ -214,3 +214,213 @@ def get_ref_paths_ARG_device(params, room_engine):
     params["images"] = images
     params["reflection_matrix"] = refl.contiguous()
     return params
+
+
+# ----------------------------------------------------------------------------------------------
+# Wall construction and the room wrapper (host side; a handful of walls per room)
+# ----------------------------------------------------------------------------------------------
+_F = np.float32
+_LIBROOM_EPS = 1e-5          # common.hpp: libroom_eps
+
+
+def _cross32(a, b):
+    return np.array([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]], _F)
+
+
+def _dot32(a, b):
+    # fixed-size 3-vector reduction order of the reference's Eigen build: x + (y + z)
+    p = (a * b).astype(_F)
+    return _F(p[0] + _F(p[1] + p[2]))
+
+
+def _area_2d(flat):
+    """geometry.cpp area_2d_polygon: signed shoelace sum over the projected corners."""
+    a = _F(0)
+    n = flat.shape[1]
+    for c1 in range(n):
+        c2 = 0 if c1 == n - 1 else c1 + 1
+        base = _F(0.5) * _F(flat[1, c2] + flat[1, c1])
+        height = _F(flat[0, c2] - flat[0, c1])
+        a = _F(a - _F(height * base))
+    return a
+
+
+class Wall_deism:
+    """Host mirror of the reference's planar 3-D wall (``libroom_deism.Wall_deism``,
+    wall.cpp:338-397 + orderPoints wall.cpp:105-143), in float32 like the Eigen original:
+
+        normal   cross(c1 - c0, c2 - c0) normalised, flipped to point away from the room centroid
+        origin   the first corner as given
+        corners  re-ordered by angle around the wall centre
+        basis / flat_corners   an orthonormal basis of the plane and the corners projected on it
+                 (any such basis gives the same polygon test; the reference takes it from a
+                 float32 Jacobi SVD, here it is the float64 SVD rounded to float32)
+        reflection_matrix      I - 2 n n^T
+
+    ``impedence_bands`` [K] is carried along (only its real part enters the attenuation,
+    wall.cpp:428,633)."""
+
+    dim = 3
+
+    def __init__(self, points, centroid, impedence, name=""):
+        corners = np.ascontiguousarray(np.asarray(points, dtype=np.float64).T.astype(_F))   # [3, n]
+        if corners.shape[0] != 3:
+            raise TypeError("The first dimension of points should be 2 or 3!")
+        if corners.shape[1] < 3:
+            raise RuntimeError("a wall needs at least three corners")
+        centroid = np.asarray(centroid, dtype=np.float64).reshape(3).astype(_F)
+        self.name = name
+        self.impedence_bands = np.asarray(impedence)
+        v1 = corners[:, 1] - corners[:, 0]
+        v2 = corners[:, 2] - corners[:, 0]
+        n = _cross32(v1, v2)
+        n = (n / np.sqrt(_dot32(n, n))).astype(_F)
+        self.origin = corners[:, 0].copy()
+        if _dot32(n, centroid - self.origin) > 0:
+            n = -n
+        self.normal = n
+        self.corners = self._order_points(corners)
+        rel = (self.corners - self.origin[:, None]).astype(np.float64)
+        U, S, _ = np.linalg.svd(rel, full_matrices=False)
+        if S[2] > _LIBROOM_EPS:
+            raise RuntimeError("The corners of the wall do not lie in a plane")           # wall.cpp:376-379
+        basis = np.stack((U[:, 0], -U[:, 1]), axis=1).astype(_F)
+        flat = (basis.T @ (self.corners - self.origin[:, None])).astype(_F)
+        if _area_2d(flat) < 0:
+            basis = np.ascontiguousarray(basis[:, ::-1])
+            flat = np.ascontiguousarray(flat[::-1, :])
+        self.basis, self.flat_corners = basis, flat
+        self.reflection_matrix = (np.eye(3, dtype=_F) - _F(2) * np.outer(n, n).astype(_F)).astype(_F)
+
+    def _order_points(self, pts):
+        center = np.zeros(3, _F)
+        for i in range(pts.shape[1]):           # sequential float32 sum, then / n (Eigen mean())
+            center = (center + pts[:, i]).astype(_F)
+        center = (center / _F(pts.shape[1])).astype(_F)
+        ref = (pts[:, 0] - center).astype(_F)
+        angles = np.zeros(pts.shape[1], _F)
+        for i in range(pts.shape[1]):
+            v = (pts[:, i] - center).astype(_F)
+            c = _cross32(v, ref)
+            ang = _F(np.arctan2(np.sqrt(_dot32(c, c)), _dot32(v, ref)))
+            if _dot32(self.normal, c) <= 0:
+                ang = _F(2 * np.pi - np.float64(ang))
+            angles[i] = ang
+        return np.ascontiguousarray(pts[:, np.argsort(angles, kind="stable")])
+
+
+def _faces_by_normal(vertices):
+    """Hull facets grouped by their rounded outward normal, in the reference's order
+    (core_deism_arg.py:935-950, 1109-1131, 1142-1185 all walk ``list(set(normals))``)."""
+    from scipy.spatial import ConvexHull
+
+    hull = ConvexHull(vertices)
+    rounded = np.round(hull.equations[:, :3], decimals=5)
+    normals = [tuple(face) for face in rounded]
+    groups = []
+    for normal in list(set(normals)):
+        groups.append([i for i in range(len(normals)) if normals[i] == normal])
+    return hull, groups
+
+
+def find_wall_centers(vertices, *choose_wall_centers):
+    """core_deism_arg.py:1109-1139."""
+    hull, groups = _faces_by_normal(np.asarray(vertices))
+    centers = []
+    for facets in groups:
+        pts = np.unique(np.concatenate([hull.points[hull.simplices[i]] for i in facets]), axis=0)
+        if not choose_wall_centers:
+            centers.append(np.mean(pts, axis=0))
+        else:
+            for wc in choose_wall_centers:
+                if np.linalg.norm(pts.mean(axis=0) - wc) < 0.0001:
+                    centers.append(np.mean(pts, axis=0))
+    return np.array(centers)
+
+
+def convex_room_volume_and_areas(vertices):
+    """core_deism_arg.py:1142-1185: hull volume and one area per wall (find_wall_centers order)."""
+    vertices = np.asarray(vertices, dtype=float)
+    if vertices.ndim != 2 or vertices.shape[1] != 3:
+        raise ValueError("vertices must be (N, 3)")
+    hull, groups = _faces_by_normal(vertices)
+    areas = []
+    for facets in groups:
+        a = 0.0
+        for i in facets:
+            tri = hull.points[hull.simplices[i]]
+            a += 0.5 * np.linalg.norm(np.cross(tri[1] - tri[0], tri[2] - tri[0]))
+        areas.append(a)
+    return float(hull.volume), np.array(areas, dtype=float)
+
+
+def rotate_room_src_rec(params):
+    """core_deism_arg.py:1265-1281."""
+    from .directivities import rotation_matrix_ZXZ
+
+    rr = np.asarray(params["roomRotation"]) * np.pi / 180
+    R = rotation_matrix_ZXZ(rr[0], rr[1], rr[2])
+    params["vertices"] = (R @ params["vertices"].T).T
+    params["posSource"] = R @ params["posSource"]
+    params["posReceiver"] = R @ params["posReceiver"]
+    params["wallCenters"] = (R @ params["wallCenters"].T).T
+    return params
+
+
+class Room_deism_cpp:
+    """Convex-room wrapper with the surface of the reference's ``Room_deism_cpp``
+    (core_deism_arg.py:823-983): walls from the hull of ``params['vertices']``, each taking the
+    impedance row of the nearest ``params['wallCenters']`` entry; ``update_images`` runs the GPU
+    reflection tree (``room_engine`` = this module's Room_deism)."""
+
+    def __init__(self, params, *choose_wall_centers):
+        self.params = params
+        self.points = np.asarray(params["vertices"])
+        self.centroid = np.mean(self.points, axis=0)
+        self.walls = []
+        self.source = params["posSource"]
+        self.microphones = [params["posReceiver"]]
+        self.c = params["soundSpeed"]
+        self.ism_order = params["maxReflOrder"]
+        self.impedence = params["impedance"]
+        self.freqs = params["freqs"]
+        self.wall_centers = (params["wallCenters"] if "wallCenters" in params
+                             else find_wall_centers(self.points))
+        if len(self.freqs) != self.impedence.shape[1]:
+            raise ValueError("The number of frequencies in the frequency array and the second "
+                             "dimension of the impedance matrix are not the same")
+        if params["convexRoom"]:
+            self.generate_walls_convex(*choose_wall_centers)
+        self.dim = self.points.shape[1]
+        if self.dim != 3:
+            raise TypeError("The room dimension should only be 2 or 3")     # 2-D rooms: not on the path
+        self.room_engine = Room_deism(self.walls, [], [], self.c, self.ism_order)
+
+    def generate_walls_convex(self, *choose_wall_centers):
+        hull, groups = _faces_by_normal(self.points)
+        for facets in groups:
+            pts = np.unique(np.concatenate([hull.points[hull.simplices[i]] for i in facets]), axis=0)
+            dist = np.linalg.norm(np.array(self.wall_centers) - np.mean(pts, axis=0), axis=1)
+            if np.min(dist) > 0.001:
+                raise ValueError("The face center is not close enough to any wall center")
+            wall = Wall_deism(pts, self.centroid, self.impedence[np.argmin(dist)])
+            if not choose_wall_centers:
+                self.walls.append(wall)
+            else:
+                for wc in choose_wall_centers:
+                    if np.linalg.norm(wall.corners.T.mean(axis=0) - wc) < 0.0001:
+                        self.walls.append(wall)
+
+    def update_images(self, source=None, receiver=None):
+        if source is not None:
+            self.source = source
+        if receiver is not None:
+            self.microphones[0] = receiver
+        # the reference appends a microphone per call (core_deism_arg.py:895); the engine here
+        # holds the current one
+        self.room_engine.microphones = []
+        self.room_engine.add_mic(np.asarray(self.microphones[0]))
+        self.room_engine.n_bands = len(self.freqs)
+        self.room_engine.image_source_model(np.asarray(self.source))
+        self.sources = self.room_engine.sources
+        self.gen_walls = self.room_engine.gen_walls

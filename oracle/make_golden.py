@@ -282,6 +282,25 @@ def small_cases():
     convex_case("x1_convex_rir_mix_o4_mono", "RIR", "MIX", 4, overrides={"sampleRate": 4000})
     convex_case("x2_convex_rir_lc_o5_N2", "RIR", "LC", 5, N=2, overrides={"sampleRate": 250})
     convex_case("x3_convex_rir_org_o3_N2", "RIR", "ORG", 3, N=2, overrides={"sampleRate": 500})
+    class_cases()
+
+
+def class_cases():
+    """Cases for the standalone DEISM class (deism_b200/core_deism.py) the other fixtures do not
+    reach: convex RTF mode (the ARG_RTF yaml), and a shoebox run driven through
+    update_source_receiver(source, receiver) / update_room / absorption input."""
+    convex_case("x4_convex_rtf_lc_o3_mono", "RTF", "LC", 3, overrides={"endFreq": 400})
+    d = ref_import.make_deism("RTF", "shoebox")
+    p = d.params
+    p["DEISM_method"], p["maxReflOrder"], p["endFreq"] = "MIX", 6, 160
+    d.update_room(roomDimensions=np.array([6.0, 4.5, 3.0]))
+    d.update_wall_materials([0.1, 0.2, 0.15, 0.1, 0.3, 0.25], None, "absorption")
+    d.update_freqs()
+    d.update_directivities()
+    d.update_source_receiver(np.array([2.0, 1.5, 1.2]), np.array([4.5, 3.0, 1.7]))
+    d.run_DEISM(if_clean_up=False)
+    im = p["images"]
+    save("s7_shoebox_rtf_mix_o6_absorption_moved", pack(d, {"meta/n_images": np.array(len(im["A_early"]) + len(im["A_late"]))}))
 
 
 def full_cases(which):
@@ -447,6 +466,7 @@ if __name__ == "__main__":
     ap.add_argument("--refit", action="store_true", help="mint only the ARG refit fixture (f2)")
     ap.add_argument("--materials", action="store_true", help="mint only the materials fixture (f4)")
     ap.add_argument("--directivities", action="store_true", help="mint only the sampled-directivity fixture")
+    ap.add_argument("--class-cases", action="store_true", help="mint only the DEISM-class fixtures")
     args = ap.parse_args()
     if args.refit:
         refit_case()
@@ -456,6 +476,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if args.directivities:
         sampled_directivity_case()
+        sys.exit(0)
+    if args.class_cases:
+        class_cases()
         sys.exit(0)
     if args.augment:
         augment_full()
