@@ -136,5 +136,6 @@ def test_baseline_c4_convex_order_10():
     # a second source / receiver pair on the same object (the reference appends a microphone per call;
     # here the engine is re-run for the current pair): still a valid room, different image set
     d.update_source_receiver(np.array([1.5, 1.0, 1.0]), np.array([3.0, 2.0, 1.5]))
+    d.update_directivities()                        # per-image source coefficients follow the new image list
     d.run_DEISM()
     assert np.all(np.isfinite(d.params["RTF"].view(np.float64)))
