@@ -13,12 +13,15 @@ runs unchanged after ``from deism_b200.core_deism import DEISM``:
     d.run_DEISM()                          # cd:608-628   -> backend.run_DEISM[_ARG] (CUDA kernels)
     p = d.get_results()                    # cd:675-769   -> rir.get_results (cuFFT)
 
+``DEISM(..., device_resident=True)`` (an addition) keeps the bulk intermediates — image lists,
+impedance on the frequency grid, directivity coefficients, convex attenuations and reflection
+matrices — as torch CUDA tensors inside ``params`` instead of NumPy arrays, so that consecutive
+stages hand each other device memory; scalars, the frequency grid and ``params["RTF"]`` stay NumPy.
+
 Every stage lands in the C-ABI library; there is no CPU fallback.  ``shoeboxImageCalcVersion``
 values other than the default name the reference's legacy CPU generators and raise here.
 """
 from __future__ import annotations
-
-import gc
 
 import numpy as np
 
@@ -29,7 +32,8 @@ from .data_loader import ConflictChecks, cmdArgsToDict, printDict
 class DEISM:
     """User-facing workflow class for shoebox and convex DEISM simulations."""
 
-    def __init__(self, mode, roomtype, silent=False, argv=None):
+    def __init__(self, mode, roomtype, silent=False, argv=None, device_resident=False):
+        self.device_resident = bool(device_resident)
         self.mode = mode
         self.roomtype = roomtype
         self.silent = silent
@@ -76,12 +80,19 @@ class DEISM:
             if version not in ("numba", "v2-numba", "numba-v2", "b200", "gpu"):
                 raise NotImplementedError(f"shoeboxImageCalcVersion={version!r} names one of the reference's "
                                           "legacy CPU generators; this engine enumerates images on the GPU")
-            p["images"] = gimages.pre_calc_images_src_rec_optimized_nofs_v2_numba(p)
+            if self.device_resident and not p.get("shoeboxCompactImages") and not p.get("shoeboxMaterializeAtten"):
+                dev, n_e, _ = gimages.shoebox_images_device(p)
+                p["images"] = {"storage": "fused"}
+                for key, t in dev.items():       # early and late are one buffer, back to back
+                    p["images"][key + "_early"], p["images"][key + "_late"] = t[:n_e], t[n_e:]
+            else:
+                p["images"] = gimages.pre_calc_images_src_rec_optimized_nofs_v2_numba(p)
         elif self.roomtype == "convex":
-            from .convex import get_ref_paths_ARG
+            from .convex import get_ref_paths_ARG, get_ref_paths_ARG_device
 
             self.room_convex.update_images(np.asarray(p["posSource"]), np.asarray(p["posReceiver"]))
-            self.params = get_ref_paths_ARG(p, self.room_convex.room_engine)
+            paths = get_ref_paths_ARG_device if self.device_resident else get_ref_paths_ARG
+            self.params = paths(p, self.room_convex.room_engine)
         for key in ("posSource", "posReceiver", "images"):
             self._update_where_tracking(key, "update_source_receiver")
         if self.roomtype == "shoebox" and self.params["DEISM_method"] in ("ORG", "LC"):
@@ -154,7 +165,7 @@ class DEISM:
 
     # ---------------------------------------------------------------- cd:407-465
     def update_freqs(self):
-        p = materials.update_freqs(self.params)
+        p = materials.update_freqs(self.params, device_impedance=self.device_resident and self.roomtype == "shoebox")
         for key in ("freqs", "waveNumbers"):
             self._update_where_tracking(key, "update_freqs")
         if p["ifReceiverNormalize"] == 1:
@@ -189,6 +200,12 @@ class DEISM:
             p = directivities.vectorize_C_vu_r(p)
         if p["DEISM_method"] in ("ORG", "MIX"):
             p = wigner.pre_calc_Wigner(p)
+        if self.device_resident:
+            import torch
+
+            for key in ("C_nm_s", "C_vu_r", "C_nm_s_vec", "C_vu_r_vec", "C_nm_s_ARG", "C_nm_s_ARG_vec"):
+                if key in p and not isinstance(p[key], torch.Tensor):
+                    p[key] = backend.to_device(np.asarray(p[key], dtype=np.complex64), torch.complex64)
         self.params = p
 
     # ---------------------------------------------------------------- cd:608-628
@@ -198,8 +215,9 @@ class DEISM:
         elif self.roomtype == "convex":
             self.params["RTF"] = backend.run_DEISM_ARG(self.params)
         if if_clean_up:
+            # (the reference also forces a gc.collect() here, cd:625-628; the image arrays carry no
+            # reference cycles and a forced collection costs 30-90 ms of host time per call)
             self.params.pop("images", None)
-            gc.collect()
 
     def run_DEISM_ray(self, if_clean_up: bool = True, if_shutdown_ray: bool = True):
         raise NotImplementedError("the Ray backend is the reference's legacy CPU fan-out; use run_DEISM()")

@@ -108,8 +108,11 @@ def merge_images(images):
     if "storage" in images:
         merged["storage"] = images["storage"]
     for key in ("A", "R_sI_r_all", "R_s_rI_all", "R_r_sI_all"):
-        merged[key] = np.concatenate([np.asarray(images[key + "_early"]),
-                                      np.asarray(images[key + "_late"])], axis=0)
+        early, late = images[key + "_early"], images[key + "_late"]
+        if isinstance(early, torch.Tensor):          # device-resident lists stay on the device
+            merged[key] = torch.cat([early, late], dim=0)
+            continue
+        merged[key] = np.concatenate([np.asarray(early), np.asarray(late)], axis=0)
     if "atten_all_early" in images and "atten_all_late" in images:
         merged["atten_all"] = np.concatenate([images["atten_all_early"],
                                               images["atten_all_late"]], axis=0)

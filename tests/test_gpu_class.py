@@ -139,3 +139,48 @@ def test_baseline_c4_convex_order_10():
     d.update_directivities()                        # per-image source coefficients follow the new image list
     d.run_DEISM()
     assert np.all(np.isfinite(d.params["RTF"].view(np.float64)))
+
+
+@pytest.mark.parametrize("case", ["s1", "s5", "s4", "x1", "x4"])
+def test_device_resident_mode_gives_the_same_result(case):
+    """DEISM(..., device_resident=True): bulk intermediates are torch CUDA tensors, same RTF / RIR."""
+    import torch
+
+    spec = {
+        "s1": ("s1_shoebox_rtf_mix_o5_mono", "RTF", "shoebox", "MIX", 5, {"endFreq": 200}, (), None),
+        "s5": ("s5_shoebox_rtf_lc_o7_mono_noang", "RTF", "shoebox", "LC", 7, {"endFreq": 300, "angDepFlag": 0}, (), None),
+        "s4": ("s4_shoebox_rir_mix_o9_N2", "RIR", "shoebox", "MIX", 9, {"sampleRate": 1500, "ifRemoveDirectPath": 1},
+               (0.08, None, "reverberationTime"), (2, 2)),
+        "x1": ("x1_convex_rir_mix_o4_mono", "RIR", "convex", "MIX", 4, {"sampleRate": 4000}, (), None),
+        "x4": ("x4_convex_rtf_lc_o3_mono", "RTF", "convex", "LC", 3, {"endFreq": 400}, (), None),
+    }[case]
+    name, mode, roomtype, method, order, overrides, mats, inject = spec
+    g = Golden(name)
+    d = DEISM(mode, roomtype, silent=True, device_resident=True)
+    d.params["DEISM_method"], d.params["maxReflOrder"] = method, order
+    d.params.update(overrides)
+    if case == "s5":
+        d.update_room(roomDimensions=np.array([5.3, 3.1, 2.7]))
+    d.update_wall_materials(*mats)
+    d.update_freqs()
+    if roomtype == "convex":
+        d.update_source_receiver()
+        d.update_directivities()
+    else:
+        if inject:
+            _inject(d, *inject)
+        else:
+            d.update_directivities()
+        d.update_source_receiver()
+    im = d.params["images"]
+    assert all(isinstance(v, torch.Tensor) and v.is_cuda for k, v in im.items()
+               if k not in ("storage", "early_indices", "late_indices"))
+    ref = g.group("images")
+    for key, val in ref.items():
+        if key == "storage" or key not in im or key.endswith("_indices"):
+            continue
+        assert np.array_equal(im[key].cpu().numpy().view(np.uint8), np.ascontiguousarray(val).view(np.uint8)), key
+    d.run_DEISM(if_clean_up=False)
+    assert isinstance(d.params["RTF"], np.ndarray) and rel_l2(d.params["RTF"], g.rtf) < TOL
+    if mode == "RIR":
+        assert rel_l2(d.get_results(), g.z["RIR"]) < TOL
