@@ -156,6 +156,9 @@ def main():
                     help="perturb Z_S across frequency so that the per-term beta path runs")
     ap.add_argument("--cpu-terms", type=float, default=None,
                     help="term budget of the CPU sample (default: ~15 s of CPU work)")
+    ap.add_argument("--sharding", default="frequency", choices=["frequency", "image"],
+                    help="N>1: contiguous frequency slabs + all_gather (default) or, for the merged "
+                         "ORG/LC image lists of few-frequency runs, image slabs + all_reduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
@@ -178,7 +181,8 @@ def main():
     cpu_terms = args.cpu_terms or cpu_rate * 15.0
 
     config = {"workload": desc, "method": method, "source_order": N, "receiver_order": V,
-              "frequencies": K, "sharding": f"freq-slab x{world}" if world > 1 else "single GPU",
+              "frequencies": K, "sharding": (f"freq-slab x{world}" if args.sharding == "frequency" else f"image-slab x{world}")
+              if world > 1 else "single GPU",
               "l2": "L2 flushed (256 MiB write) between timed steps",
               "impedance": "general (per-term beta)" if args.general_impedance
               else "as shipped (frequency-flat: beta per image)"}
@@ -220,10 +224,21 @@ def main():
     I = workloads.n_images(full_images)
     terms = I * K
 
-    # frequency slab of this rank
-    ps, lo, hi = distributed.shard_frequencies(p, rank, world)
-    ps["images"] = full_images
+    # frequency slab (or image slab) of this rank
+    by_image = args.sharding == "image" and world > 1
+    if by_image:
+        if method == "MIX":
+            raise SystemExit("--sharding image needs a merged image list (ORG or LC workload)")
+        p_all = dict(p)
+        p_all["images"] = full_images
+        ps, ilo, ihi = distributed.shard_images(p_all, rank, world)
+        full_images = ps["images"]
+        lo, hi = 0, K
+    else:
+        ps, lo, hi = distributed.shard_frequencies(p, rank, world)
+        ps["images"] = full_images
     Ks = hi - lo
+    I_rank = workloads.n_images(full_images)      # this rank's images (all of them unless --sharding image)
 
     def pin(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -272,7 +287,10 @@ def main():
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     def combine(slab):
-        """The one collective of the path: frequency slabs -> full RTF on every rank."""
+        """The one collective of the path: frequency slabs -> full RTF on every rank (all_gather),
+        or the sum of the per-rank partial RTFs over image slabs (all_reduce)."""
+        if by_image:
+            return distributed.reduce_image_slabs(slab)
         return distributed.gather_frequency_slabs(slab, K)
 
     def step_device():
@@ -382,7 +400,7 @@ def main():
         ms_k, n_k = prof[dom]
         per_launch_ms = ms_k / n_k
         if dom == "lc_main":
-            n_late = len(full_images["A_late"]) if method == "MIX" else I
+            n_late = len(full_images["A_late"]) if method == "MIX" else I_rank
             Js, Jr = (N + 1) ** 2, (V + 1) ** 2
             fpt = lc_flops_per_term(Js, Jr, args.general_impedance, 0.75 * p["maxReflOrder"])
             units = n_late * Ks
@@ -393,7 +411,7 @@ def main():
                     peak_tf, peak_kind = extras["fp64_peak_dfma_tflops"], "dfma"
         elif dom == "org_consume":
             fpt = org_consume_flops_per_term(N, V)
-            units = I * Ks
+            units = I_rank * Ks
         else:
             fpt, units = None, None
         traffic = None

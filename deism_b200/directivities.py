@@ -45,7 +45,9 @@ def _flatten(C, order):
 
         vec = torch.stack([C[:, int(n), int(m)] for n, m in zip(n_all, m_all)], dim=1)
         return n_all, m_all, vec.to(torch.complex64).contiguous()
-    vec = np.zeros((C.shape[0], J) + C.shape[3:], dtype="complex")
+    # (the reference fills a complex128 array and rounds it to complex64; complex64 input gives the
+    # same values without the double-width temporary)
+    vec = np.zeros((C.shape[0], J) + C.shape[3:], dtype=np.complex64 if C.dtype == np.complex64 else "complex")
     for j in range(J):
         vec[:, j] = C[:, n_all[j], m_all[j]]
     return n_all, m_all, vec.astype(np.complex64)
