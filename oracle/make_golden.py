@@ -354,6 +354,73 @@ def augment_full():
         print("  augmented", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def choras_job(kind):
+    """A CHORAS job file (examples/exampleInput_Deism.json layout) with its geometry block filled."""
+    names = ("wall1", "wall3", "wall2", "wall4", "floor", "ceiling")      # DEISM order x1 x2 y1 y2 z1 z2
+    if kind == "shoebox":
+        L = (5.0, 4.0, 3.0)
+        verts = [[x, y, z] for x in (0, L[0]) for y in (0, L[1]) for z in (0, L[2])]
+        centers = [[0, 2, 1.5], [5, 2, 1.5], [2.5, 0, 1.5], [2.5, 4, 1.5], [2.5, 2, 0], [2.5, 2, 3]]
+        areas = [12.0, 12.0, 15.0, 15.0, 20.0, 20.0]
+        volume = 60.0
+        src, rec = (1.2, 1.4, 1.5), (3.6, 2.7, 1.2)
+    else:
+        # the tilted-ceiling room of configSingleParam_ARG_RIR.yml, walls named in its wallCenters order
+        verts = [[0, 0, 0], [0, 0, 3.5], [0, 3, 2.5], [0, 3, 0], [4, 0, 0], [4, 0, 3.5], [4, 3, 2.5], [4, 3, 0]]
+        centers = [[0, 1.5, 1.5], [2, 3, 1.25], [4, 1.5, 1.5], [2, 0, 1.75], [2, 1.5, 0], [2, 1.5, 3]]
+        areas = [9.0, 10.0, 9.0, 14.0, 12.0, 4 * np.sqrt(10.0)]
+        volume = 36.0
+        src, rec = (1.1, 1.1, 1.3), (2.9, 1.9, 1.3)
+    absorb = {"wall1": "0.10, 0.12, 0.15, 0.20, 0.25", "wall3": "0.30, 0.28, 0.25, 0.22, 0.20",
+              "wall2": "0.05, 0.06, 0.08, 0.10, 0.12", "wall4": "0.15, 0.15, 0.15, 0.15, 0.15",
+              "floor": "0.02, 0.03, 0.04, 0.05, 0.06", "ceiling": "0.60, 0.69, 0.71, 0.70, 0.63"}
+    return {"absorption_coefficients": absorb, "should_cancel": False,
+            "geometry": [{"vertices": verts, "room_volume": volume,
+                          "room_areas": dict(zip(names, [float(a) for a in areas])),
+                          "wall_centers": {n: ", ".join(f"{v:.4f}" for v in c) for n, c in zip(names, centers)}}],
+            "results": [{"sourceX": src[0], "sourceY": src[1], "sourceZ": src[2], "resultType": "Deism",
+                         "frequencies": [125, 250, 500, 1000, 2000],
+                         "responses": [{"x": rec[0], "y": rec[1], "z": rec[2], "receiverResults": []}]}]}
+
+
+def choras_cases():
+    """The reference's CHORAS flow (examples/DeismInterface.py:167-243, minus the Gmsh geometry sync
+    that fills the geometry block) through the reference's own DEISM class."""
+    import json
+
+    names = ("wall1", "wall3", "wall2", "wall4", "floor", "ceiling")
+    for kind, overrides in (("shoebox", {"sampleRate": 2000, "maxReflOrder": 8}),
+                            ("convex", {"sampleRate": 1000, "maxReflOrder": 4})):
+        job = choras_job(kind)
+        geo, res = job["geometry"][0], job["results"][0]
+        bands = np.array(res["frequencies"])
+        num = lambda v: np.array([float(x) for x in v.split(",")]) if isinstance(v, str) else np.array([float(v)])
+        absorption, centers, areas = np.zeros((6, len(bands))), np.zeros((6, 3)), np.zeros((6, 1))
+        for i, w in enumerate(names):
+            absorption[i, :] = num(job["absorption_coefficients"][w])
+            centers[i, :] = num(geo["wall_centers"][w])
+            areas[i, :] = num(geo["room_areas"][w])
+        vertices = np.array(geo["vertices"])
+        d = ref_import.make_deism("RIR", kind)
+        d.params.update(overrides)
+        dims = vertices.max(axis=0) - vertices.min(axis=0) if kind == "shoebox" else vertices
+        d.update_room(dims, centers, geo["room_volume"], areas)
+        d.update_wall_materials(absorption, bands, "absorption")
+        d.update_freqs()
+        d.params["posSource"] = np.array([res["sourceX"], res["sourceY"], res["sourceZ"]])
+        d.params["posReceiver"] = np.array([res["responses"][0][k] for k in "xyz"])
+        d.update_source_receiver()
+        d.update_directivities()
+        d.run_DEISM(if_clean_up=True)
+        rtf = np.array(d.params["RTF"], copy=True)
+        rir = np.asarray(d.get_results())
+        save(f"j_choras_{kind}", {"job_json": np.array(json.dumps(job)), "RTF": rtf, "RIR": rir,
+                                  "overrides_json": np.array(json.dumps(overrides)),
+                                  "impedance": np.asarray(d.params["impedance"]),
+                                  "reverberationTime": np.asarray(d.params["reverberationTime"])})
+        print(f"[j_choras_{kind}] K={len(rtf)} T60={d.params['reverberationTime']}")
+
+
 def refit_case(name="r1_arg_refit_N3", n_img=40, N=3, n_dir=50, seed=3):
     """the reference's cal_C_nm_s_new (cd:1545-1605) + vectorize_C_nm_s_ARG
     (cd:1193-1217) on the reflection matrices of the x2 convex fixture and a synthetic sampled
@@ -467,6 +534,7 @@ if __name__ == "__main__":
     ap.add_argument("--materials", action="store_true", help="mint only the materials fixture (f4)")
     ap.add_argument("--directivities", action="store_true", help="mint only the sampled-directivity fixture")
     ap.add_argument("--class-cases", action="store_true", help="mint only the DEISM-class fixtures")
+    ap.add_argument("--choras", action="store_true", help="mint only the CHORAS job fixtures")
     args = ap.parse_args()
     if args.refit:
         refit_case()
@@ -479,6 +547,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if args.class_cases:
         class_cases()
+        sys.exit(0)
+    if args.choras:
+        choras_cases()
         sys.exit(0)
     if args.augment:
         augment_full()
