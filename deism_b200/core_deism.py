@@ -40,6 +40,7 @@ class DEISM:
         self.auto_update = True
         self.track_updated_where = True
         self._argv = argv
+        self._compute = None          # slab compute callback; tests inject one to run without a GPU
         self.init_params()
         self.update_room()
 
@@ -210,10 +211,22 @@ class DEISM:
 
     # ---------------------------------------------------------------- cd:608-628
     def run_DEISM(self, if_clean_up: bool = True, if_shutdown_ray: bool = True):
-        if self.roomtype == "shoebox":
-            self.params["RTF"] = backend.run_DEISM(self.params)
-        elif self.roomtype == "convex":
-            self.params["RTF"] = backend.run_DEISM_ARG(self.params)
+        """One process per GPU: when ``torch.distributed`` is initialised with more than one rank
+        (e.g. the script runs under torchrun with the NCCL backend) every rank computes its contiguous
+        frequency slab and one all_gather leaves the full ``params["RTF"]`` on all of them
+        (``params["b200Sharding"]``: "frequency" (default), "image" for merged ORG / LC lists, "off")."""
+        import torch.distributed as dist
+
+        compute = self._compute or (backend.run_DEISM_device if self.roomtype == "shoebox"
+                                    else backend.run_DEISM_ARG_device)
+        mode = self.params.get("b200Sharding", "frequency")
+        if mode != "off" and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            from . import distributed
+
+            rtf = distributed.run_sharded(self.params, compute, mode=mode)
+        else:
+            rtf = compute(self.params)
+        self.params["RTF"] = rtf.cpu().numpy()
         if if_clean_up:
             # (the reference also forces a gc.collect() here, cd:625-628; the image arrays carry no
             # reference cycles and a forced collection costs 30-90 ms of host time per call)

@@ -64,6 +64,37 @@ def test_sharded_run_equals_single(tmp_path, name, mode, world):
         assert rel_l2(got, g.rtf) < 1e-12, (name, r)
 
 
+def _class_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from conftest import Golden as G
+    from deism_b200.core_deism import DEISM
+    from oracle import oracle
+
+    oracle.set_num_threads(1)
+    d = DEISM("RTF", "shoebox", silent=True)
+    d.params.update(G("s2_shoebox_rtf_lc_o6_N3").params())       # state after the update_* stages
+    d._compute = lambda q: torch.from_numpy(oracle.run_DEISM(q))
+    d.run_DEISM()
+    np.save(os.path.join(out_dir, f"r{rank}.npy"), d.params["RTF"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_class_run_shards_under_torch_distributed(tmp_path):
+    """DEISM.run_DEISM() inside an initialised process group: frequency slabs + all_gather, the full
+    RTF in params on every rank (the slab compute is the CPU oracle here)."""
+    port = _free_port()
+    mp.spawn(_class_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    g = Golden("s2_shoebox_rtf_lc_o6_N3")
+    for r in range(2):
+        got = np.load(tmp_path / f"r{r}.npy")
+        assert got.dtype == np.complex128 and rel_l2(got, g.rtf) < 1e-12
+
+
 def test_slab_bounds_cover_everything():
     from deism_b200 import distributed as D
 
