@@ -240,6 +240,10 @@ class DEISM:
                                transition_width_high=None):
         return rir.create_bandpass_window(freqs, f_low, f_high, transition_width_low, transition_width_high)
 
+    def apply_highpass_filter(self, data, fs, fcut=30.0, zero_phase=True):
+        """cd:531-541."""
+        return rir.highpass_RIR(data, fs, fcut, zero_phase=zero_phase)
+
     def get_results(self, highpass_filter: bool = False, bandpass_window: bool = True,
                     cut_freq: float = 30.0, zero_phase: bool = True):
         if highpass_filter and bandpass_window:
@@ -247,7 +251,7 @@ class DEISM:
         if self.mode == "RTF":
             return self.params["RTF"]
         p = rir.get_results(self.params, mode="RIR", highpass_filter=highpass_filter,
-                            bandpass_window=bandpass_window)
+                            bandpass_window=bandpass_window, cut_freq=cut_freq, zero_phase=zero_phase)
         if bandpass_window:
             # the reference leaves the windowed spectrum in params["RTF"] (cd:744)
             fs = self.params["sampleRate"]

@@ -354,6 +354,23 @@ def augment_full():
         print("  augmented", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def highpass_case(name="h1_rir_highpass"):
+    """DEISM.get_results(highpass_filter=True, bandpass_window=False) (cd:754-757, utilities.py:22-92)
+    of the reference on the frozen RTF of the s4 fixture: zero-phase and causal."""
+    z = np.load(os.path.join(GOLDEN, "s4_shoebox_rir_mix_o9_N2.npz"))
+    d = ref_import.make_deism("RIR", "shoebox")
+    d.params["sampleRate"] = 1500
+    d.update_wall_materials(0.08, None, "reverberationTime")
+    d.update_freqs()
+    assert np.array_equal(d.params["freqs"], z["params/freqs"])
+    out = {}
+    for tag, zero_phase, cut in (("zero_phase_30", True, 30.0), ("causal_100", False, 100.0)):
+        d.params["RTF"] = np.array(z["RTF"], copy=True)
+        out["RIR_" + tag] = np.asarray(d.get_results(highpass_filter=True, bandpass_window=False,
+                                                     cut_freq=cut, zero_phase=zero_phase))
+    save(name, out)
+
+
 def choras_job(kind):
     """A CHORAS job file (examples/exampleInput_Deism.json layout) with its geometry block filled."""
     names = ("wall1", "wall3", "wall2", "wall4", "floor", "ceiling")      # DEISM order x1 x2 y1 y2 z1 z2
@@ -535,6 +552,7 @@ if __name__ == "__main__":
     ap.add_argument("--directivities", action="store_true", help="mint only the sampled-directivity fixture")
     ap.add_argument("--class-cases", action="store_true", help="mint only the DEISM-class fixtures")
     ap.add_argument("--choras", action="store_true", help="mint only the CHORAS job fixtures")
+    ap.add_argument("--highpass", action="store_true", help="mint only the high-pass RIR fixture")
     args = ap.parse_args()
     if args.refit:
         refit_case()
@@ -550,6 +568,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if args.choras:
         choras_cases()
+        sys.exit(0)
+    if args.highpass:
+        highpass_case()
         sys.exit(0)
     if args.augment:
         augment_full()

@@ -27,3 +27,13 @@ def test_rtf_mode_passthrough_and_errors():
     assert np.array_equal(rir.get_results(g.params(), g.rtf, mode="RTF"), g.rtf)
     with pytest.raises(ValueError):
         rir.get_results(g.params(), g.rtf, highpass_filter=True, bandpass_window=True)
+
+
+def test_highpass_variant_matches_reference():
+    from deism_b200 import rir
+
+    g, h = Golden("s4_shoebox_rir_mix_o9_N2"), Golden("h1_rir_highpass")
+    for tag, zero_phase, cut in (("zero_phase_30", True, 30.0), ("causal_100", False, 100.0)):
+        got = rir.get_results(g.params(), g.rtf, mode="RIR", highpass_filter=True, bandpass_window=False,
+                              cut_freq=cut, zero_phase=zero_phase)
+        assert rel_l2(got, h.z["RIR_" + tag]) < 1e-12
