@@ -216,6 +216,47 @@ __device__ __forceinline__ void cpow_uint_n(cplx (&base)[NQ], unsigned e, cplx (
         }
     }
 }
+// Real base, integer power, NQ chains at once (one DMUL per step instead of a complex product).
+template <int NQ>
+__device__ __forceinline__ void rpow_uint_n(double (&base)[NQ], unsigned e, double (&out)[NQ]) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) out[q] = 1.0;
+    while (e) {
+        if (e & 1u) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) out[q] *= base[q];
+        }
+        e >>= 1;
+        if (e) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) base[q] *= base[q];
+        }
+    }
+}
+// 1/x for the per-term chains: hardware seed + two Newton steps (<= 1 ulp).
+__device__ __forceinline__ double rcp_newton(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    return fma(fma(-x, r, 1.0), r, r);
+}
+// ref_coef with that reciprocal (the per-image / materialising callers keep the IEEE division)
+__device__ __forceinline__ cplx ref_coef_fast(double cos_t, cplx zeta) {
+    const double zr = zeta.x * cos_t, zi = zeta.y * cos_t;
+    const double ax = zr - 1.0, bx = zr + 1.0;
+    const double inv = rcp_newton(fma(bx, bx, zi * zi));
+    return cmake(fma(ax, bx, zi * zi) * inv, fma(zi, bx, -ax * zi) * inv);
+}
+// An impedance whose imaginary part is below 2 ulp of its real part is treated as real: the
+// reference's material conversions return Re + 1e-16j (cd:807-880), for which the complex factor
+// (zeta c - 1)/(zeta c + 1) differs from the real one by ~1e-17 absolutely — two orders below the
+// rounding of zeta c - 1 itself.  The real chain is one real division and real powers per wall.
+__device__ __forceinline__ bool z_is_real(cplx z) { return fabs(z.y) <= 4.0e-16 * fabs(z.x); }
+// (t - 1)/(t + 1) = 1 - 2/(t + 1) with the hardware reciprocal seed and two Newton steps (<= 1 ulp
+// on 1/(t+1)): a third of the instructions of the IEEE division sequence.
+__device__ __forceinline__ double real_ref_coef(double t) {
+    return fma(-2.0, rcp_newton(t + 1.0), 1.0);
+}
 template <int NQ>
 __device__ __forceinline__ void shoebox_atten_n(const cplx *__restrict__ Z, long zstride, const int (&fq)[NQ],
                                                 double cx, double cy, double cz, const unsigned char *e,
@@ -223,23 +264,50 @@ __device__ __forceinline__ void shoebox_atten_n(const cplx *__restrict__ Z, long
     const double c3[3] = {cx, cy, cz};
 #pragma unroll
     for (int w = 0; w < 3; ++w) {
-        cplx b1[NQ], z2[NQ], p[NQ];
-        bool same = true;
+        cplx z1[NQ], z2[NQ];
+        bool same = true, real = true;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-            const cplx z1 = Z[(2 * w) * zstride + fq[q]];
+            z1[q] = Z[(2 * w) * zstride + fq[q]];
             z2[q] = Z[(2 * w + 1) * zstride + fq[q]];
-            same = same && csame(z1, z2[q]);
-            b1[q] = ref_coef(c3[w], z1);
+            same = same && csame(z1[q], z2[q]);
+            real = real && z_is_real(z1[q]) && z_is_real(z2[q]);
         }
         const unsigned e1 = e[2 * w], e2 = e[2 * w + 1];
+        if (real) {
+            double r1[NQ], rp[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                r1[q] = real_ref_coef(z1[q].x * c3[w]);
+            }
+            if (same) {
+                rpow_uint_n<NQ>(r1, e1 + e2, rp);
+            } else {
+                double r2[NQ], rp2[NQ];
+                rpow_uint_n<NQ>(r1, e1, rp);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    r2[q] = real_ref_coef(z2[q].x * c3[w]);
+                }
+                rpow_uint_n<NQ>(r2, e2, rp2);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) rp[q] *= rp2[q];
+            }
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                out[q] = w == 0 ? cmake(rp[q], 0.0) : cmake(out[q].x * rp[q], out[q].y * rp[q]);
+            continue;
+        }
+        cplx b1[NQ], p[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) b1[q] = ref_coef_fast(c3[w], z1[q]);
         if (same) {
             cpow_uint_n<NQ>(b1, e1 + e2, p);
         } else {
             cplx b2[NQ], p2[NQ];
             cpow_uint_n<NQ>(b1, e1, p);
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) b2[q] = ref_coef(c3[w], z2[q]);
+            for (int q = 0; q < NQ; ++q) b2[q] = ref_coef_fast(c3[w], z2[q]);
             cpow_uint_n<NQ>(b2, e2, p2);
 #pragma unroll
             for (int q = 0; q < NQ; ++q) p[q] = cmul(p[q], p2[q]);
@@ -247,6 +315,15 @@ __device__ __forceinline__ void shoebox_atten_n(const cplx *__restrict__ Z, long
 #pragma unroll
         for (int q = 0; q < NQ; ++q) out[q] = w == 0 ? p[q] : cmul(out[q], p[q]);
     }
+}
+
+// one (image, frequency) term inside a main loop: the chains above with NQ = 1
+__device__ __forceinline__ cplx shoebox_atten_term(const cplx *__restrict__ Z, long zstride, double cx, double cy,
+                                                   double cz, const unsigned char *e) {
+    const int fq[1] = {0};
+    cplx out[1];
+    shoebox_atten_n<1>(Z, zstride, fq, cx, cy, cz, e, out);
+    return out[0];
 }
 
 // Per-image attenuation geometry shared by images.cu / lc.cu / org.cu

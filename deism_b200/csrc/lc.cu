@@ -643,7 +643,7 @@ lc_main_kernel(LcMainArgs a) {
                     att = rec.a_flat;
                 } else {
                     if (fused) {
-                        att = shoebox_atten(&Zs[0][fq], TF, rec.cx, rec.cy, rec.cz, rec.e);
+                        att = shoebox_atten_term(&Zs[0][fq], TF, rec.cx, rec.cy, rec.cz, rec.e);
                         if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
                     } else {
                         const long img = i0 + il, f = f0 + fq;

@@ -668,7 +668,7 @@ org_consume_kernel(OrgConsumeArgs a) {
                     } else if (flat) {
                         att = rec.atten_flat;
                     } else if (fused) {
-                        att = shoebox_atten(&sm.Z[0][fq], ORG_TF, rec.cx, rec.cy, rec.cz, rec.e);
+                        att = shoebox_atten_term(&sm.Z[0][fq], ORG_TF, rec.cx, rec.cy, rec.cz, rec.e);
                         if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
                     } else {
                         const long f = f0 + fq;

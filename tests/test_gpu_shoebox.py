@@ -84,9 +84,10 @@ def test_lc_fused(name):
     assert rel_l2(got, g.rtf) < RTF_TOL
 
 
+@pytest.mark.parametrize("kind", ["complex", "real_plus_1e-16j", "real_same_opposite_walls", "mixed"])
 @pytest.mark.parametrize("name", ["s5_shoebox_rtf_lc_o7_mono_noang", "s1_shoebox_rtf_mix_o5_mono",
                                   "s4_shoebox_rir_mix_o9_N2", "s2_shoebox_rtf_lc_o6_N3"])
-def test_frequency_dependent_impedance_fused_vs_materialised(name):
+def test_frequency_dependent_impedance_fused_vs_materialised(name, kind):
     """Impedance that varies with frequency (complex, different per wall): the in-kernel per-term
     attenuation (monopole, tensor-core and ORG kernels) against the same run fed with the
     attenuation array materialised by the image generator and against the CPU oracle on it."""
@@ -99,7 +100,16 @@ def test_frequency_dependent_impedance_fused_vs_materialised(name):
     ramp = 1.0 + 0.3 * np.linspace(0.0, 1.0, K)
     Z = np.asarray(p["impedance"], dtype=np.complex128) * ramp[None, :]
     Z = Z * (1.0 + 0.1 * np.arange(6))[:, None] + 1j * (2.0 - 3.0 * np.linspace(0, 1, K))[None, :]
-    p["impedance"] = Z
+    if kind == "real_plus_1e-16j":
+        # what the reference's material conversions return (cd:807-880): the kernels' real chain
+        Z = Z.real + 1e-16j
+    elif kind == "real_same_opposite_walls":
+        Z = Z.real[[0, 0, 2, 2, 4, 4]] + 0j
+    elif kind == "mixed":
+        # x walls complex, y walls real, z walls real except at a few frequencies
+        Z = np.concatenate([Z[:2], Z.real[2:4] + 1e-16j, Z.real[4:] + 0j])
+        Z[4:, ::7] += 0.5j
+    p["impedance"] = np.ascontiguousarray(Z)
     method = p["DEISM_method"]
     fused = im.pre_calc_images_src_rec_optimized_nofs_v2_numba(p)
     mat = im.pre_calc_images_src_rec_optimized_nofs_v2_numba(p, materialize=True)
