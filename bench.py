@@ -42,7 +42,26 @@ sys.path.insert(0, ROOT)
 # real x complex: 4 flops per harmonic and term instead of 8), i.e. the cheapest formulation known
 # to us, not the reference's complex x complex loop.
 # --------------------------------------------------------------------------------------
-def lc_flops_per_term(Js, Jr, fused_per_term, mean_order):
+def wall_factor_flops(mean_order, real_impedance, same_opposite_walls=True):
+    """Flops the per-term attenuation chain EXECUTES (common.cuh shoebox_atten_n), per term: per wall
+    pair one wall factor and one power by squaring of the summed exponent (two of each when the two
+    walls of the pair differ), then the product of the three pairs and the complex64 rounding.
+      real chain   : factor = t, t+1, reciprocal seed + 2 Newton steps (8), 1 - 2r (2)      = 12
+                     power  = ~1.5 log2(e) real multiplies (squarings + set bits)
+      complex chain: factor = zr, zi, +-1 (4), |den|^2 (3), reciprocal (9), numerator (8)    = 24
+                     power  = ~1.5 log2(e) complex multiplies of 6 flops
+    e = mean exponent per pair = mean_order / 3."""
+    import math
+
+    e = max(2.0, mean_order / 3.0)
+    mults = 1.5 * math.log2(e)
+    chains = 3 * (1 if same_opposite_walls else 2)
+    if real_impedance:
+        return chains * (12 + mults) + 4 + 2
+    return chains * (24 + 6 * mults) + 12 + 2
+
+
+def lc_flops_per_term(Js, Jr, fused_per_term, mean_order, real_impedance=False, same_opposite_walls=True):
     if Js == 1 and Jr == 1:
         # monopole kernel: no contraction; per term one step of the rotation recurrence (complex
         # mul 6 + first-order grid correction 5), the accumulate (2) and 1/16 of a sincos
@@ -50,7 +69,7 @@ def lc_flops_per_term(Js, Jr, fused_per_term, mean_order):
     else:
         f = 4 * (Js + Jr) + 52
     if fused_per_term:
-        f += 140 + 6 * mean_order
+        f += wall_factor_flops(mean_order, real_impedance, same_opposite_walls)
     return f
 
 
@@ -402,7 +421,11 @@ def main():
         if dom == "lc_main":
             n_late = len(full_images["A_late"]) if method == "MIX" else I_rank
             Js, Jr = (N + 1) ** 2, (V + 1) ** 2
-            fpt = lc_flops_per_term(Js, Jr, args.general_impedance, 0.75 * p["maxReflOrder"])
+            Zh = np.asarray(p["impedance"])
+            z_real = bool(np.all(np.abs(Zh.imag) <= 4e-16 * np.abs(Zh.real)))       # common.cuh z_is_real
+            z_same = bool(np.array_equal(Zh[0::2], Zh[1::2]))
+            fpt = round(lc_flops_per_term(Js, Jr, args.general_impedance, 0.75 * p["maxReflOrder"], z_real,
+                                          z_same), 1)
             units = n_late * Ks
             if Js == 1 and Jr == 1:
                 dom_kernel = "lc_mono_kernel"      # what deism_lc_shoebox launches for monopoles

@@ -52,12 +52,17 @@ def report(path, out, title):
         isrc, iex, ist = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("Warp Stall Sampling (All Samples)")
         ops, samp = collections.Counter(), collections.Counter()
         for r in rows[2:]:
+            if len(r) <= max(isrc, iex, ist):
+                continue                   # section breaks of a report that holds several kernels
             toks = r[isrc].split()
             if not toks:
                 continue
             op = toks[1] if toks[0].startswith("@") and len(toks) > 1 else toks[0]
-            ops[op] += int(r[iex] or 0)
-            samp[op] += int(r[ist] or 0)
+            try:
+                ops[op] += int(r[iex] or 0)
+                samp[op] += int(r[ist] or 0)
+            except ValueError:
+                continue                   # a repeated header row
         lines += ["SASS opcodes by warp-instructions executed: " + ", ".join(f"{k} {v}" for k, v in ops.most_common(10)), "",
                   "SASS opcodes by stall samples: " + ", ".join(f"{k} {v}" for k, v in samp.most_common(8)), ""]
     open(out, "w").write("\n".join(lines) + "\n")
