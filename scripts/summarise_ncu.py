@@ -51,9 +51,15 @@ def report(path, out, title):
         hdr = rows[1]
         isrc, iex, ist = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("Warp Stall Sampling (All Samples)")
         ops, samp = collections.Counter(), collections.Counter()
+        seen, skip = {rows[0][1] if len(rows[0]) > 1 else ""}, False
         for r in rows[2:]:
-            if len(r) <= max(isrc, iex, ist):
-                continue                   # section breaks of a report that holds several kernels
+            if r and r[0] == "Kernel Name":
+                # a report with several kernels lists one section per result (and may list a kernel
+                # twice): the opcode mix is that of the FIRST kernel only
+                skip = True
+                continue
+            if skip or len(r) <= max(isrc, iex, ist):
+                continue
             toks = r[isrc].split()
             if not toks:
                 continue
