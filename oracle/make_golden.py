@@ -354,6 +354,31 @@ def augment_full():
         print("  augmented", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def scripted_case(name="c1_scripted"):
+    """examples/deism_singleparam_example.py:21-38 call for call (BASELINE configs[0] "as scripted":
+    RIR mode, room 10 x 8 x 2.5 m, T60 = 1 s -> 24 000 frequencies, reflection order 30)."""
+    t0 = time.time()
+    d = ref_import.make_deism("RIR", "shoebox")
+    d.update_room(roomDimensions=np.array([10.0, 8.0, 2.5]))
+    d.update_wall_materials(datain=1, datatype="reverberationTime")
+    d.params["sampleRate"] = 48000
+    d.params["reverberationTime"] = 1
+    d.update_freqs()
+    d.update_directivities()
+    d.params["maxReflOrder"] = 30
+    t1 = time.time()
+    d.update_source_receiver()
+    t2 = time.time()
+    im = d.params["images"]
+    nimg = len(im["A_early"]) + len(im["A_late"])
+    d.run_DEISM(if_clean_up=True, if_shutdown_ray=True)
+    t3 = time.time()
+    print(f"[{name}] I={nimg} K={len(d.params['freqs'])} setup {t1 - t0:.2f}s images {t2 - t1:.2f}s run {t3 - t2:.2f}s (cold)")
+    save(name, {"RTF": np.asarray(d.params["RTF"]), "meta/n_images": np.array(nimg),
+                "meta/t_images_s": np.array(t2 - t1), "meta/t_run_cold_s": np.array(t3 - t2),
+                "params/impedance_col0": np.ascontiguousarray(np.asarray(d.params["impedance"])[:, 0])})
+
+
 def highpass_case(name="h1_rir_highpass"):
     """DEISM.get_results(highpass_filter=True, bandpass_window=False) (cd:754-757, utilities.py:22-92)
     of the reference on the frozen RTF of the s4 fixture: zero-phase and causal."""
@@ -553,6 +578,7 @@ if __name__ == "__main__":
     ap.add_argument("--class-cases", action="store_true", help="mint only the DEISM-class fixtures")
     ap.add_argument("--choras", action="store_true", help="mint only the CHORAS job fixtures")
     ap.add_argument("--highpass", action="store_true", help="mint only the high-pass RIR fixture")
+    ap.add_argument("--scripted", action="store_true", help="mint only the as-scripted example fixture")
     args = ap.parse_args()
     if args.refit:
         refit_case()
@@ -571,6 +597,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if args.highpass:
         highpass_case()
+        sys.exit(0)
+    if args.scripted:
+        scripted_case()
         sys.exit(0)
     if args.augment:
         augment_full()

@@ -141,7 +141,7 @@ def test_baseline_c4_convex_order_10():
     assert np.all(np.isfinite(d.params["RTF"].view(np.float64)))
 
 
-@pytest.mark.parametrize("case", ["s1", "s5", "s4", "x1", "x4"])
+@pytest.mark.parametrize("case", ["s1", "s5", "s4", "s3", "x1", "x4"])
 def test_device_resident_mode_gives_the_same_result(case):
     """DEISM(..., device_resident=True): bulk intermediates are torch CUDA tensors, same RTF / RIR."""
     import torch
@@ -151,6 +151,8 @@ def test_device_resident_mode_gives_the_same_result(case):
         "s5": ("s5_shoebox_rtf_lc_o7_mono_noang", "RTF", "shoebox", "LC", 7, {"endFreq": 300, "angDepFlag": 0}, (), None),
         "s4": ("s4_shoebox_rir_mix_o9_N2", "RIR", "shoebox", "MIX", 9, {"sampleRate": 1500, "ifRemoveDirectPath": 1},
                (0.08, None, "reverberationTime"), (2, 2)),
+        "s3": ("s3_shoebox_rtf_org_o4_N3V2", "RTF", "shoebox", "ORG", 4,
+               {"startFreq": 50, "endFreq": 2000, "freqStep": 50}, (), (3, 2)),
         "x1": ("x1_convex_rir_mix_o4_mono", "RIR", "convex", "MIX", 4, {"sampleRate": 4000}, (), None),
         "x4": ("x4_convex_rtf_lc_o3_mono", "RTF", "convex", "LC", 3, {"endFreq": 400}, (), None),
     }[case]
@@ -184,3 +186,23 @@ def test_device_resident_mode_gives_the_same_result(case):
     assert isinstance(d.params["RTF"], np.ndarray) and rel_l2(d.params["RTF"], g.rtf) < TOL
     if mode == "RIR":
         assert rel_l2(d.get_results(), g.z["RIR"]) < TOL
+
+
+def test_reference_example_script_as_scripted():
+    """examples/deism_singleparam_example.py (BASELINE configs[0] "as scripted": RIR mode, 10 x 8 x 2.5 m,
+    T60 = 1 s -> 24 000 frequencies, order 30) against the reference's run of its own script."""
+    import importlib.util
+    import os
+
+    from conftest import ROOT
+
+    spec = importlib.util.spec_from_file_location("example_script",
+                                                  os.path.join(ROOT, "examples", "deism_singleparam_example.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = Golden("c1_scripted")
+    P, rir = mod.main(device_resident=False)
+    assert P.shape == g.rtf.shape and rel_l2(P, g.rtf) < TOL
+    assert rir.shape == (48000,) and np.all(np.isfinite(rir))
+    P2, _ = mod.main(device_resident=True)
+    assert rel_l2(P2, g.rtf) < TOL
