@@ -98,7 +98,29 @@ def estimate_imp_t60(z, ref, V, S, c):
     return np.abs(ref - _LN10_24 * V / c / S / d) / ref * 100
 
 
-def _fit_impedance(objective):
+_paris_grid_cache = {}
+
+
+def _paris_error_grid(grid, target):
+    """_paris_error for a whole vector of impedances at once: the same element-wise operations and the
+    same pairwise row sums as the scalar calls (bit-equal values, hence the same argmin).  The Paris
+    integral does not depend on the target, so it is evaluated once per grid and kept."""
+    from scipy.integrate import trapezoid
+
+    grid = np.asarray(grid, dtype=float)
+    key = (grid.shape[0], float(grid[0]), float(grid[-1]))
+    est = _paris_grid_cache.get(key)
+    if est is None:
+        z = grid[:, None]
+        ct = np.cos(_THETA)[None, :]
+        est = trapezoid(4 * z * ct * np.sin(2 * _THETA)[None, :] / (z ** 2 * ct ** 2 + 2 * z * ct + 1), _THETA, axis=1)
+        _paris_grid_cache[key] = est
+    if abs(target) < 1e-10:
+        return np.full(grid.shape[0], 1e6)
+    return np.where(np.isfinite(est), np.abs(target - est) / target * 100, 1e6)
+
+
+def _fit_impedance(objective, grid_objective=None):
     from scipy.optimize import least_squares
 
     result = None
@@ -111,20 +133,32 @@ def _fit_impedance(objective):
             continue
     if result is None or not result.success:
         grid = np.linspace(1, 1000, 1000)
-        return grid[int(np.argmin([objective(z) for z in grid]))] + 1e-16j
+        errors = grid_objective(grid) if grid_objective is not None else [objective(z) for z in grid]
+        return grid[int(np.argmin(errors))] + 1e-16j
     return result.x[0] + 1e-16j
+
+
+def _abs_to_imp_scalar(t):
+    """cd:880-909.  least_squares hands the objective a length-1 array, for which get_imp_abs raises
+    (shape mismatch with the scalar target) — in the reference as here — so every value ends in the
+    1000-point grid search; that search is evaluated in one vectorised pass."""
+    return _fit_impedance(lambda z: get_imp_abs(z, t), lambda grid: _paris_error_grid(grid, t))
 
 
 def convert_abs_to_imp(abs_coeff):
     if np.isscalar(abs_coeff):
-        return _fit_impedance(lambda z: get_imp_abs(z, abs_coeff))
+        return _abs_to_imp_scalar(abs_coeff)
     a = np.asarray(abs_coeff)
     if a.ndim == 1:
         a = a.reshape(-1, 1)
     imp = np.zeros_like(a, dtype=complex)
+    done = {}                                  # band tables repeat values across walls
     for i in range(a.shape[0]):
         for j in range(a.shape[1]):
-            imp[i, j] = _fit_impedance(lambda z, t=a[i, j]: get_imp_abs(z, t))
+            key = float(a[i, j])
+            if key not in done:
+                done[key] = _abs_to_imp_scalar(a[i, j])
+            imp[i, j] = done[key]
     return imp
 
 

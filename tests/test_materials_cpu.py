@@ -108,3 +108,21 @@ def test_choras_json_wire_format(tmp_path):
     path.write_text(json.dumps(job))
     with pytest.raises(KeyError):
         M.read_choras_json(str(path))
+
+
+def test_vectorised_paris_grid_is_bit_equal_to_the_scalar_objective():
+    """convert_abs_to_imp ends in the reference's 1000-point grid search (cd:897-905); the vectorised
+    evaluation of that grid must select the same impedance: equal error values, bit for bit."""
+    from deism_b200 import materials as M
+
+    grid = np.linspace(1, 1000, 1000)
+    for target in (0.01, 0.1, 0.3, 0.63, 0.71, 0.95, 0.999, 1e-12):
+        scalar = np.array([M._paris_error(z, target) for z in grid])
+        assert np.array_equal(scalar, M._paris_error_grid(grid, target))
+    rng = np.random.default_rng(3)
+    table = rng.uniform(0.02, 0.9, (6, 3))
+    got = M.convert_abs_to_imp(table)
+    for i in range(6):
+        for j in range(3):
+            want = grid[int(np.argmin([M._paris_error(z, table[i, j]) for z in grid]))] + 1e-16j
+            assert got[i, j] == want
