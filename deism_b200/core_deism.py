@@ -40,7 +40,6 @@ class DEISM:
         self.auto_update = True
         self.track_updated_where = True
         self._argv = argv
-        self._compute = None          # slab compute callback; tests inject one to run without a GPU
         self.init_params()
         self.update_room()
 
@@ -217,8 +216,7 @@ class DEISM:
         (``params["b200Sharding"]``: "frequency" (default), "image" for merged ORG / LC lists, "off")."""
         import torch.distributed as dist
 
-        compute = self._compute or (backend.run_DEISM_device if self.roomtype == "shoebox"
-                                    else backend.run_DEISM_ARG_device)
+        compute = backend.run_DEISM_device if self.roomtype == "shoebox" else backend.run_DEISM_ARG_device
         mode = self.params.get("b200Sharding", "frequency")
         if mode != "off" and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             from . import distributed

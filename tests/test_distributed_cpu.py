@@ -77,7 +77,10 @@ def _class_worker(rank, world, port, out_dir):
     oracle.set_num_threads(1)
     d = DEISM("RTF", "shoebox", silent=True)
     d.params.update(G("s2_shoebox_rtf_lc_o6_N3").params())       # state after the update_* stages
-    d._compute = lambda q: torch.from_numpy(oracle.run_DEISM(q))
+    # no GPU in this container: the CUDA slab compute is swapped for the CPU oracle IN THIS TEST PROCESS
+    # (the class itself has no such switch); what is under test is the sharding + gather around it
+    from deism_b200 import backend
+    backend.run_DEISM_device = lambda q, dev=None: torch.from_numpy(oracle.run_DEISM(q))
     d.run_DEISM()
     np.save(os.path.join(out_dir, f"r{rank}.npy"), d.params["RTF"])
     dist.barrier()
