@@ -26,6 +26,7 @@
 //                       source coefficients: the ARG form (pb:388-460) and the shoebox
 //                       cross-check [algo 2]
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -848,6 +849,33 @@ struct deism_org_plan {
 
 namespace deism {
 
+// A second stream per device for the image-independent half of deism_org_shoebox (coefficient
+// transposes + B table), which runs next to the image-dependent half (class sort, records, harmonic
+// rows) and joins it before the consume kernel.  DEISM_ORG_NO_FORK=1 keeps everything on one stream.
+struct OrgSide {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static OrgSide *org_side() {
+    static OrgSide tab[64];
+    static std::mutex mu;
+    static const bool off = [] { const char *e = getenv("DEISM_ORG_NO_FORK"); return e && e[0] == '1'; }();
+    if (off) return nullptr;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    OrgSide &o = tab[dev];
+    if (!o.s) {
+        if (cudaStreamCreateWithFlags(&o.s, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&o.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&o.join, cudaEventDisableTiming) != cudaSuccess) {
+            o.s = nullptr;
+            return nullptr;
+        }
+    }
+    return &o;
+}
+
 static int plan_build(int N, int V, const float *h_W1, const float *h_W2, deism_org_plan *P) {
     const int Lmax = N + V + 1, nseg = Lmax * Lmax;
     OrgLists L;
@@ -1040,11 +1068,18 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
     double *Bp = (double *)workspace(WS_ORG_B, (size_t)8 * n_ftiles * b_rows * sizeof(double));
     if (!CsT || !Bp) return DEISM_ERR_NOMEM;
     bt_elem *CrT = CsT + (size_t)NMs * K;
-    DEISM_CUDA_TRY(cudaMemsetAsync(Bp, 0, (size_t)8 * n_ftiles * b_rows * sizeof(double), st));
-    transpose_c64_kernel<<<(unsigned)(((long)K * NMs + 255) / 256), 256, 0, st>>>(
+    OrgSide *side = org_side();
+    cudaStream_t bs = st;                 // stream of the image-independent half
+    if (side) {
+        DEISM_CUDA_TRY(cudaEventRecord(side->fork, st));
+        DEISM_CUDA_TRY(cudaStreamWaitEvent(side->s, side->fork, 0));
+        bs = side->s;
+    }
+    DEISM_CUDA_TRY(cudaMemsetAsync(Bp, 0, (size_t)8 * n_ftiles * b_rows * sizeof(double), bs));
+    transpose_c64_kernel<<<(unsigned)(((long)K * NMs + 255) / 256), 256, 0, bs>>>(
         (const float2 *)d_C_nm_s, K, NMs, CsT);
     DEISM_LAUNCH_CHECK("transpose_c64_kernel");
-    transpose_c64_kernel<<<(unsigned)(((long)K * NMr + 255) / 256), 256, 0, st>>>(
+    transpose_c64_kernel<<<(unsigned)(((long)K * NMr + 255) / 256), 256, 0, bs>>>(
         (const float2 *)d_C_vu_r, K, NMr, CrT);
     DEISM_LAUNCH_CHECK("transpose_c64_kernel");
     BtableArgs ba;
@@ -1053,11 +1088,12 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
     ba.CsT = CsT; ba.CrT = CrT; ba.k = d_k; ba.Bp = Bp;
     {
         dim3 grid((unsigned)((K + 127) / 128), (unsigned)(Lmax * (Lmax + 1) / 2), 2);
-        prof_begin("org_btable", st);
-        org_btable_kernel<<<grid, 128, 0, st>>>(ba);
-        prof_end("org_btable", st);
+        prof_begin("org_btable", bs);
+        org_btable_kernel<<<grid, 128, 0, bs>>>(ba);
+        prof_end("org_btable", bs);
         DEISM_LAUNCH_CHECK("org_btable_kernel");
     }
+    if (side) DEISM_CUDA_TRY(cudaEventRecord(side->join, side->s));
 
     const long n_pad_cap = (n_images + ORG_TI - 1) / ORG_TI * ORG_TI + 8 * ORG_TI;
     const long n_tiles_cap = n_pad_cap / ORG_TI;
@@ -1097,6 +1133,7 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
         return set_error(DEISM_ERR_INVALID, "ORG consume kernel needs %zu B of shared memory", consume_smem);
     DEISM_CUDA_TRY(cudaFuncSetAttribute(org_consume_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)consume_smem));
+    if (side) DEISM_CUDA_TRY(cudaStreamWaitEvent(st, side->join, 0));
     dim3 grid((unsigned)n_ftiles, (unsigned)n_chunks);
     prof_begin("org_consume", st);
     org_consume_kernel<<<grid, ORG_THREADS, consume_smem, st>>>(ca);
