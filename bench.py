@@ -405,6 +405,23 @@ def main():
                     best, peak_kind = tf.value, nm
         peak_tf = best or None
     if rank == 0 and world == 1 and not args.no_extras:
+        # third witness of the FP64 denominator: cuBLAS DGEMM through torch, 6144^3
+        try:
+            n = 6144
+            A = torch.randn((n, n), dtype=torch.float64, device=dev)
+            B = torch.randn((n, n), dtype=torch.float64, device=dev)
+            torch.matmul(A, B)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(3):
+                torch.matmul(A, B)
+            e1.record()
+            torch.cuda.synchronize()
+            extras["fp64_cublas_dgemm_tflops"] = round(3 * 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12, 2)
+            del A, B
+        except Exception as exc:       # pragma: no cover
+            extras["fp64_cublas_dgemm_tflops"] = f"unavailable: {exc}"
         t0 = time.perf_counter()
         for _ in range(3):
             gimages.shoebox_images_device(p, dev)
