@@ -175,3 +175,36 @@ def test_random_convex_rooms_against_compiled_reference_walls():
             assert np.array_equal(mine.origin, np.asarray(ref.origin).reshape(3))
             assert np.array_equal(mine.corners, np.asarray(ref.corners))
             assert np.array_equal(mine.reflection_matrix, np.asarray(ref.reflection_matrix))
+
+
+def test_yaml_lookup_order_and_legacy_keys(tmp_path, monkeypatch):
+    """readYaml: ./examples/<name> wins over ./<name> wins over the packaged default (data_loader.py:398-409);
+    the old YAML key `absorpCoefficient` is still read (data_loader.py:843-848); convex flags parse."""
+    import yaml
+
+    base = yaml.safe_load(open(f"{data_loader.CONFIG_DIR}/configSingleParam_RTF.yml"))
+    monkeypatch.chdir(tmp_path)
+    assert DEISM("RTF", "shoebox", silent=True).params["maxReflOrder"] == 25             # packaged default
+    cfg = dict(base)
+    cfg["Reflections"] = {"angleDependentFlag": 0, "absorpCoefficient": [0.1] * 6, "maxReflectionOrder": 3}
+    (tmp_path / "configSingleParam_RTF.yml").write_text(yaml.safe_dump(cfg, sort_keys=False))
+    p = DEISM("RTF", "shoebox", silent=True).params
+    assert p["maxReflOrder"] == 3 and p["givenMaterials"] == ["absorption"] and p["absorption"] == [0.1] * 6
+    (tmp_path / "examples").mkdir()
+    cfg["Reflections"]["maxReflectionOrder"] = 7
+    (tmp_path / "examples" / "configSingleParam_RTF.yml").write_text(yaml.safe_dump(cfg, sort_keys=False))
+    assert DEISM("RTF", "shoebox", silent=True).params["maxReflOrder"] == 7
+    c = DEISM("RIR", "convex", silent=True, argv=["-ifconvex", "1", "-nro", "3", "-fs", "8000", "--run", "--quiet"])
+    assert c.params["convexRoom"] == 1 and c.params["maxReflOrder"] == 3 and c.params["sampleRate"] == 8000
+    with pytest.raises(SystemExit):
+        DEISM("RIR", "convex", silent=True, argv=["-room", "1", "2", "3"])              # shoebox-only flag
+
+
+def test_material_no_order_means_minus_one(tmp_path, monkeypatch):
+    import yaml
+
+    cfg = yaml.safe_load(open(f"{data_loader.CONFIG_DIR}/configSingleParam_RTF.yml"))
+    cfg["Reflections"]["maxReflectionOrder"] = None
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / "configSingleParam_RTF.yml").write_text(yaml.safe_dump(cfg, sort_keys=False))
+    assert DEISM("RTF", "shoebox", silent=True).params["maxReflOrder"] == -1              # data_loader.py:823-829
