@@ -856,6 +856,21 @@ struct OrgSide {
     cudaStream_t s = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
 };
+// Joins the side stream back into the caller's stream on EVERY way out of the function once the fork
+// has happened (also the error returns): whatever the caller's stream does next — including the
+// caller's allocator recycling the input buffers — is ordered after the side stream's reads.
+struct OrgJoin {
+    OrgSide *side = nullptr;
+    cudaStream_t st = nullptr;
+    bool recorded = false, joined = false;
+    void record() {
+        if (side && !recorded) { cudaEventRecord(side->join, side->s); recorded = true; }
+    }
+    void join() {
+        if (side && !joined) { record(); cudaStreamWaitEvent(st, side->join, 0); joined = true; }
+    }
+    ~OrgJoin() { join(); }
+};
 static OrgSide *org_side() {
     static OrgSide tab[64];
     static std::mutex mu;
@@ -1070,10 +1085,12 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
     bt_elem *CrT = CsT + (size_t)NMs * K;
     OrgSide *side = org_side();
     cudaStream_t bs = st;                 // stream of the image-independent half
+    OrgJoin joiner;
     if (side) {
         DEISM_CUDA_TRY(cudaEventRecord(side->fork, st));
         DEISM_CUDA_TRY(cudaStreamWaitEvent(side->s, side->fork, 0));
         bs = side->s;
+        joiner.side = side; joiner.st = st;
     }
     DEISM_CUDA_TRY(cudaMemsetAsync(Bp, 0, (size_t)8 * n_ftiles * b_rows * sizeof(double), bs));
     transpose_c64_kernel<<<(unsigned)(((long)K * NMs + 255) / 256), 256, 0, bs>>>(
@@ -1093,7 +1110,7 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
         prof_end("org_btable", bs);
         DEISM_LAUNCH_CHECK("org_btable_kernel");
     }
-    if (side) DEISM_CUDA_TRY(cudaEventRecord(side->join, side->s));
+    joiner.record();
 
     const long n_pad_cap = (n_images + ORG_TI - 1) / ORG_TI * ORG_TI + 8 * ORG_TI;
     const long n_tiles_cap = n_pad_cap / ORG_TI;
@@ -1133,7 +1150,7 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
         return set_error(DEISM_ERR_INVALID, "ORG consume kernel needs %zu B of shared memory", consume_smem);
     DEISM_CUDA_TRY(cudaFuncSetAttribute(org_consume_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)consume_smem));
-    if (side) DEISM_CUDA_TRY(cudaStreamWaitEvent(st, side->join, 0));
+    joiner.join();
     dim3 grid((unsigned)n_ftiles, (unsigned)n_chunks);
     prof_begin("org_consume", st);
     org_consume_kernel<<<grid, ORG_THREADS, consume_smem, st>>>(ca);
