@@ -64,7 +64,7 @@ def test_sharded_run_equals_single(tmp_path, name, mode, world):
         assert rel_l2(got, g.rtf) < 1e-12, (name, r)
 
 
-def _class_worker(rank, world, port, out_dir):
+def _class_worker(rank, world, port, out_dir, name="s2_shoebox_rtf_lc_o6_N3", sharding=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     sys.path.insert(0, ROOT)
@@ -76,7 +76,9 @@ def _class_worker(rank, world, port, out_dir):
 
     oracle.set_num_threads(1)
     d = DEISM("RTF", "shoebox", silent=True)
-    d.params.update(G("s2_shoebox_rtf_lc_o6_N3").params())       # state after the update_* stages
+    d.params.update(G(name).params())                             # state after the update_* stages
+    if sharding:
+        d.params["b200Sharding"] = sharding
     # no GPU in this container: the CUDA slab compute is swapped for the CPU oracle IN THIS TEST PROCESS
     # (the class itself has no such switch); what is under test is the sharding + gather around it
     from deism_b200 import backend
@@ -96,6 +98,18 @@ def test_class_run_shards_under_torch_distributed(tmp_path):
     for r in range(2):
         got = np.load(tmp_path / f"r{r}.npy")
         assert got.dtype == np.complex128 and rel_l2(got, g.rtf) < 1e-12
+
+
+@pytest.mark.parametrize("sharding", ["image", "off"])
+def test_class_sharding_modes(tmp_path, sharding):
+    """params["b200Sharding"]: "image" cuts the merged ORG image list and all_reduces, "off" lets every
+    rank compute everything."""
+    port = _free_port()
+    name = "s3_shoebox_rtf_org_o4_N3V2"
+    mp.spawn(_class_worker, args=(2, port, str(tmp_path), name, sharding), nprocs=2, join=True)
+    g = Golden(name)
+    for r in range(2):
+        assert rel_l2(np.load(tmp_path / f"r{r}.npy"), g.rtf) < 1e-12
 
 
 def test_slab_bounds_cover_everything():
