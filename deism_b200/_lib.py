@@ -53,6 +53,7 @@ class ConvexWalls(C.Structure):
 _vp, _i32, _i64, _dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
 _SIGNATURES = {
     "deism_b200_version": (C.c_int, []),
+    "deism_b200_source_hash": (C.c_char_p, []),
     "deism_last_error": (C.c_char_p, []),
     "deism_device_info": (C.c_int, [_i32, _vp, _vp, _vp, _vp]),
     "deism_release_workspace": (C.c_int, []),
@@ -70,6 +71,8 @@ _SIGNATURES = {
     "deism_org_plan_destroy": (C.c_int, [_vp]),
     "deism_org_shoebox": (C.c_int, [_i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                     _vp, _i32, _i32, _vp, _vp]),
+    "deism_org_shoebox_c128": (C.c_int, [_i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                         _vp, _i32, _vp, _vp]),
     "deism_lc_arg": (C.c_int, [_i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                _vp, _i64, _vp, _i32, _vp]),
     "deism_org_arg": (C.c_int, [_i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -93,12 +96,55 @@ def build(verbose: bool = False) -> str:
     return LIB_PATH
 
 
+_HASHED = ("api.cu", "images.cu", "lc.cu", "org.cu", "arg.cu", "convex.cu", "wigner.cu", "refit.cu",
+           "materials.cu", "common.cuh", os.path.join("..", "..", "include", "deism_b200.h"))
+
+
+def source_hash() -> str:
+    """Fingerprint of the sources next to this file — the Makefile's SRCHASH (same files, same
+    order); None when the sources are not there (a binary-only deployment)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    try:
+        for name in _HASHED:
+            with open(os.path.join(CSRC, name), "rb") as fh:
+                h.update(fh.read())
+    except OSError:
+        return None
+    return h.hexdigest()[:16]
+
+
+def _stale(path) -> bool:
+    """True when the .so at `path` was built from other sources than the ones in the tree.  The
+    fingerprint is read from the file (marker string), not through dlopen: a probe handle would
+    pin the old image in the process and the rebuilt file could not replace it."""
+    want = source_hash()
+    if want is None or os.environ.get("DEISM_B200_SKIP_HASH") == "1":
+        return False
+    marker = b"DEISM_SRC_HASH="
+    try:
+        with open(path, "rb") as fh:
+            blob = fh.read()
+    except OSError:
+        return True
+    i = blob.find(marker)
+    return i < 0 or blob[i + len(marker):i + len(marker) + 16].decode("ascii", "replace") != want
+
+
 def lib():
-    """Load the shared library (building it if the in-tree .so is absent)."""
+    """Load the shared library.  It is (re)built first when the in-tree .so is absent or was built
+    from other sources than the ones next to it (the .so is git-ignored, so a checkout or an edit
+    can leave an old binary behind); a binary that is still stale after the build is refused."""
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             build()
+        elif _stale(LIB_PATH):
+            build()
+            if _stale(LIB_PATH):
+                raise RuntimeError(f"{LIB_PATH} does not match the sources in {CSRC} "
+                                   "(deism_b200_source_hash) and rebuilding did not help")
         handle = C.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)   # AttributeError if the header and the .so diverge

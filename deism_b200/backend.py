@@ -46,12 +46,71 @@ def _stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class DeviceArray:
+    """NumPy-facing handle of an array that lives on the GPU.
+
+    The reference's contract is "every intermediate in ``params`` is a NumPy array"; for the bulk
+    arrays this engine produces on the device and consumes on the device again (the convex
+    attenuation ``[K, I]``, 27 MB at C4) a round trip through host memory is the whole cost of the
+    step.  A DeviceArray quacks like the NumPy array (``shape``, ``dtype``, ``len``, indexing,
+    ``np.asarray``) and copies to the host the first time somebody actually looks at the values;
+    ``to_device`` hands the kernels the tensor itself."""
+
+    def __init__(self, tensor, dtype=None):
+        self.tensor = tensor
+        self._np_dtype = np.dtype(dtype) if dtype is not None else None
+        self._host = None
+
+    def _materialise(self):
+        if self._host is None:
+            a = self.tensor.cpu().numpy()
+            self._host = a.astype(self._np_dtype) if self._np_dtype is not None and a.dtype != self._np_dtype else a
+        return self._host
+
+    shape = property(lambda self: tuple(self.tensor.shape))
+    ndim = property(lambda self: self.tensor.dim())
+    dtype = property(lambda self: self._np_dtype if self._np_dtype is not None else self._materialise().dtype)
+    size = property(lambda self: self.tensor.numel())
+    T = property(lambda self: self._materialise().T)
+    real = property(lambda self: self._materialise().real)
+    imag = property(lambda self: self._materialise().imag)
+
+    def __len__(self):
+        return int(self.tensor.shape[0])
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._materialise()
+        return a.astype(dtype) if dtype is not None and np.dtype(dtype) != a.dtype else a
+
+    def __getitem__(self, idx):
+        return self._materialise()[idx]
+
+    def astype(self, dtype, *args, **kwargs):
+        return self._materialise().astype(dtype, *args, **kwargs)
+
+
+def _broadcast_base(a):
+    """(base, reps) when the NumPy array `a` is a broadcast view along its LAST axis (stride 0,
+    e.g. the monopole coefficients of every image, which are one column repeated I times):
+    base = a[..., :1] made contiguous; else None."""
+    if isinstance(a, np.ndarray) and a.ndim >= 2 and a.shape[-1] > 1 and a.strides[-1] == 0:
+        return np.ascontiguousarray(a[..., :1]), int(a.shape[-1])
+    return None
+
+
 def to_device(x, dtype, dev=None):
     """NumPy / torch (host or device) -> contiguous device tensor of ``dtype``."""
     dev = dev or _device()
+    if isinstance(x, DeviceArray):
+        x = x.tensor
     if isinstance(x, torch.Tensor):
         t = x
     else:
+        bc = _broadcast_base(x)
+        if bc is not None:
+            # upload the one distinct column and repeat it on the device (HBM write, no PCIe)
+            base = to_device(bc[0], dtype, dev)
+            return base.expand(*base.shape[:-1], bc[1]).contiguous()
         a = np.asarray(x)
         if not a.flags["C_CONTIGUOUS"] or not a.flags["ALIGNED"]:
             a = np.ascontiguousarray(a)
@@ -77,21 +136,36 @@ def _vec3(x):
 
 
 def _c64_on_device(x, dev):
-    """Directivity coefficients travel as complex64 — the reference stores them as complex64
-    (cd:1184,1236,1258,1329) and only up-casts inside the kernels (pb:556-557)."""
+    """Directivity coefficients travel as complex64 — the reference's own pipeline stores them as
+    complex64 (cd:1184,1236,1258,1329) and only up-casts inside the kernels (pb:556-557).  Any other
+    input dtype (complex128, real) is converted, never refused; the shoebox ORG path keeps a
+    caller's complex128 tables at full precision instead (``_coef_on_device``)."""
+    if isinstance(x, (torch.Tensor, DeviceArray)):
+        return to_device(x, torch.complex64, dev)
+    a = x if isinstance(x, np.ndarray) else np.asarray(x)
+    if a.dtype != np.complex64:
+        a = a.astype(np.complex64)
+    return to_device(a, torch.complex64, dev)
+
+
+def _coef_on_device(x, dev):
+    """ORG coefficient tables: (device tensor, is_complex128).  complex64 stays complex64; a
+    caller's own complex128 tables go to the complex128 entry point when they are not
+    complex64-representable (the reference up-casts whatever it is given, pb:556-557)."""
+    if isinstance(x, DeviceArray):
+        x = x.tensor
     if isinstance(x, torch.Tensor):
         if x.dtype == torch.complex128:
-            raise NotImplementedError("complex128 directivity coefficients are not supported; the "
-                                      "reference stores complex64 (core_deism.py:1184)")
-        return to_device(x, torch.complex64, dev)
-    a = np.asarray(x)
-    if a.dtype != np.complex64:
-        a64 = a.astype(np.complex64)
-        if not np.array_equal(a64.astype(np.complex128), a.astype(np.complex128)):
-            raise NotImplementedError("directivity coefficients must be complex64-representable "
-                                      "(core_deism.py:1184)")
-        a = a64
-    return to_device(a, torch.complex64, dev)
+            return to_device(x, torch.complex128, dev), True
+        return to_device(x, torch.complex64, dev), False
+    a = x if isinstance(x, np.ndarray) else np.asarray(x)
+    if a.dtype == np.complex64:
+        return to_device(a, torch.complex64, dev), False
+    a128 = a.astype(np.complex128, copy=False)
+    a64 = a128.astype(np.complex64)
+    if np.array_equal(a64.astype(np.complex128), a128):
+        return to_device(a64, torch.complex64, dev), False
+    return to_device(a128, torch.complex128, dev), True
 
 
 class _AttenSpec:
@@ -240,20 +314,31 @@ def _run_org(params, images, suffix, out, accumulate, dev):
             out.zero_()
         return
     N, V = int(params["sourceOrder"]), int(params["receiverOrder"])
-    Cs = _c64_on_device(params["C_nm_s"], dev)
-    Cr = _c64_on_device(params["C_vu_r"], dev)
+    algo = int(params.get("b200OrgAlgo", 0))
+    Cs, s128 = _coef_on_device(params["C_nm_s"], dev)
+    Cr, r128 = _coef_on_device(params["C_vu_r"], dev)
+    wide = (s128 or r128) and algo != 2
+    if wide:
+        Cs, Cr = Cs.to(torch.complex128), Cr.to(torch.complex128)
+    else:
+        Cs, Cr = Cs.to(torch.complex64), Cr.to(torch.complex64)
     if tuple(Cs.shape) != (K, N + 1, 2 * N + 1) or tuple(Cr.shape) != (K, V + 1, 2 * V + 1):
         raise ValueError("C_nm_s / C_vu_r must be [K, N+1, 2N+1] / [K, V+1, 2V+1]")
     plan = _org_plan(params["Wigner"], N, V)
-    algo = int(params.get("b200OrgAlgo", 0))
     for lo, hi in _image_batches(params, images, suffix, n_images, K):
         A = to_device(A_all[lo:hi], torch.int32, dev)
         R = to_device(images["R_sI_r_all" + suffix][lo:hi], torch.float32, dev)
         spec = _AttenSpec(params, images, suffix, dev, lo, hi)
-        rc = lib().deism_org_shoebox(
-            hi - lo, K, N, V, _ptr(Cs), _ptr(Cr), None, None, _ptr(A),
-            _ptr(R), spec.ref(), _ptr(k), _ptr(out), 1 if (accumulate or lo > 0) else 0, algo,
-            plan.ptr, _stream_ptr())
+        if wide:
+            rc = lib().deism_org_shoebox_c128(
+                hi - lo, K, N, V, _ptr(Cs), _ptr(Cr), None, None, _ptr(A),
+                _ptr(R), spec.ref(), _ptr(k), _ptr(out), 1 if (accumulate or lo > 0) else 0,
+                plan.ptr, _stream_ptr())
+        else:
+            rc = lib().deism_org_shoebox(
+                hi - lo, K, N, V, _ptr(Cs), _ptr(Cr), None, None, _ptr(A),
+                _ptr(R), spec.ref(), _ptr(k), _ptr(out), 1 if (accumulate or lo > 0) else 0, algo,
+                plan.ptr, _stream_ptr())
         check(rc, "deism_org_shoebox")
         del spec, A, R
 
@@ -304,7 +389,7 @@ def _run_mix_from_host(params, images, out, dev):
     staged = []
     with torch.cuda.stream(side):
         for key in ("C_nm_s", "C_vu_r"):
-            p[key] = _c64_on_device(params[key], dev)
+            p[key] = _coef_on_device(params[key], dev)[0]
             staged.append(p[key])
         early = dict(images)
         for key, dt in (("A_early", torch.int32), ("R_sI_r_all_early", torch.float32)):

@@ -167,11 +167,24 @@ def get_ref_paths_ARG(params, room_engine):
     reflection_matrix = np.moveaxis(reflection_matrix, 0, 2)
     R_sI_r_all = get_R_sI_to_r_from_room(np.asarray(params["posReceiver"]),
                                          room_engine.sources).astype(np.float32)
-    atten_all = np.asarray(room_engine.attenuations, dtype=np.complex64)
+    dev_arrays = getattr(room_engine, "device_arrays", None)
+    if dev_arrays is not None:
+        # this module's engine: the [K, I] attenuation was produced on the GPU and is consumed
+        # there again; params sees a NumPy-facing handle that only visits the host if somebody
+        # reads the values (backend.DeviceArray)
+        from .backend import DeviceArray
+
+        att = dev_arrays["attenuations"]
+        if params["ifRemoveDirectPath"]:
+            att = att[:, 1:]
+        atten_all = DeviceArray(att.to(torch.complex64).contiguous(), np.complex64)
+    else:
+        atten_all = np.asarray(room_engine.attenuations, dtype=np.complex64)
+        if params["ifRemoveDirectPath"]:
+            atten_all = atten_all[:, 1:]
     if params["ifRemoveDirectPath"]:
         R_sI_r_all = R_sI_r_all[:, 1:]
         reflection_matrix = reflection_matrix[:, :, 1:]
-        atten_all = atten_all[:, 1:]
     images = {"R_sI_r_all": R_sI_r_all, "atten_all": atten_all}
     if params["DEISM_method"] == "MIX":
         # NB: computed from the un-sliced orders even when the direct path was removed — the

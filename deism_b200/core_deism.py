@@ -210,17 +210,26 @@ class DEISM:
 
     # ---------------------------------------------------------------- cd:608-628
     def run_DEISM(self, if_clean_up: bool = True, if_shutdown_ray: bool = True):
-        """One process per GPU: when ``torch.distributed`` is initialised with more than one rank
-        (e.g. the script runs under torchrun with the NCCL backend) every rank computes its contiguous
-        frequency slab and one all_gather leaves the full ``params["RTF"]`` on all of them
-        (``params["b200Sharding"]``: "frequency" (default), "image" for merged ORG / LC lists, "off")."""
+        """One process per GPU.  Multi-GPU is opt-in: with ``params["b200Sharding"]`` set to
+        "frequency" (contiguous frequency slabs + one all_gather) or "image" (image slabs of a merged
+        ORG / LC list + one all_reduce) — or the environment variable DEISM_B200_SHARDING — and
+        ``torch.distributed`` initialised with more than one rank (e.g. torchrun, NCCL backend, each
+        rank after ``torch.cuda.set_device(LOCAL_RANK)``), every rank computes its slab and the
+        collective leaves the full ``params["RTF"]`` on all of them.  The default is "off": a script
+        that uses torchrun for data parallelism (one room per rank) keeps computing whole, independent
+        simulations.  Before sharding, the ranks verify that they hold the same job."""
+        import os
+
         import torch.distributed as dist
 
         compute = backend.run_DEISM_device if self.roomtype == "shoebox" else backend.run_DEISM_ARG_device
-        mode = self.params.get("b200Sharding", "frequency")
+        mode = self.params.get("b200Sharding") or os.environ.get("DEISM_B200_SHARDING", "off")
+        if mode not in ("off", "frequency", "image"):
+            raise ValueError(f"b200Sharding must be 'off', 'frequency' or 'image', got {mode!r}")
         if mode != "off" and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             from . import distributed
 
+            distributed.check_same_job(self.params)
             rtf = distributed.run_sharded(self.params, compute, mode=mode)
         else:
             rtf = compute(self.params)

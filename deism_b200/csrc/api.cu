@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "srchash.h"   // build/srchash.h, written by the Makefile
 
 namespace deism {
 
@@ -62,6 +63,53 @@ int check_device() {
     }
     if (!s.ok) return set_error(DEISM_ERR_CUDA, "device %d is not sm_100", dev);
     return DEISM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// One call in flight per device (include/deism_b200.h "Threading").  The library keeps per-device
+// state that a call's kernels read while they run: cached scratch buffers, the __constant__ tables
+// of the (n,m) bases / row geometry / walls, the ORG side stream.  CallGuard makes that safe for
+// any mix of host threads and streams: a per-device mutex serialises the host side of the entry
+// points, and an event recorded when a call returns makes the NEXT call's stream wait for the
+// previous call's kernels whenever the two calls use different streams.  Same-stream callers (the
+// normal case) pay one cudaEventRecord per call.
+// ---------------------------------------------------------------------------------------
+struct DeviceGate {
+    std::mutex mu;
+    cudaEvent_t last = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool have_last = false;
+};
+static DeviceGate g_gate[64];
+
+CallGuard::CallGuard(void *stream) : st_(stream) {
+    if (cudaGetDevice(&dev_) != cudaSuccess || dev_ < 0 || dev_ >= 64) { dev_ = -1; return; }
+    DeviceGate &g = g_gate[dev_];
+    g.mu.lock();
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing((cudaStream_t)st_, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+    capturing_ = cap != cudaStreamCaptureStatusNone;
+    if (!capturing_ && g.have_last && g.last_stream != (cudaStream_t)st_)
+        cudaStreamWaitEvent((cudaStream_t)st_, g.last, 0);
+}
+
+CallGuard::~CallGuard() {
+    if (dev_ < 0) return;
+    DeviceGate &g = g_gate[dev_];
+    if (!capturing_) {
+        if (!g.last && cudaEventCreateWithFlags(&g.last, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            g.last = nullptr;
+        }
+        if (g.last && cudaEventRecord(g.last, (cudaStream_t)st_) == cudaSuccess) {
+            g.last_stream = (cudaStream_t)st_;
+            g.have_last = true;
+        } else {
+            cudaGetLastError();
+            g.have_last = false;
+        }
+    }
+    g.mu.unlock();
 }
 
 int sm_count() {
@@ -289,6 +337,11 @@ extern "C" int deism_b200_version(void) { return 100; }   // 0.1.0
 
 extern "C" const char *deism_last_error(void) { return g_err; }
 
+// the marker is also searched for in the file by deism_b200/_lib.py (no dlopen needed to tell
+// whether the binary is stale)
+static const char g_src_marker[] = "DEISM_SRC_HASH=" DEISM_SRC_HASH;
+extern "C" const char *deism_b200_source_hash(void) { return g_src_marker + 15; }
+
 extern "C" uint64_t deism_kernel_launch_count(void) {
     return __atomic_load_n(&g_launches, __ATOMIC_RELAXED);
 }
@@ -352,6 +405,7 @@ extern "C" int deism_profile_get(const char *kernel, double *ms_total, int *laun
 extern "C" int deism_fp64_peak(int kind, int iters, double *tflops, double *ms_out) {
     int rc = check_device();
     if (rc) return rc;
+    CallGuard call_guard(nullptr);
     if (iters <= 0) iters = 2000;
     double *sink = (double *)workspace(WS_BENCH, 256);
     if (!sink) return DEISM_ERR_NOMEM;

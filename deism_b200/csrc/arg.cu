@@ -144,6 +144,7 @@ extern "C" int deism_lc_arg(int64_t n_images, int64_t K, int Js, int Jr, const i
                             int64_t n_sel, double *d_out, int accumulate, void *stream) {
     int rc = check_device();
     if (rc) return rc;
+    CallGuard call_guard(stream);
     cudaStream_t st = (cudaStream_t)stream;
     if (K <= 0) return DEISM_OK;
     if (!d_out || !d_k) return set_error(DEISM_ERR_INVALID, "null d_out/d_k");
@@ -154,7 +155,6 @@ extern "C" int deism_lc_arg(int64_t n_images, int64_t K, int Js, int Jr, const i
     }
     if (Js <= 0 || Jr <= 0 || Js > ARG_JMAX || Jr > ARG_JMAX)
         return set_error(DEISM_ERR_INVALID, "Js/Jr out of range (1..%d)", ARG_JMAX);
-    if (K > 65535) return set_error(DEISM_ERR_INVALID, "ARG LC supports K <= 65535");
     if (!h_n_all || !h_m_all || !h_v_all || !h_u_all || !d_C_s_ARG_vec || !d_C_r_vec || !d_R_sI_r ||
         !d_atten)
         return set_error(DEISM_ERR_INVALID, "null input pointer");
@@ -219,6 +219,8 @@ extern "C" int deism_lc_arg(int64_t n_images, int64_t K, int Js, int Jr, const i
     ma.n_sel = n_sel; ma.n_images = n_images; ma.K = K; ma.Js = Js; ma.Jr = Jr;
     ma.Cs = (const float2 *)d_C_s_ARG_vec; ma.Cr = (const float2 *)d_C_r_vec; ma.Ys = Ys; ma.Yr = Yr;
     ma.r = r; ma.atten = (const float2 *)d_atten; ma.k = d_k; ma.sel = sel; ma.partial = partial;
+    if ((K + ARG_KT - 1) / ARG_KT > 65535)
+        return set_error(DEISM_ERR_INVALID, "ARG LC supports K <= %d", 65535 * ARG_KT);
     dim3 grid((unsigned)nblk, (unsigned)((K + ARG_KT - 1) / ARG_KT));
     prof_begin("arg_lc", st);
     arg_lc_kernel<<<grid, 128, 0, st>>>(ma);

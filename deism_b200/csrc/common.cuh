@@ -26,6 +26,19 @@ int smem_optin_bytes();   // largest dynamic shared memory a CTA may opt into
 void prof_begin(const char *name, cudaStream_t st);
 void prof_end(const char *name, cudaStream_t st);
 
+// Serialises the entry points per device and orders calls issued on different streams (api.cu).
+class CallGuard {
+public:
+    explicit CallGuard(void *stream);
+    ~CallGuard();
+    CallGuard(const CallGuard &) = delete;
+    CallGuard &operator=(const CallGuard &) = delete;
+private:
+    void *st_;
+    int dev_ = -1;
+    bool capturing_ = false;
+};
+
 enum WsSlot {
     WS_LC_IMG = 0, WS_LC_YS, WS_LC_YR, WS_PARTIAL, WS_FLAGS, WS_SMALL, WS_ORG_B, WS_ORG_IMG,
     WS_ORG_Y, WS_ORG_LIST, WS_ARG_IDX, WS_CONVEX_A, WS_CONVEX_B, WS_CONVEX_C, WS_CONVEX_D,

@@ -393,16 +393,17 @@ __global__ void __launch_bounds__(CVX_THREADS)
 cvx_atten_kernel(long n_images, long K, const int32_t *orders, const float *cosv,
                  const unsigned char *path, const float *imp /* [W][K] */, float *out /* [K][I] */) {
     long img = (long)blockIdx.x * CVX_THREADS + threadIdx.x;
-    long k = blockIdx.y;
     if (img >= n_images) return;
     int depth = orders[img];
-    float t = 1.0f;
-    for (int s = depth - 1; s >= 0; --s) {
-        float zc = __fmul_rn(imp[(long)path[img * CVX_MAX_ORDER + s] * K + k], cosv[img * CVX_MAX_ORDER + s]);
-        float a = __fdiv_rn(__fsub_rn(zc, 1.0f), __fadd_rn(zc, 1.0f));
-        t = __fmul_rn(a, t);
+    for (long k = blockIdx.y; k < K; k += gridDim.y) {
+        float t = 1.0f;
+        for (int s = depth - 1; s >= 0; --s) {
+            float zc = __fmul_rn(imp[(long)path[img * CVX_MAX_ORDER + s] * K + k], cosv[img * CVX_MAX_ORDER + s]);
+            float a = __fdiv_rn(__fsub_rn(zc, 1.0f), __fadd_rn(zc, 1.0f));
+            t = __fmul_rn(a, t);
+        }
+        out[k * n_images + img] = t;
     }
-    out[k * n_images + img] = t;
 }
 
 // ---- growable device buffers that keep their contents --------------------------------------
@@ -422,7 +423,14 @@ struct CvxState {
     long imp_cap = 0;
     bool valid = false;
 };
-static CvxState g_cvx;
+// one state per device (the pointers belong to the device that was current when they were
+// allocated); the per-device CallGuard serialises access
+static CvxState g_cvx_dev[64];
+static CvxState *cvx_state() {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    return &g_cvx_dev[dev];
+}
 
 template <typename T> static int grow_keep(T *&ptr, long old_n, long new_n) {
     T *np_ = nullptr;
@@ -453,7 +461,7 @@ static int ensure_nodes(CvxState &S, long need) {
     return DEISM_OK;
 }
 
-static int upload_walls(const deism_convex_walls *w) {
+static int upload_walls(const deism_convex_walls *w, cudaStream_t st) {
     if (!w || !w->h_normal || !w->h_origin || !w->h_basis || !w->h_flat_corners || !w->h_n_corners ||
         !w->h_reflection)
         return set_error(DEISM_ERR_INVALID, "null wall table");
@@ -475,7 +483,10 @@ static int upload_walls(const deism_convex_walls *w) {
                 h.flat[i][r][c] = w->h_flat_corners[((size_t)i * 2 + r) * w->max_corners + c];
         h.n_corners[i] = nc;
     }
-    DEISM_CUDA_TRY(cudaMemcpyToSymbol(c_walls, &h, sizeof(h)));
+    // on the caller's stream (non-blocking streams are not ordered against the legacy stream, and
+    // the previous fill's kernels may still be reading c_walls); the caller synchronises `st`
+    // before `h` can be rewritten
+    DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_walls, &h, sizeof(h), 0, cudaMemcpyHostToDevice, st));
     return DEISM_OK;
 }
 
@@ -488,14 +499,17 @@ extern "C" int deism_convex_images_count(const deism_convex_walls *walls, const 
                                          void *stream) {
     int rc = check_device();
     if (rc) return rc;
+    CallGuard call_guard(stream);
     cudaStream_t st = (cudaStream_t)stream;
     if (!h_source || !h_mic || !h_n_images) return set_error(DEISM_ERR_INVALID, "null pointer");
     if (ism_order < 0 || ism_order >= CVX_MAX_ORDER)
         return set_error(DEISM_ERR_INVALID, "ism_order must be 0..%d", CVX_MAX_ORDER - 1);
-    rc = upload_walls(walls);
+    rc = upload_walls(walls, st);
     if (rc) return rc;
-    DEISM_CUDA_TRY(cudaMemcpyToSymbol(c_mic, h_mic, 3 * sizeof(float)));
-    CvxState &S = g_cvx;
+    DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_mic, h_mic, 3 * sizeof(float), 0, cudaMemcpyHostToDevice, st));
+    CvxState *Sp = cvx_state();
+    if (!Sp) return set_error(DEISM_ERR_CUDA, "no current device");
+    CvxState &S = *Sp;
     S.valid = false;
     S.n_nodes = 0;
     rc = ensure_nodes(S, 1L << 16);
@@ -524,8 +538,10 @@ extern "C" int deism_convex_images_count(const deism_convex_walls *walls, const 
         long nb = (n + CVX_THREADS - 1) / CVX_THREADS;
         if (nb > S.block_cap) {
             if (S.block_sums) cudaFree(S.block_sums);
+            S.block_sums = nullptr;
+            S.block_cap = 0;
+            DEISM_CUDA_TRY(cudaMalloc(&S.block_sums, (size_t)nb * 2 * sizeof(int)));
             S.block_cap = nb * 2;
-            DEISM_CUDA_TRY(cudaMalloc(&S.block_sums, (size_t)S.block_cap * sizeof(int)));
         }
         cvx_count_kernel<<<(unsigned)nb, CVX_THREADS, 0, st>>>(S.N, lo, hi, S.block_sums);
         DEISM_LAUNCH_CHECK("cvx_count_kernel");
@@ -582,8 +598,11 @@ extern "C" int deism_convex_images_fill(const deism_convex_walls *walls, int64_t
                                         float *d_reflection, void *stream) {
     int rc = check_device();
     if (rc) return rc;
+    CallGuard call_guard(stream);
     cudaStream_t st = (cudaStream_t)stream;
-    CvxState &S = g_cvx;
+    CvxState *Sp = cvx_state();
+    if (!Sp) return set_error(DEISM_ERR_CUDA, "no current device");
+    CvxState &S = *Sp;
     if (!S.valid) return set_error(DEISM_ERR_INVALID, "call deism_convex_images_count first");
     if (!walls) return set_error(DEISM_ERR_INVALID, "null walls");
     const long I = S.n_images;
@@ -592,10 +611,13 @@ extern "C" int deism_convex_images_fill(const deism_convex_walls *walls, int64_t
         if (S.cosv) cudaFree(S.cosv);
         if (S.path) cudaFree(S.path);
         if (S.orders_tmp) cudaFree(S.orders_tmp);
-        S.out_cap = I + I / 2;
-        DEISM_CUDA_TRY(cudaMalloc(&S.cosv, (size_t)S.out_cap * CVX_MAX_ORDER * sizeof(float)));
-        DEISM_CUDA_TRY(cudaMalloc(&S.path, (size_t)S.out_cap * CVX_MAX_ORDER));
-        DEISM_CUDA_TRY(cudaMalloc(&S.orders_tmp, (size_t)S.out_cap * sizeof(int32_t)));
+        S.cosv = nullptr; S.path = nullptr; S.orders_tmp = nullptr;
+        S.out_cap = 0;              // stays 0 (and the pointers null) if an allocation below fails
+        const long want = I + I / 2;
+        DEISM_CUDA_TRY(cudaMalloc(&S.cosv, (size_t)want * CVX_MAX_ORDER * sizeof(float)));
+        DEISM_CUDA_TRY(cudaMalloc(&S.path, (size_t)want * CVX_MAX_ORDER));
+        DEISM_CUDA_TRY(cudaMalloc(&S.orders_tmp, (size_t)want * sizeof(int32_t)));
+        S.out_cap = want;
     }
     CvxOut o;
     o.n_images = I; o.sources = d_sources; o.orders = S.orders_tmp; o.gen_walls = d_gen_walls;
@@ -607,18 +629,20 @@ extern "C" int deism_convex_images_fill(const deism_convex_walls *walls, int64_t
         DEISM_CUDA_TRY(cudaMemcpyAsync(d_orders, S.orders_tmp, (size_t)I * sizeof(int32_t),
                                        cudaMemcpyDeviceToDevice, st));
     if (d_attenuations) {
-        if (K <= 0 || K > 65535) return set_error(DEISM_ERR_INVALID, "K must be 1..65535");
+        if (K <= 0) return set_error(DEISM_ERR_INVALID, "K must be positive");
         if (!walls->h_impedance) return set_error(DEISM_ERR_INVALID, "null h_impedance");
         long need = (long)walls->n_walls * K;
         if (need > S.imp_cap) {
             if (S.imp) cudaFree(S.imp);
-            S.imp_cap = need;
+            S.imp = nullptr;
+            S.imp_cap = 0;
             DEISM_CUDA_TRY(cudaMalloc(&S.imp, (size_t)need * sizeof(float)));
+            S.imp_cap = need;
         }
         DEISM_CUDA_TRY(cudaMemcpyAsync(S.imp, walls->h_impedance, (size_t)need * sizeof(float),
                                        cudaMemcpyHostToDevice, st));
         DEISM_CUDA_TRY(cudaStreamSynchronize(st));
-        dim3 grid((unsigned)((I + CVX_THREADS - 1) / CVX_THREADS), (unsigned)K);
+        dim3 grid((unsigned)((I + CVX_THREADS - 1) / CVX_THREADS), (unsigned)(K < 65535 ? K : 65535));
         cvx_atten_kernel<<<grid, CVX_THREADS, 0, st>>>(I, K, S.orders_tmp, S.cosv, S.path, S.imp,
                                                       d_attenuations);
         DEISM_LAUNCH_CHECK("cvx_atten_kernel");

@@ -229,6 +229,7 @@ extern "C" int deism_shoebox_count_images(const double h_room_size[3], const dou
                                           int64_t *d_late_counts, void *stream) {
     int rc = check_device();
     if (rc) return rc;
+    CallGuard call_guard(stream);
     LatticeParams P;
     rc = fill_lattice(P, h_room_size, h_pos_source, h_pos_receiver, max_dist_sq, N_o, N_o_ORG,
                       remove_direct);
@@ -249,6 +250,7 @@ extern "C" int deism_shoebox_fill_images(const double h_room_size[3], const doub
                                          float *d_R_s_rI_late, float *d_R_r_sI_late, void *stream) {
     int rc = check_device();
     if (rc) return rc;
+    CallGuard call_guard(stream);
     LatticeParams P;
     rc = fill_lattice(P, h_room_size, h_pos_source, h_pos_receiver, max_dist_sq, N_o, N_o_ORG,
                       remove_direct);
@@ -267,6 +269,7 @@ extern "C" int deism_shoebox_attenuation(int64_t n_images, int64_t K, const deis
                                          void *d_out, int out_c128, void *stream) {
     int rc = check_device();
     if (rc) return rc;
+    CallGuard call_guard(stream);
     if (!spec || !d_out) return set_error(DEISM_ERR_INVALID, "null spec/out");
     if (spec->mode != DEISM_ATTEN_FUSED_ROOM && spec->mode != DEISM_ATTEN_FUSED_ANGLES)
         return set_error(DEISM_ERR_INVALID, "deism_shoebox_attenuation needs a FUSED_* spec");

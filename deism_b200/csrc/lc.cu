@@ -984,6 +984,7 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
                                 const double *d_k, double *d_out, int accumulate, void *stream) {
     int rc = check_device();
     if (rc) return rc;
+    CallGuard call_guard(stream);
     cudaStream_t st = (cudaStream_t)stream;
     if (K <= 0) return DEISM_OK;
     if (!d_out || !d_k) return set_error(DEISM_ERR_INVALID, "null d_out/d_k");

@@ -94,6 +94,7 @@ extern "C" int deism_pchip_interp(int rows, int n_bands, int64_t K, const double
                                   void *stream) {
     int rc = check_device();
     if (rc) return rc;
+    CallGuard call_guard(stream);
     if (rows <= 0 || K <= 0) return DEISM_OK;
     if (n_bands < 1 || n_bands > PCHIP_MAXB)
         return set_error(DEISM_ERR_INVALID, "n_bands %d outside 1..%d", n_bands, PCHIP_MAXB);

@@ -122,7 +122,11 @@ static void build_lists(int N, int V, const float *W1, const float *W2, OrgLists
 // tables stay L2-resident at 16 bytes per element: 15 MB at C3 size).
 typedef double2 bt_elem;
 __device__ __forceinline__ bt_elem bt_make(float2 v) { return make_double2((double)v.x, (double)v.y); }
-__global__ void transpose_c64_kernel(const float2 *__restrict__ in, long K, int J, bt_elem *out) {
+__device__ __forceinline__ bt_elem bt_make(double2 v) { return v; }
+// IN = float2 (the reference's complex64 storage, cd:1184) or double2 (a caller's own complex128
+// coefficients, which the reference's ORG path would use at full precision, pb:556-557)
+template <typename IN>
+__global__ void transpose_coef_kernel(const IN *__restrict__ in, long K, int J, bt_elem *out) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= K * J) return;
     long k = i / J;
@@ -762,8 +766,9 @@ struct OrgDirectArgs {
 
 __global__ void __launch_bounds__(128) org_direct_kernel(OrgDirectArgs a) {
     __shared__ double2 red[128];
-    const long kidx = blockIdx.y;
     const long s = (long)blockIdx.x * 128 + threadIdx.x;
+    // frequencies beyond the grid's y extent (65535) are taken in further passes
+    for (long kidx = blockIdx.y; kidx < a.K; kidx += gridDim.y) {
     cplx P = cmake(0.0, 0.0);
     if (s < a.n_sel) {
         const long img = a.sel ? a.sel[s] : s;
@@ -834,6 +839,8 @@ __global__ void __launch_bounds__(128) org_direct_kernel(OrgDirectArgs a) {
         __syncthreads();
     }
     if (threadIdx.x == 0) a.partial[(long)blockIdx.x * a.K + kidx] = red[0];
+    __syncthreads();
+    }
 }
 
 }  // namespace deism
@@ -972,13 +979,14 @@ extern "C" int deism_org_plan_destroy(deism_org_plan *plan) {
     return DEISM_OK;
 }
 
-extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, const float *d_C_nm_s,
-                                 const float *d_C_vu_r, const float *h_W1, const float *h_W2,
-                                 const int32_t *d_A, const float *d_R_sI_r,
-                                 const deism_shoebox_atten *atten, const double *d_k, double *d_out,
-                                 int accumulate, int algo, const deism_org_plan *plan, void *stream) {
+static int org_shoebox_impl(int64_t n_images, int64_t K, int N, int V, const void *d_C_nm_s,
+                            const void *d_C_vu_r, int coef_c128, const float *h_W1, const float *h_W2,
+                            const int32_t *d_A, const float *d_R_sI_r,
+                            const deism_shoebox_atten *atten, const double *d_k, double *d_out,
+                            int accumulate, int algo, const deism_org_plan *plan, void *stream) {
     int rc = check_device();
     if (rc) return rc;
+    CallGuard call_guard(stream);
     cudaStream_t st = (cudaStream_t)stream;
     if (K <= 0) return DEISM_OK;
     if (!d_out || !d_k) return set_error(DEISM_ERR_INVALID, "null d_out/d_k");
@@ -1006,6 +1014,8 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
     rc = launch_z_flat(atten, K, flags, st);
     if (rc) return rc;
 
+    if (algo == 2 && coef_c128)
+        return set_error(DEISM_ERR_INVALID, "the direct ORG sum (algo 2) takes complex64 coefficients");
     if (algo == 2) {
         // ---- direct quintuple sum per (image, frequency) ----
         OrgImage *rec = (OrgImage *)workspace(WS_ORG_IMG, (size_t)n_images * sizeof(OrgImage));
@@ -1029,8 +1039,7 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
         da.Cr = (const float2 *)d_C_vu_r; da.Y = Y; da.rec = rec; da.sel = nullptr; da.k = d_k;
         da.mode = atten->mode; da.atten = atten->d_atten; da.Z = (const cplx *)atten->d_Z_S;
         da.shoebox = 1; da.partial = partial;
-        if (K > 65535) return set_error(DEISM_ERR_INVALID, "direct ORG supports K <= 65535");
-        dim3 grid((unsigned)nblk, (unsigned)K);
+        dim3 grid((unsigned)nblk, (unsigned)(K < 65535 ? K : 65535));
         prof_begin("org_direct", st);
     org_direct_kernel<<<grid, 128, 0, st>>>(da);
     prof_end("org_direct", st);
@@ -1093,12 +1102,21 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
         joiner.side = side; joiner.st = st;
     }
     DEISM_CUDA_TRY(cudaMemsetAsync(Bp, 0, (size_t)8 * n_ftiles * b_rows * sizeof(double), bs));
-    transpose_c64_kernel<<<(unsigned)(((long)K * NMs + 255) / 256), 256, 0, bs>>>(
-        (const float2 *)d_C_nm_s, K, NMs, CsT);
-    DEISM_LAUNCH_CHECK("transpose_c64_kernel");
-    transpose_c64_kernel<<<(unsigned)(((long)K * NMr + 255) / 256), 256, 0, bs>>>(
-        (const float2 *)d_C_vu_r, K, NMr, CrT);
-    DEISM_LAUNCH_CHECK("transpose_c64_kernel");
+    if (coef_c128) {
+        transpose_coef_kernel<double2><<<(unsigned)(((long)K * NMs + 255) / 256), 256, 0, bs>>>(
+            (const double2 *)d_C_nm_s, K, NMs, CsT);
+        DEISM_LAUNCH_CHECK("transpose_coef_kernel");
+        transpose_coef_kernel<double2><<<(unsigned)(((long)K * NMr + 255) / 256), 256, 0, bs>>>(
+            (const double2 *)d_C_vu_r, K, NMr, CrT);
+        DEISM_LAUNCH_CHECK("transpose_coef_kernel");
+    } else {
+        transpose_coef_kernel<float2><<<(unsigned)(((long)K * NMs + 255) / 256), 256, 0, bs>>>(
+            (const float2 *)d_C_nm_s, K, NMs, CsT);
+        DEISM_LAUNCH_CHECK("transpose_coef_kernel");
+        transpose_coef_kernel<float2><<<(unsigned)(((long)K * NMr + 255) / 256), 256, 0, bs>>>(
+            (const float2 *)d_C_vu_r, K, NMr, CrT);
+        DEISM_LAUNCH_CHECK("transpose_coef_kernel");
+    }
     BtableArgs ba;
     ba.K = K; ba.n_ftiles = n_ftiles; ba.nseg = nseg; ba.R_tot = R_tot;
     for (int i = 0; i < 2; ++i) { ba.ent[i] = d_ent[i]; ba.seg[i] = d_seg[i]; }
@@ -1159,6 +1177,24 @@ extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, cons
     return launch_reduce_partials(partial, n_chunks, K, d_out, accumulate, st);
 }
 
+extern "C" int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V, const float *d_C_nm_s,
+                                 const float *d_C_vu_r, const float *h_W1, const float *h_W2,
+                                 const int32_t *d_A, const float *d_R_sI_r,
+                                 const deism_shoebox_atten *atten, const double *d_k, double *d_out,
+                                 int accumulate, int algo, const deism_org_plan *plan, void *stream) {
+    return org_shoebox_impl(n_images, K, N, V, d_C_nm_s, d_C_vu_r, 0, h_W1, h_W2, d_A, d_R_sI_r, atten, d_k,
+                            d_out, accumulate, algo, plan, stream);
+}
+
+extern "C" int deism_org_shoebox_c128(int64_t n_images, int64_t K, int N, int V, const double *d_C_nm_s,
+                                      const double *d_C_vu_r, const float *h_W1, const float *h_W2,
+                                      const int32_t *d_A, const float *d_R_sI_r,
+                                      const deism_shoebox_atten *atten, const double *d_k, double *d_out,
+                                      int accumulate, const deism_org_plan *plan, void *stream) {
+    return org_shoebox_impl(n_images, K, N, V, d_C_nm_s, d_C_vu_r, 1, h_W1, h_W2, d_A, d_R_sI_r, atten, d_k,
+                            d_out, accumulate, 1, plan, stream);
+}
+
 extern "C" int deism_org_arg(int64_t n_images, int64_t K, int N, int V, const float *d_C_nm_s_ARG,
                              const float *d_C_vu_r, const float *h_W1, const float *h_W2,
                              const float *d_R_sI_r, const float *d_atten, const double *d_k,
@@ -1166,6 +1202,7 @@ extern "C" int deism_org_arg(int64_t n_images, int64_t K, int N, int V, const fl
                              const deism_org_plan *plan, void *stream) {
     int rc = check_device();
     if (rc) return rc;
+    CallGuard call_guard(stream);
     cudaStream_t st = (cudaStream_t)stream;
     if (K <= 0) return DEISM_OK;
     if (!d_out || !d_k) return set_error(DEISM_ERR_INVALID, "null d_out/d_k");
@@ -1177,7 +1214,6 @@ extern "C" int deism_org_arg(int64_t n_images, int64_t K, int N, int V, const fl
     if (N < 0 || V < 0 || N > 20 || V > 20) return set_error(DEISM_ERR_INVALID, "orders must be 0..20");
     if (!d_C_nm_s_ARG || !d_C_vu_r || !d_R_sI_r || !d_atten)
         return set_error(DEISM_ERR_INVALID, "null input pointer");
-    if (K > 65535) return set_error(DEISM_ERR_INVALID, "ARG ORG supports K <= 65535");
     const int Lmax = N + V + 1, nseg = Lmax * Lmax;
     const int NMs = (N + 1) * (2 * N + 1), NMr = (V + 1) * (2 * V + 1);
     PlanGuard guard;
@@ -1217,7 +1253,7 @@ extern "C" int deism_org_arg(int64_t n_images, int64_t K, int N, int V, const fl
     da.Cs = (const float2 *)d_C_nm_s_ARG; da.sk = (long)NMs * n_images; da.snm = n_images; da.si = 1;
     da.Cr = (const float2 *)d_C_vu_r; da.Y = Y; da.rec = rec; da.sel = sel; da.k = d_k;
     da.mode = -1; da.atten = d_atten; da.Z = nullptr; da.shoebox = 0; da.partial = partial;
-    dim3 grid((unsigned)nblk, (unsigned)K);
+    dim3 grid((unsigned)nblk, (unsigned)(K < 65535 ? K : 65535));
     prof_begin("org_direct", st);
     org_direct_kernel<<<grid, 128, 0, st>>>(da);
     prof_end("org_direct", st);

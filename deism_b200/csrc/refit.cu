@@ -330,6 +330,7 @@ extern "C" int deism_arg_refit(int64_t n_images, int64_t K, int N, int64_t n_dir
                                const double *d_k, double r0, float *d_C_vec, void *stream) {
     int rc = check_device();
     if (rc) return rc;
+    CallGuard call_guard(stream);
     cudaStream_t st = (cudaStream_t)stream;
     if (n_images <= 0 || K <= 0) return DEISM_OK;
     if (N < 0 || N > RF_NMAX)

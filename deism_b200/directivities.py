@@ -45,6 +45,11 @@ def _flatten(C, order):
 
         vec = torch.stack([C[:, int(n), int(m)] for n, m in zip(n_all, m_all)], dim=1)
         return n_all, m_all, vec.to(torch.complex64).contiguous()
+    if isinstance(C, np.ndarray) and C.ndim == 4 and C.shape[3] > 1 and C.strides[3] == 0:
+        # per-image coefficients that are one column broadcast over the images (monopole source,
+        # cd:1623-1640): flatten the column and keep the broadcast, no [K, J, I] copy
+        _, _, base = _flatten(np.ascontiguousarray(C[..., :1]), order)
+        return n_all, m_all, np.broadcast_to(base, base.shape[:2] + (C.shape[3],))
     # (the reference fills a complex128 array and rounds it to complex64; complex64 input gives the
     # same values without the double-width temporary)
     vec = np.zeros((C.shape[0], J) + C.shape[3:], dtype=np.complex64 if C.dtype == np.complex64 else "complex")
@@ -251,8 +256,10 @@ def init_source_directivities_ARG(params):
         n_img = int(refl.shape[0])
         params["C_nm_s_ARG"] = torch.from_numpy(c).to(refl.device).expand(-1, 1, 1, n_img).contiguous()
     else:
+        # the reference multiplies by ones((1, 1, 1, I)) (cd:1636-1639): the same values as a
+        # read-only broadcast view, without K x I copies of one column (54 MB at C4)
         n_img = refl.shape[2]
-        params["C_nm_s_ARG"] = c * np.ones((1, 1, 1, n_img)).astype(np.complex64)
+        params["C_nm_s_ARG"] = np.broadcast_to(c, (c.shape[0], 1, 1, n_img))
     params["sourceOrder"] = 0
     _track(params, ("C_nm_s_ARG", "sourceOrder"), "init_source_directivities")
     return params

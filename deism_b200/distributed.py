@@ -35,7 +35,42 @@ def slab_counts(n: int, world: int):
 def _slice0(x, lo, hi):
     if isinstance(x, torch.Tensor):
         return x[lo:hi].contiguous()
+    if hasattr(x, "tensor") and isinstance(getattr(x, "tensor"), torch.Tensor):   # backend.DeviceArray
+        return type(x)(x.tensor[lo:hi].contiguous(), x.dtype)
     return np.ascontiguousarray(np.asarray(x)[lo:hi])
+
+
+def check_same_job(params, group=None):
+    """Sharding splits ONE simulation over the ranks; ranks that hold different simulations (a
+    script that uses torchrun for data parallelism, one room per rank) must not be spliced together.
+    Every rank hashes what defines the job (wave numbers, geometry, image count, method, orders);
+    the hashes are compared with one all_gather and a mismatch raises on every rank."""
+    import hashlib
+
+    h = hashlib.sha256()
+    wn = params["waveNumbers"]
+    wn = wn.detach().cpu().numpy() if isinstance(wn, torch.Tensor) else np.asarray(wn)
+    h.update(np.ascontiguousarray(wn, dtype=np.float64).tobytes())
+    for key in ("posSource", "posReceiver", "roomSize", "vertices"):
+        if params.get(key) is not None:
+            h.update(np.ascontiguousarray(np.asarray(params[key], dtype=np.float64)).tobytes())
+    images = params.get("images") or {}
+    for key in ("A", "A_early", "A_late", "R_sI_r_all"):
+        if key in images and images[key] is not None:
+            h.update(f"{key}:{tuple(images[key].shape)}".encode())
+    h.update(f"{params.get('DEISM_method')}:{params.get('sourceOrder')}:{params.get('receiverOrder')}".encode())
+    mine = np.frombuffer(h.digest()[:8], dtype=np.int64).copy()
+    world = dist.get_world_size(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(mine).to(dev)
+    bufs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(bufs, t, group=group)
+    vals = {int(b.item()) for b in bufs}
+    if len(vals) != 1:
+        raise RuntimeError(
+            "deism_b200: params['b200Sharding'] splits ONE simulation over the ranks of the process "
+            "group, but the ranks hold different jobs (wave numbers, geometry, image lists or orders "
+            "differ).  Leave b200Sharding at 'off' when every rank simulates its own room.")
 
 
 def shard_frequencies(params, rank: int, world: int):

@@ -13,7 +13,8 @@
  *     reference's arrays can be handed over without transposition;
  *   - "d_" pointers are DEVICE pointers on the current CUDA device, "h_" pointers are HOST
  *     pointers (small tables and scalars only).  Bulk host<->device staging is the caller's
- *     job; deism_b200/backend.py does it with pinned torch buffers for NumPy callers;
+ *     job; deism_b200/backend.py does it for NumPy callers (asynchronous copies from the
+ *     caller's arrays as they are, pageable or pinned);
  *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream);
  *     device-pointer entry points are asynchronous with respect to the host unless noted;
  *   - return value: DEISM_OK (0) or a DEISM_ERR_* code; deism_last_error() gives the message
@@ -22,6 +23,23 @@
  *   - the caller owns every buffer it passes; the library keeps no pointer after a call
  *     returns (device scratch is library-owned, cached per device, freed by
  *     deism_release_workspace()).
+ *
+ * Threading (SURVEY 8b "Threading": the reference's kernels are driven by one Python thread)
+ *   - every entry point may be called from any host thread, on any stream, for any device;
+ *   - the library keeps per-device state that a call's kernels read while they run (cached
+ *     scratch, the constant-memory tables of the (n,m) bases, row geometry and walls, one side
+ *     stream), so it admits ONE call in flight per device and enforces that itself: a per-device
+ *     mutex serialises the host side of the entry points, and when two consecutive calls on a
+ *     device use DIFFERENT streams the second call's stream is made to wait (cudaStreamWaitEvent)
+ *     for the first call's kernels.  Calls on one stream queue back to back without any wait;
+ *     calls on different devices never wait for each other;
+ *   - deism_convex_images_count + deism_convex_images_fill are one two-phase operation whose
+ *     intermediate result lives in that per-device state: issue them from one thread with no
+ *     other convex call on the device in between;
+ *   - during CUDA-graph stream capture the cross-stream ordering is the capturer's job (no
+ *     event is recorded or waited on while `stream` is capturing);
+ *   - deism_last_error() is thread-local; deism_profile_* and deism_release_workspace() are
+ *     control calls for a quiescent library (no compute call in flight).
  */
 #ifndef DEISM_B200_H
 #define DEISM_B200_H
@@ -49,6 +67,10 @@ extern "C" {
 /* ------------------------------------------------------------------------------------ */
 DEISM_API int deism_b200_version(void);          /* 10000*major + 100*minor + patch */
 DEISM_API const char *deism_last_error(void);    /* message of the last failing call */
+/* First 16 hex digits of the SHA-256 of the sources (csrc/*.cu, common.cuh, this header) the
+ * binary was built from; deism_b200/_lib.py refuses (rebuilds) a library whose fingerprint does
+ * not match the sources next to it. */
+DEISM_API const char *deism_b200_source_hash(void);
 /* Fills SM count, HBM bytes and compute capability of `device` (or the current one if <0). */
 DEISM_API int deism_device_info(int device, int *sm_count, size_t *hbm_bytes, int *cc_major,
                                 int *cc_minor);
@@ -156,6 +178,17 @@ DEISM_API int deism_org_shoebox(int64_t n_images, int64_t K, int N, int V,
                                 const float *d_R_sI_r, const deism_shoebox_atten *atten,
                                 const double *d_k, double *d_out, int accumulate, int algo,
                                 const deism_org_plan *plan, void *stream);
+
+/* The same with complex128 coefficient tables (d_C_nm_s: complex128[K,N+1,2N+1], d_C_vu_r:
+ * complex128[K,V+1,2V+1]).  The reference's own pipeline stores complex64 (cd:1184,1236) and its
+ * ORG path up-casts whatever it is handed (pb:556-557), so a caller's own complex128 tables are
+ * used at full precision there; this entry point does the same (factorised algorithm). */
+DEISM_API int deism_org_shoebox_c128(int64_t n_images, int64_t K, int N, int V,
+                                     const double *d_C_nm_s, const double *d_C_vu_r,
+                                     const float *h_W1, const float *h_W2, const int32_t *d_A,
+                                     const float *d_R_sI_r, const deism_shoebox_atten *atten,
+                                     const double *d_k, double *d_out, int accumulate,
+                                     const deism_org_plan *plan, void *stream);
 
 /* Convex DEISM-ARG LC (pb:328-385).  d_C_s_ARG_vec: complex64[K,Js,I] (image index innermost,
  * cd:1193-1217), d_C_r_vec: complex64[K,Jr], d_R_sI_r: float32[3,I] (component-major),

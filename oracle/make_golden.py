@@ -320,6 +320,12 @@ def full_cases(which):
         shoebox_case("c3_sub100", "RTF", "ORG", 25, N=10, V=10, store_images=False,
                      store_inputs=False,
                      overrides={"startFreq": 40, "endFreq": 4000, "freqStep": 40})
+    if "c3full" in which:
+        # the whole 2:2:4000 Hz grid of C3 (2 000 frequencies, ~8 core-hours of the reference's
+        # Numba kernel): coefficients drawn for K=2000, i.e. what workloads.build("c3") draws.
+        shoebox_case("c3_full", "RTF", "ORG", 25, N=10, V=10, store_images=False,
+                     store_inputs=False,
+                     overrides={"startFreq": 2, "endFreq": 4000, "freqStep": 2})
     if "c4" in which:
         convex_case("c4_full", "RIR", "MIX", 10, store_inputs=False)
     if "c5" in which:

@@ -28,6 +28,7 @@ if __name__ == "__main__":
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
+    os.environ["DEISM_B200_SHARDING"] = "frequency"      # multi-GPU is opt-in (core_deism.DEISM.run_DEISM)
     d, rows, n_img, K, _ = bench_class.run(case, None, True)           # cold pass (context, scratch)
     times = []
     for _ in range(5):

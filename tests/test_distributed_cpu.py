@@ -64,7 +64,7 @@ def test_sharded_run_equals_single(tmp_path, name, mode, world):
         assert rel_l2(got, g.rtf) < 1e-12, (name, r)
 
 
-def _class_worker(rank, world, port, out_dir, name="s2_shoebox_rtf_lc_o6_N3", sharding=None):
+def _class_worker(rank, world, port, out_dir, name="s2_shoebox_rtf_lc_o6_N3", sharding=None, perturb=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     sys.path.insert(0, ROOT)
@@ -82,22 +82,60 @@ def _class_worker(rank, world, port, out_dir, name="s2_shoebox_rtf_lc_o6_N3", sh
     # no GPU in this container: the CUDA slab compute is swapped for the CPU oracle IN THIS TEST PROCESS
     # (the class itself has no such switch); what is under test is the sharding + gather around it
     from deism_b200 import backend
-    backend.run_DEISM_device = lambda q, dev=None: torch.from_numpy(oracle.run_DEISM(q))
-    d.run_DEISM()
-    np.save(os.path.join(out_dir, f"r{rank}.npy"), d.params["RTF"])
+    seen = []
+
+    def compute(q, dev=None):
+        seen.append(len(q["waveNumbers"]))
+        return torch.from_numpy(oracle.run_DEISM(q))
+
+    backend.run_DEISM_device = compute
+    if perturb and rank == 1:      # this rank simulates another receiver position: not the same job
+        d.params["posReceiver"] = np.asarray(d.params["posReceiver"], dtype=float) + 0.01
+    try:
+        d.run_DEISM()
+        np.save(os.path.join(out_dir, f"r{rank}.npy"), d.params["RTF"])
+        np.save(os.path.join(out_dir, f"seen{rank}.npy"), np.asarray(seen))
+    except RuntimeError as exc:
+        with open(os.path.join(out_dir, f"err{rank}.txt"), "w") as fh:
+            fh.write(str(exc))
     dist.barrier()
     dist.destroy_process_group()
 
 
 def test_class_run_shards_under_torch_distributed(tmp_path):
-    """DEISM.run_DEISM() inside an initialised process group: frequency slabs + all_gather, the full
-    RTF in params on every rank (the slab compute is the CPU oracle here)."""
+    """DEISM.run_DEISM() inside an initialised process group with params["b200Sharding"] =
+    "frequency": frequency slabs + all_gather, the full RTF in params on every rank (the slab
+    compute is the CPU oracle here)."""
     port = _free_port()
-    mp.spawn(_class_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    g = Golden("s2_shoebox_rtf_lc_o6_N3")
+    name = "s2_shoebox_rtf_lc_o6_N3"
+    mp.spawn(_class_worker, args=(2, port, str(tmp_path), name, "frequency"), nprocs=2, join=True)
+    g = Golden(name)
     for r in range(2):
         got = np.load(tmp_path / f"r{r}.npy")
         assert got.dtype == np.complex128 and rel_l2(got, g.rtf) < 1e-12
+        assert int(np.load(tmp_path / f"seen{r}.npy")[0]) < g.rtf.shape[0]      # a slab, not the grid
+
+
+def test_class_sharding_is_opt_in(tmp_path):
+    """Without b200Sharding a process group changes nothing: every rank computes its own whole
+    simulation (a torchrun script that runs one room per rank must not be spliced together)."""
+    port = _free_port()
+    name = "s2_shoebox_rtf_lc_o6_N3"
+    mp.spawn(_class_worker, args=(2, port, str(tmp_path), name, None), nprocs=2, join=True)
+    g = Golden(name)
+    for r in range(2):
+        assert rel_l2(np.load(tmp_path / f"r{r}.npy"), g.rtf) < 1e-12
+        assert int(np.load(tmp_path / f"seen{r}.npy")[0]) == g.rtf.shape[0]
+
+
+def test_class_sharding_refuses_different_jobs(tmp_path):
+    """Sharding over ranks that hold different simulations raises on every rank instead of splicing
+    slabs of unrelated RTFs."""
+    port = _free_port()
+    name = "s2_shoebox_rtf_lc_o6_N3"
+    mp.spawn(_class_worker, args=(2, port, str(tmp_path), name, "frequency", True), nprocs=2, join=True)
+    for r in range(2):
+        assert "different jobs" in open(tmp_path / f"err{r}.txt").read()
 
 
 @pytest.mark.parametrize("sharding", ["image", "off"])
