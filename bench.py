@@ -54,21 +54,24 @@ L2_NOTE = "L2 flushed (256 MiB write) between timed steps"
 # to us, not the reference's complex x complex loop.
 # --------------------------------------------------------------------------------------
 def wall_factor_flops(mean_order, real_impedance, same_opposite_walls=True):
-    """Flops the per-term attenuation chain EXECUTES (common.cuh shoebox_atten_n), per term: per wall
-    pair one wall factor and one power by squaring of the summed exponent (two of each when the two
-    walls of the pair differ), then the product of the three pairs and the complex64 rounding.
-      real chain   : factor = t, t+1, reciprocal seed + 2 Newton steps (8), 1 - 2r (2)      = 12
-                     power  = ~1.5 log2(e) real multiplies (squarings + set bits)
-      complex chain: factor = zr, zi, +-1 (4), |den|^2 (3), reciprocal (9), numerator (8)    = 24
-                     power  = ~1.5 log2(e) complex multiplies of 6 flops
+    """Flops the per-term attenuation chain EXECUTES (common.cuh), per term.
+      real tile (shoebox_atten_real_n): per wall a factor 1 - 2/(zeta c + 1) = t, t+1, reciprocal
+                     seed + one Newton step (4), 1 - 2r (2) = 8; then ONE simultaneous
+                     square-and-multiply over the exponents: per bit of the largest exponent a
+                     squaring and ~0.9 multiplies per wall (a warp holds 8 images: a multiply runs
+                     when any of them has the bit); float rounding and 1/r = 2
+      complex chain (shoebox_atten_n): factor = zr, zi, +-1 (4), |den|^2 (3), reciprocal (9),
+                     numerator (8) = 24; power = ~1.5 log2(e) complex multiplies of 6 flops per
+                     wall pair; product of the pairs 12; rounding 2
     e = mean exponent per pair = mean_order / 3."""
     import math
 
     e = max(2.0, mean_order / 3.0)
-    mults = 1.5 * math.log2(e)
     chains = 3 * (1 if same_opposite_walls else 2)
     if real_impedance:
-        return chains * (12 + mults) + 4 + 2
+        bits = math.log2(e) + 1.5          # the largest of the exponents a warp sees
+        return chains * 8 + bits * (1 + 0.9 * chains) + 2
+    mults = 1.5 * math.log2(e)
     return chains * (24 + 6 * mults) + 12 + 2
 
 
@@ -410,6 +413,7 @@ def measure_shoebox(c, name, steps, warmup, general=False, sharding="frequency",
         res = combine(backend.run_DEISM_device(p_np, dev))
         return res.cpu().numpy() if rank == 0 or world == 1 else res[:1].cpu()
 
+    graphs_on = backend.USE_GRAPHS
     result = None
     for _ in range(max(warmup, 1)):
         result = step_device()
@@ -425,14 +429,22 @@ def measure_shoebox(c, name, steps, warmup, general=False, sharding="frequency",
             parity_worst = float(np.max(np.abs(got - ref) / np.abs(ref)))
             parity_note = f"all {K} frequencies against the reference's own run_DEISM"
 
+    # per-kernel times: a short pass with the library's event brackets on and graph replay off
+    # (events cannot be timed inside a replayed graph); then the timed region proper
+    backend.USE_GRAPHS = False
     c.lib.deism_profile_enable(1)
     c.lib.deism_profile_reset()
+    n_prof = min(steps, 3)
+    timed(c, step_device, n_prof)
+    prof = profile_read(c)
+    c.lib.deism_profile_enable(0)
+    backend.USE_GRAPHS = graphs_on
+    kernel_ms = {nm: round(ms / n, 4) for nm, (ms, n) in prof.items()}
+    for _ in range(2):          # first call with these buffers runs eagerly, the second one captures
+        step_device()
     launches0 = _lib.launch_count()
     dev_ms, wall_ms = timed(c, step_device, steps)
     launches = _lib.launch_count() - launches0
-    prof = profile_read(c)
-    c.lib.deism_profile_enable(0)
-    kernel_ms = {nm: round(ms / n, 4) for nm, (ms, n) in prof.items()}
     ms_per_step = max_over_ranks(c, dev_ms) / steps
 
     for _ in range(2):
@@ -479,7 +491,7 @@ def measure_shoebox(c, name, steps, warmup, general=False, sharding="frequency",
                         "traffic": traffic,
                         "algorithmic_flops_per_term": fpt, "terms_per_launch": units,
                         "kernel_ms_per_launch": round(per_launch_ms, 4),
-                        "kernel_share_of_step": round(ms_k / steps / ms_per_step, 4),
+                        "kernel_share_of_step": round(ms_k / n_prof / ms_per_step, 4),
                         "step_level_frac": round(fpt * units / (ms_per_step * 1e-3) / 1e12 / peak_tf, 4)
                         if peak_tf else None,
                         "peak_source": f"measured in this run: deism_fp64_peak {peak_kind} "
@@ -496,6 +508,7 @@ def measure_shoebox(c, name, steps, warmup, general=False, sharding="frequency",
                           "host_buffers": "plain (pageable) NumPy through backend.run_DEISM, result as NumPy"}
                          if pg_ms else None),
         "gpu_launches": int(launches),
+        "cuda_graph_replay": bool(graphs_on),
         "roofline": roofline,
         "parity_rel_l2_vs_reference": parity,
         "parity_worst_single_frequency": parity_worst,

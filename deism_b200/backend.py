@@ -98,6 +98,61 @@ def _broadcast_base(a):
     return None
 
 
+class _Staging:
+    """Pinned staging buffers for pageable NumPy inputs.
+
+    A reference caller holds plain NumPy arrays.  ``cudaMemcpyAsync`` from pageable memory goes
+    through the driver's own bounce buffer on one thread and blocks the host (measured on the B200
+    box: 1.76 ms for 33 MiB); copying into a pinned buffer first with torch's multi-threaded
+    ``copy_`` and issuing a truly asynchronous H2D from there is twice as fast (0.81 ms) and leaves
+    the host free to queue the kernels.  Buffers are recycled per power-of-two size class; a buffer
+    is reused only after the event recorded behind its last H2D has completed."""
+
+    MIN_BYTES = 1 << 18          # below this the pageable path is as fast
+    MAX_BYTES = 1 << 28          # larger arrays (materialised atten slabs) go the pageable way
+    PER_CLASS = 8
+    CAP_BYTES = 1 << 30
+
+    def __init__(self):
+        self.pool = {}           # (device index, size class) -> list of [pinned uint8 tensor, event]
+        self.total = 0
+
+    def upload(self, a, dev):
+        """a: C-contiguous NumPy array -> device tensor of the same dtype/shape, or None when the
+        array should take the direct path."""
+        nbytes = a.nbytes
+        if nbytes < self.MIN_BYTES or nbytes > self.MAX_BYTES:
+            return None
+        src = torch.from_numpy(a)
+        if src.is_pinned():
+            return None
+        size = 1 << (nbytes - 1).bit_length()
+        slots = self.pool.setdefault((dev.index, size), [])
+        slot = None
+        for cand in slots:
+            if cand[1] is None or cand[1].query():
+                slot = cand
+                break
+        if slot is None:
+            # never wait for a buffer: its H2D may sit behind a whole step of queued kernels
+            if len(slots) >= self.PER_CLASS or self.total + size > self.CAP_BYTES:
+                return None
+            slot = [torch.empty(size, dtype=torch.uint8).pin_memory(), None]
+            slots.append(slot)
+            self.total += size
+        # plain bytes: a vectorised, multi-threaded memcpy whatever the element type
+        flat = torch.from_numpy(a.reshape(-1).view(np.uint8))
+        slot[0][:nbytes].copy_(flat)
+        t = slot[0][:nbytes].to(dev, non_blocking=True).view(src.dtype).reshape(src.shape)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        slot[1] = ev
+        return t
+
+
+_staging = _Staging()
+
+
 def to_device(x, dtype, dev=None):
     """NumPy / torch (host or device) -> contiguous device tensor of ``dtype``."""
     dev = dev or _device()
@@ -116,7 +171,9 @@ def to_device(x, dtype, dev=None):
             a = np.ascontiguousarray(a)
         if not a.flags["WRITEABLE"]:
             a = a.copy()
-        t = torch.from_numpy(a)
+        t = _staging.upload(a, dev) if a.dtype != np.float16 else None
+        if t is None:
+            t = torch.from_numpy(a)
     if t.dtype != dtype:
         t = t.to(dtype)
     return t.to(dev, non_blocking=True).contiguous()
@@ -343,9 +400,7 @@ def _run_org(params, images, suffix, out, accumulate, dev):
         del spec, A, R
 
 
-def run_DEISM_device(params, dev=None):
-    """As run_DEISM but returns the complex128[K] result as a device tensor (no read-back)."""
-    dev = dev or _device()
+def _run_DEISM_eager(params, dev):
     method = params["DEISM_method"]
     images = params["images"]
     K = int(np.asarray(params["waveNumbers"]).shape[0]) \
@@ -365,6 +420,160 @@ def run_DEISM_device(params, dev=None):
     else:
         raise ValueError(f"Unknown DEISM method: {method}")
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# CUDA-graph replay of repeated calls
+# ----------------------------------------------------------------------------------------------
+# A run_DEISM call is ~15-25 kernel launches and as many torch copies; for the sub-millisecond
+# workloads (BASELINE C1, the monopole run of C2, an 8-GPU frequency slab) launch gaps and host
+# dispatch are a third of the step.  When a call comes again with the SAME buffers — every array
+# input a CUDA tensor or a PINNED host array at the same address and shape, the same scalars —
+# the second call is captured into a CUDA graph (the pinned host->device copies become memcpy
+# nodes: they re-read the host buffers at every replay) and later calls replay it.  Arrays in
+# pageable memory are never captured (the driver stages them synchronously).  A graph bakes in the
+# library's scratch pointers and constant tables: it is dropped when deism_state_generation()
+# moves.  DEISM_B200_GRAPHS=0 (or backend.USE_GRAPHS = False) turns the mechanism off.
+import os as _os
+
+USE_GRAPHS = _os.environ.get("DEISM_B200_GRAPHS", "1") != "0"
+_GRAPH_CACHE_MAX = 16
+_graphs = {}        # key -> {"graph", "out", "gen", "n_kernels", "keep"}
+_graph_seen = {}    # key -> generation at the last eager call with this key
+
+
+def _arr_key(x):
+    """Identity of an array input for the graph cache, or None when it cannot be captured."""
+    if isinstance(x, DeviceArray):
+        x = x.tensor
+    if isinstance(x, torch.Tensor):
+        if x.is_cuda or x.is_pinned():
+            return ("t", x.data_ptr(), tuple(x.shape), tuple(x.stride()), str(x.dtype), x.is_cuda)
+        return None
+    if isinstance(x, np.ndarray):
+        if x.nbytes < 4096:          # small tables: by value
+            return ("v", x.shape, str(x.dtype), x.tobytes())
+        if not x.flags["C_CONTIGUOUS"] or _broadcast_base(x) is not None:
+            return None
+        if not torch.from_numpy(x if x.flags["WRITEABLE"] else x.copy()).is_pinned():
+            return None
+        return ("p", x.ctypes.data, x.shape, str(x.dtype))
+    return None
+
+
+def _graph_key(params, dev):
+    images = params["images"]
+    parts = [params["DEISM_method"], dev.index, int(params.get("angDepFlag", 0)),
+             int(params.get("sourceOrder", 0)), int(params.get("receiverOrder", 0)),
+             int(params.get("b200OrgAlgo", 0)), str(images.get("storage"))]
+    for name in ("roomSize", "posSource", "posReceiver"):
+        v = params.get(name)
+        parts.append(None if v is None else np.asarray(v, dtype=np.float64).tobytes())
+    for name in ("n_all", "m_all", "v_all", "u_all"):
+        v = params.get(name)
+        parts.append(None if v is None else np.asarray(v, dtype=np.int64).tobytes())
+    w = params.get("Wigner")
+    parts.append(None if w is None else id(w["W_2_all"]))
+    for name in ("waveNumbers", "impedance", "C_nm_s", "C_vu_r", "C_nm_s_vec", "C_vu_r_vec"):
+        v = params.get(name)
+        if v is None:
+            parts.append(None)
+            continue
+        k = _arr_key(v if isinstance(v, (torch.Tensor, DeviceArray)) else np.asarray(v))
+        if k is None:
+            return None
+        parts.append(k)
+    for name in sorted(images):
+        v = images[name]
+        if isinstance(v, (np.ndarray, torch.Tensor, DeviceArray)):
+            k = _arr_key(v)
+            if k is None:
+                return None
+            parts.append((name, k))
+        else:
+            parts.append((name, str(v)))
+    return tuple(parts)
+
+
+def _pin_small_tables(params):
+    """Small NumPy tables are part of the graph key BY VALUE and may live in pageable memory, which a
+    captured copy cannot read: the capture reads pinned copies (kept alive with the graph)."""
+    keep = []
+
+    def pinned(x):
+        if isinstance(x, np.ndarray) and x.nbytes < 4096 and x.nbytes > 0:
+            t = torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
+            keep.append(t)
+            return t.numpy()
+        return x
+
+    q = dict(params)
+    for name in ("waveNumbers", "impedance", "C_nm_s", "C_vu_r", "C_nm_s_vec", "C_vu_r_vec"):
+        if name in q and q[name] is not None and not isinstance(q[name], (torch.Tensor, DeviceArray)):
+            q[name] = pinned(np.asarray(q[name]))
+    q["images"] = {k: pinned(v) for k, v in params["images"].items()}
+    return q, keep
+
+
+def _graphs_allowed():
+    if not USE_GRAPHS:
+        return False
+    if torch.cuda.is_current_stream_capturing():
+        return False
+    return True
+
+
+def run_DEISM_device(params, dev=None):
+    """As run_DEISM but returns the complex128[K] result as a device tensor (no read-back)."""
+    dev = dev or _device()
+    if params["DEISM_method"] not in ("ORG", "LC", "MIX"):
+        raise ValueError(f"Unknown DEISM method: {params['DEISM_method']}")
+    key = _graph_key(params, dev) if _graphs_allowed() else None
+    if key is None:
+        return _run_DEISM_eager(params, dev)
+    gen = int(lib().deism_state_generation())
+    hit = _graphs.get(key)
+    if hit is not None and hit["gen"] == gen:
+        hit["graph"].replay()
+        check(lib().deism_graph_replayed(hit["n_kernels"], _stream_ptr()), "deism_graph_replayed")
+        return hit["out"].clone()
+    if hit is not None:
+        del _graphs[key]
+    if _graph_seen.get(key) != gen:
+        # first sight of these buffers (or the library state moved): run eagerly — this is also the
+        # warm-up that sizes the scratch and uploads the constant tables
+        out = _run_DEISM_eager(params, dev)
+        _graph_seen[key] = int(lib().deism_state_generation())
+        return out
+    # second call with the same buffers and an unchanged library: capture it
+    torch.cuda.synchronize(dev)
+    captured, keep = _pin_small_tables(params)
+    n0 = _lib.launch_count()
+    graph = torch.cuda.CUDAGraph()
+    try:
+        with torch.cuda.graph(graph):
+            out = _run_DEISM_eager(captured, dev)
+    except Exception:
+        # anything that cannot be captured: fall back for good for this key
+        _graph_seen[key] = -1
+        torch.cuda.synchronize(dev)
+        return _run_DEISM_eager(params, dev)
+    n_kernels = _lib.launch_count() - n0
+    if int(lib().deism_state_generation()) != gen:      # the capture itself moved the state: not replayable
+        _graph_seen[key] = -1
+        return _run_DEISM_eager(params, dev)
+    if len(_graphs) >= _GRAPH_CACHE_MAX:
+        _graphs.pop(next(iter(_graphs)))
+    _graphs[key] = {"graph": graph, "out": out, "gen": gen, "n_kernels": int(n_kernels), "keep": keep}
+    graph.replay()
+    check(lib().deism_graph_replayed(int(n_kernels), _stream_ptr()), "deism_graph_replayed")
+    return out.clone()
+
+
+def clear_graphs():
+    """Drop every captured graph (and the device memory their private pools hold)."""
+    _graphs.clear()
+    _graph_seen.clear()
 
 
 _copy_streams = {}
@@ -387,6 +596,7 @@ def _run_mix_from_host(params, images, out, dev):
     if side is None:
         side = _copy_streams[dev.index] = torch.cuda.Stream(dev)
     staged = []
+    side.wait_stream(main)          # fork (under graph capture the side stream must join the capture)
     with torch.cuda.stream(side):
         for key in ("C_nm_s", "C_vu_r"):
             p[key] = _coef_on_device(params[key], dev)[0]

@@ -24,6 +24,11 @@ int set_error(int code, const char *fmt, ...) {
 
 void count_launch(int n) { __atomic_add_fetch(&g_launches, (uint64_t)n, __ATOMIC_RELAXED); }
 
+// Generation of the library's per-device state that a captured CUDA graph bakes in: scratch
+// pointers and the contents of the __constant__ tables.  Bumped whenever either changes.
+static uint64_t g_generation = 1;
+void bump_generation() { __atomic_add_fetch(&g_generation, (uint64_t)1, __ATOMIC_RELAXED); }
+
 struct DeviceState {
     bool checked = false;
     bool ok = false;
@@ -139,6 +144,7 @@ void *workspace(int slot, size_t bytes) {
     if (bytes < 256) bytes = 256;
     if (s->ws_bytes[slot] >= bytes) return s->ws[slot];
     std::lock_guard<std::mutex> lk(g_mu);
+    bump_generation();
     if (s->ws[slot]) {
         cudaFree(s->ws[slot]);   // synchronises: no kernel still reads the old buffer
         s->ws[slot] = nullptr;
@@ -185,6 +191,9 @@ static ProfSlot *prof_slot(const char *name) {
 }
 static void prof_record(const char *name, cudaStream_t st) {
     if (!g_prof_on) return;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;     // timing events cannot be captured
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cap != cudaStreamCaptureStatusNone) return;
     std::lock_guard<std::mutex> lk(g_mu);
     ProfSlot *s = prof_slot(name);
     if (s->used == s->ev.size()) {
@@ -359,10 +368,24 @@ extern "C" int deism_device_info(int device, int *sm_count_out, size_t *hbm_byte
     return DEISM_OK;
 }
 
+// A replayed CUDA graph launches the kernels it captured without passing through the entry points:
+// the replaying host code reports them here (n = kernels in the graph) and fences the stream so
+// that the one-call-in-flight ordering also covers the replayed work.
+extern "C" int deism_graph_replayed(int n_kernels, void *stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    if (n_kernels > 0) count_launch(n_kernels);
+    CallGuard call_guard(stream);
+    return DEISM_OK;
+}
+
+extern "C" uint64_t deism_state_generation(void) { return __atomic_load_n(&g_generation, __ATOMIC_RELAXED); }
+
 extern "C" int deism_release_workspace(void) {
     DeviceState *s = state();
     if (!s) return set_error(DEISM_ERR_CUDA, "no current device");
     std::lock_guard<std::mutex> lk(g_mu);
+    bump_generation();
     for (int i = 0; i < WS_NSLOTS; ++i) {
         if (s->ws[i]) cudaFree(s->ws[i]);
         s->ws[i] = nullptr;

@@ -180,6 +180,7 @@ extern "C" int deism_lc_arg(int64_t n_images, int64_t K, int Js, int Jr, const i
             memcmp(last[1], hm, Js * sizeof(int)) || memcmp(last[2], hv, Jr * sizeof(int)) ||
             memcmp(last[3], hu, Jr * sizeof(int))) {
             last_dev = -1;
+            bump_generation();
             DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_arg_n, hn, Js * sizeof(int), 0, cudaMemcpyHostToDevice, st));
             DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_arg_m, hm, Js * sizeof(int), 0, cudaMemcpyHostToDevice, st));
             DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_arg_v, hv, Jr * sizeof(int), 0, cudaMemcpyHostToDevice, st));

@@ -18,6 +18,7 @@ namespace deism {
 // ---------------------------------------------------------------------------------------
 int set_error(int code, const char *fmt, ...);
 void count_launch(int n = 1);
+void bump_generation();                   // scratch pointers or __constant__ tables changed
 int check_device();                       // DEISM_OK iff current device is sm_100
 void *workspace(int slot, size_t bytes);  // cached device scratch; nullptr on failure
 int sm_count();
@@ -330,6 +331,77 @@ __device__ __forceinline__ void shoebox_atten_n(const cplx *__restrict__ Z, long
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Real impedances on every wall and frequency of a tile (decided once per CTA): the attenuation is
+// REAL, and the whole product  prod_w beta_w^{e_w}  is formed by ONE simultaneous square-and-multiply
+// over the (up to six) exponents — one squaring per bit position instead of one per wall — from
+// wall factors 1 - 2/(zeta c + 1).  29 FP64 instructions per term instead of the 66 of the general
+// chain above (which carries a complex accumulator through the three wall pairs).
+//   NEWTON = 1: one Newton step on the hardware reciprocal seed (2^-23 -> 2^-46).  Enough wherever
+//               the attenuation is rounded to complex64 right after (DEISM_ATTEN_FUSED_ROOM, the
+//               reference's default storage, cd:2921-2928): a value moves to the neighbouring float
+//               only if it lies within 2^-46 of a rounding boundary (~3e-7 of the values, one
+//               float ulp of ONE term each).
+//   NEWTON = 2: <= 1 ulp of FP64 (compact storage, not rounded).
+// ---------------------------------------------------------------------------------------
+template <int NEWTON>
+__device__ __forceinline__ double real_ref_coef_n(double t) {
+    const double x = t + 1.0;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    if (NEWTON > 1) r = fma(fma(-x, r, 1.0), r, r);
+    return fma(-2.0, r, 1.0);
+}
+template <int NQ, int NEWTON>
+__device__ __forceinline__ void shoebox_atten_real_n(const cplx *__restrict__ Z, long zstride, const int (&fq)[NQ],
+                                                     double cx, double cy, double cz, const unsigned char *e,
+                                                     double (&out)[NQ]) {
+    const double c3[3] = {cx, cy, cz};
+    double b[6][NQ];
+    unsigned ex[6];
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+        bool same = true;
+        double z1[NQ], z2[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            z1[q] = Z[(2 * w) * zstride + fq[q]].x;
+            z2[q] = Z[(2 * w + 1) * zstride + fq[q]].x;
+            same = same && z1[q] == z2[q];
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) b[2 * w][q] = real_ref_coef_n<NEWTON>(z1[q] * c3[w]);
+        if (same) {
+            ex[2 * w] = (unsigned)e[2 * w] + (unsigned)e[2 * w + 1];
+            ex[2 * w + 1] = 0u;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) b[2 * w + 1][q] = 1.0;
+        } else {
+            ex[2 * w] = e[2 * w];
+            ex[2 * w + 1] = e[2 * w + 1];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) b[2 * w + 1][q] = real_ref_coef_n<NEWTON>(z2[q] * c3[w]);
+        }
+    }
+    const unsigned all = ex[0] | ex[1] | ex[2] | ex[3] | ex[4] | ex[5];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) out[q] = 1.0;
+    if (all == 0u) return;
+    // left-to-right over the bit positions of the largest exponent
+    for (int bit = 31 - __clz(all); bit >= 0; --bit) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) out[q] *= out[q];
+#pragma unroll
+        for (int s_ = 0; s_ < 6; ++s_) {
+            if ((ex[s_] >> bit) & 1u) {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) out[q] *= b[s_][q];
+            }
+        }
+    }
+}
+
 // one (image, frequency) term inside a main loop: the chains above with NQ = 1
 __device__ __forceinline__ cplx shoebox_atten_term(const cplx *__restrict__ Z, long zstride, double cx, double cy,
                                                    double cz, const unsigned char *e) {
@@ -398,6 +470,32 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned
                  : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+#if defined(DEISM_MBAR_TEST)
+    // spin on the non-suspending test
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+#elif defined(DEISM_MBAR_HINT)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"((unsigned)DEISM_MBAR_HINT)
+        : "memory");
+#else
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -409,6 +507,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -421,6 +520,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
             smem_u32(dst)),
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+// 16-byte asynchronous copy global -> shared (LDGSTS, L2 only) and the mbarrier arrival that fires
+// when all of the executing thread's earlier cp.async have landed (.noinc: it counts against the
+// barrier's expected arrivals)
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(unsigned long long *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // D(8x8) += A(8x4) * B(4x8), FP64 tensor core
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {

@@ -486,6 +486,7 @@ static int upload_walls(const deism_convex_walls *w, cudaStream_t st) {
     // on the caller's stream (non-blocking streams are not ordered against the legacy stream, and
     // the previous fill's kernels may still be reading c_walls); the caller synchronises `st`
     // before `h` can be rewritten
+    bump_generation();
     DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_walls, &h, sizeof(h), 0, cudaMemcpyHostToDevice, st));
     return DEISM_OK;
 }
@@ -506,6 +507,7 @@ extern "C" int deism_convex_images_count(const deism_convex_walls *walls, const 
         return set_error(DEISM_ERR_INVALID, "ism_order must be 0..%d", CVX_MAX_ORDER - 1);
     rc = upload_walls(walls, st);
     if (rc) return rc;
+    bump_generation();
     DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_mic, h_mic, 3 * sizeof(float), 0, cudaMemcpyHostToDevice, st));
     CvxState *Sp = cvx_state();
     if (!Sp) return set_error(DEISM_ERR_CUDA, "no current device");

@@ -288,15 +288,32 @@ __host__ __device__ inline LcCarve lc_carve(int WN, bool cres_on, int rows, int 
 // Factors (atten/r) exp(-ikr) of ONE image at the four frequencies a thread owns, for an impedance
 // that varies with frequency: the wall exponents are shared by the four, so their attenuations are
 // built together (shoebox_atten_n).  Only the general instantiation of the main kernel carries it.
+#ifndef LC_REAL_CHAIN
+#define LC_REAL_CHAIN 1     // 0: the general (complex-capable) wall-factor chain everywhere (A/B builds)
+#endif
 __device__ __forceinline__ void lc_general_factors(const cplx *Zs, int TF, const double *kf, const double *dkd,
                                                 const double *dkd8, const LcImage *recp, int fqa,
-                                                bool round_to_c64, bool uniform_k, double2 *fac, int stride) {
+                                                bool round_to_c64, bool uniform_k, bool real_tile, double2 *fac,
+                                                int stride) {
     constexpr int NQ = 2 * LC_NT;
     static_assert(LC_NT == 2, "frequency offsets below assume two n-tiles per warp");
     const LcImage &rec = *recp;
     const int fqs[NQ] = {fqa, fqa + 1, fqa + 8, fqa + 9};
     cplx att[NQ], Eq[NQ];
-    shoebox_atten_n<NQ>(Zs, TF, fqs, rec.cx, rec.cy, rec.cz, rec.e, att);
+    double att_r[NQ];
+    if (real_tile) {
+        if (round_to_c64) {
+            shoebox_atten_real_n<NQ, 1>(Zs, TF, fqs, rec.cx, rec.cy, rec.cz, rec.e, att_r);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) att_r[q] = (double)__double2float_rn(att_r[q]) * rec.inv_r;
+        } else {
+            shoebox_atten_real_n<NQ, 2>(Zs, TF, fqs, rec.cx, rec.cy, rec.cz, rec.e, att_r);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) att_r[q] *= rec.inv_r;
+        }
+    } else {
+        shoebox_atten_n<NQ>(Zs, TF, fqs, rec.cx, rec.cy, rec.cz, rec.e, att);
+    }
     auto rot_step = [](cplx F, cplx rot, double dr) {
         F = cmul(F, rot);
         return cmake(fma(F.y, dr, F.x), fma(-F.x, dr, F.y));
@@ -315,6 +332,11 @@ __device__ __forceinline__ void lc_general_factors(const cplx *Zs, int TF, const
             sincos_cw(kf[fqs[q]] * rec.r, &sn, &cs);
             Eq[q] = cmake(cs, -sn);
         }
+    }
+    if (real_tile) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) fac[(long)q * stride] = cmake(att_r[q] * Eq[q].x, att_r[q] * Eq[q].y);
+        return;
     }
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
@@ -393,14 +415,19 @@ lc_main_kernel(LcMainArgs a) {
             dkd8[q] = f + 8 < a.K ? (a.k[f + 8] - kk) - 8.0 * dk : 0.0;
         }
     }
+    // Per-term attenuation with every impedance of the frequency tile real (what the material
+    // conversions return): the real chain of common.cuh (shoebox_atten_real_n), decided per CTA.
+    bool z_real_here = true;
     if (fused && !flat) {
         for (int i = tid; i < 6 * TF; i += THREADS) {
             int w = i / TF, q = i % TF;
             long f = f0 + q;
-            Zs[w][q] = f < a.K ? a.Z[(long)w * a.K + f] : cmake(1.0, 0.0);
+            const cplx z = f < a.K ? a.Z[(long)w * a.K + f] : cmake(1.0, 0.0);
+            Zs[w][q] = z;
+            z_real_here = z_real_here && z_is_real(z);
         }
     }
-    __syncthreads();
+    const bool real_tile = __syncthreads_and(z_real_here) && fused && !flat && LC_REAL_CHAIN;
 
     // producer: chunk = JC harmonics of one pass for one image tile -> one bulk copy (Y), plus the
     // matching coefficient rows when they are not resident
@@ -628,7 +655,7 @@ lc_main_kernel(LcMainArgs a) {
 #pragma unroll 1
                 for (int mt = 0; mt < 2; ++mt)
                     lc_general_factors(&Zs[0][0], TF, kf, dkd, dkd8, &recs[rb][wm * 16 + mt * 8 + g], fqa,
-                                       a.mode == DEISM_ATTEN_FUSED_ROOM, uniform_k,
+                                       a.mode == DEISM_ATTEN_FUSED_ROOM, uniform_k, real_tile,
                                        &facp[mt * 2 * NT][tid], THREADS);
             } else {
             cplx E = cmake(1.0, 0.0), E0 = E;
@@ -758,6 +785,7 @@ lc_mono_kernel(LcMonoArgs a) {
     const bool flat = fused && a.flags[0] != 0;
     const bool uniform_k = a.flags[1] != 0;
     if ((flat && uniform_k) != FAST) return;
+    bool z_real_here = true;
     {
         const double dk = *reinterpret_cast<const double *>(a.flags + 2);
         for (int q = tid; q < TF; q += LM_THREADS) {
@@ -770,10 +798,13 @@ lc_mono_kernel(LcMonoArgs a) {
             for (int i = tid; i < 6 * TF; i += LM_THREADS) {
                 const int w = i / TF, q = i % TF;
                 const long f = f0 + q;
-                Zs[w][q] = f < a.K ? a.Z[(long)w * a.K + f] : cmake(1.0, 0.0);
+                const cplx z = f < a.K ? a.Z[(long)w * a.K + f] : cmake(1.0, 0.0);
+                Zs[w][q] = z;
+                z_real_here = z_real_here && z_is_real(z);
             }
     }
-    __syncthreads();
+    // every impedance of the frequency tile real: the real wall-factor chain (common.cuh)
+    const bool real_tile = __syncthreads_and(z_real_here) && fused && !flat && LC_REAL_CHAIN;
     const int q0 = fg * FPT;
     cplx P[FPT];
 #pragma unroll
@@ -803,7 +834,21 @@ lc_mono_kernel(LcMonoArgs a) {
 #pragma unroll
                 for (int q = 0; q < FPT; ++q) att[q] = rec.a_flat;
             } else {
-                if (fused) {
+                if (fused && real_tile) {
+                    int fqs[FPT];
+                    double ar[FPT];
+#pragma unroll
+                    for (int q = 0; q < FPT; ++q) fqs[q] = q0 + q;
+                    if (a.mode == DEISM_ATTEN_FUSED_ROOM) {
+                        shoebox_atten_real_n<FPT, 1>(&Zs[0][0], TF, fqs, rec.cx, rec.cy, rec.cz, rec.e, ar);
+#pragma unroll
+                        for (int q = 0; q < FPT; ++q) att[q] = cmake((double)__double2float_rn(ar[q]), 0.0);
+                    } else {
+                        shoebox_atten_real_n<FPT, 2>(&Zs[0][0], TF, fqs, rec.cx, rec.cy, rec.cz, rec.e, ar);
+#pragma unroll
+                        for (int q = 0; q < FPT; ++q) att[q] = cmake(ar[q], 0.0);
+                    }
+                } else if (fused) {
                     int fqs[FPT];
 #pragma unroll
                     for (int q = 0; q < FPT; ++q) fqs[q] = q0 + q;
@@ -962,11 +1007,17 @@ static void build_real_basis(int J, const int64_t *n, const int64_t *m, LcBasis 
     }
 }
 
+int launch_k_uniform(const double *d_k, long K, int *flags, cudaStream_t st) {
+    k_uniform_kernel<<<1, 256, 0, st>>>(d_k, K, flags);
+    DEISM_LAUNCH_CHECK("k_uniform_kernel");
+    return DEISM_OK;
+}
+
 int launch_z_flat(const deism_shoebox_atten *at, long K, int *flags, cudaStream_t st) {
     DEISM_CUDA_TRY(cudaMemsetAsync(flags, 0, 4 * sizeof(int), st));
     if (at->mode == DEISM_ATTEN_FUSED_ROOM || at->mode == DEISM_ATTEN_FUSED_ANGLES) {
-        int one = 1;
-        DEISM_CUDA_TRY(cudaMemcpyAsync(flags, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+        // flags[0] = 1 (little endian) without a host source: the call stays CUDA-graph capturable
+        DEISM_CUDA_TRY(cudaMemsetAsync(flags, 1, 1, st));
         z_flat_kernel<<<32, 256, 0, st>>>((const cplx *)at->d_Z_S, K, flags);
         DEISM_LAUNCH_CHECK("z_flat_kernel");
     }
@@ -1023,6 +1074,7 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
         std::lock_guard<std::mutex> lk(basis_mu);
         if (dev != uploaded_dev || memcmp(hb, uploaded, sizeof(hb)) != 0) {
             uploaded_dev = -1;
+            bump_generation();
             DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_lc_basis, hb, sizeof(hb), 0, cudaMemcpyHostToDevice, st));
             DEISM_CUDA_TRY(cudaStreamSynchronize(st));   // hb is on the stack
             memcpy(uploaded, hb, sizeof(hb));

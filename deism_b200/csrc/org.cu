@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -38,6 +39,7 @@ int launch_reduce_partials(const cplx *partial, long n_chunks, long K, double *d
                            cudaStream_t st);
 int validate_atten(const deism_shoebox_atten *at);
 int launch_z_flat(const deism_shoebox_atten *at, long K, int *flags, cudaStream_t st);
+int launch_k_uniform(const double *d_k, long K, int *flags, cudaStream_t st);   // flags[1], dk at flags+2
 
 // One non-zero quintuple (n,m,v,u,l) of the coupling, stored in the segment of its (l,mu).
 struct OrgEntry {
@@ -62,10 +64,27 @@ __device__ __forceinline__ OrgEntryReg load_entry(const OrgEntry *p) {
     return e;
 }
 
+// B-table form of the same list.  The class-1 list (m' = -m) is the class-0 list with the source
+// coefficient of (n, -m) in place of (n, m): same (v, u), same G, same segment.  One entry therefore
+// feeds both classes from ONE receiver-coefficient load.  Inside a segment the entries are grouped
+// by the parities (m & 1, n & 1) that decide the mirror sign (-1)^{b m + c n}, then ordered by (n, m)
+// so that consecutive entries reuse the source coefficients.
+struct BtEntry {
+    double G;
+    int16_t idx_s;    // n*(2N+1) + wrap(m)    -> C_s[k, n, m]     (class 0)
+    int16_t idx_sn;   // n*(2N+1) + wrap(-m)   -> C_s[k, n, -m]    (class 1)
+    int16_t idx_r;    // v*(2V+1) + wrap(-u)   -> C_r[k, v, -u]
+    int16_t pad;
+};
+static_assert(sizeof(BtEntry) == 16, "BtEntry must be 16 bytes");
+
 struct OrgLists {
     // class a = (p_x+p_y)&1 selects m' = m (a=0) or -m (a=1)
     std::vector<OrgEntry> entries[2];
     std::vector<int> seg[2];   // Lmax^2 + 1 offsets, segment index = l*l + l + mu
+    std::vector<BtEntry> bt;   // class-0 entries, by (segment, parity group, n, m, v)
+    std::vector<int> bt_seg;   // 4 * Lmax^2 + 1 offsets, index = 4 * segment + 2 * (m & 1) + (n & 1)
+    std::vector<int2> jobs;    // (l, |mu|) pairs, most entries first
     long nnz = 0;
 };
 
@@ -111,6 +130,33 @@ static void build_lists(int N, int V, const float *W1, const float *W2, OrgLists
         L.seg[a][nseg] = (int)L.entries[a].size();
     }
     L.nnz = (long)L.entries[0].size();
+    // ---- B-table lists from the class-0 buckets (already in (n, m, v) order inside a segment) ----
+    L.bt.clear();
+    L.bt_seg.assign(4 * nseg + 1, 0);
+    for (int sgm = 0; sgm < nseg; ++sgm) {
+        for (int pg = 0; pg < 4; ++pg) {
+            L.bt_seg[4 * sgm + pg] = (int)L.bt.size();
+            for (int j = L.seg[0][sgm]; j < L.seg[0][sgm + 1]; ++j) {
+                const OrgEntry &e = L.entries[0][j];
+                if ((((int)e.m & 1) << 1 | ((int)e.n & 1)) != pg) continue;
+                BtEntry b;
+                b.G = e.G; b.idx_s = e.idx_s; b.idx_r = e.idx_r; b.pad = 0;
+                const int m = e.m, n = e.n;
+                b.idx_sn = (int16_t)(n * M2 + ((-m) < 0 ? -m + M2 : -m));
+                L.bt.push_back(b);
+            }
+        }
+    }
+    L.bt_seg[4 * nseg] = (int)L.bt.size();
+    L.jobs.clear();
+    for (int l = 0; l < Lmax; ++l)
+        for (int am = 0; am <= l; ++am) L.jobs.push_back(make_int2(l, am));
+    auto job_size = [&](const int2 &j) {
+        const int s1 = j.x * j.x + j.x + j.y, s2 = j.x * j.x + j.x - j.y;
+        return (L.bt_seg[4 * s1 + 4] - L.bt_seg[4 * s1]) + (j.y ? L.bt_seg[4 * s2 + 4] - L.bt_seg[4 * s2] : 0);
+    };
+    std::stable_sort(L.jobs.begin(), L.jobs.end(),
+                     [&](const int2 &a, const int2 &b) { return job_size(a) > job_size(b); });
 }
 
 // ---------------------------------------------------------------------------------------
@@ -138,18 +184,26 @@ __global__ void transpose_coef_kernel(const IN *__restrict__ in, long K, int J, 
 // factorised path: operand-plane geometry.  Segment (l, mu) lives at row rowoff(l) + mu + l of a
 // plane set; every l block is padded to a multiple of 4 rows (the DMMA k extent) with zeros.
 // ---------------------------------------------------------------------------------------
-constexpr int ORG_TI = 32;        // images per tile
-constexpr int ORG_TF = 32;        // frequencies per tile
-#ifndef ORG_NT
-#define ORG_NT 1                  // n-tiles (8 freqs) per warp: 1 -> 2x4 warps of 16x8, 2 -> 2x2 warps of 16x16
+#ifndef ORG_TI_
+#define ORG_TI_ 64
 #endif
-constexpr int ORG_WN = 4 / ORG_NT;             // warps along frequency
-constexpr int ORG_THREADS = 64 * ORG_WN;       // 2 (image) x ORG_WN (frequency) warps
-constexpr int ORG_RC = 48;        // (l,mu) rows per staged chunk (whole degrees; grows to the widest degree)
-constexpr int ORG_OS = 36;        // Y row stride in doubles (32 images + 4 pad: 4 mod 16)
+constexpr int ORG_TI = ORG_TI_;   // images per tile
+constexpr int ORG_TF = 32;        // frequencies per tile
+constexpr int ORG_WM = ORG_TI / 16;            // warps along images (16 images each)
+constexpr int ORG_WN = 4;                      // warps along frequency (8 frequencies each)
+constexpr int ORG_THREADS = 32 * ORG_WM * ORG_WN;
+constexpr int ORG_CTAS_PER_SM = ORG_THREADS <= 256 ? 2 : 1;
+#ifndef ORG_RC_
+#define ORG_RC_ 96                // 2 stages of 104 KB: the bulk-copy engine takes one stage at a time and
+#endif                            // >= ~550 clk per stage however small (scripts/probes/tma_probe.cu)
+constexpr int ORG_RC = ORG_RC_;   // (l,mu) rows per staged chunk (whole degrees; grows to the widest degree)
+constexpr int ORG_OS = ORG_TI + 4;// Y row stride in doubles (tile + 4 pad: 4 mod 16 -> conflict-free fragments)
 constexpr int ORG_BS = 34;        // B plane stride: a row of 2 planes is 68 = 4 mod 16 doubles
 constexpr int ORG_LMAX = 48;
 constexpr int ORG_MAXCHUNKS = 256;
+#ifndef ORG_MAXST
+#define ORG_MAXST 4               // most ring stages
+#endif
 constexpr int SORT_THREADS = 1024;
 __constant__ int c_org_rowoff[ORG_LMAX + 1];
 __constant__ int4 c_org_chunks[ORG_MAXCHUNKS];   // row0, nrows, first degree, one past the last degree
@@ -237,13 +291,189 @@ __global__ void __launch_bounds__(128) org_btable_kernel(BtableArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// B table, second form (round 2): CTA = FT frequencies x every (l, |mu|) job.
+//
+// The first form streams the transposed coefficient tables from L2 once per coupling entry and is
+// bound by that stream (64 B/clk/SM: 66 clk per warp-entry against 26 clk of FP64 work).  Here the
+// coefficient tile of the CTA's FT frequencies — every (n, m) row of C_s and C_r, widened to
+// complex128, 118 KB at N = V = 10 and FT = 16 — is staged in shared memory once, straight from
+// the caller's [K][(n,m)] tables (no transposed copies), and every job reads it from there.
+//   * lane = (frequency kk, slice h): the 32 / FT slices of a warp split a sub-segment's entries
+//     and are summed by shuffles at the end of the job;
+//   * one entry feeds both m'-classes from one receiver-coefficient load (BtEntry);
+//   * entries of a sub-segment share their mirror parities: the four mirror-sign variants are
+//     formed from the sub-segment's two sums instead of four FMAs per entry (6 FP64 instructions
+//     per entry and class instead of 12);
+//   * warps pull jobs (largest first) from a counter in shared memory.
+// ---------------------------------------------------------------------------------------
+struct Btable2Args {
+    long K, n_ftiles;
+    int R_tot, NMs, NMr, n_jobs, n_split;
+    const BtEntry *ent;
+    const int *seg;           // 4 * nseg + 1
+    const int2 *jobs;
+    const void *Cs, *Cr;      // the caller's [K][NMs] / [K][NMr] tables (complex64 or complex128)
+    const double *k;
+    double *Bp;
+};
+
+constexpr int BT2_THREADS = 512;
+
+template <int FT, typename IN>
+__global__ void __launch_bounds__(BT2_THREADS, 1) org_btable2_kernel(Btable2Args a) {
+    constexpr int RS = FT + 1;        // row stride in double2 (odd: staging stores spread over the banks)
+    constexpr int NH = 32 / FT;       // entry slices per warp
+    extern __shared__ __align__(16) unsigned char bt_smem_raw[];
+    double2 *CsS = reinterpret_cast<double2 *>(bt_smem_raw);
+    double2 *CrS = CsS + (size_t)a.NMs * RS;
+    int *counter = reinterpret_cast<int *>(CrS + (size_t)a.NMr * RS);
+    const int tid = threadIdx.x, lane = tid & 31;
+    int4 *ebuf = reinterpret_cast<int4 *>(counter + 4) + (tid >> 5) * 32;     // this warp's entry batch
+    const long k0 = (long)blockIdx.x * FT;
+    {
+        const IN *ins = reinterpret_cast<const IN *>(a.Cs), *inr = reinterpret_cast<const IN *>(a.Cr);
+        for (int i = tid; i < a.NMs * FT; i += BT2_THREADS) {
+            const int kk = i / a.NMs, j = i - kk * a.NMs;
+            CsS[j * RS + kk] = k0 + kk < a.K ? bt_make(ins[(k0 + kk) * a.NMs + j]) : make_double2(0.0, 0.0);
+        }
+        for (int i = tid; i < a.NMr * FT; i += BT2_THREADS) {
+            const int kk = i / a.NMr, j = i - kk * a.NMr;
+            CrS[j * RS + kk] = k0 + kk < a.K ? bt_make(inr[(k0 + kk) * a.NMr + j]) : make_double2(0.0, 0.0);
+        }
+        if (tid == 0) *counter = 0;
+    }
+    __syncthreads();
+    const int kk = lane % FT, h = lane / FT;
+    const long k = k0 + kk;
+    const double ik = k < a.K ? 1.0 / a.k[k] : 0.0;
+    const double2 *csl = CsS + kk, *crl = CrS + kk;
+    const long ft = k / ORG_TF;
+    const int q = (int)(k % ORG_TF);
+
+    for (;;) {
+        int jn = 0;
+        if (lane == 0) jn = atomicAdd(counter, 1);
+        jn = __shfl_sync(0xffffffffu, jn, 0);
+        const int job = (int)blockIdx.y + a.n_split * jn;      // this CTA's share: every n_split-th job
+        if (job >= a.n_jobs) break;
+        const int2 jb = a.jobs[job];
+        const int l = jb.x, am = jb.y;
+        cplx V[2][2][4];      // [class][mu sign][mirror variant 2b + c]
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int sg = 0; sg < 2; ++sg)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) V[c][sg][v] = cmake(0.0, 0.0);
+#pragma unroll
+        for (int sg = 0; sg < 2; ++sg) {
+            if (sg == 1 && am == 0) break;
+            const int sgm = l * l + l + (sg ? -am : am);
+#pragma unroll
+            for (int pg = 0; pg < 4; ++pg) {
+                const int lo = a.seg[4 * sgm + pg], hi = a.seg[4 * sgm + pg + 1];
+                if (hi == lo) continue;
+                const int per = (hi - lo + NH - 1) / NH;
+                const int my_lo = lo + h * per;
+                const int my_hi = my_lo + per < hi ? my_lo + per : hi;
+                cplx a0 = cmake(0.0, 0.0), a1 = cmake(0.0, 0.0);
+                int prev = -1;
+                double2 cs0 = make_double2(0.0, 0.0), cs1 = cs0;
+                // Entries are fetched FT per slice at a time, one per lane (a coalesced 16 x FT byte
+                // read per slice), parked in the warp's shared-memory buffer and consumed from there:
+                // a 16-byte entry read straight from global memory by every lane is a 32-byte-sector
+                // L2 round trip every other entry (measured: 440 clk per entry).  The next batch is in
+                // flight while the current one is consumed.
+                auto fetch = [&](int b) {
+                    const int j = my_lo + b + kk;
+                    int4 raw = __ldg(reinterpret_cast<const int4 *>(a.ent + (j < my_hi ? j : hi - 1)));
+                    if (j >= my_hi) { raw.x = 0; raw.y = 0; }      // G = 0: a padding entry adds nothing
+                    return raw;
+                };
+                int4 nxt = fetch(0);
+#pragma unroll 1
+                for (int b = 0; b < per; b += FT) {
+                    __syncwarp();
+                    ebuf[lane] = nxt;
+                    __syncwarp();
+                    if (b + FT < per) nxt = fetch(b + FT);
+                    const int nt = per - b < FT ? per - b : FT;
+#pragma unroll 2
+                    for (int t = 0; t < nt; ++t) {
+                        const int4 raw = ebuf[h * FT + t];
+                        const double G = __hiloint2double(raw.y, raw.x);
+                        const int is = (int)(short)(raw.z & 0xffff), isn = (int)(short)((raw.z >> 16) & 0xffff);
+                        const int ir = (int)(short)(raw.w & 0xffff);
+                        if (is != prev) { cs0 = csl[is * RS]; cs1 = csl[isn * RS]; prev = is; }
+                        const double2 cr = crl[ir * RS];
+                        const cplx d0 = cmul(cs0, cr), d1 = cmul(cs1, cr);
+                        a0.x = fma(G, d0.x, a0.x); a0.y = fma(G, d0.y, a0.y);
+                        a1.x = fma(G, d1.x, a1.x); a1.y = fma(G, d1.y, a1.y);
+                    }
+                }
+                // mirror variants v = 2b + c carry (-1)^{b m + c n}; pg = 2 (m & 1) + (n & 1)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const bool neg = ((((v >> 1) & (pg >> 1)) ^ ((v & 1) & (pg & 1))) & 1) != 0;
+                    if (neg) {
+                        V[0][sg][v].x -= a0.x; V[0][sg][v].y -= a0.y;
+                        V[1][sg][v].x -= a1.x; V[1][sg][v].y -= a1.y;
+                    } else {
+                        V[0][sg][v].x += a0.x; V[0][sg][v].y += a0.y;
+                        V[1][sg][v].x += a1.x; V[1][sg][v].y += a1.y;
+                    }
+                }
+            }
+        }
+        // sum the entry slices of the warp
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int sg = 0; sg < 2; ++sg)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+#pragma unroll
+                    for (int o = FT; o < 32; o <<= 1) {
+                        V[c][sg][v].x += __shfl_xor_sync(0xffffffffu, V[c][sg][v].x, o);
+                        V[c][sg][v].y += __shfl_xor_sync(0xffffffffu, V[c][sg][v].y, o);
+                    }
+                }
+        if (h == 0 && k < a.K) {
+            const long row_a = c_org_rowoff[l] + (am ? 2 * am - 1 : 0);
+            const double sm = (am & 1) ? -1.0 : 1.0;
+#pragma unroll
+            for (int cls = 0; cls < 2; ++cls)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const int b = v >> 1, c = v & 1;
+                    const int pz = c, py = b ^ c, px = cls ^ py;
+                    const int par = px * 4 + py * 2 + pz;
+                    // B = (i/k) acc;  a-row: B+ + (-1)^mu B-;  b-row: i (B+ - (-1)^mu B-)
+                    const cplx p_ = V[cls][0][v], m_ = V[cls][1][v];
+                    const double sx = p_.x + sm * m_.x, sy = p_.y + sm * m_.y;
+                    const double dx = p_.x - sm * m_.x, dy = p_.y - sm * m_.y;
+                    double *p = a.Bp + (((long)par * a.n_ftiles + ft) * a.R_tot + row_a) * 2 * ORG_BS + q;
+                    p[0] = -sy * ik;            // (i/k)(sx + i sy) = (-sy + i sx)/k
+                    p[ORG_BS] = sx * ik;
+                    if (am) {
+                        p += 2 * ORG_BS;        // i (i/k)(dx + i dy) = (-dx - i dy)/k
+                        p[0] = -dx * ik;
+                        p[ORG_BS] = -dy * ik;
+                    }
+                }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // image grouping by parity class (stable counting sort, one CTA) and per-image tables
 // ---------------------------------------------------------------------------------------
-struct OrgImage {   // 80 bytes
+struct OrgImage {   // 96 bytes
     double r, inv_r;
     double cx, cy, cz;
     unsigned char e[8];
     double2 atten_flat;
+    double2 rot;    // exp(-i dk r): one frequency step on a uniform wave-number grid
     long orig;      // index in the caller's image list (-1 = padding)
     int par, pad;
 };
@@ -328,6 +558,7 @@ struct OrgPrepArgs {
     RoomGeom room;
     double *Yp;                 // factorised path: real rows [tile][R_tot][ORG_OS] (pre-zeroed)
     int R_tot;
+    const int *flags;           // flags[1]: uniform k grid, *(double *)(flags + 2) = dk (or nullptr)
 };
 
 constexpr int ORG_PREP_Y = 8;
@@ -388,6 +619,7 @@ org_prep_kernel(OrgPrepArgs a, OrgImage *rec_out, cplx *Y) {
     rec.cx = rec.cy = rec.cz = 1.0;
     for (int i = 0; i < 8; ++i) rec.e[i] = 0;
     rec.atten_flat = cmake(1.0, 0.0);
+    rec.rot = cmake(1.0, 0.0);
     if (img < 0) {   // padding: contributes exactly zero
         rec.r = 1.0; rec.inv_r = 1.0; rec.atten_flat = cmake(0.0, 0.0);
         rec_out[pos] = rec;
@@ -404,6 +636,11 @@ org_prep_kernel(OrgPrepArgs a, OrgImage *rec_out, cplx *Y) {
         rec.r = (double)a.R_sI_r[img * 3 + 2];
     }
     rec.inv_r = 1.0 / rec.r;
+    if (a.flags) {
+        double sn, cs;
+        sincos_cw(*reinterpret_cast<const double *>(a.flags + 2) * rec.r, &sn, &cs);
+        rec.rot = cmake(cs, -sn);
+    }
     if (a.A) {
         const int32_t *A6 = a.A + img * 6;
         rec.par = ((A6[3] & 1) << 2) | ((A6[4] & 1) << 1) | (A6[5] & 1);
@@ -434,16 +671,23 @@ org_prep_kernel(OrgPrepArgs a, OrgImage *rec_out, cplx *Y) {
 // ---------------------------------------------------------------------------------------
 // consume kernel (factorised form) on the FP64 tensor cores.
 //
-// Per (l): T_l[img,k] = sum_mu Y_l^mu(img) * B[par][l,mu][k], in the real-harmonic row basis a
-// real [32 img x rows(l)] by complex [rows(l) x 32 freq] product = two real DMMA m8n8k4 GEMMs;
-// then P[img,k] += h_l(k r_img) * T_l[img,k] with the h_l recurrence of every pair kept
-// in registers (pb:86-118, j and y carried as one complex number).  (l, mu) rows are streamed
-// in chunks of <= 12 through a two-stage TMA bulk-copy pipeline.
+// Per degree l: T_l[img,k] = sum_mu Y_l^mu(img) * B[par][l,mu][k], in the real-harmonic row basis a
+// real [64 img x rows(l)] by complex [rows(l) x 32 freq] product = two real DMMA m8n8k4 GEMMs;
+// then P[k] += (atten h_l)(k r_img) * T_l[img,k] with the h_l recurrence of every pair kept in
+// registers (pb:86-118, j and y carried as one complex number) and the attenuation of the pair
+// folded into the recurrence's two start values (it is linear).  (l, mu) rows are streamed in
+// chunks of whole degrees through a ring of TMA bulk copies.
+//
+// CTA = 64 images x 32 frequencies, 4 x 4 warps of 16 x 8 (a thread owns four (image, frequency)
+// pairs: its recurrence state is 20 doubles), one CTA per SM.  Against the 32 x 32 tile of round 1
+// every B row is shared by four image groups and every Y row by four frequency groups: 35 % less
+// L2 -> SM operand traffic per DMMA and half as many stage hand-overs.
 // ---------------------------------------------------------------------------------------
 struct OrgConsumeArgs {
     long K, n_ftiles;
     int Lmax, R_tot, ncpt;    // chunks per tile
     int rc;                   // rows a stage holds
+    int nst;                  // ring stages
     const double *Bp;         // [8][n_ftiles][R_tot][2][ORG_BS]
     const double *Yp;         // [tiles][R_tot][ORG_OS]
     const OrgImage *rec;      // [n_pad]
@@ -457,29 +701,33 @@ struct OrgConsumeArgs {
     cplx *partial;            // [n_chunks][K]
 };
 
-// fixed part of the shared memory; the two operand stages (rc rows of B then rc rows of Y each)
-// follow it
+// fixed part of the shared memory; the operand stages (rc rows of B then rc rows of Y each) follow
+// it.  The final reduction over the row groups that share a frequency aliases the stages.
 struct OrgSmem {
-    double2 red[16][ORG_TF];           // final reduction over the row groups that share a frequency
     OrgImage rec[2][ORG_TI];           // per-image records of the current / next tile (TMA)
     double2 Z[6][ORG_TF];
-    double kf[ORG_TF], invk[ORG_TF];
-    unsigned long long full[2], recfull[2];
-    int done[2], recdone[2];
+    double kf[ORG_TF], invk[ORG_TF], dkd[ORG_TF];      // dkd: deviation of one step from the uniform grid
+    unsigned long long full[ORG_MAXST], recfull[2];
+    int done[ORG_MAXST], recdone[2];
 };
 static_assert(sizeof(OrgSmem) % 16 == 0, "stages must stay 16-byte aligned");
 static_assert(sizeof(OrgImage) % 16 == 0, "records are moved by bulk copies");
 
-// Degrees are whole inside a chunk.  Per degree l the first k-step shares a basic block with the
-// accumulation of degree l-1 (P_pair += h_{l-1} T_{l-1}, reads T before the DMMAs overwrite it) and
-// with the h_l recurrence (independent of T), so that scalar FP64 work issues in the shadow of the
-// DMMAs; the remaining k-steps run in a loop that keeps the next fragments in flight.  Operand
-// chunks and the per-image records arrive by TMA; the last warp out of a buffer refills it; the
-// attenuation of a pair is applied by the thread that owns the pair: no CTA-wide barrier in the
-// tile loop.
-__global__ void __launch_bounds__(ORG_THREADS, 2)
+// D = A*B (accumulator input zero: the first k-step of a degree needs no cleared registers)
+__device__ __forceinline__ void dmma884_z(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%4};\n"
+                 : "=d"(d0), "=d"(d1)
+                 : "d"(a), "d"(b), "d"(0.0));
+}
+
+// Degrees are whole inside a chunk.  The accumulators and the recurrence registers ping-pong with
+// the parity of l (T[l&1], H[l&1] = atten*h_l), so a degree's first k-step starts a fresh
+// accumulator (D = A*B) while the scalar work of the degree before it — P += H_{l-1} T_{l-1} and
+// the recurrence step to H_l, both independent of the running DMMAs — issues in their shadow, and
+// no register is ever cleared or rotated.  Operand chunks and the per-image records arrive by TMA;
+// the last warp out of a buffer refills it: no CTA-wide barrier in the tile loop.
+__global__ void __launch_bounds__(ORG_THREADS, ORG_CTAS_PER_SM)
 org_consume_kernel(OrgConsumeArgs a) {
-    constexpr int NT = ORG_NT;
     constexpr int NWARPS = ORG_THREADS / 32;
     extern __shared__ __align__(128) unsigned char org_smem_raw[];
     OrgSmem &sm = *reinterpret_cast<OrgSmem *>(org_smem_raw);
@@ -488,32 +736,38 @@ org_consume_kernel(OrgConsumeArgs a) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;
-    const int wm = warp / ORG_WN, wn = warp % ORG_WN;   // warp tile: 16 images x 8*NT frequencies
+    const int wm = warp / ORG_WN, wn = warp % ORG_WN;   // warp tile: 16 images x 8 frequencies
     const long f0 = (long)blockIdx.x * ORG_TF;
     const long n_tiles_all = a.meta[8] / ORG_TI;
     long tile_lo = (long)blockIdx.y * a.tiles_per_chunk;
     long tile_hi = tile_lo + a.tiles_per_chunk;
     if (tile_hi > n_tiles_all) tile_hi = n_tiles_all;
     const int n_tiles = tile_hi > tile_lo ? (int)(tile_hi - tile_lo) : 0;
-    const int ncpt = a.ncpt;
+    const int ncpt = a.ncpt, nst = a.nst;
     const int total = n_tiles * ncpt;
 
     const bool fused = a.mode == DEISM_ATTEN_FUSED_ROOM || a.mode == DEISM_ATTEN_FUSED_ANGLES;
     const bool flat = fused && a.flags[0] != 0;
 
     if (tid == 0) {
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&sm.full[b], 1);
-            mbar_init(&sm.recfull[b], 1);
-            sm.done[b] = 0; sm.recdone[b] = 0;
-        }
+#ifdef ORG_LDGSTS
+        for (int b = 0; b < nst; ++b) { mbar_init(&sm.full[b], 32); sm.done[b] = 0; }
+#else
+        for (int b = 0; b < nst; ++b) { mbar_init(&sm.full[b], 1); sm.done[b] = 0; }
+#endif
+        for (int b = 0; b < 2; ++b) { mbar_init(&sm.recfull[b], 1); sm.recdone[b] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int q = tid; q < ORG_TF; q += ORG_THREADS) {
-        long f = f0 + q;
-        double kk = f < a.K ? a.k[f] : 1.0;
-        sm.kf[q] = kk;
-        sm.invk[q] = 1.0 / kk;
+    const bool uniform_k = a.flags[1] != 0;
+    {
+        const double dk = *reinterpret_cast<const double *>(a.flags + 2);
+        for (int q = tid; q < ORG_TF; q += ORG_THREADS) {
+            long f = f0 + q;
+            double kk = f < a.K ? a.k[f] : 1.0;
+            sm.kf[q] = kk;
+            sm.invk[q] = 1.0 / kk;
+            sm.dkd[q] = f + 1 < a.K ? (a.k[f + 1] - kk) - dk : 0.0;
+        }
     }
     if (fused && !flat) {
         for (int i = tid; i < 6 * ORG_TF; i += ORG_THREADS) {
@@ -536,17 +790,42 @@ org_consume_kernel(OrgConsumeArgs a) {
         const unsigned bb = (unsigned)(ch.y * 2 * ORG_BS * 8), yb = (unsigned)(ch.y * ORG_OS * 8);
         unsigned char *S = stages + (unsigned)stage * stage_bytes;
         mbar_expect_tx(&sm.full[stage], bb + yb);
+#ifndef ORG_TMA_SPLIT
         bulk_g2s(S, Bg, bb, &sm.full[stage]);
         bulk_g2s(S + (unsigned)a.rc * 2 * ORG_BS * 8, Yg, yb, &sm.full[stage]);
+#else
+        // several copies of whole rows in flight per stage instead of two large ones
+        for (int r0 = 0; r0 < ch.y; r0 += ORG_TMA_SPLIT) {
+            const int nr = ch.y - r0 < ORG_TMA_SPLIT ? ch.y - r0 : ORG_TMA_SPLIT;
+            bulk_g2s(S + (unsigned)r0 * 2 * ORG_BS * 8, Bg + (long)r0 * 2 * ORG_BS, (unsigned)(nr * 2 * ORG_BS * 8),
+                     &sm.full[stage]);
+            bulk_g2s(S + (unsigned)a.rc * 2 * ORG_BS * 8 + (unsigned)r0 * ORG_OS * 8, Yg + (long)r0 * ORG_OS,
+                     (unsigned)(nr * ORG_OS * 8), &sm.full[stage]);
+        }
+#endif
     };
-
-    double T[2][2][NT][2];      // [Re|Im][m-tile][n-tile][2]
-    cplx hm[2][NT][2], hc[2][NT][2], Pp[2][NT][2];   // per pair [mt][nt][e]: h_{l-1}, h_l, sum_l h_l T_l
-    double xinv[2][NT][2];      // 1 / (k r) of the pair
-    cplx P[NT][2];              // [nt][e], summed over this thread's images
+#ifdef ORG_LDGSTS
+    // The same refill done by a whole warp with 16-byte cp.async (LDGSTS): the bulk-copy engine takes
+    // one stage at a time (>= ~550 clk per stage however small, scripts/probes/tma_probe.cu), plain
+    // asynchronous copies spread over the L2 slices and pipeline freely.
+    auto issue_warp = [&](int tile_ord, int local, int stage) {
+        const long tile = tile_ord + tile_lo;
+        const int4 ch = c_org_chunks[local];
+        const long p0 = tile * ORG_TI;
+        int par = 0;
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) { P[nt][0] = cmake(0.0, 0.0); P[nt][1] = cmake(0.0, 0.0); }
-
+        for (int q = 1; q < 8; ++q) par += (p0 >= a.meta[q]);
+        const unsigned char *Bg = reinterpret_cast<const unsigned char *>(
+            a.Bp + (((long)par * a.n_ftiles + blockIdx.x) * a.R_tot + ch.x) * 2 * ORG_BS);
+        const unsigned char *Yg = reinterpret_cast<const unsigned char *>(a.Yp + (tile * a.R_tot + ch.x) * ORG_OS);
+        const unsigned bb = (unsigned)(ch.y * 2 * ORG_BS * 8), yb = (unsigned)(ch.y * ORG_OS * 8);
+        unsigned char *S = stages + (unsigned)stage * stage_bytes;
+        unsigned char *SY = S + (unsigned)a.rc * 2 * ORG_BS * 8;
+        for (unsigned off = lane * 16; off < bb; off += 512) cp_async16(S + off, Bg + off);
+        for (unsigned off = lane * 16; off < yb; off += 512) cp_async16(SY + off, Yg + off);
+        cp_async_mbar_arrive(&sm.full[stage]);
+    };
+#endif
     auto issue_records = [&](int tile_ord) {
         const int rb = tile_ord & 1;
         mbar_expect_tx(&sm.recfull[rb], (unsigned)(ORG_TI * sizeof(OrgImage)));
@@ -556,25 +835,117 @@ org_consume_kernel(OrgConsumeArgs a) {
     if (tid == 0 && total > 0) {
         issue_records(0);
         if (n_tiles > 1) issue_records(1);
-        issue(0, 0, 0);
-        if (total > 1) issue(ncpt > 1 ? 0 : 1, ncpt > 1 ? 1 : 0, 1);
+#ifndef ORG_LDGSTS
+        int l0 = 0, t0 = 0;
+        for (int s = 0; s < nst && s < total; ++s) {
+            issue(t0, l0, s);
+            if (++l0 == ncpt) { l0 = 0; ++t0; }
+        }
+#endif
     }
-    // (pt, pl): the chunk two ahead of the current one
-    int pt = 2 / ncpt, pl = 2 % ncpt;
-    int c = 0;
+#ifdef ORG_LDGSTS
+    if (warp == 0 && total > 0) {
+        int l0 = 0, t0 = 0;
+        for (int s = 0; s < nst && s < total; ++s) {
+            issue_warp(t0, l0, s);
+            if (++l0 == ncpt) { l0 = 0; ++t0; }
+        }
+    }
+#endif
+    // (pt, pl): the chunk nst ahead of the current one
+    int pt = nst / ncpt, pl = nst % ncpt;
+    int c = 0, stage = 0;
+    unsigned phase = 0;
 
-    // P_pair += h * T, T = 0: closes the degree whose h the recurrence reached last
-    auto accumulate = [&]() {
+    // [parity of l][Re|Im][m-tile][e]: accumulators; H[parity][m-tile][e] = atten * h_l of the pair
+    double T[2][2][2][2];
+    cplx H[2][2][2];
+    double xinv[2][2];          // 1 / (k r) of the pair
+    cplx P[2] = {cmake(0.0, 0.0), cmake(0.0, 0.0)};      // [e], summed over this thread's images
+
+    // one degree l of parity PAR = l & 1 (compile-time roles of the two register sets)
+    auto degree = [&](auto par_tag, const int l, const double *Bs, const double *Ys, const int row0) {
+        constexpr int PAR = decltype(par_tag)::value;
+        const int row = c_org_rowoff[l] - row0;
+        const int ksn = (c_org_rowoff[l + 1] - c_org_rowoff[l]) >> 2;    // k-steps of degree l
+        const double *Yw = Ys + (row + t4) * ORG_OS + wm * 16 + g;
+        const double *Bw = Bs + (row + t4) * 2 * ORG_BS + wn * 8 + g;
+        auto load_frag = [&](int ks, double (&af)[2], double (&bf)[2]) {
+#ifndef ORG_KO_LDS
+            af[0] = Yw[ks * 4 * ORG_OS];
+            af[1] = Yw[ks * 4 * ORG_OS + 8];
+            bf[0] = Bw[ks * 8 * ORG_BS];
+            bf[1] = Bw[ks * 8 * ORG_BS + ORG_BS];
+#else
+            af[0] = (double)ks; af[1] = xinv[0][0]; bf[0] = xinv[1][1]; bf[1] = (double)l;
+#endif
+        };
+        auto mma_frag = [&](const double (&af)[2], const double (&bf)[2]) {
+#ifndef ORG_KO_MMA
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+            for (int p = 0; p < 2; ++p)
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
+                for (int mt = 0; mt < 2; ++mt)
+                    dmma884(T[PAR][p][mt][0], T[PAR][p][mt][1], af[mt], bf[p]);
+#else
+            T[PAR][0][0][0] += af[0] * bf[0]; T[PAR][1][1][1] += af[1] * bf[1];
+#endif
+        };
+        double af[2], bf[2];
+        load_frag(0, af, bf);
+#ifndef ORG_KO_MMA
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+                dmma884_z(T[PAR][p][mt][0], T[PAR][p][mt][1], af[mt], bf[p]);
+#else
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) { T[PAR][p][mt][0] = af[mt]; T[PAR][p][mt][1] = bf[p]; }
+#endif
+        // degree l-1: P += H_{l-1} T_{l-1}; then H_l = (2l-1)/(kr) H_{l-1} - H_{l-2} overwrites H_{l-2}
+#ifdef ORG_KO_SCALAR
+        if (l == 12345) P[0].x += T[PAR ^ 1][0][0][0] + T[PAR ^ 1][1][1][1] + T[PAR ^ 1][0][1][0] + T[PAR ^ 1][1][0][1] + T[PAR ^ 1][0][0][1] + T[PAR ^ 1][1][1][0] + T[PAR ^ 1][0][1][1] + T[PAR ^ 1][1][0][0];
+        else
+#endif
+        {
+            const double cl = (double)(2 * l - 1);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    cfma(Pp[mt][nt][e], hc[mt][nt][e], cmake(T[0][mt][nt][e], T[1][mt][nt][e]));
-                    T[0][mt][nt][e] = 0.0; T[1][mt][nt][e] = 0.0;
+                    const cplx hp = H[PAR ^ 1][mt][e];
+                    cfma(P[e], hp, cmake(T[PAR ^ 1][0][mt][e], T[PAR ^ 1][1][mt][e]));
+                    const double cf = cl * xinv[mt][e];
+                    H[PAR][mt][e] = cmake(fma(cf, hp.x, -H[PAR][mt][e].x), fma(cf, hp.y, -H[PAR][mt][e].y));
                 }
+        }
+        // remaining k-steps, two per trip with ping-pong fragment registers: the loads of one step
+        // are in flight while the other multiplies
+        if (ksn > 1) {
+            double a2[2], b2[2];
+            load_frag(1, af, bf);
+            int ks = 2;
+#pragma unroll 1
+            for (; ks + 1 < ksn; ks += 2) {
+                load_frag(ks, a2, b2);
+                mma_frag(af, bf);
+                load_frag(ks + 1, af, bf);
+                mma_frag(a2, b2);
+            }
+            if (ks < ksn) {
+                load_frag(ks, a2, b2);
+                mma_frag(af, bf);
+                mma_frag(a2, b2);
+            } else {
+                mma_frag(af, bf);
+            }
+        }
     };
+    using Even = std::integral_constant<int, 0>;
+    using Odd = std::integral_constant<int, 1>;
 
 #pragma unroll 1
     for (int tt = 0; tt < n_tiles; ++tt) {
@@ -583,140 +954,56 @@ org_consume_kernel(OrgConsumeArgs a) {
         // Spherical Hankel recurrence of this thread's DMMA-mapped pairs (pb:86-118), h = (j, -y).
         // It is started two orders early, from h_{-2} and h_{-1} (j_{-1} = cos x / x, y_{-1} =
         // sin x / x, f_{l-2} = (2l-1)/x f_{l-1} - f_l), so that every degree, 0 and 1 included,
-        // takes the same branch-free step h_l = (2l-1)/x h_{l-1} - h_{l-2}.
+        // takes the same branch-free step h_l = (2l-1)/x h_{l-1} - h_{l-2}; both start values carry
+        // the pair's attenuation.
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
             const OrgImage &rec = sm.rec[rb][wm * 16 + mt * 8 + g];
             const double r = rec.r, ir = rec.inv_r;
+            double cs0 = 1.0, sn0 = 0.0;
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int fq = wn * 8 * NT + nt * 8 + 2 * t4 + e;
-                    double sn, cs;
-                    sincos_cw(sm.kf[fq] * r, &sn, &cs);
-                    const double i1 = sm.invk[fq] * ir;
-                    xinv[mt][nt][e] = i1;
-                    const double ci = cs * i1, si = sn * i1;
-                    hc[mt][nt][e] = cmake(ci, -si);                                   // h_{-1}
-                    hm[mt][nt][e] = cmake(fma(-ci, i1, -si), fma(si, i1, -ci));       // h_{-2}
-                    Pp[mt][nt][e] = cmake(0.0, 0.0);
-                    T[0][mt][nt][e] = 0.0; T[1][mt][nt][e] = 0.0;
-                }
-        }
-        // (T = 0 at the start of a tile: the first accumulate adds nothing)
-#pragma unroll 1
-        for (int local = 0; local < ncpt; ++local) {
-            const int stage = c & 1;
-            const int4 ch = c_org_chunks[local];
-            mbar_wait(&sm.full[stage], (unsigned)((c >> 1) & 1));
-            const double *Bs = reinterpret_cast<const double *>(stages + (unsigned)stage * stage_bytes);
-            const double *Ys = Bs + a.rc * 2 * ORG_BS;
-#pragma unroll 1
-            for (int l = ch.z; l < ch.w; ++l) {
-                const int row = c_org_rowoff[l] - ch.x;
-                const int ksn = (c_org_rowoff[l + 1] - c_org_rowoff[l]) >> 2;    // k-steps of degree l
-                const double *Yw = Ys + (row + t4) * ORG_OS + wm * 16 + g;
-                const double *Bw = Bs + (row + t4) * 2 * ORG_BS + wn * 8 * NT + g;
-                auto load_frag = [&](int ks, double (&af)[2], double (&bf)[2][NT]) {
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) af[mt] = Yw[ks * 4 * ORG_OS + mt * 8];
-#pragma unroll
-                    for (int p = 0; p < 2; ++p)
-#pragma unroll
-                        for (int nt = 0; nt < NT; ++nt) bf[p][nt] = Bw[(ks * 8 + p) * ORG_BS + nt * 8];
-                };
-                auto mma_frag = [&](const double (&af)[2], const double (&bf)[2][NT]) {
-#pragma unroll
-                    for (int p = 0; p < 2; ++p)
-#pragma unroll
-                        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                            for (int nt = 0; nt < NT; ++nt)
-                                dmma884(T[p][mt][nt][0], T[p][mt][nt][1], af[mt], bf[p][nt]);
-                };
-                double af[2], bf[2][NT];
-                accumulate();
-                load_frag(0, af, bf);
-                mma_frag(af, bf);
-                {   // advance the recurrence to degree l: h_l = (2l-1)/(kr) h_{l-1} - h_{l-2}
-                    const double cl = (double)(2 * l - 1);
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                const double cf = cl * xinv[mt][nt][e];
-                                const cplx hn = cmake(fma(cf, hc[mt][nt][e].x, -hm[mt][nt][e].x),
-                                                      fma(cf, hc[mt][nt][e].y, -hm[mt][nt][e].y));
-                                hm[mt][nt][e] = hc[mt][nt][e];
-                                hc[mt][nt][e] = hn;
-                            }
-                }
-                // remaining k-steps, two per trip with ping-pong fragment registers: the loads of one
-                // step are in flight while the other multiplies
-                if (ksn > 1) {
-                    double a2[2], b2[2][NT];
-                    load_frag(1, af, bf);
-                    int ks = 2;
-#pragma unroll 1
-                    for (; ks + 1 < ksn; ks += 2) {
-                        load_frag(ks, a2, b2);
-                        mma_frag(af, bf);
-                        load_frag(ks + 1, af, bf);
-                        mma_frag(a2, b2);
-                    }
-                    if (ks < ksn) {
-                        load_frag(ks, a2, b2);
-                        mma_frag(af, bf);
-                        mma_frag(a2, b2);
-                    } else {
-                        mma_frag(af, bf);
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0 && atomicAdd(&sm.done[stage], 1) == NWARPS - 1) {
-                // last warp out of this stage: refill it with the chunk two ahead
-                sm.done[stage] = 0;
-                if (c + 2 < total) issue(pt, pl, stage);
-            }
-            ++c;
-            if (++pl == ncpt) { pl = 0; ++pt; }
-        }
-        accumulate();
-        // ---- P += atten * P_pair, the attenuation taken by the thread that owns the pair ----
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            const OrgImage &rec = sm.rec[rb][wm * 16 + mt * 8 + g];
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int fq = wn * 8 * NT + nt * 8 + 2 * t4 + e;
-                    cplx att;
-                    if (rec.orig < 0) {
-                        att = cmake(0.0, 0.0);
-                    } else if (flat) {
-                        att = rec.atten_flat;
-                    } else if (fused) {
-                        att = shoebox_atten_term(&sm.Z[0][fq], ORG_TF, rec.cx, rec.cy, rec.cz, rec.e);
-                        if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
-                    } else {
-                        const long f = f0 + fq;
-                        att = cmake(0.0, 0.0);
-                        if (f < a.K) {
-                            if (a.mode == DEISM_ATTEN_C64) {
-                                float2 v = ((const float2 *)a.atten)[rec.orig * a.K + f];
-                                att = cmake((double)v.x, (double)v.y);
-                            } else {
-                                att = ((const cplx *)a.atten)[rec.orig * a.K + f];
-                            }
+            for (int e = 0; e < 2; ++e) {
+                const int fq = wn * 8 + 2 * t4 + e;
+                cplx att;
+                if (rec.orig < 0) {
+                    att = cmake(0.0, 0.0);
+                } else if (flat) {
+                    att = rec.atten_flat;
+                } else if (fused) {
+                    att = shoebox_atten_term(&sm.Z[0][fq], ORG_TF, rec.cx, rec.cy, rec.cz, rec.e);
+                    if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
+                } else {
+                    const long f = f0 + fq;
+                    att = cmake(0.0, 0.0);
+                    if (f < a.K) {
+                        if (a.mode == DEISM_ATTEN_C64) {
+                            float2 v = ((const float2 *)a.atten)[rec.orig * a.K + f];
+                            att = cmake((double)v.x, (double)v.y);
+                        } else {
+                            att = ((const cplx *)a.atten)[rec.orig * a.K + f];
                         }
                     }
-                    cfma(P[nt][e], att, Pp[mt][nt][e]);
                 }
+                // exp(-i k r) = (cs, -sn): on a uniform grid the odd frequency of the thread's pair is
+                // one rotation by exp(-i dk r) (and the first-order term of the grid's own rounding)
+                // away from the even one (Q8, as in lc.cu)
+                double sn, cs;
+                if (e == 0 || !uniform_k) {
+                    sincos_cw(sm.kf[fq] * r, &sn, &cs);
+                } else {
+                    const double dr = sm.dkd[fq - 1] * r;
+                    const cplx F = cmul(cmake(cs0, -sn0), rec.rot);
+                    cs = fma(F.y, dr, F.x);
+                    sn = -fma(-F.x, dr, F.y);
+                }
+                cs0 = cs; sn0 = sn;
+                const double i1 = sm.invk[fq] * ir;
+                xinv[mt][e] = i1;
+                const double ci = cs * i1, si = sn * i1;
+                H[1][mt][e] = cmul(att, cmake(ci, -si));                                   // h_{-1}
+                H[0][mt][e] = cmul(att, cmake(fma(-ci, i1, -si), fma(si, i1, -ci)));       // h_{-2}
+                T[1][0][mt][e] = 0.0; T[1][1][mt][e] = 0.0;     // degree 0 adds H_{-1} * 0
+            }
         }
         __syncwarp();
         if (lane == 0 && atomicAdd(&sm.recdone[rb], 1) == NWARPS - 1) {
@@ -724,18 +1011,68 @@ org_consume_kernel(OrgConsumeArgs a) {
             sm.recdone[rb] = 0;
             if (tt + 2 < n_tiles) issue_records(tt + 2);
         }
+#pragma unroll 1
+        for (int local = 0; local < ncpt; ++local) {
+            const int4 ch = c_org_chunks[local];
+            mbar_wait(&sm.full[stage], phase);
+            const double *Bs = reinterpret_cast<const double *>(stages + (unsigned)stage * stage_bytes);
+            const double *Ys = Bs + a.rc * 2 * ORG_BS;
+            int l = ch.z;
+            if (l & 1) { degree(Odd{}, l, Bs, Ys, ch.x); ++l; }
+#pragma unroll 1
+            for (; l + 1 < ch.w; l += 2) {
+                degree(Even{}, l, Bs, Ys, ch.x);
+                degree(Odd{}, l + 1, Bs, Ys, ch.x);
+            }
+            if (l < ch.w) degree(Even{}, l, Bs, Ys, ch.x);
+            __syncwarp();
+#ifdef ORG_LDGSTS
+            {
+                int last = 0;
+                if (lane == 0) {
+                    last = atomicAdd(&sm.done[stage], 1) == NWARPS - 1;
+                    if (last) sm.done[stage] = 0;
+                }
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if (last && c + nst < total) issue_warp(pt, pl, stage);
+            }
+#else
+            if (lane == 0 && atomicAdd(&sm.done[stage], 1) == NWARPS - 1) {
+                // last warp out of this stage: refill it with the chunk nst ahead
+                sm.done[stage] = 0;
+                if (c + nst < total) issue(pt, pl, stage);
+            }
+#endif
+            ++c;
+            if (++stage == nst) { stage = 0; phase ^= 1u; }
+            if (++pl == ncpt) { pl = 0; ++pt; }
+        }
+        // the last degree of the tile
+        if ((a.Lmax - 1) & 1) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    cfma(P[e], H[1][mt][e], cmake(T[1][0][mt][e], T[1][1][mt][e]));
+        } else {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    cfma(P[e], H[0][mt][e], cmake(T[0][0][mt][e], T[0][1][mt][e]));
+        }
     }
 
-    double2 (*red)[ORG_TF] = sm.red;
+    // ---- reduce over the 8 row groups x ORG_WM image warps that share a frequency (aliases the stages) ----
+    __syncthreads();
+    double2 (*red)[ORG_TF] = reinterpret_cast<double2 (*)[ORG_TF]>(stages);
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) red[wm * 8 + g][wn * 8 * NT + nt * 8 + 2 * t4 + e] = P[nt][e];
+    for (int e = 0; e < 2; ++e) red[wm * 8 + g][wn * 8 + 2 * t4 + e] = P[e];
     __syncthreads();
     if (tid < ORG_TF) {
         cplx s = cmake(0.0, 0.0);
-#pragma unroll
-        for (int y = 0; y < 16; ++y) s = cadd(s, red[y][tid]);
+#pragma unroll 8
+        for (int y = 0; y < 8 * ORG_WM; ++y) s = cadd(s, red[y][tid]);
         long f = f0 + tid;
         if (f < a.K) a.partial[(long)blockIdx.y * a.K + f] = s;
     }
@@ -851,6 +1188,10 @@ struct deism_org_plan {
     void *d_block;
     const deism::OrgEntry *d_ent[2];
     const int *d_seg[2];
+    const deism::BtEntry *d_bt;     // B-table form (class-0 entries by segment and parity group)
+    const int *d_bt_seg;
+    const int2 *d_jobs;
+    int n_jobs;
     long nnz;
 };
 
@@ -902,28 +1243,40 @@ static int plan_build(int N, int V, const float *h_W1, const float *h_W2, deism_
     const int Lmax = N + V + 1, nseg = Lmax * Lmax;
     OrgLists L;
     build_lists(N, V, h_W1, h_W2, L);
-    size_t ent_bytes = (L.entries[0].size() + L.entries[1].size()) * sizeof(OrgEntry);
-    size_t seg_bytes = 2 * (size_t)(nseg + 1) * sizeof(int);
+    auto up16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    const size_t e0_b = up16(L.entries[0].size() * sizeof(OrgEntry)), e1_b = up16(L.entries[1].size() * sizeof(OrgEntry));
+    const size_t bt_b = up16(L.bt.size() * sizeof(BtEntry));
+    const size_t seg_b = up16((size_t)(nseg + 1) * sizeof(int)), bts_b = up16(L.bt_seg.size() * sizeof(int));
+    const size_t job_b = up16(L.jobs.size() * sizeof(int2));
     unsigned char *base = nullptr;
-    if (cudaMalloc(&base, ent_bytes + seg_bytes + 64) != cudaSuccess) {
+    if (cudaMalloc(&base, e0_b + e1_b + bt_b + 2 * seg_b + bts_b + job_b + 64) != cudaSuccess) {
         cudaGetLastError();
         return set_error(DEISM_ERR_NOMEM, "cudaMalloc of the coupling plan failed");
     }
-    OrgEntry *e0 = (OrgEntry *)base, *e1 = e0 + L.entries[0].size();
-    int *s0 = (int *)(base + ent_bytes), *s1 = s0 + nseg + 1;
-    cudaError_t e = cudaSuccess;
-    if (!L.entries[0].empty())
-        e = cudaMemcpy(e0, L.entries[0].data(), L.entries[0].size() * sizeof(OrgEntry), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && !L.entries[1].empty())
-        e = cudaMemcpy(e1, L.entries[1].data(), L.entries[1].size() * sizeof(OrgEntry), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(s0, L.seg[0].data(), (nseg + 1) * sizeof(int), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(s1, L.seg[1].data(), (nseg + 1) * sizeof(int), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
+    unsigned char *cur = base;
+    auto put = [&](const void *src, size_t bytes, size_t padded) -> void * {
+        void *dst = cur;
+        cur += padded;
+        if (bytes && cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+        return dst;
+    };
+    void *e0 = put(L.entries[0].data(), L.entries[0].size() * sizeof(OrgEntry), e0_b);
+    void *e1 = put(L.entries[1].data(), L.entries[1].size() * sizeof(OrgEntry), e1_b);
+    void *bt = put(L.bt.data(), L.bt.size() * sizeof(BtEntry), bt_b);
+    void *s0 = put(L.seg[0].data(), (nseg + 1) * sizeof(int), seg_b);
+    void *s1 = put(L.seg[1].data(), (nseg + 1) * sizeof(int), seg_b);
+    void *bs = put(L.bt_seg.data(), L.bt_seg.size() * sizeof(int), bts_b);
+    void *jb = put(L.jobs.data(), L.jobs.size() * sizeof(int2), job_b);
+    if (!e0 || !e1 || !bt || !s0 || !s1 || !bs || !jb) {
+        cudaError_t e = cudaGetLastError();
         cudaFree(base);
         return set_error(DEISM_ERR_CUDA, "coupling plan upload failed: %s", cudaGetErrorString(e));
     }
     P->N = N; P->V = V; P->nseg = nseg; P->d_block = base; P->nnz = L.nnz;
-    P->d_ent[0] = e0; P->d_ent[1] = e1; P->d_seg[0] = s0; P->d_seg[1] = s1;
+    P->d_ent[0] = (const OrgEntry *)e0; P->d_ent[1] = (const OrgEntry *)e1;
+    P->d_seg[0] = (const int *)s0; P->d_seg[1] = (const int *)s1;
+    P->d_bt = (const BtEntry *)bt; P->d_bt_seg = (const int *)bs; P->d_jobs = (const int2 *)jb;
+    P->n_jobs = (int)L.jobs.size();
     cudaGetDevice(&P->device);
     return DEISM_OK;
 }
@@ -1013,6 +1366,8 @@ static int org_shoebox_impl(int64_t n_images, int64_t K, int N, int V, const voi
     if (!flags) return DEISM_ERR_NOMEM;
     rc = launch_z_flat(atten, K, flags, st);
     if (rc) return rc;
+    rc = launch_k_uniform(d_k, K, flags, st);
+    if (rc) return rc;
 
     if (algo == 2 && coef_c128)
         return set_error(DEISM_ERR_INVALID, "the direct ORG sum (algo 2) takes complex64 coefficients");
@@ -1027,7 +1382,7 @@ static int org_shoebox_impl(int64_t n_images, int64_t K, int N, int V, const voi
         pa.n_images = n_images; pa.n_pad_cap = n_images; pa.Lmax = Lmax; pa.perm = nullptr;
         pa.meta = nullptr; pa.R_sI_r = d_R_sI_r; pa.component_major = 0; pa.mode = atten->mode;
         pa.angdep = atten->ang_dep_flag; pa.A = d_A; pa.Z = (const cplx *)atten->d_Z_S; pa.K = K;
-        pa.Yp = nullptr; pa.R_tot = 0;
+        pa.Yp = nullptr; pa.R_tot = 0; pa.flags = nullptr;
         fill_room(pa.room, atten);
         org_prep_kernel<<<(unsigned)((n_images + 127) / 128), 128, 0, st>>>(pa, rec, Y);
         DEISM_LAUNCH_CHECK("org_prep_kernel");
@@ -1075,6 +1430,7 @@ static int org_shoebox_impl(int64_t n_images, int64_t K, int N, int V, const voi
         std::lock_guard<std::mutex> lk(geom_mu);
         if (dev != uploaded_dev || Lmax != uploaded_lmax) {
             uploaded_dev = -1;
+            bump_generation();
             DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_org_rowoff, rowoff, (Lmax + 1) * sizeof(int), 0,
                                                    cudaMemcpyHostToDevice, st));
             DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_org_chunks, chunks, ncpt * sizeof(int4), 0,
@@ -1086,12 +1442,26 @@ static int org_shoebox_impl(int64_t n_images, int64_t K, int N, int V, const voi
 
     const long n_ftiles = (K + ORG_TF - 1) / ORG_TF;
     const size_t b_rows = (size_t)R_tot * 2 * ORG_BS, y_rows = (size_t)R_tot * ORG_OS;
-    if ((long)(NMs > NMr ? NMs : NMr) * K >= 2147483647L)
-        return set_error(DEISM_ERR_INVALID, "too many frequencies for the B-table's 32-bit row offsets");
-    bt_elem *CsT = (bt_elem *)workspace(WS_ORG_SMALL, (size_t)(NMs + NMr) * K * sizeof(bt_elem));
     double *Bp = (double *)workspace(WS_ORG_B, (size_t)8 * n_ftiles * b_rows * sizeof(double));
-    if (!CsT || !Bp) return DEISM_ERR_NOMEM;
-    bt_elem *CrT = CsT + (size_t)NMs * K;
+    if (!Bp) return DEISM_ERR_NOMEM;
+    // B-table form: the widest frequency tile whose coefficient rows fit in shared memory
+    int bt_ft = 0;
+    size_t bt_smem = 0;
+    for (int ft = 16; ft >= 4 && !bt_ft; ft >>= 1) {
+        bt_smem = (size_t)(NMs + NMr) * (ft + 1) * sizeof(double2) + 16 + (size_t)BT2_THREADS * sizeof(int4);
+        if ((long)bt_smem <= (long)smem_optin_bytes()) bt_ft = ft;
+    }
+#ifdef ORG_BTABLE_V1
+    bt_ft = 0;
+#endif
+    bt_elem *CsT = nullptr, *CrT = nullptr;
+    if (!bt_ft) {
+        if ((long)(NMs > NMr ? NMs : NMr) * K >= 2147483647L)
+            return set_error(DEISM_ERR_INVALID, "too many frequencies for the B-table's 32-bit row offsets");
+        CsT = (bt_elem *)workspace(WS_ORG_SMALL, (size_t)(NMs + NMr) * K * sizeof(bt_elem));
+        if (!CsT) return DEISM_ERR_NOMEM;
+        CrT = CsT + (size_t)NMs * K;
+    }
     OrgSide *side = org_side();
     cudaStream_t bs = st;                 // stream of the image-independent half
     OrgJoin joiner;
@@ -1102,6 +1472,50 @@ static int org_shoebox_impl(int64_t n_images, int64_t K, int N, int V, const voi
         joiner.side = side; joiner.st = st;
     }
     DEISM_CUDA_TRY(cudaMemsetAsync(Bp, 0, (size_t)8 * n_ftiles * b_rows * sizeof(double), bs));
+    if (bt_ft) {
+        Btable2Args b2;
+        b2.K = K; b2.n_ftiles = n_ftiles; b2.R_tot = R_tot; b2.NMs = NMs; b2.NMr = NMr;
+        b2.n_jobs = guard.use->n_jobs; b2.ent = guard.use->d_bt; b2.seg = guard.use->d_bt_seg;
+        b2.jobs = guard.use->d_jobs; b2.Cs = d_C_nm_s; b2.Cr = d_C_vu_r; b2.k = d_k; b2.Bp = Bp;
+        // CTAs = frequency tiles x job shares; among 1..12 shares take the split that fills whole
+        // waves of one CTA per SM best (every share re-stages the coefficient tile: ~1 % each)
+        const long nx = (K + bt_ft - 1) / bt_ft, sms = sm_count();
+        int split = 1;
+        double best = 1e30;
+        for (int sp = 1; sp <= 12 && sp <= b2.n_jobs; ++sp) {
+            const long ctas = nx * sp;
+            const double cost = (double)((ctas + sms - 1) / sms) / (double)ctas * (1.0 + 0.01 * sp);
+            if (cost < best - 1e-12) { best = cost; split = sp; }
+        }
+        // a warp should see several jobs (largest first, pulled dynamically), or the longest job
+        // decides the CTA's time: no more shares than leave ~8 jobs per warp
+        {
+            const int max_split = b2.n_jobs / (8 * (BT2_THREADS / 32)) > 1 ? b2.n_jobs / (8 * (BT2_THREADS / 32)) : 1;
+            if (split > max_split) split = max_split;
+            if (const char *e = getenv("DEISM_BT_SPLIT")) { const int v = atoi(e); if (v > 0) split = v; }
+        }
+        b2.n_split = split;
+        dim3 grid((unsigned)nx, (unsigned)split);
+        prof_begin("org_btable", bs);
+#define DEISM_BT2_LAUNCH(FT, IN)                                                                       \
+        do {                                                                                           \
+            DEISM_CUDA_TRY(cudaFuncSetAttribute(org_btable2_kernel<FT, IN>,                             \
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_smem)); \
+            org_btable2_kernel<FT, IN><<<grid, BT2_THREADS, bt_smem, bs>>>(b2);                         \
+        } while (0)
+        if (coef_c128) {
+            if (bt_ft == 16) DEISM_BT2_LAUNCH(16, double2);
+            else if (bt_ft == 8) DEISM_BT2_LAUNCH(8, double2);
+            else DEISM_BT2_LAUNCH(4, double2);
+        } else {
+            if (bt_ft == 16) DEISM_BT2_LAUNCH(16, float2);
+            else if (bt_ft == 8) DEISM_BT2_LAUNCH(8, float2);
+            else DEISM_BT2_LAUNCH(4, float2);
+        }
+#undef DEISM_BT2_LAUNCH
+        prof_end("org_btable", bs);
+        DEISM_LAUNCH_CHECK("org_btable2_kernel");
+    } else {
     if (coef_c128) {
         transpose_coef_kernel<double2><<<(unsigned)(((long)K * NMs + 255) / 256), 256, 0, bs>>>(
             (const double2 *)d_C_nm_s, K, NMs, CsT);
@@ -1128,6 +1542,7 @@ static int org_shoebox_impl(int64_t n_images, int64_t K, int N, int V, const voi
         prof_end("org_btable", bs);
         DEISM_LAUNCH_CHECK("org_btable_kernel");
     }
+    }
     joiner.record();
 
     const long n_pad_cap = (n_images + ORG_TI - 1) / ORG_TI * ORG_TI + 8 * ORG_TI;
@@ -1144,28 +1559,54 @@ static int org_shoebox_impl(int64_t n_images, int64_t K, int N, int V, const voi
     pa.n_images = n_images; pa.n_pad_cap = n_pad_cap; pa.Lmax = Lmax; pa.perm = perm; pa.meta = meta;
     pa.R_sI_r = d_R_sI_r; pa.component_major = 0; pa.mode = atten->mode; pa.angdep = atten->ang_dep_flag;
     pa.A = d_A; pa.Z = (const cplx *)atten->d_Z_S; pa.K = K;
-    pa.Yp = Yp; pa.R_tot = R_tot;
+    pa.Yp = Yp; pa.R_tot = R_tot; pa.flags = flags;
     fill_room(pa.room, atten);
     org_prep_kernel<<<(unsigned)((n_pad_cap + 31) / 32), dim3(32, ORG_PREP_Y), 0, st>>>(pa, rec, nullptr);
     DEISM_LAUNCH_CHECK("org_prep_kernel");
 
-    long n_chunks = (long)sm_count() * 2 * 8 / n_ftiles;
-    if (n_chunks < 1) n_chunks = 1;
-    if (n_chunks > n_tiles_cap) n_chunks = n_tiles_cap;
-    if (n_chunks > 65535) n_chunks = 65535;
-    long tiles_per_chunk = (n_tiles_cap + n_chunks - 1) / n_chunks;
-    n_chunks = (n_tiles_cap + tiles_per_chunk - 1) / tiles_per_chunk;
+    // ring depth: as many stages as fit next to the fixed part (one CTA per SM)
+    const size_t stage_bytes = (size_t)rc_rows * (2 * ORG_BS + ORG_OS) * 8;
+    int nst = (int)(((size_t)smem_optin_bytes() / ORG_CTAS_PER_SM - (ORG_CTAS_PER_SM > 1 ? 1024 : 0) -
+                     sizeof(OrgSmem)) / stage_bytes);
+    if (nst > ORG_MAXST) nst = ORG_MAXST;
+    if (nst < 2)
+        return set_error(DEISM_ERR_INVALID, "ORG consume kernel: two stages of %zu B do not fit in shared memory",
+                         stage_bytes);
+    // Work split: CTA = (frequency tile, chunk of image tiles).  The tile count is known on the
+    // device only (class padding); its upper bound is close.  Among chunk sizes that keep >= 6
+    // tiles per CTA pick the one whose CTA count fills whole waves of one CTA per SM best.
+    const long n_tiles_est = (n_images + ORG_TI - 1) / ORG_TI + 4;
+    long tiles_per_chunk = 1;
+    {
+        const long sms = sm_count();
+        double best = -1.0;
+        for (long tpc = 6; tpc <= 24; ++tpc) {
+            const long chunks = (n_tiles_est + tpc - 1) / tpc;
+            const double waves = (double)(chunks * n_ftiles) / (double)sms;
+            const double whole = (double)(long)(waves + 0.999999);
+            // time ~ whole waves of tpc tiles; useful work ~ n_tiles_est * n_ftiles / sms tiles
+            const double eff = ((double)n_tiles_est * n_ftiles / sms) / (whole * tpc);
+            if (eff > best + 1e-9) { best = eff; tiles_per_chunk = tpc; }
+        }
+        if (n_tiles_est * n_ftiles <= 6 * sms) tiles_per_chunk = (n_tiles_est * n_ftiles + sms - 1) / sms;
+        if (tiles_per_chunk < 1) tiles_per_chunk = 1;
+    }
+    long n_chunks = (n_tiles_cap + tiles_per_chunk - 1) / tiles_per_chunk;
+    if (n_chunks > 65535) {
+        n_chunks = 65535;
+        tiles_per_chunk = (n_tiles_cap + n_chunks - 1) / n_chunks;
+        n_chunks = (n_tiles_cap + tiles_per_chunk - 1) / tiles_per_chunk;
+    }
     cplx *partial = (cplx *)workspace(WS_ORG_PARTIAL, (size_t)n_chunks * K * sizeof(cplx));
     if (!partial) return DEISM_ERR_NOMEM;
 
     OrgConsumeArgs ca;
     ca.K = K; ca.n_ftiles = n_ftiles; ca.Lmax = Lmax; ca.R_tot = R_tot; ca.ncpt = ncpt; ca.rc = rc_rows;
+    ca.nst = nst;
     ca.Bp = Bp; ca.Yp = Yp; ca.rec = rec; ca.meta = meta; ca.k = d_k; ca.mode = atten->mode;
     ca.atten = atten->d_atten; ca.Z = (const cplx *)atten->d_Z_S; ca.flags = flags;
     ca.tiles_per_chunk = tiles_per_chunk; ca.partial = partial;
-    const size_t consume_smem = sizeof(OrgSmem) + (size_t)2 * rc_rows * (2 * ORG_BS + ORG_OS) * 8;
-    if ((int)consume_smem > smem_optin_bytes())
-        return set_error(DEISM_ERR_INVALID, "ORG consume kernel needs %zu B of shared memory", consume_smem);
+    const size_t consume_smem = sizeof(OrgSmem) + (size_t)nst * stage_bytes;
     DEISM_CUDA_TRY(cudaFuncSetAttribute(org_consume_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)consume_smem));
     joiner.join();
@@ -1243,7 +1684,7 @@ extern "C" int deism_org_arg(int64_t n_images, int64_t K, int N, int V, const fl
     pa.n_images = n_images; pa.n_pad_cap = n_images; pa.Lmax = Lmax; pa.perm = nullptr; pa.meta = nullptr;
     pa.R_sI_r = d_R_sI_r; pa.component_major = 1; pa.mode = DEISM_ATTEN_C64; pa.angdep = 0;
     pa.A = nullptr; pa.Z = nullptr; pa.K = K;
-    pa.Yp = nullptr; pa.R_tot = 0;
+    pa.Yp = nullptr; pa.R_tot = 0; pa.flags = nullptr;
     for (int i = 0; i < 3; ++i) pa.room.LL[i] = pa.room.xs[i] = pa.room.xr[i] = 0.0;
     org_prep_kernel<<<(unsigned)((n_images + 127) / 128), 128, 0, st>>>(pa, rec, Y);
     DEISM_LAUNCH_CHECK("org_prep_kernel");

@@ -75,6 +75,16 @@ DEISM_API const char *deism_b200_source_hash(void);
 DEISM_API int deism_device_info(int device, int *sm_count, size_t *hbm_bytes, int *cc_major,
                                 int *cc_minor);
 DEISM_API int deism_release_workspace(void);     /* frees cached device scratch */
+/* CUDA-graph support.  After a first (warm-up) call with given shapes the shoebox entry points
+ * neither allocate nor synchronise, so a caller may capture them into a CUDA graph and replay it
+ * (deism_b200/backend.py does).  A captured graph bakes in the library's scratch pointers and the
+ * contents of its constant-memory tables; this counter changes whenever either changes: replay a
+ * graph only while it still has the value it had at capture. */
+DEISM_API uint64_t deism_state_generation(void);
+/* To be called right after launching a captured graph of entry-point calls on `stream`: adds the
+ * graph's kernel count to deism_kernel_launch_count() and lets the library order its next call
+ * behind the replayed work. */
+DEISM_API int deism_graph_replayed(int n_kernels, void *stream);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 DEISM_API uint64_t deism_kernel_launch_count(void);
 /* Per-kernel device timing for the roofline report: when enabled, the accumulation entry points
