@@ -93,21 +93,45 @@ def org_consume_flops_per_term(N, V):
 
 
 def clocks_sampler(stop, out, gpu_index):
-    """nvidia-smi clocks line of B200_PROFILING.md, sampled during the timed region."""
+    """The clocks line of B200_PROFILING.md (SM clock, max SM clock, power, throttle reasons), sampled
+    during the timed region.  NVML in-process (nvidia_ml_py): forking nvidia-smi ten times a second
+    out of a process with gigabytes of pinned and device mappings stalls the host threads that the
+    end-to-end legs are timing; nvidia-smi is the fallback."""
+    nv = None
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        nv = (pynvml, h)
+    except Exception:
+        nv = None
     q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
     while not stop.is_set():
         try:
-            r = subprocess.run(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={q}",
-                                "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                               timeout=5)
-            parts = [x.strip() for x in r.stdout.strip().split(",")]
-            if len(parts) >= 7:
-                out.append(parts)
+            if nv is not None:
+                m, h = nv
+                r = m.nvmlDeviceGetCurrentClocksEventReasons(h)
+                act = lambda bit: "Active" if r & bit else "Not Active"
+                out.append([str(m.nvmlDeviceGetClockInfo(h, m.NVML_CLOCK_SM)),
+                            str(m.nvmlDeviceGetMaxClockInfo(h, m.NVML_CLOCK_SM)),
+                            str(m.nvmlDeviceGetPowerUsage(h) / 1000.0),
+                            act(m.nvmlClocksEventReasonHwSlowdown), act(m.nvmlClocksEventReasonHwThermalSlowdown),
+                            act(m.nvmlClocksEventReasonSwThermalSlowdown), act(m.nvmlClocksEventReasonSwPowerCap)])
+            else:
+                r = subprocess.run(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={q}",
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                   timeout=5)
+                parts = [x.strip() for x in r.stdout.strip().split(",")]
+                if len(parts) >= 7:
+                    out.append(parts)
         except Exception:
             pass
-        stop.wait(0.1)
+        stop.wait(0.05 if nv is not None else 0.1)
 
 
 def summarise_clocks(samples):
@@ -286,6 +310,8 @@ def timed(c, fn, n):
         b.record()
     barrier(c)
     wall = (time.perf_counter() - w0) * 1e3
+    if os.environ.get("DEISM_BENCH_DEBUG") and c.rank == 0:
+        print("per-step ms:", [round(a.elapsed_time(b), 3) for a, b in evs], file=sys.stderr)
     return sum(a.elapsed_time(b) for a, b in evs), wall
 
 
@@ -449,6 +475,15 @@ def measure_shoebox(c, name, steps, warmup, general=False, sharding="frequency",
 
     for _ in range(2):
         step_e2e()
+    if os.environ.get("DEISM_BENCH_PROFILE") == name and rank == 0:      # debugging aid
+        import cProfile
+        import pstats
+
+        pr = cProfile.Profile()
+        pr.enable()
+        timed(c, step_e2e, steps)
+        pr.disable()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(25)
     e2e_ms, _ = timed(c, step_e2e, steps)
     e2e_ms = max_over_ranks(c, e2e_ms) / steps
     pg_ms = None

@@ -98,6 +98,10 @@ def _broadcast_base(a):
     return None
 
 
+class _NotCapturable(RuntimeError):
+    """Raised inside a CUDA-graph capture when the call turns out not to be replayable."""
+
+
 class _Staging:
     """Pinned staging buffers for pageable NumPy inputs.
 
@@ -171,12 +175,19 @@ def to_device(x, dtype, dev=None):
             a = np.ascontiguousarray(a)
         if not a.flags["WRITEABLE"]:
             a = a.copy()
-        t = _staging.upload(a, dev) if a.dtype != np.float16 else None
+        capturing = torch.cuda.is_current_stream_capturing()
+        t = None if capturing else _staging.upload(a, dev)
         if t is None:
             t = torch.from_numpy(a)
+            if capturing and not t.is_pinned():
+                # a captured copy must re-read the CALLER's buffer at every replay: pageable
+                # memory cannot be captured, and a staged copy would replay stale bytes
+                raise _NotCapturable("pageable host array inside a graph capture")
+    # host -> device in the source dtype, conversions on the device (no pageable temporaries)
+    t = t.to(dev, non_blocking=True)
     if t.dtype != dtype:
         t = t.to(dtype)
-    return t.to(dev, non_blocking=True).contiguous()
+    return t.contiguous()
 
 
 def _ptr(t):
@@ -257,9 +268,8 @@ class _AttenSpec:
             else:
                 raise KeyError(f"images has no 'atten_all{suffix}' and storage={storage!r}")
             A = to_device(images["A" + suffix][sl], torch.int32, dev)
-            Z = to_device(np.asarray(params["impedance"], dtype=np.complex128)
-                          if not isinstance(params["impedance"], torch.Tensor)
-                          else params["impedance"], torch.complex128, dev)
+            Z = params["impedance"]
+            Z = to_device(Z if isinstance(Z, (torch.Tensor, DeviceArray)) else np.asarray(Z), torch.complex128, dev)
             if Z.dim() != 2 or Z.shape[0] != 6:
                 raise ValueError("params['impedance'] must have shape [6, K]")
             s.d_A, s.d_Z_S = A.data_ptr(), Z.data_ptr()
@@ -440,6 +450,7 @@ USE_GRAPHS = _os.environ.get("DEISM_B200_GRAPHS", "1") != "0"
 _GRAPH_CACHE_MAX = 16
 _graphs = {}        # key -> {"graph", "out", "gen", "n_kernels", "keep"}
 _graph_seen = {}    # key -> generation at the last eager call with this key
+_graph_never = set()    # keys whose capture failed: always eager
 
 
 def _arr_key(x):
@@ -529,7 +540,7 @@ def run_DEISM_device(params, dev=None):
     if params["DEISM_method"] not in ("ORG", "LC", "MIX"):
         raise ValueError(f"Unknown DEISM method: {params['DEISM_method']}")
     key = _graph_key(params, dev) if _graphs_allowed() else None
-    if key is None:
+    if key is None or key in _graph_never:
         return _run_DEISM_eager(params, dev)
     gen = int(lib().deism_state_generation())
     hit = _graphs.get(key)
@@ -554,13 +565,15 @@ def run_DEISM_device(params, dev=None):
         with torch.cuda.graph(graph):
             out = _run_DEISM_eager(captured, dev)
     except Exception:
-        # anything that cannot be captured: fall back for good for this key
-        _graph_seen[key] = -1
+        # anything that cannot be captured: always eager for these buffers from now on
+        if len(_graph_never) > 256:
+            _graph_never.clear()
+        _graph_never.add(key)
         torch.cuda.synchronize(dev)
         return _run_DEISM_eager(params, dev)
     n_kernels = _lib.launch_count() - n0
     if int(lib().deism_state_generation()) != gen:      # the capture itself moved the state: not replayable
-        _graph_seen[key] = -1
+        _graph_never.add(key)
         return _run_DEISM_eager(params, dev)
     if len(_graphs) >= _GRAPH_CACHE_MAX:
         _graphs.pop(next(iter(_graphs)))
@@ -574,6 +587,7 @@ def clear_graphs():
     """Drop every captured graph (and the device memory their private pools hold)."""
     _graphs.clear()
     _graph_seen.clear()
+    _graph_never.clear()
 
 
 _copy_streams = {}
@@ -588,15 +602,20 @@ def _run_mix_from_host(params, images, out, dev):
     p["waveNumbers"] = to_device(params["waveNumbers"], torch.float64, dev)        # shared: once
     if params.get("impedance") is not None:
         Z = params["impedance"]
-        p["impedance"] = to_device(Z if isinstance(Z, torch.Tensor) else np.asarray(Z, dtype=np.complex128),
+        p["impedance"] = to_device(Z if isinstance(Z, (torch.Tensor, DeviceArray)) else np.asarray(Z),
                                    torch.complex128, dev)
     main = torch.cuda.current_stream(dev)
+    # fork point of the copy stream: BEFORE the LC work is queued, so that the ORG inputs travel
+    # underneath the LC kernels (under graph capture this is also what joins the side stream to the
+    # capture)
+    fork = torch.cuda.Event()
+    fork.record(main)
     _run_lc(p, images, "_late", out, False, dev)
     side = _copy_streams.get(dev.index)
     if side is None:
         side = _copy_streams[dev.index] = torch.cuda.Stream(dev)
     staged = []
-    side.wait_stream(main)          # fork (under graph capture the side stream must join the capture)
+    side.wait_event(fork)
     with torch.cuda.stream(side):
         for key in ("C_nm_s", "C_vu_r"):
             p[key] = _coef_on_device(params[key], dev)[0]

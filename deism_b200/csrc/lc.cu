@@ -1117,8 +1117,19 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
 
     // image tiles are cut into n_chunks CTAs per ftile: ~`waves` waves of CTAs over the SMs, picked
     // so that the last wave is as full as possible
-    static const int waves = getenv("DEISM_LC_WAVES") ? atoi(getenv("DEISM_LC_WAVES")) : 16;
+    // (a CTA's prologue — the resident coefficient planes, the first operand chunks — is ~4 us: a CTA
+    // should live for >= ~48 tiles, so a frequency slab of a multi-GPU run takes fewer, longer waves)
+    static const int waves_env = getenv("DEISM_LC_WAVES") ? atoi(getenv("DEISM_LC_WAVES")) : 0;
     const long slots = (long)sm_count() * ctas_per_sm;
+    int waves = 16;
+    if (waves_env > 0) {
+        waves = waves_env;
+    } else {
+        const long per_slot = n_ftiles * n_img_tiles / slots;
+        waves = (int)(per_slot / 48);
+        if (waves < 4) waves = 4;
+        if (waves > 16) waves = 16;
+    }
     long n_chunks = 1, tiles_per_chunk = n_img_tiles;
     {
         const long min_chunks = n_img_tiles * (ncs + ncr) / (1L << 30) + 1;  // chunk counter is an int

@@ -479,6 +479,7 @@ struct OrgImage {   // 96 bytes
 };
 
 // meta[0..8]   : first padded position of class c (multiple of ORG_TI); meta[8] = total padded
+// meta[9..16]  : number of real images of class c (they sit at the start of the class's positions)
 // perm[pos]    : original image index or -1
 __global__ void __launch_bounds__(SORT_THREADS)
 org_sort_kernel(const int32_t *__restrict__ A, long n_images, long *perm, long *meta, long perm_cap) {
@@ -510,6 +511,7 @@ org_sort_kernel(const int32_t *__restrict__ A, long n_images, long *perm, long *
             pos += (cnt[c] + ORG_TI - 1) / ORG_TI * ORG_TI;
         }
         meta[8] = pos;
+        for (int c = 0; c < 8; ++c) meta[9 + c] = cnt[c];      // real images of class c: positions meta[c] ..
     }
     __syncthreads();
     for (long i = tid; i < perm_cap; i += SORT_THREADS) perm[i] = -1;
@@ -1079,6 +1081,105 @@ org_consume_kernel(OrgConsumeArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// The same factorised sum for a FEW images (the early images of DEISM-MIX: 25 at mixEarlyOrder 2):
+// grouped by parity class and padded to tiles of 64 they would be eight tiles of mostly padding
+// (0.25 ms at C5 size for 25 images).  Here a thread owns one frequency and walks the images of its
+// lane: T_l = sum_mu Y_l^mu(img) B[par][l,mu][k] in plain FMAs over the 2l+1 real rows (no DMMA
+// k-step padding either), same recurrence, same operand tables.  Warp = 32 frequencies of one
+// image: the Y value is a broadcast, the B row a coalesced 256-byte read.
+// ---------------------------------------------------------------------------------------
+constexpr int ORG_SMALL_LANES = 4;        // images in flight per CTA (one warp each)
+constexpr int ORG_SMALL_MAX_IMAGES = 512;
+struct OrgSmallArgs {
+    long K, n_ftiles, n_images;
+    int Lmax, R_tot;
+    const double *Bp, *Yp;
+    const OrgImage *rec;
+    const long *meta;
+    const double *k;
+    int mode;
+    const void *atten;
+    const cplx *Z;
+    const int *flags;
+    cplx *partial;
+};
+
+__global__ void __launch_bounds__(32 * ORG_SMALL_LANES) org_small_kernel(OrgSmallArgs a) {
+    __shared__ double2 red[ORG_SMALL_LANES][32];
+    const int q = threadIdx.x & 31, j = threadIdx.x >> 5;
+    const long ft = blockIdx.x, f = ft * ORG_TF + q;
+    const bool live_f = f < a.K;
+    const double kk = live_f ? a.k[f] : 1.0, ik = 1.0 / kk;
+    const bool fused = a.mode == DEISM_ATTEN_FUSED_ROOM || a.mode == DEISM_ATTEN_FUSED_ANGLES;
+    const bool flat = fused && a.flags[0] != 0;
+    cplx P = cmake(0.0, 0.0);
+    // image i of the class-grouped order: class c holds meta[9 + c] real images from position meta[c]
+    for (long i = (long)blockIdx.y * ORG_SMALL_LANES + j; i < a.n_images; i += (long)gridDim.y * ORG_SMALL_LANES) {
+        int par = 0;
+        long before = 0;
+        for (int c = 0; c < 7; ++c) {
+            const long nc = a.meta[9 + c];
+            if (i >= before + nc) { before += nc; par = c + 1; }
+            else break;
+        }
+        const long pos = a.meta[par] + (i - before);
+        const OrgImage rec = a.rec[pos];
+        cplx att;
+        if (flat) {
+            att = rec.atten_flat;
+        } else if (fused) {
+            att = shoebox_atten(a.Z + (live_f ? f : 0), a.K, rec.cx, rec.cy, rec.cz, rec.e);
+            if (a.mode == DEISM_ATTEN_FUSED_ROOM) att = round_c64(att);
+        } else if (!live_f) {
+            att = cmake(0.0, 0.0);
+        } else if (a.mode == DEISM_ATTEN_C64) {
+            const float2 v = ((const float2 *)a.atten)[rec.orig * a.K + f];
+            att = cmake((double)v.x, (double)v.y);
+        } else {
+            att = ((const cplx *)a.atten)[rec.orig * a.K + f];
+        }
+        double sn, cs;
+        sincos_cw(kk * rec.r, &sn, &cs);
+        const double i1 = ik * rec.inv_r;
+        const double ci = cs * i1, si = sn * i1;
+        cplx hc = cmul(att, cmake(ci, -si));                                   // atten * h_{-1}
+        cplx hm = cmul(att, cmake(fma(-ci, i1, -si), fma(si, i1, -ci)));       // atten * h_{-2}
+        const double *Yrow = a.Yp + (pos / ORG_TI) * (long)a.R_tot * ORG_OS + pos % ORG_TI;
+        const double *Brow = a.Bp + (((long)par * a.n_ftiles + ft) * a.R_tot) * 2 * ORG_BS + q;
+        for (int l = 0; l < a.Lmax; ++l) {
+            const double cf = (double)(2 * l - 1) * i1;
+            const cplx h = cmake(fma(cf, hc.x, -hm.x), fma(cf, hc.y, -hm.y));
+            hm = hc; hc = h;
+            const int r0 = c_org_rowoff[l];
+            double tx = 0.0, ty = 0.0, ux = 0.0, uy = 0.0;       // two partial sums: twice the loads in flight
+            int r = r0;
+#pragma unroll 4
+            for (; r + 1 < r0 + 2 * l + 1; r += 2) {
+                const double y0 = __ldg(Yrow + (long)r * ORG_OS), y1 = __ldg(Yrow + (long)(r + 1) * ORG_OS);
+                tx = fma(y0, __ldg(Brow + (long)r * 2 * ORG_BS), tx);
+                ty = fma(y0, __ldg(Brow + (long)r * 2 * ORG_BS + ORG_BS), ty);
+                ux = fma(y1, __ldg(Brow + (long)(r + 1) * 2 * ORG_BS), ux);
+                uy = fma(y1, __ldg(Brow + (long)(r + 1) * 2 * ORG_BS + ORG_BS), uy);
+            }
+            {   // 2l+1 is odd: the last row
+                const double y0 = __ldg(Yrow + (long)r * ORG_OS);
+                tx = fma(y0, __ldg(Brow + (long)r * 2 * ORG_BS), tx);
+                ty = fma(y0, __ldg(Brow + (long)r * 2 * ORG_BS + ORG_BS), ty);
+            }
+            cfma(P, h, cmake(tx + ux, ty + uy));
+        }
+    }
+    red[j][q] = P;
+    __syncthreads();
+    if (j == 0 && live_f) {
+        cplx s_ = red[0][q];
+#pragma unroll
+        for (int t = 1; t < ORG_SMALL_LANES; ++t) s_ = cadd(s_, red[t][q]);
+        a.partial[(long)blockIdx.y * a.K + f] = s_;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // direct kernel: thread = image, blockIdx.y = frequency.  Source coefficients are addressed
 // as Cs[k*sk + nm*snm + img*si] (complex64): shoebox [K][NM] (si = 0) or ARG [K][NM][I].
 // ---------------------------------------------------------------------------------------
@@ -1444,12 +1545,37 @@ static int org_shoebox_impl(int64_t n_images, int64_t K, int N, int V, const voi
     const size_t b_rows = (size_t)R_tot * 2 * ORG_BS, y_rows = (size_t)R_tot * ORG_OS;
     double *Bp = (double *)workspace(WS_ORG_B, (size_t)8 * n_ftiles * b_rows * sizeof(double));
     if (!Bp) return DEISM_ERR_NOMEM;
-    // B-table form: the widest frequency tile whose coefficient rows fit in shared memory
-    int bt_ft = 0;
+    // B-table form: frequency tile width FT (16, 8 or 4: its coefficient rows must fit in shared
+    // memory) and number of job shares per tile.  CTA time ~ FT / shares, CTAs = tiles x shares, one
+    // CTA per SM: take the pair that needs the fewest CTA-times (few frequencies -> narrow tiles and
+    // more shares, so that a frequency slab of a multi-GPU run still fills the SMs); a share keeps
+    // >= 4 jobs per warp so that the dynamic job queue can balance them.
+    int bt_ft = 0, bt_split = 1;
     size_t bt_smem = 0;
-    for (int ft = 16; ft >= 4 && !bt_ft; ft >>= 1) {
-        bt_smem = (size_t)(NMs + NMr) * (ft + 1) * sizeof(double2) + 16 + (size_t)BT2_THREADS * sizeof(int4);
-        if ((long)bt_smem <= (long)smem_optin_bytes()) bt_ft = ft;
+    {
+        const long sms = sm_count();
+        const int n_jobs_ = guard.use->n_jobs;
+        const int max_split = n_jobs_ / (4 * (BT2_THREADS / 32)) > 1 ? n_jobs_ / (4 * (BT2_THREADS / 32)) : 1;
+        double best = 1e300;
+        for (int ft = 16; ft >= 4; ft >>= 1) {
+            const size_t need = (size_t)(NMs + NMr) * (ft + 1) * sizeof(double2) + 16 + (size_t)BT2_THREADS * sizeof(int4);
+            if ((long)need > (long)smem_optin_bytes()) continue;
+            const long nx = (K + ft - 1) / ft;
+            for (int sp = 1; sp <= max_split && sp <= 12; ++sp) {
+                // a CTA's fixed time (launch, staging, the queue's tail) in units of "all jobs for one
+                // frequency": ~4.5 us against ~3.3e-4 us per coupling entry
+                const double fixed = 13600.0 / (double)(guard.use->nnz > 0 ? guard.use->nnz : 1);
+                // narrow tiles run the same entry with fewer frequencies per lane group: measured
+                // 1.8x the time per (entry, frequency) at FT = 4, ~1.3x at FT = 8
+                const double slow = ft >= 16 ? 1.0 : ft == 8 ? 1.3 : 1.9;
+                const double cost = ((double)ft * slow / sp + fixed) * (double)((nx * sp + sms - 1) / sms);
+                if (cost < best * (1.0 - 1e-9)) { best = cost; bt_ft = ft; bt_split = sp; bt_smem = need; }
+            }
+        }
+        if (const char *e = getenv("DEISM_BT_SPLIT")) { const int v = atoi(e); if (v > 0) bt_split = v; }
+        if (getenv("DEISM_DEBUG"))
+            fprintf(stderr, "[deism] btable: K=%ld nnz=%ld jobs=%d -> FT=%d shares=%d smem=%zu\n", (long)K,
+                    guard.use->nnz, n_jobs_, bt_ft, bt_split, bt_smem);
     }
 #ifdef ORG_BTABLE_V1
     bt_ft = 0;
@@ -1477,23 +1603,8 @@ static int org_shoebox_impl(int64_t n_images, int64_t K, int N, int V, const voi
         b2.K = K; b2.n_ftiles = n_ftiles; b2.R_tot = R_tot; b2.NMs = NMs; b2.NMr = NMr;
         b2.n_jobs = guard.use->n_jobs; b2.ent = guard.use->d_bt; b2.seg = guard.use->d_bt_seg;
         b2.jobs = guard.use->d_jobs; b2.Cs = d_C_nm_s; b2.Cr = d_C_vu_r; b2.k = d_k; b2.Bp = Bp;
-        // CTAs = frequency tiles x job shares; among 1..12 shares take the split that fills whole
-        // waves of one CTA per SM best (every share re-stages the coefficient tile: ~1 % each)
-        const long nx = (K + bt_ft - 1) / bt_ft, sms = sm_count();
-        int split = 1;
-        double best = 1e30;
-        for (int sp = 1; sp <= 12 && sp <= b2.n_jobs; ++sp) {
-            const long ctas = nx * sp;
-            const double cost = (double)((ctas + sms - 1) / sms) / (double)ctas * (1.0 + 0.01 * sp);
-            if (cost < best - 1e-12) { best = cost; split = sp; }
-        }
-        // a warp should see several jobs (largest first, pulled dynamically), or the longest job
-        // decides the CTA's time: no more shares than leave ~8 jobs per warp
-        {
-            const int max_split = b2.n_jobs / (8 * (BT2_THREADS / 32)) > 1 ? b2.n_jobs / (8 * (BT2_THREADS / 32)) : 1;
-            if (split > max_split) split = max_split;
-            if (const char *e = getenv("DEISM_BT_SPLIT")) { const int v = atoi(e); if (v > 0) split = v; }
-        }
+        const long nx = (K + bt_ft - 1) / bt_ft;
+        const int split = bt_split;
         b2.n_split = split;
         dim3 grid((unsigned)nx, (unsigned)split);
         prof_begin("org_btable", bs);
@@ -1547,7 +1658,7 @@ static int org_shoebox_impl(int64_t n_images, int64_t K, int N, int V, const voi
 
     const long n_pad_cap = (n_images + ORG_TI - 1) / ORG_TI * ORG_TI + 8 * ORG_TI;
     const long n_tiles_cap = n_pad_cap / ORG_TI;
-    long *perm = (long *)workspace(WS_ARG_IDX, (size_t)(n_pad_cap + 16) * sizeof(long));
+    long *perm = (long *)workspace(WS_ARG_IDX, (size_t)(n_pad_cap + 32) * sizeof(long));
     OrgImage *rec = (OrgImage *)workspace(WS_ORG_IMG, (size_t)n_pad_cap * sizeof(OrgImage));
     double *Yp = (double *)workspace(WS_ORG_Y, (size_t)n_tiles_cap * y_rows * sizeof(double));
     if (!perm || !rec || !Yp) return DEISM_ERR_NOMEM;
@@ -1564,6 +1675,24 @@ static int org_shoebox_impl(int64_t n_images, int64_t K, int N, int V, const voi
     org_prep_kernel<<<(unsigned)((n_pad_cap + 31) / 32), dim3(32, ORG_PREP_Y), 0, st>>>(pa, rec, nullptr);
     DEISM_LAUNCH_CHECK("org_prep_kernel");
 
+    if (n_images <= ORG_SMALL_MAX_IMAGES) {
+        // few images: the scalar kernel (no class-tile padding), one warp per image and frequency tile
+        long n_chunks_s = (n_images + ORG_SMALL_LANES - 1) / ORG_SMALL_LANES;
+        while (n_chunks_s > 1 && n_chunks_s * n_ftiles > 64L * sm_count()) n_chunks_s = (n_chunks_s + 1) / 2;
+        cplx *partial_s = (cplx *)workspace(WS_ORG_PARTIAL, (size_t)n_chunks_s * K * sizeof(cplx));
+        if (!partial_s) return DEISM_ERR_NOMEM;
+        OrgSmallArgs sa;
+        sa.K = K; sa.n_ftiles = n_ftiles; sa.n_images = n_images; sa.Lmax = Lmax; sa.R_tot = R_tot; sa.Bp = Bp;
+        sa.Yp = Yp; sa.rec = rec; sa.meta = meta; sa.k = d_k; sa.mode = atten->mode; sa.atten = atten->d_atten;
+        sa.Z = (const cplx *)atten->d_Z_S; sa.flags = flags; sa.partial = partial_s;
+        joiner.join();
+        dim3 grid_s((unsigned)n_ftiles, (unsigned)n_chunks_s);
+        prof_begin("org_consume", st);
+        org_small_kernel<<<grid_s, 32 * ORG_SMALL_LANES, 0, st>>>(sa);
+        prof_end("org_consume", st);
+        DEISM_LAUNCH_CHECK("org_small_kernel");
+        return launch_reduce_partials(partial_s, n_chunks_s, K, d_out, accumulate, st);
+    }
     // ring depth: as many stages as fit next to the fixed part (one CTA per SM)
     const size_t stage_bytes = (size_t)rc_rows * (2 * ORG_BS + ORG_OS) * 8;
     int nst = (int)(((size_t)smem_optin_bytes() / ORG_CTAS_PER_SM - (ORG_CTAS_PER_SM > 1 ? 1024 : 0) -

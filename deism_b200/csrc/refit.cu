@@ -28,9 +28,8 @@
 
 namespace deism {
 
-constexpr int RF_NMAX = 7;                        // source order supported by the shared-memory budget
-constexpr int RF_JMAX = (RF_NMAX + 1) * (RF_NMAX + 1);
-constexpr int RF_CH = 128;                        // samples per chunk
+constexpr int RF_NMAX = 11;                       // source order the shared-memory budget admits (J = 144)
+constexpr int RF_CH = 128;                        // most samples per chunk (fewer at high orders)
 constexpr int RF_THREADS = 256;
 constexpr int RF_TI = 64, RF_TF = 32;             // apply kernel CTA tile: images x frequencies
 constexpr int RF_SC = 24;                         // samples per staged chunk (multiple of 4)
@@ -68,61 +67,68 @@ __device__ __forceinline__ void reflected_direction(const double *R, const doubl
     *ct = cs;
 }
 
-struct RefitSmem {
+// Shared memory of refit_pinv_kernel: header, then G[J][J+1] (normal matrix, then its lower Cholesky
+// factor) and y[ch][J+1] (real harmonics of a chunk of `ch` samples, one row per thread), sized for
+// the order of the call.
+struct RefitSmemHead {
     double R[9];
-    int bad;
-    double G[RF_JMAX][RF_JMAX + 1];          // normal matrix, then its Cholesky factor (lower)
-    double y[RF_CH][RF_JMAX + 1];            // real harmonics of a chunk of samples, one row per thread
+    int bad, pad;
 };
+static size_t refit_smem_bytes(int J, int ch) {
+    return sizeof(RefitSmemHead) + (size_t)(J + ch) * (J + 1) * sizeof(double);
+}
 
 // W layout: [group][image tile][sample < n_dir_pad][a|b][RF_WS] doubles, image within the tile
 // fastest; group g < npairs is the pair (a_m, b_m), g >= npairs the single a_0 of n = g - npairs
 // (its b row stays zero).  Pre-zeroed: padded samples, images and rows contribute nothing.
 __global__ void __launch_bounds__(RF_THREADS)
-refit_pinv_kernel(long n_images, long n_itiles, int N, long n_dir, long n_dir_pad,
+refit_pinv_kernel(long n_images, long n_itiles, int N, int ch, long n_dir, long n_dir_pad,
                   const float *__restrict__ refl, const double *__restrict__ X, double *W, int *status) {
     extern __shared__ __align__(16) unsigned char rf_smem_raw[];
-    RefitSmem &sm = *reinterpret_cast<RefitSmem *>(rf_smem_raw);
+    RefitSmemHead &sm = *reinterpret_cast<RefitSmemHead *>(rf_smem_raw);
     const long img = blockIdx.x;
     const int tid = threadIdx.x;
     const int J = (N + 1) * (N + 1), npairs = N * (N + 1) / 2;
+    const int GS = J + 1;                                        // row stride of G and y
+    double *G = reinterpret_cast<double *>(rf_smem_raw + sizeof(RefitSmemHead));
+    double *Ych = G + (size_t)J * GS;
     if (tid < 9) sm.R[tid] = (double)refl[img * 9 + tid];
     if (tid == 0) sm.bad = 0;
-    for (int e = tid; e < J * J; e += RF_THREADS) sm.G[e / J][e % J] = 0.0;
+    for (int e = tid; e < J * J; e += RF_THREADS) G[(e / J) * GS + e % J] = 0.0;
     __syncthreads();
 
     // ---- pass 1: G = sum_s y(s) y(s)^T ----
-    for (long s0 = 0; s0 < n_dir; s0 += RF_CH) {
-        const int ns = (int)(n_dir - s0 < RF_CH ? n_dir - s0 : RF_CH);
+    for (long s0 = 0; s0 < n_dir; s0 += ch) {
+        const int ns = (int)(n_dir - s0 < ch ? n_dir - s0 : ch);
         if (tid < ns) {
             double phi, ct;
             reflected_direction(sm.R, X, n_dir, s0 + tid, &phi, &ct);
-            real_harmonics(N, phi, ct, &sm.y[tid][0], 1);
+            real_harmonics(N, phi, ct, Ych + (size_t)tid * GS, 1);
         }
         __syncthreads();
         for (int e = tid; e < J * J; e += RF_THREADS) {
             const int q = e / J, q2 = e % J;
             if (q2 > q) continue;
             double acc = 0.0;
-            for (int t = 0; t < ns; ++t) acc = fma(sm.y[t][q], sm.y[t][q2], acc);
-            sm.G[q][q2] += acc;
+            for (int t = 0; t < ns; ++t) acc = fma(Ych[t * GS + q], Ych[t * GS + q2], acc);
+            G[q * GS + q2] += acc;
         }
         __syncthreads();
     }
     // ---- Cholesky G = L L^T (lower triangle in place), column by column ----
     for (int c = 0; c < J; ++c) {
         if (tid == 0) {
-            double d = sm.G[c][c];
-            for (int t = 0; t < c; ++t) d = fma(-sm.G[c][t], sm.G[c][t], d);
+            double d = G[(c) * GS + (c)];
+            for (int t = 0; t < c; ++t) d = fma(-G[(c) * GS + (t)], G[(c) * GS + (t)], d);
             if (!(d > 0.0)) { sm.bad = 1; d = 1.0; }
-            sm.G[c][c] = sqrt(d);
+            G[(c) * GS + (c)] = sqrt(d);
         }
         __syncthreads();
-        const double inv = 1.0 / sm.G[c][c];
+        const double inv = 1.0 / G[(c) * GS + (c)];
         for (int r = c + 1 + tid; r < J; r += RF_THREADS) {
-            double v = sm.G[r][c];
-            for (int t = 0; t < c; ++t) v = fma(-sm.G[r][t], sm.G[c][t], v);
-            sm.G[r][c] = v * inv;
+            double v = G[(r) * GS + (c)];
+            for (int t = 0; t < c; ++t) v = fma(-G[(r) * GS + (t)], G[(c) * GS + (t)], v);
+            G[(r) * GS + (c)] = v * inv;
         }
         __syncthreads();
     }
@@ -131,22 +137,22 @@ refit_pinv_kernel(long n_images, long n_itiles, int N, long n_dir, long n_dir_pa
         return;
     }
     // ---- pass 2: w(s) = G^-1 y(s), one sample per thread ----
-    for (long s0 = 0; s0 < n_dir; s0 += RF_CH) {
-        const int ns = (int)(n_dir - s0 < RF_CH ? n_dir - s0 : RF_CH);
+    for (long s0 = 0; s0 < n_dir; s0 += ch) {
+        const int ns = (int)(n_dir - s0 < ch ? n_dir - s0 : ch);
         if (tid < ns) {
             double phi, ct;
             reflected_direction(sm.R, X, n_dir, s0 + tid, &phi, &ct);
-            double *y = &sm.y[tid][0];
+            double *y = Ych + (size_t)tid * GS;
             real_harmonics(N, phi, ct, y, 1);
             for (int r = 0; r < J; ++r) {                       // L z = y
                 double v = y[r];
-                for (int t = 0; t < r; ++t) v = fma(-sm.G[r][t], y[t], v);
-                y[r] = v / sm.G[r][r];
+                for (int t = 0; t < r; ++t) v = fma(-G[(r) * GS + (t)], y[t], v);
+                y[r] = v / G[(r) * GS + (r)];
             }
             for (int r = J - 1; r >= 0; --r) {                  // L^T w = z
                 double v = y[r];
-                for (int t = r + 1; t < J; ++t) v = fma(-sm.G[t][r], y[t], v);
-                y[r] = v / sm.G[r][r];
+                for (int t = r + 1; t < J; ++t) v = fma(-G[(t) * GS + (r)], y[t], v);
+                y[r] = v / G[(r) * GS + (r)];
             }
             const long s = s0 + tid;
             const long itile = img / RF_TI;
@@ -357,11 +363,17 @@ extern "C" int deism_arg_refit(int64_t n_images, int64_t K, int N, int64_t n_dir
     DEISM_CUDA_TRY(cudaMemsetAsync(W, 0, w_bytes, st));
     DEISM_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int), st));
 
+    // samples per chunk: as many as the shared memory left by G admits (two CTAs per SM up to order 7)
+    int ch = RF_CH;
+    while (ch > 32 && refit_smem_bytes(J, ch) > (size_t)smem_optin_bytes() / (N <= 7 ? 2 : 1) - 1024) ch /= 2;
+    const size_t pinv_smem = refit_smem_bytes(J, ch);
+    if (pinv_smem > (size_t)smem_optin_bytes())
+        return set_error(DEISM_ERR_INVALID, "source order %d needs %zu B of shared memory", N, pinv_smem);
     DEISM_CUDA_TRY(cudaFuncSetAttribute(refit_pinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)sizeof(RefitSmem)));
+                                        (int)pinv_smem));
     prof_begin("refit_pinv", st);
-    refit_pinv_kernel<<<(unsigned)n_images, RF_THREADS, sizeof(RefitSmem), st>>>(
-        n_images, n_itiles, N, n_dir, n_dir_pad, d_reflection, d_coords, W, status);
+    refit_pinv_kernel<<<(unsigned)n_images, RF_THREADS, pinv_smem, st>>>(
+        n_images, n_itiles, N, ch, n_dir, n_dir_pad, d_reflection, d_coords, W, status);
     prof_end("refit_pinv", st);
     DEISM_LAUNCH_CHECK("refit_pinv_kernel");
     refit_hankel_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(K, N, d_k, r0, Hinv);

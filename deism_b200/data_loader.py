@@ -283,3 +283,33 @@ def printDict(params):
     for key, val in params.items():
         if np.ndim(val) == 0 or np.size(val) <= 12:
             print(f"  {key}: {val}")
+
+
+def load_directive_pressure(silentMode, src_or_rec, name):
+    """data_loader.py:1099-1145: the sampled directional pressure field of a source / receiver profile,
+    ``<data>/sampled_directivity/<source|receiver>/<name>.mat`` with the reference's lookup rule
+    (``./examples/data`` when an ``examples/data`` directory is visible from the CWD, else ``data``)
+    and its errors: (freqs_mesh flattened, Psh [K, n_dir], Dir_all [n_dir, 2], r0)."""
+    import os
+
+    import scipy.io as sio
+
+    path = "data/sampled_directivity"
+    if os.path.exists("examples/data"):
+        path = "./examples/" + path
+    data_location = "{}/{}/{}.mat".format(path, src_or_rec, name)
+    try:
+        with open(data_location, "rb") as file:
+            FEM_data = sio.loadmat(file)
+    except FileNotFoundError:
+        raise FileNotFoundError(f"File {data_location} not found.")
+    except Exception as e:
+        raise RuntimeError(f"An error occurred while loading the file: {e}")
+    freqs_all = FEM_data["freqs_mesh"].flatten()
+    pressure = FEM_data["Psh"]
+    Dir_all = FEM_data["Dir_all"]
+    r0 = FEM_data["r0"]
+    if not silentMode:
+        print("Load directivity data from {}, ".format(path), end="")
+        print(f"sampled on {len(Dir_all)} directions and {len(freqs_all)} frequencies. ", end="")
+    return freqs_all, pressure, Dir_all, r0

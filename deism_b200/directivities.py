@@ -12,11 +12,12 @@ contract as the reference:
                                                        1481-1509, 1193-1217   [GPU: deism_arg_refit]
     rotation_matrix_ZXZ                                                  ~ shared_utils.py:9-26
 
-Sampled (non-monopole) directivities need the .mat data sets that are absent from the reference
-tree (.MISSING_LARGE_BLOBS); callers inject the sampled field as ``params["sampledSource"]`` /
-``params["sampledReceiver"]`` = ``{"freqs", "Psh", "Dir_all", "r0"}`` (what
-``load_directive_pressure`` returns, data_loader.py:1099-1145), or ready coefficients ``C_nm_s`` /
-``C_vu_r`` (complex64 [K, N+1, 2N+1], signed m indexed NumPy-style) and call the vectorisers.
+Sampled (non-monopole) directivities are read from the ``.mat`` profile ``sourceType`` /
+``receiverType`` names (``data_loader.load_directive_pressure``, the reference's lookup rule; the data
+sets themselves are absent from the reference tree, .MISSING_LARGE_BLOBS), unless the caller injects
+the sampled field as ``params["sampledSource"]`` / ``params["sampledReceiver"]`` = ``{"freqs",
+"Psh", "Dir_all", "r0"}`` (what the loader returns), or ready coefficients ``C_nm_s`` / ``C_vu_r``
+(complex64 [K, N+1, 2N+1], signed m indexed NumPy-style) followed by the vectorisers.
 """
 from __future__ import annotations
 
@@ -124,13 +125,22 @@ def get_directivity_coefs(k, maxSHorder, Pmnr0, r0):
 
 
 def _sampled(params, which):
-    """The tuple load_directive_pressure returns (data_loader.py:1099-1145), injected by the caller
-    as params['sampledSource' | 'sampledReceiver'] = {freqs, Psh, Dir_all, r0}: the reference's
-    .mat data sets are absent from its tree."""
+    """(Psh, Dir_all) of the sampled field: ``params['sampledSource' | 'sampledReceiver']`` =
+    ``{freqs, Psh, Dir_all, r0}`` when the caller injected it, else the reference's own route —
+    ``load_directive_pressure`` (data_loader.py:1099-1145) on the ``.mat`` profile named by
+    ``sourceType`` / ``receiverType`` — with the reference's checks (cd:1269-1283): a radius that
+    differs from ``radiusSource`` / ``radiusReceiver`` only warns, different frequencies raise."""
     smp = params.get("sampled" + which)
     if smp is None:
-        raise FileNotFoundError(f"sampled {which.lower()} directivities: the .mat data sets are absent from "
-                                f"the reference tree; provide params['sampled{which}']")
+        from .data_loader import load_directive_pressure
+
+        freqs, Psh, Dir_all, r0 = load_directive_pressure(params.get("silentMode", 1), which.lower(),
+                                                          params[which.lower() + "Type"])
+        smp = {"freqs": freqs, "Psh": Psh, "Dir_all": Dir_all, "r0": r0}
+    r0 = np.asarray(smp.get("r0", params.get("radius" + which, 0.0)), dtype=float).ravel()
+    if r0.size and "radius" + which in params and np.abs(r0[0] - params["radius" + which]) > 1e-3:
+        print(f"Warning: The radius of the {which.lower()} is {r0[0]}, not the same as the one defined in "
+              f"params['radius{which}']")
     if not np.allclose(smp["freqs"], params["freqs"]):
         raise ValueError("The frequencies in the directivity data are not the same as the ones "
                          "defined in params['freqs']")

@@ -266,7 +266,8 @@ DEISM_API int deism_convex_images_fill(const deism_convex_walls *walls, int64_t 
  *   d_coords     : float64[3,n_dir] Cartesian sampling directions (already rotated, cd:1676-1699)
  *   d_Psh        : complex128[K,n_dir] sampled pressures
  *   d_C_vec      : out, complex64[K,(N+1)^2,I], image index innermost (= C_nm_s_ARG_vec)
- * N <= 7.  DEISM_ERR_INVALID if the directions do not determine the fit. */
+ * N <= 11 (the normal matrix of the fit lives in shared memory).  DEISM_ERR_INVALID if the
+ * directions do not determine the fit. */
 DEISM_API int deism_arg_refit(int64_t n_images, int64_t K, int N, int64_t n_dir,
                               const float *d_reflection, const double *d_coords,
                               const double *d_Psh, const double *d_k, double r0, float *d_C_vec,

@@ -102,3 +102,38 @@ def test_sampled_directivities_match_reference_fixture():
     bad = dict(p, freqs=f["freqs"] + 1.0)
     with pytest.raises(ValueError):
         D.init_source_directivities(bad)
+
+
+def test_sampled_directivities_from_mat_profiles(tmp_path, monkeypatch):
+    """The reference's own route: sourceType / receiverType name a .mat profile under
+    data/sampled_directivity/<source|receiver>/ (data_loader.py:1099-1145).  The data sets are absent
+    from the reference tree, so the profile is written here from the fixture's sampled field; the
+    coefficients must equal the ones computed from the injected field (= the reference's, fixture d1)."""
+    import os
+
+    import scipy.io as sio
+
+    from deism_b200 import data_loader, directivities as D
+
+    f = np.load(os.path.join(os.path.dirname(__file__), "golden", "d1_sampled_directivities.npz"))
+    for kind, key, r0 in (("source", "Psh_source", 0.4), ("receiver", "Psh_receiver", 0.5)):
+        d = tmp_path / "data" / "sampled_directivity" / kind
+        d.mkdir(parents=True)
+        sio.savemat(str(d / "probe.mat"), {"freqs_mesh": f["freqs"][None, :], "Psh": f[key], "Dir_all": f["Dir_all"],
+                                           "r0": np.array([[r0]])})
+    monkeypatch.chdir(tmp_path)
+    freqs, Psh, Dir_all, r0 = data_loader.load_directive_pressure(1, "source", "probe")
+    assert np.array_equal(freqs, f["freqs"]) and np.array_equal(Psh, f["Psh_source"]) and float(r0) == 0.4
+    with pytest.raises(FileNotFoundError):
+        data_loader.load_directive_pressure(1, "source", "no_such_profile")
+    base = {"freqs": f["freqs"], "waveNumbers": f["waveNumbers"], "silentMode": 1,
+            "sourceOrder": int(f["sourceOrder"]), "receiverOrder": int(f["receiverOrder"]), "radiusSource": 0.4,
+            "radiusReceiver": 0.5, "orientSource": f["orientSource"], "orientReceiver": f["orientReceiver"],
+            "ifReceiverNormalize": 1, "pointSrcStrength": f["pointSrcStrength"]}
+    p_mat = dict(base, sourceType="probe", receiverType="probe")
+    p_inj = dict(base, sourceType="probe", receiverType="probe",
+                 sampledSource={"freqs": f["freqs"], "Psh": f["Psh_source"], "Dir_all": f["Dir_all"], "r0": 0.4},
+                 sampledReceiver={"freqs": f["freqs"], "Psh": f["Psh_receiver"], "Dir_all": f["Dir_all"], "r0": 0.5})
+    for fn, key in ((D.init_source_directivities, "C_nm_s"), (D.init_receiver_directivities, "C_vu_r")):
+        a, b = fn(dict(p_mat))[key], fn(dict(p_inj))[key]
+        assert a.dtype == np.complex64 and np.array_equal(a, b)

@@ -117,9 +117,9 @@ def test_arg_refit_reference_fixture():
 
 
 @pytest.mark.parametrize("I,K,N,n_dir", [(1, 1, 0, 1), (5, 3, 1, 4), (130, 37, 2, 31), (77, 20, 5, 200),
-                                         (9, 33, 7, 150)])
+                                         (9, 33, 7, 150), (6, 17, 10, 300), (3, 9, 11, 333)])
 def test_arg_refit_vs_oracle(I, K, N, n_dir):
-    """Ragged sizes, orders 0..7, proper and improper orthogonal matrices (float32), against the
+    """Ragged sizes, orders 0..11, proper and improper orthogonal matrices (float32), against the
     NumPy restatement (pinv per image)."""
     from deism_b200 import directivities as D
     from oracle import oracle
@@ -149,8 +149,8 @@ def test_arg_refit_errors():
     with pytest.raises(ValueError):          # 10 directions cannot determine 16 coefficients
         D.cal_C_nm_s_ARG_vec_device(np.eye(3, dtype=np.float32)[None], P, X, dict(base, sourceOrder=3))
     with pytest.raises(ValueError):          # order above the kernel's budget
-        D.cal_C_nm_s_ARG_vec_device(np.eye(3, dtype=np.float32)[None], np.ones((2, 100), complex),
-                                    np.random.default_rng(0).standard_normal((3, 100)), dict(base, sourceOrder=8))
+        D.cal_C_nm_s_ARG_vec_device(np.eye(3, dtype=np.float32)[None], np.ones((2, 200), complex),
+                                    np.random.default_rng(0).standard_normal((3, 200)), dict(base, sourceOrder=12))
     with pytest.raises(ValueError):          # all directions identical: rank-deficient fit
         D.cal_C_nm_s_ARG_vec_device(np.eye(3, dtype=np.float32)[None], P, np.tile([[0.], [0.], [1.]], (1, 10)),
                                     dict(base, sourceOrder=1))
