@@ -182,7 +182,8 @@ __global__ void transpose_coef_kernel(const IN *__restrict__ in, long K, int J, 
 
 // ---------------------------------------------------------------------------------------
 // factorised path: operand-plane geometry.  Segment (l, mu) lives at row rowoff(l) + mu + l of a
-// plane set; every l block is padded to a multiple of 4 rows (the DMMA k extent) with zeros.
+// plane set; the block of an odd l has one zero pad row (2l + 2 rows = whole DMMA k-steps), the block of an
+// even l none (see org_consume_kernel).
 // ---------------------------------------------------------------------------------------
 #ifndef ORG_TI_
 #define ORG_TI_ 64
@@ -206,6 +207,11 @@ constexpr int ORG_MAXCHUNKS = 256;
 #endif
 constexpr int SORT_THREADS = 1024;
 __constant__ int c_org_rowoff[ORG_LMAX + 1];
+// normalisation sqrt((2l+1)/(4 pi) (l-|mu|)!/(l+|mu|)!) of Y_l^mu, index l (l + 1) / 2 + |mu|: computed on
+// the host with the operations of _sph_harm_numba (pb:70-76: the factorial ratio as a running
+// product, then one division and one square root — IEEE on both sides, so the table holds the values
+// the per-element evaluation produced)
+__device__ double g_org_norm[ORG_LMAX * (ORG_LMAX + 1) / 2];
 __constant__ int4 c_org_chunks[ORG_MAXCHUNKS];   // row0, nrows, first degree, one past the last degree
 
 // Real-harmonic rows.  Y_l^{-mu} = (-1)^mu conj(Y_l^mu), so with Y_l^mu = a + i b (mu > 0)
@@ -482,69 +488,81 @@ struct OrgImage {   // 96 bytes
 // meta[9..16]  : number of real images of class c (they sit at the start of the class's positions)
 // perm[pos]    : original image index or -1
 __global__ void __launch_bounds__(SORT_THREADS)
-org_sort_kernel(const int32_t *__restrict__ A, long n_images, long *perm, long *meta, long perm_cap) {
-    __shared__ long cnt[8], base[8];
-    __shared__ int wtot[SORT_THREADS / 32][8];
+org_sort_kernel(const int32_t *__restrict__ A, long n_images, long *perm, long *meta, long perm_cap,
+                int par_smem) {
+    // Stable counting sort by parity class in one CTA: thread t owns the contiguous slice
+    // [t * per, (t + 1) * per) of the image list, so "stable" = (thread order, then order inside the
+    // slice).  Per class: counts per thread -> exclusive scan over the threads (warp shuffles + one
+    // pass over the warp totals) -> every thread places its own images in order.
+    __shared__ long base[9];
+    __shared__ int wsum[8][SORT_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 8) cnt[tid] = 0;
-    __syncthreads();
-    // pass 1: counts
-    long local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (long i = tid; i < n_images; i += SORT_THREADS) {
+    const long per = (n_images + SORT_THREADS - 1) / SORT_THREADS;
+    const long lo = (long)tid * per, hi = lo + per < n_images ? lo + per : n_images;
+    // parity classes of all images, read once with coalesced loads into shared memory (when they
+    // fit: par_smem != 0); the slices then walk shared memory instead of strided global memory
+    extern __shared__ unsigned char sort_par[];
+    auto parity = [&](long i) {
         const int32_t *a = A + i * 6;
-        int par = ((a[3] & 1) << 2) | ((a[4] & 1) << 1) | (a[5] & 1);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) local[c] += (par == c);
+        return ((a[3] & 1) << 2) | ((a[4] & 1) << 1) | (a[5] & 1);
+    };
+    if (par_smem) {
+        for (long i = tid; i < n_images; i += SORT_THREADS) sort_par[i] = (unsigned char)parity(i);
+        __syncthreads();
     }
+    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long i = lo; i < hi; ++i) {
+        const int par = par_smem ? (int)sort_par[i] : parity(i);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) cnt[c] += (par == c);
+    }
+    int off[8];        // images of class c in lower threads of this warp
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        long v = local[c];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0) atomicAdd((unsigned long long *)&cnt[c], (unsigned long long)v);
+        int v = cnt[c];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
+        }
+        off[c] = v - cnt[c];
+        if (lane == 31) wsum[c][warp] = v;
+    }
+    __syncthreads();
+    if (tid < 8) {     // exclusive scan of the warp totals of class tid
+        int run = 0;
+        for (int w = 0; w < SORT_THREADS / 32; ++w) { const int t = wsum[tid][w]; wsum[tid][w] = run; run += t; }
+        base[tid] = run;      // class total, for now
     }
     __syncthreads();
     if (tid == 0) {
         long pos = 0;
         for (int c = 0; c < 8; ++c) {
+            const long n = base[c];
             meta[c] = pos;
+            meta[9 + c] = n;               // real images of class c: positions meta[c] .. meta[c] + n - 1
             base[c] = pos;
-            pos += (cnt[c] + ORG_TI - 1) / ORG_TI * ORG_TI;
+            pos += (n + ORG_TI - 1) / ORG_TI * ORG_TI;
         }
         meta[8] = pos;
-        for (int c = 0; c < 8; ++c) meta[9 + c] = cnt[c];      // real images of class c: positions meta[c] ..
+        base[8] = pos;
     }
     __syncthreads();
-    for (long i = tid; i < perm_cap; i += SORT_THREADS) perm[i] = -1;
-    __syncthreads();
-    // pass 2: stable placement, chunk by chunk
-    for (long i0 = 0; i0 < n_images; i0 += SORT_THREADS) {
-        long i = i0 + tid;
-        int par = -1;
-        if (i < n_images) {
-            const int32_t *a = A + i * 6;
-            par = ((a[3] & 1) << 2) | ((a[4] & 1) << 1) | (a[5] & 1);
-        }
-        int rank = 0;
+    long p[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            unsigned ball = __ballot_sync(0xffffffffu, par == c);
-            if (par == c) rank = __popc(ball & ((1u << lane) - 1u));
-            if (lane == 0) wtot[warp][c] = __popc(ball);
-        }
-        __syncthreads();
-        if (par >= 0) {
-            long off = base[par];
-            for (int w = 0; w < warp; ++w) off += wtot[w][par];
-            perm[off + rank] = i;
-        }
-        __syncthreads();
-        if (tid < 8) {
-            long t = 0;
-            for (int w = 0; w < SORT_THREADS / 32; ++w) t += wtot[w][tid];
-            base[tid] += t;
-        }
-        __syncthreads();
+    for (int c = 0; c < 8; ++c) p[c] = base[c] + wsum[c][warp] + off[c];
+    for (long i = lo; i < hi; ++i) {
+        const int par = par_smem ? (int)sort_par[i] : parity(i);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (par == c) perm[p[c]++] = i;
     }
+    // padding positions: behind the real images of every class, and behind the last class
+    for (int c = 0; c < 8; ++c) {
+        const long first = meta[c] + meta[9 + c], last = c < 7 ? meta[c + 1] : base[8];
+        for (long q = first + tid; q < last; q += SORT_THREADS) perm[q] = -1;
+    }
+    for (long q = base[8] + tid; q < perm_cap; q += SORT_THREADS) perm[q] = -1;
 }
 
 struct OrgPrepArgs {
@@ -585,9 +603,7 @@ __device__ __forceinline__ void org_harmonic_rows(const OrgPrepArgs &a, long pos
                 p_val = (ct * (double)(2 * l - 1) * p1 - (double)(l + am - 1) * p0) / (double)(l - am);
                 p0 = p1; p1 = p_val;
             }
-            double ratio = 1.0;
-            for (int i = l - am + 1; i <= l + am; ++i) ratio *= (double)i;
-            const double np_ = sqrt((double)(2 * l + 1) / (4.0 * 3.14159265358979323846) / ratio) * p_val;
+            const double np_ = g_org_norm[l * (l + 1) / 2 + am] * p_val;
             double *p = a.Yp + (tile * a.R_tot + c_org_rowoff[l] + (am ? 2 * am - 1 : 0)) * ORG_OS + it;
             p[0] = np_ * cs;
             if (am) p[ORG_OS] = np_ * sn;
@@ -865,11 +881,15 @@ org_consume_kernel(OrgConsumeArgs a) {
     double xinv[2][2];          // 1 / (k r) of the pair
     cplx P[2] = {cmake(0.0, 0.0), cmake(0.0, 0.0)};      // [e], summed over this thread's images
 
-    // one degree l of parity PAR = l & 1 (compile-time roles of the two register sets)
+    // one degree l of parity PAR = l & 1 (compile-time roles of the two register sets).
+    // Row block of degree l: a_0, a_1, b_1, ..., a_l, b_l (2l + 1 real rows).  For ODD l that is
+    // 3 mod 4: one zero pad row completes the last DMMA k-step.  For EVEN l the 2l rows behind a_0
+    // are whole k-steps, and the a_0 row is a rank-one update done in plain multiplies: it starts
+    // the accumulator (T = Y_l^0 x B[l,0]) — 8 DMUL instead of a mostly empty k-step of 4 DMMAs.
     auto degree = [&](auto par_tag, const int l, const double *Bs, const double *Ys, const int row0) {
         constexpr int PAR = decltype(par_tag)::value;
-        const int row = c_org_rowoff[l] - row0;
-        const int ksn = (c_org_rowoff[l + 1] - c_org_rowoff[l]) >> 2;    // k-steps of degree l
+        const int row = c_org_rowoff[l] - row0 + (PAR == 0 ? 1 : 0);      // first row of the k-steps
+        const int ksn = PAR == 0 ? (l >> 1) : ((l + 1) >> 1);              // k-steps of degree l
         const double *Yw = Ys + (row + t4) * ORG_OS + wm * 16 + g;
         const double *Bw = Bs + (row + t4) * 2 * ORG_BS + wn * 8 + g;
         auto load_frag = [&](int ks, double (&af)[2], double (&bf)[2]) {
@@ -894,19 +914,40 @@ org_consume_kernel(OrgConsumeArgs a) {
 #endif
         };
         double af[2], bf[2];
-        load_frag(0, af, bf);
+        int ks = 0;            // k-steps issued so far
+        if (PAR == 0) {
+            // a_0 row: this thread's two images (rows g, g + 8 of the D fragment) and two frequencies
+            const double *y0 = Ys + (row - 1) * ORG_OS + wm * 16 + g;
+            const double *b0 = Bs + (row - 1) * 2 * ORG_BS + wn * 8 + 2 * t4;
+            const double ya[2] = {y0[0], y0[8]};
+            const double2 bre = *reinterpret_cast<const double2 *>(b0);
+            const double2 bim = *reinterpret_cast<const double2 *>(b0 + ORG_BS);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                T[0][0][mt][0] = ya[mt] * bre.x; T[0][0][mt][1] = ya[mt] * bre.y;
+                T[0][1][mt][0] = ya[mt] * bim.x; T[0][1][mt][1] = ya[mt] * bim.y;
+            }
+            if (ksn > 0) {
+                load_frag(0, af, bf);
+                mma_frag(af, bf);
+                ks = 1;
+            }
+        } else {
+            load_frag(0, af, bf);
 #ifndef ORG_KO_MMA
 #pragma unroll
-        for (int p = 0; p < 2; ++p)
+            for (int p = 0; p < 2; ++p)
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-                dmma884_z(T[PAR][p][mt][0], T[PAR][p][mt][1], af[mt], bf[p]);
+                for (int mt = 0; mt < 2; ++mt)
+                    dmma884_z(T[PAR][p][mt][0], T[PAR][p][mt][1], af[mt], bf[p]);
 #else
 #pragma unroll
-        for (int p = 0; p < 2; ++p)
+            for (int p = 0; p < 2; ++p)
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) { T[PAR][p][mt][0] = af[mt]; T[PAR][p][mt][1] = bf[p]; }
+                for (int mt = 0; mt < 2; ++mt) { T[PAR][p][mt][0] = af[mt]; T[PAR][p][mt][1] = bf[p]; }
 #endif
+            ks = 1;
+        }
         // degree l-1: P += H_{l-1} T_{l-1}; then H_l = (2l-1)/(kr) H_{l-1} - H_{l-2} overwrites H_{l-2}
 #ifdef ORG_KO_SCALAR
         if (l == 12345) P[0].x += T[PAR ^ 1][0][0][0] + T[PAR ^ 1][1][1][1] + T[PAR ^ 1][0][1][0] + T[PAR ^ 1][1][0][1] + T[PAR ^ 1][0][0][1] + T[PAR ^ 1][1][1][0] + T[PAR ^ 1][0][1][1] + T[PAR ^ 1][1][0][0];
@@ -926,10 +967,10 @@ org_consume_kernel(OrgConsumeArgs a) {
         }
         // remaining k-steps, two per trip with ping-pong fragment registers: the loads of one step
         // are in flight while the other multiplies
-        if (ksn > 1) {
+        if (ks < ksn) {
             double a2[2], b2[2];
-            load_frag(1, af, bf);
-            int ks = 2;
+            load_frag(ks, af, bf);
+            ++ks;
 #pragma unroll 1
             for (; ks + 1 < ksn; ks += 2) {
                 load_frag(ks, a2, b2);
@@ -1505,13 +1546,15 @@ static int org_shoebox_impl(int64_t n_images, int64_t K, int N, int V, const voi
 
     // ---- factorised path ----
     if (Lmax > ORG_LMAX) return set_error(DEISM_ERR_INVALID, "N+V+1 > %d", ORG_LMAX);
-    // plane geometry: rows(l) = roundup4(2l+1); chunks hold whole degrees, <= rc rows each
+    // plane geometry: rows(l) = 2l+1 (even l) or 2l+2 (odd l); chunks hold whole degrees, <= rc rows each
     int rowoff[ORG_LMAX + 1];
     int4 chunks[ORG_MAXCHUNKS];
     int ncpt = 0, R_tot = 0, rc_rows = ORG_RC;
     for (int l = 0; l < Lmax; ++l) {
         rowoff[l] = R_tot;
-        const int rows = (2 * l + 1 + 3) / 4 * 4;
+        // 2l + 1 real rows; odd degrees carry one zero pad row (whole DMMA k-steps), even degrees
+        // none (their a_0 row is a rank-one update in the consume kernel)
+        const int rows = (l & 1) ? 2 * l + 2 : 2 * l + 1;
         if (rows > rc_rows) rc_rows = rows;
         R_tot += rows;
     }
@@ -1532,6 +1575,15 @@ static int org_shoebox_impl(int64_t n_images, int64_t K, int N, int V, const voi
         if (dev != uploaded_dev || Lmax != uploaded_lmax) {
             uploaded_dev = -1;
             bump_generation();
+            static double norm[ORG_LMAX * (ORG_LMAX + 1) / 2];      // guarded by geom_mu; consumed before the sync below returns
+            for (int l = 0; l < Lmax; ++l)
+                for (int am = 0; am <= l; ++am) {
+                    double ratio = 1.0;
+                    for (int i = l - am + 1; i <= l + am; ++i) ratio *= (double)i;
+                    norm[l * (l + 1) / 2 + am] = sqrt((double)(2 * l + 1) / (4.0 * 3.14159265358979323846) / ratio);
+                }
+            DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(g_org_norm, norm, (size_t)Lmax * (Lmax + 1) / 2 * sizeof(double), 0,
+                                                   cudaMemcpyHostToDevice, st));
             DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_org_rowoff, rowoff, (Lmax + 1) * sizeof(int), 0,
                                                    cudaMemcpyHostToDevice, st));
             DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(c_org_chunks, chunks, ncpt * sizeof(int4), 0,
@@ -1664,7 +1716,13 @@ static int org_shoebox_impl(int64_t n_images, int64_t K, int N, int V, const voi
     if (!perm || !rec || !Yp) return DEISM_ERR_NOMEM;
     DEISM_CUDA_TRY(cudaMemsetAsync(Yp, 0, (size_t)n_tiles_cap * y_rows * sizeof(double), st));
     long *meta = perm + n_pad_cap;
-    org_sort_kernel<<<1, SORT_THREADS, 0, st>>>(d_A, n_images, perm, meta, n_pad_cap);
+    {
+        const size_t par_bytes = (size_t)n_images <= 200000 ? ((size_t)n_images + 15) & ~(size_t)15 : 0;
+        if (par_bytes > 48 * 1024)
+            DEISM_CUDA_TRY(cudaFuncSetAttribute(org_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)par_bytes));
+        org_sort_kernel<<<1, SORT_THREADS, par_bytes, st>>>(d_A, n_images, perm, meta, n_pad_cap, par_bytes ? 1 : 0);
+    }
     DEISM_LAUNCH_CHECK("org_sort_kernel");
     OrgPrepArgs pa;
     pa.n_images = n_images; pa.n_pad_cap = n_pad_cap; pa.Lmax = Lmax; pa.perm = perm; pa.meta = meta;
