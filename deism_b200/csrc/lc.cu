@@ -95,12 +95,22 @@ struct LcPrepArgs {
 // (m = -n..n) keeps its size, J' = J.
 constexpr int LC_JMAX = 256;            // caller's harmonics per pass (order <= 15)
 constexpr int LC_QMAX = 2 * LC_JMAX;    // real functions (J' <= 2 J, = J for complete sets)
+constexpr int LC_MCOLS = 66;            // distinct |m| (orders up to 64 are accepted)
 struct LcBasis {
     int Jq;
     unsigned char qn[LC_QMAX], qm[LC_QMAX], qim[LC_QMAX];   // y_q = (qim ? Im : Re) Y_qn^qm
     short cptr[LC_QMAX + 1];                                // contributions of q: cptr[q]..cptr[q+1]
     short cj[2 * LC_JMAX];                                  //   caller's column j
     unsigned char cp[2 * LC_JMAX];                          //   weight i^cp
+    // evaluation program of the per-image harmonic rows: the distinct (n, |m|) of the basis grouped
+    // into columns of equal |m| (ascending), ascending n inside a column — one sincos(|m| phi) and
+    // one upward Legendre pass per column instead of one of each per (n, |m|)
+    int ncol;
+    unsigned char col_m[LC_MCOLS];
+    short col_ptr[LC_MCOLS + 1];
+    unsigned char ent_n[LC_JMAX];
+    short ent_q[LC_JMAX];                                   // q of the a function (b = q + 1 when |m| > 0)
+    double ent_norm[LC_JMAX];                               // sqrt((2n+1)/(4 pi) (n-|m|)!/(n+|m|)!), host-made
 };
 __constant__ LcBasis c_lc_basis[2];
 
@@ -141,14 +151,41 @@ __global__ void __launch_bounds__(256) k_uniform_kernel(const double *__restrict
 __device__ __forceinline__ void fill_y(double *Y, long base, int pass, int J_pad, double phi, double ct,
                                        bool live) {
     const LcBasis &B = c_lc_basis[pass];
-    cplx y = cmake(0.0, 0.0);
-    for (int q = 0; q < J_pad; ++q) {
-        double v = 0.0;
-        if (live && q < B.Jq) {
-            if (!B.qim[q]) y = sph_harm_dev(B.qm[q], B.qn[q], phi, ct);   // b follows its a
-            v = B.qim[q] ? y.y : y.x;
+    if (!live) {
+        for (int q = 0; q < J_pad; ++q) Y[base + (long)q * LC_YS] = 0.0;
+        return;
+    }
+    for (int q = B.Jq; q < J_pad; ++q) Y[base + (long)q * LC_YS] = 0.0;
+    // Column by column (|m| fixed): P_m^m, then P_n^m upwards — the recurrence, the operations and
+    // their order are those of sph_harm_dev (pb:40-83), which restarts them for every (n, m); the
+    // normalisation comes from the host-made table (same operations, IEEE division and square root).
+    const double somx2 = sqrt(fma(-ct, ct, 1.0));
+    for (int c = 0; c < B.ncol; ++c) {
+        const int am = B.col_m[c];
+        double pmm = 1.0, fact = 1.0;
+        for (int i = 0; i < am; ++i) { pmm *= -fact * somx2; fact += 2.0; }
+        double sn, cs;
+        sincos_cw((double)am * phi, &sn, &cs);
+        double p0 = pmm, p1 = ct * (double)(2 * am + 1) * pmm;     // P_am^am, P_{am+1}^am
+        int n = am;
+        for (int e = B.col_ptr[c]; e < B.col_ptr[c + 1]; ++e) {
+            const int want = B.ent_n[e];
+            double p_val;
+            if (want == am) {
+                p_val = p0;
+            } else {
+                if (n < am + 1) n = am + 1;
+                for (; n < want; ++n) {
+                    const double pll = (ct * (double)(2 * n + 1) * p1 - (double)(n + am) * p0) / (double)(n + 1 - am);
+                    p0 = p1; p1 = pll;
+                }
+                p_val = p1;
+            }
+            const double np_ = B.ent_norm[e] * p_val;
+            const int q = B.ent_q[e];
+            Y[base + (long)q * LC_YS] = np_ * cs;
+            if (am) Y[base + (long)(q + 1) * LC_YS] = np_ * sn;
         }
-        Y[base + (long)q * LC_YS] = v;
     }
 }
 
@@ -785,7 +822,6 @@ lc_mono_kernel(LcMonoArgs a) {
     const bool flat = fused && a.flags[0] != 0;
     const bool uniform_k = a.flags[1] != 0;
     if ((flat && uniform_k) != FAST) return;
-    bool z_real_here = true;
     {
         const double dk = *reinterpret_cast<const double *>(a.flags + 2);
         for (int q = tid; q < TF; q += LM_THREADS) {
@@ -798,13 +834,13 @@ lc_mono_kernel(LcMonoArgs a) {
             for (int i = tid; i < 6 * TF; i += LM_THREADS) {
                 const int w = i / TF, q = i % TF;
                 const long f = f0 + q;
-                const cplx z = f < a.K ? a.Z[(long)w * a.K + f] : cmake(1.0, 0.0);
-                Zs[w][q] = z;
-                z_real_here = z_real_here && z_is_real(z);
+                Zs[w][q] = f < a.K ? a.Z[(long)w * a.K + f] : cmake(1.0, 0.0);
             }
     }
-    // every impedance of the frequency tile real: the real wall-factor chain (common.cuh)
-    const bool real_tile = __syncthreads_and(z_real_here) && fused && !flat && LC_REAL_CHAIN;
+    __syncthreads();
+    // (the simultaneous-power real chain of lc_main_kernel does not pay here: a warp holds 32
+    // different images, so every bit of every exponent slot is taken by some lane — measured 0.61 ms
+    // against 0.55 ms for the per-wall loops at C2 size)
     const int q0 = fg * FPT;
     cplx P[FPT];
 #pragma unroll
@@ -834,21 +870,7 @@ lc_mono_kernel(LcMonoArgs a) {
 #pragma unroll
                 for (int q = 0; q < FPT; ++q) att[q] = rec.a_flat;
             } else {
-                if (fused && real_tile) {
-                    int fqs[FPT];
-                    double ar[FPT];
-#pragma unroll
-                    for (int q = 0; q < FPT; ++q) fqs[q] = q0 + q;
-                    if (a.mode == DEISM_ATTEN_FUSED_ROOM) {
-                        shoebox_atten_real_n<FPT, 1>(&Zs[0][0], TF, fqs, rec.cx, rec.cy, rec.cz, rec.e, ar);
-#pragma unroll
-                        for (int q = 0; q < FPT; ++q) att[q] = cmake((double)__double2float_rn(ar[q]), 0.0);
-                    } else {
-                        shoebox_atten_real_n<FPT, 2>(&Zs[0][0], TF, fqs, rec.cx, rec.cy, rec.cz, rec.e, ar);
-#pragma unroll
-                        for (int q = 0; q < FPT; ++q) att[q] = cmake(ar[q], 0.0);
-                    }
-                } else if (fused) {
+                if (fused) {
                     int fqs[FPT];
 #pragma unroll
                     for (int q = 0; q < FPT; ++q) fqs[q] = q0 + q;
@@ -1005,6 +1027,25 @@ static void build_real_basis(int J, const int64_t *n, const int64_t *m, LcBasis 
             B.cj[c] = (short)j; B.cp[c] = (unsigned char)((pa + (mm > 0 ? 1 : 3)) & 3);
         }
     }
+    // evaluation program: columns of equal |m|, ascending n
+    B.ncol = 0;
+    int ne = 0;
+    for (int am = 0; am <= 64; ++am) {
+        bool any = false;
+        for (int n = am; n <= 64; ++n)
+            for (int q = 0; q < B.Jq; ++q) {
+                if (B.qim[q] || B.qm[q] != am || B.qn[q] != n) continue;
+                if (!any) { B.col_m[B.ncol] = (unsigned char)am; B.col_ptr[B.ncol] = (short)ne; any = true; }
+                double ratio = 1.0;
+                for (int i = n - am + 1; i <= n + am; ++i) ratio *= (double)i;
+                B.ent_n[ne] = (unsigned char)n;
+                B.ent_q[ne] = (short)q;
+                B.ent_norm[ne] = sqrt((double)(2 * n + 1) / (4.0 * 3.14159265358979323846) / ratio);
+                ++ne;
+            }
+        if (any) ++B.ncol;
+    }
+    B.col_ptr[B.ncol] = (short)ne;
 }
 
 int launch_k_uniform(const double *d_k, long K, int *flags, cudaStream_t st) {

@@ -83,11 +83,18 @@ def launches(path, out, title):
         v *= {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "nsecond": 1e-6}.get(row["Metric Unit"], 1.0)
         agg[name][0] += 1
         agg[name][1] += v
-    tot = sum(v[1] for v in agg.values())
+    # the FP64 peak micro-benchmarks run once per process, outside every timed region
+    outside = {k: v for k, v in agg.items() if "peak_kernel" in k or "dmma_fed" in k}
+    inside = {k: v for k, v in agg.items() if k not in outside}
+    tot = sum(v[1] for v in inside.values())
     lines = [f"# {title}", "", f"source: `{path}` (ncu --metrics gpu__time_duration.sum --clock-control none; "
-             "cold-cache, serialised: compare SHARES)", "", "| kernel | launches | total ms | share |", "|---|---|---|---|"]
-    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        lines.append(f"| {k[:70]} | {v[0]} | {v[1]:.3f} | {v[1] / tot:.3f} |")
+             "cold-cache, serialised: compare SHARES)", "", "| kernel | launches | total ms | ms per launch | share |",
+             "|---|---|---|---|---|"]
+    for k, v in sorted(inside.items(), key=lambda kv: -kv[1][1]):
+        lines.append(f"| {k[:70]} | {v[0]} | {v[1]:.3f} | {v[1] / v[0]:.4f} | {v[1] / tot:.3f} |")
+    if outside:
+        lines += ["", "outside the timed region (roofline denominators, once per process): "
+                  + ", ".join(f"{k.split('::')[-1]} {v[1]:.1f} ms" for k, v in outside.items())]
     open(out, "w").write("\n".join(lines) + "\n")
 
 
