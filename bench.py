@@ -403,6 +403,10 @@ def measure_shoebox(c, name, steps, warmup, general=False, sharding="frequency",
     if method == "ORG":
         used_img = ["A", "R_sI_r_all"]
     h2d_bytes = sum(p_host["images"][key].nbytes for key in used_img)
+    if world > 1 and not by_image and os.environ.get("DEISM_B200_REPLICATE_IMAGES", "0") == "1":   # row slabs
+        h2d_bytes = sum(-(-p_host["images"][key].shape[0] // world) * p_host["images"][key][0].nbytes
+                        if p_host["images"][key].shape[0] >= 4 * world else p_host["images"][key].nbytes
+                        for key in used_img)
     h2d_bytes += sum(p_host[key].nbytes for key in ("waveNumbers", "impedance"))
     if method in ("LC", "MIX"):
         h2d_bytes += sum(p_host[key].nbytes for key in ("C_nm_s_vec", "C_vu_r_vec"))
@@ -432,7 +436,10 @@ def measure_shoebox(c, name, steps, warmup, general=False, sharding="frequency",
         return combine(backend.run_DEISM_device(p_dev, dev))
 
     def step_e2e():
-        res = combine(backend.run_DEISM_device(p_host, dev))   # H2D of every input inside
+        # H2D of every input inside (DEISM_B200_REPLICATE_IMAGES=1: the image list enters the node
+        # once — every rank uploads its row slab, the slabs are all_gathered over NVLink)
+        q = p_host if by_image else distributed.replicate_images(p_host, dev)
+        res = combine(backend.run_DEISM_device(q, dev))
         return res.cpu() if rank == 0 or world == 1 else res[:1].cpu()
 
     def step_pageable():
@@ -486,6 +493,11 @@ def measure_shoebox(c, name, steps, warmup, general=False, sharding="frequency",
         pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(25)
     e2e_ms, _ = timed(c, step_e2e, steps)
     e2e_ms = max_over_ranks(c, e2e_ms) / steps
+    # the end-to-end path must return what the device-resident one returned (rank 0 holds both)
+    e2e_diff = None
+    if rank == 0:
+        got_e2e, got_dev = step_e2e().numpy(), result.cpu().numpy()
+        e2e_diff = float(np.linalg.norm(got_e2e - got_dev) / np.linalg.norm(got_dev))
     pg_ms = None
     if pageable:
         for _ in range(2):
@@ -538,7 +550,7 @@ def measure_shoebox(c, name, steps, warmup, general=False, sharding="frequency",
         "steps": steps, "warmup": max(warmup, 1),
         "e2e": {"value": terms / (e2e_ms * 1e-3), "unit": "terms/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
-                "host_buffers": "pinned NumPy"},
+                "host_buffers": "pinned NumPy", "rel_diff_vs_device_resident_result": e2e_diff},
         "e2e_pageable": ({"value": terms / (pg_ms * 1e-3), "unit": "terms/s", "ms_per_step": pg_ms,
                           "host_buffers": "plain (pageable) NumPy through backend.run_DEISM, result as NumPy"}
                          if pg_ms else None),

@@ -330,27 +330,15 @@ __host__ __device__ inline LcCarve lc_carve(int WN, bool cres_on, int rows, int 
 #endif
 __device__ __forceinline__ void lc_general_factors(const cplx *Zs, int TF, const double *kf, const double *dkd,
                                                 const double *dkd8, const LcImage *recp, int fqa,
-                                                bool round_to_c64, bool uniform_k, bool real_tile, double2 *fac,
-                                                int stride) {
+                                                bool round_to_c64, bool uniform_k, bool real_tile,
+                                                bool pairs_tile, double2 *fac, int stride) {
     constexpr int NQ = 2 * LC_NT;
     static_assert(LC_NT == 2, "frequency offsets below assume two n-tiles per warp");
     const LcImage &rec = *recp;
     const int fqs[NQ] = {fqa, fqa + 1, fqa + 8, fqa + 9};
-    cplx att[NQ], Eq[NQ];
-    double att_r[NQ];
-    if (real_tile) {
-        if (round_to_c64) {
-            shoebox_atten_real_n<NQ, 1>(Zs, TF, fqs, rec.cx, rec.cy, rec.cz, rec.e, att_r);
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) att_r[q] = (double)__double2float_rn(att_r[q]) * rec.inv_r;
-        } else {
-            shoebox_atten_real_n<NQ, 2>(Zs, TF, fqs, rec.cx, rec.cy, rec.cz, rec.e, att_r);
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) att_r[q] *= rec.inv_r;
-        }
-    } else {
-        shoebox_atten_n<NQ>(Zs, TF, fqs, rec.cx, rec.cy, rec.cz, rec.e, att);
-    }
+    // E = exp(-i k r) / r first: independent of the wall factors, so its sincos and rotation steps
+    // fill the latency of the reciprocal and power chains below
+    cplx Eq[NQ];
     auto rot_step = [](cplx F, cplx rot, double dr) {
         F = cmul(F, rot);
         return cmake(fma(F.y, dr, F.x), fma(-F.x, dr, F.y));
@@ -358,7 +346,7 @@ __device__ __forceinline__ void lc_general_factors(const cplx *Zs, int TF, const
     if (uniform_k) {
         double sn, cs;
         sincos_cw(kf[fqa] * rec.r, &sn, &cs);
-        Eq[0] = cmake(cs, -sn);
+        Eq[0] = cmake(cs * rec.inv_r, -sn * rec.inv_r);
         Eq[1] = rot_step(Eq[0], rec.rot, dkd[fqa] * rec.r);
         Eq[2] = rot_step(Eq[0], rec.rot8, dkd8[fqa] * rec.r);
         Eq[3] = rot_step(Eq[2], rec.rot, dkd[fqa + 8] * rec.r);
@@ -367,20 +355,28 @@ __device__ __forceinline__ void lc_general_factors(const cplx *Zs, int TF, const
         for (int q = 0; q < NQ; ++q) {
             double sn, cs;
             sincos_cw(kf[fqs[q]] * rec.r, &sn, &cs);
-            Eq[q] = cmake(cs, -sn);
+            Eq[q] = cmake(cs * rec.inv_r, -sn * rec.inv_r);
         }
     }
     if (real_tile) {
+        double att_r[NQ];
+        if (round_to_c64) {
+            if (pairs_tile) shoebox_atten_real_n<NQ, 1, true>(Zs, TF, fqs, rec.cx, rec.cy, rec.cz, rec.e, att_r);
+            else shoebox_atten_real_n<NQ, 1, false>(Zs, TF, fqs, rec.cx, rec.cy, rec.cz, rec.e, att_r);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) att_r[q] = (double)__double2float_rn(att_r[q]);
+        } else {
+            if (pairs_tile) shoebox_atten_real_n<NQ, 2, true>(Zs, TF, fqs, rec.cx, rec.cy, rec.cz, rec.e, att_r);
+            else shoebox_atten_real_n<NQ, 2, false>(Zs, TF, fqs, rec.cx, rec.cy, rec.cz, rec.e, att_r);
+        }
 #pragma unroll
         for (int q = 0; q < NQ; ++q) fac[(long)q * stride] = cmake(att_r[q] * Eq[q].x, att_r[q] * Eq[q].y);
         return;
     }
+    cplx att[NQ];
+    shoebox_atten_n<NQ>(Zs, TF, fqs, rec.cx, rec.cy, rec.cz, rec.e, att);
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-        cplx a_ = round_to_c64 ? round_c64(att[q]) : att[q];
-        a_ = cmake(a_.x * rec.inv_r, a_.y * rec.inv_r);
-        fac[(long)q * stride] = cmul(a_, Eq[q]);
-    }
+    for (int q = 0; q < NQ; ++q) fac[(long)q * stride] = cmul(round_to_c64 ? round_c64(att[q]) : att[q], Eq[q]);
 }
 
 // The main loop has NO CTA-wide barrier and no waiting producer: Y (and, when they stream, C)
@@ -454,17 +450,23 @@ lc_main_kernel(LcMainArgs a) {
     }
     // Per-term attenuation with every impedance of the frequency tile real (what the material
     // conversions return): the real chain of common.cuh (shoebox_atten_real_n), decided per CTA.
-    bool z_real_here = true;
+    // ... and whether the two walls of every axis carry the same impedance throughout the tile (an
+    // axis is then one base with the summed exponent).
+    bool z_real_here = true, pairs_here = true;
     if (fused && !flat) {
-        for (int i = tid; i < 6 * TF; i += THREADS) {
+        for (int i = tid; i < 3 * TF; i += THREADS) {
             int w = i / TF, q = i % TF;
             long f = f0 + q;
-            const cplx z = f < a.K ? a.Z[(long)w * a.K + f] : cmake(1.0, 0.0);
-            Zs[w][q] = z;
-            z_real_here = z_real_here && z_is_real(z);
+            const cplx z1 = f < a.K ? a.Z[(long)(2 * w) * a.K + f] : cmake(1.0, 0.0);
+            const cplx z2 = f < a.K ? a.Z[(long)(2 * w + 1) * a.K + f] : cmake(1.0, 0.0);
+            Zs[2 * w][q] = z1;
+            Zs[2 * w + 1][q] = z2;
+            z_real_here = z_real_here && z_is_real(z1) && z_is_real(z2);
+            pairs_here = pairs_here && z1.x == z2.x;
         }
     }
     const bool real_tile = __syncthreads_and(z_real_here) && fused && !flat && LC_REAL_CHAIN;
+    const bool pairs_tile = __syncthreads_and(pairs_here) && real_tile;
 
     // producer: chunk = JC harmonics of one pass for one image tile -> one bulk copy (Y), plus the
     // matching coefficient rows when they are not resident
@@ -692,7 +694,7 @@ lc_main_kernel(LcMainArgs a) {
 #pragma unroll 1
                 for (int mt = 0; mt < 2; ++mt)
                     lc_general_factors(&Zs[0][0], TF, kf, dkd, dkd8, &recs[rb][wm * 16 + mt * 8 + g], fqa,
-                                       a.mode == DEISM_ATTEN_FUSED_ROOM, uniform_k, real_tile,
+                                       a.mode == DEISM_ATTEN_FUSED_ROOM, uniform_k, real_tile, pairs_tile,
                                        &facp[mt * 2 * NT][tid], THREADS);
             } else {
             cplx E = cmake(1.0, 0.0), E0 = E;
@@ -830,17 +832,23 @@ lc_mono_kernel(LcMonoArgs a) {
             kf[q] = kk;
             dkd[q] = f + 1 < a.K ? (a.k[f + 1] - kk) - dk : 0.0;
         }
-        if (fused && !flat)
-            for (int i = tid; i < 6 * TF; i += LM_THREADS) {
-                const int w = i / TF, q = i % TF;
-                const long f = f0 + q;
-                Zs[w][q] = f < a.K ? a.Z[(long)w * a.K + f] : cmake(1.0, 0.0);
-            }
     }
-    __syncthreads();
-    // (the simultaneous-power real chain of lc_main_kernel does not pay here: a warp holds 32
-    // different images, so every bit of every exponent slot is taken by some lane — measured 0.61 ms
-    // against 0.55 ms for the per-wall loops at C2 size)
+    // Real impedances, equal on the two walls of every axis, throughout the frequency tile: the
+    // three-base simultaneous power of common.cuh.  (With six bases it does not pay here — a warp
+    // holds 32 different images, so every bit of every exponent slot is taken by some lane: measured
+    // 0.61 ms against 0.55 ms for the per-wall loops at C2 size.)
+    bool pairs_here = true;
+    if (fused && !flat)
+        for (int i = tid; i < 3 * TF; i += LM_THREADS) {
+            const int w = i / TF, q = i % TF;
+            const long f = f0 + q;
+            const cplx z1 = f < a.K ? a.Z[(long)(2 * w) * a.K + f] : cmake(1.0, 0.0);
+            const cplx z2 = f < a.K ? a.Z[(long)(2 * w + 1) * a.K + f] : cmake(1.0, 0.0);
+            Zs[2 * w][q] = z1;
+            Zs[2 * w + 1][q] = z2;
+            pairs_here = pairs_here && z_is_real(z1) && z_is_real(z2) && z1.x == z2.x;
+        }
+    const bool pairs_tile = __syncthreads_and(pairs_here) && fused && !flat && LC_REAL_CHAIN;
     const int q0 = fg * FPT;
     cplx P[FPT];
 #pragma unroll
@@ -874,10 +882,23 @@ lc_mono_kernel(LcMonoArgs a) {
                     int fqs[FPT];
 #pragma unroll
                     for (int q = 0; q < FPT; ++q) fqs[q] = q0 + q;
-                    shoebox_atten_n<FPT>(&Zs[0][0], TF, fqs, rec.cx, rec.cy, rec.cz, rec.e, att);
-                    if (a.mode == DEISM_ATTEN_FUSED_ROOM) {
+                    if (pairs_tile) {
+                        double ar[FPT];
+                        if (a.mode == DEISM_ATTEN_FUSED_ROOM) {
+                            shoebox_atten_real_n<FPT, 1, true>(&Zs[0][0], TF, fqs, rec.cx, rec.cy, rec.cz, rec.e, ar);
 #pragma unroll
-                        for (int q = 0; q < FPT; ++q) att[q] = round_c64(att[q]);
+                            for (int q = 0; q < FPT; ++q) att[q] = cmake((double)__double2float_rn(ar[q]), 0.0);
+                        } else {
+                            shoebox_atten_real_n<FPT, 2, true>(&Zs[0][0], TF, fqs, rec.cx, rec.cy, rec.cz, rec.e, ar);
+#pragma unroll
+                            for (int q = 0; q < FPT; ++q) att[q] = cmake(ar[q], 0.0);
+                        }
+                    } else {
+                        shoebox_atten_n<FPT>(&Zs[0][0], TF, fqs, rec.cx, rec.cy, rec.cz, rec.e, att);
+                        if (a.mode == DEISM_ATTEN_FUSED_ROOM) {
+#pragma unroll
+                            for (int q = 0; q < FPT; ++q) att[q] = round_c64(att[q]);
+                        }
                     }
                 } else {
 #pragma unroll

@@ -1,12 +1,10 @@
 mkdir -p gpurun_out/r02
-export DEISM_B200_GRAPHS=0
-B="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras --no-configs"
-python bench.py --workload c5 --steps 2 --warmup 1 --no-cpu-baseline --no-extras --no-configs > /dev/null 2>&1 || exit 1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r02/p_launches_c5.csv $B --workload c5 > /dev/null 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r02/p_launches_c3.csv $B --workload c3 > /dev/null 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r02/p_launches_c1.csv $B --workload c1 > /dev/null 2>&1
-ncu --set full --import-source on --clock-control none -k regex:"lc_main_kernel" -c 1 -s 2 -o gpurun_out/r02/p_lc_main_c5 $B --workload c5 > /dev/null 2>&1
-ncu --set full --import-source on --clock-control none -k regex:"lc_main_kernel" -c 2 -s 4 -o gpurun_out/r02/p_lc_main_c5_general $B --workload c5 --general-impedance > /dev/null 2>&1
-ncu --set full --import-source on --clock-control none -k regex:"org_consume_kernel|org_btable2" -c 2 -s 4 -o gpurun_out/r02/p_org_c3 $B --workload c3 > /dev/null 2>&1
-ncu --set full --import-source on --clock-control none -k regex:"lc_mono_kernel" -c 1 -s 2 -o gpurun_out/r02/p_lc_mono_c1 $B --workload c1 > /dev/null 2>&1
-ls -la gpurun_out/r02 | grep " p_"
+python -m pytest tests/test_gpu_shoebox.py -x -q -m gpu -k "frequency_dependent" 2>&1 | tail -3
+for w in c5 c2mono; do
+python bench.py --workload $w --general-impedance --no-configs --steps 10 --warmup 3 > gpurun_out/r02/u_$w.json 2> gpurun_out/r02/u_$w.err
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/r02/u_$w.json').read().strip().split('\n')[-1])
+print('$w', 'ms', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['ms_per_step'],3), d.get('kernel_ms_per_launch'), d['roofline']['frac'])
+PY
+done

@@ -91,3 +91,38 @@ def test_wigner_orthogonality():
             for l in range(abs(n - v), n + v + 1):
                 s = np.sum(W2[n, v, l] ** 2)
                 assert abs(s - 1.0) < 1e-6
+
+
+def test_library_carries_the_fingerprint_of_its_sources():
+    """The .so is git-ignored: a checkout or an edit can leave an old binary next to new sources.
+    The build bakes the hash of csrc/*.cu, common.cuh and the header into the library; the loader
+    compares it with the sources in the tree and rebuilds (or refuses) a stale one."""
+    from deism_b200 import _lib
+
+    want = _lib.source_hash()
+    assert want is not None and len(want) == 16
+    assert _lib.lib().deism_b200_source_hash().decode() == want
+    assert not _lib._stale(_lib.LIB_PATH)
+    # a binary built from other sources is recognised without being dlopen'ed
+    import shutil
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as tmp:
+        other = os.path.join(tmp, "libother.so")
+        shutil.copy(_lib.LIB_PATH, other)
+        blob = open(other, "rb").read()
+        i = blob.find(b"DEISM_SRC_HASH=")
+        assert i > 0
+        with open(other, "wb") as fh:
+            fh.write(blob[:i + 15] + b"0123456789abcdef" + blob[i + 31:])
+        assert _lib._stale(other)
+
+
+def test_generation_counter_and_graph_hooks_exist_without_a_gpu():
+    from deism_b200 import _lib
+
+    handle = _lib.lib()
+    g = int(handle.deism_state_generation())
+    assert g >= 1
+    assert handle.deism_graph_replayed(0, None) == 2       # no device: DEISM_ERR_CUDA, loudly
+    assert b"no CPU fallback" in handle.deism_last_error()
