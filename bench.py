@@ -87,9 +87,16 @@ def lc_flops_per_term(Js, Jr, fused_per_term, mean_order, real_impedance=False, 
     return f
 
 
-def org_consume_flops_per_term(N, V):
+def org_consume_flops_per_term(N, V, upward=False):
+    """Flops per (image, frequency) term of the ORG factorised sum, L = N + V + 1 degrees: the
+    degree contractions (real-harmonic rows x Re/Im planes: 4 (2l+1) per degree = 4 L^2), the sum
+    over degrees, and the pair's start values (sincos, attenuation product).  The kernel takes the
+    sum over degrees by Clenshaw's recurrence with the tensor core adding e_{l+2}: one multiply and
+    two FMAs per degree (5 L).  `upward=True` is the count of the upward Hankel recurrence +
+    complex accumulate the kernel ran before (14 L) — the same mathematical sum, kept so that the
+    two rounds' fractions can be compared."""
     L = N + V + 1
-    return 4 * L * L + 14 * L + 40      # contraction + h_l recurrence/accumulate + sincos
+    return 4 * L * L + (14 if upward else 5) * L + 40
 
 
 def clocks_sampler(stop, out, gpu_index):
@@ -537,6 +544,9 @@ def measure_shoebox(c, name, steps, warmup, general=False, sharding="frequency",
                         "frac": round(achieved / peak_tf, 4) if peak_tf else None,
                         "traffic": traffic,
                         "algorithmic_flops_per_term": fpt, "terms_per_launch": units,
+                        **({"frac_on_upward_recurrence_flop_count": round(
+                            org_consume_flops_per_term(N, V, upward=True) * units / (per_launch_ms * 1e-3)
+                            / 1e12 / peak_tf, 4)} if dom == "org_consume" and peak_tf else {}),
                         "kernel_ms_per_launch": round(per_launch_ms, 4),
                         "kernel_share_of_step": round(ms_k / n_prof / ms_per_step, 4),
                         "step_level_frac": round(fpt * units / (ms_per_step * 1e-3) / 1e12 / peak_tf, 4)

@@ -731,19 +731,29 @@ struct OrgSmem {
 static_assert(sizeof(OrgSmem) % 16 == 0, "stages must stay 16-byte aligned");
 static_assert(sizeof(OrgImage) % 16 == 0, "records are moved by bulk copies");
 
-// D = A*B (accumulator input zero: the first k-step of a degree needs no cleared registers)
-__device__ __forceinline__ void dmma884_z(double &d0, double &d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%4};\n"
+// D = A*B + C with C and D in DIFFERENT registers: the first k-step of a degree reads the finished
+// sum two degrees up as its accumulator input and leaves it intact for the scalar step that still
+// needs it (no copies, no cleared registers).
+__device__ __forceinline__ void dmma884_c(double &d0, double &d1, double a, double b, double c0, double c1) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};\n"
                  : "=d"(d0), "=d"(d1)
-                 : "d"(a), "d"(b), "d"(0.0));
+                 : "d"(a), "d"(b), "d"(c0), "d"(c1));
 }
 
-// Degrees are whole inside a chunk.  The accumulators and the recurrence registers ping-pong with
-// the parity of l (T[l&1], H[l&1] = atten*h_l), so a degree's first k-step starts a fresh
-// accumulator (D = A*B) while the scalar work of the degree before it — P += H_{l-1} T_{l-1} and
-// the recurrence step to H_l, both independent of the running DMMAs — issues in their shadow, and
-// no register is ever cleared or rotated.  Operand chunks and the per-image records arrive by TMA;
-// the last warp out of a buffer refills it: no CTA-wide barrier in the tile loop.
+// The sum over degrees  sum_l h_l(kr) T_l  (h_l the spherical Hankel function, T_l = Y_l . B_l the
+// degree's contraction) is taken by CLENSHAW's backward recurrence instead of by running h_l upwards
+// and accumulating h_l T_l:  h_{l+1} = a_l h_l - h_{l-1}, a_l = (2l+1)/(kr), gives
+//     b_l = T_l + a_l b_{l+1} - b_{l+2}  (l = L-1 .. 0),   sum = h_0 b_0 - h_{-1} b_1 = (e^{-ikr}/kr)(i b_0 - b_1).
+// With signs s_l = + + - - + + ... folded into the harmonic rows (e_l = s_l b_l, the prep kernel's
+// normalisation table carries s_l) the recurrence reads  e_l = s_l T_l + (+-a_l) e_{l+1} + e_{l+2}:
+// e_{l+2} IS the DMMA accumulator input of degree l, so the tensor core adds it for free, and what
+// is left per (image, frequency) pair and degree is one multiply (a_l) and two FMAs (Re, Im) — three
+// FP64 instructions where the upward recurrence + complex accumulate took seven, and 16 registers
+// less.  As accurate as the upward form over kr = 0.04 .. 2000 (checked against 60-digit sums).
+// Degrees are whole inside a chunk and run DOWNWARDS; the two register sets ping-pong with the
+// parity of l, so the scalar step that finishes e_{l+1} issues in the shadow of degree l's DMMAs.
+// Operand chunks and the per-image records arrive by TMA; the last warp out of a buffer refills it:
+// no CTA-wide barrier in the tile loop.
 __global__ void __launch_bounds__(ORG_THREADS, ORG_CTAS_PER_SM)
 org_consume_kernel(OrgConsumeArgs a) {
     constexpr int NWARPS = ORG_THREADS / 32;
@@ -875,17 +885,18 @@ org_consume_kernel(OrgConsumeArgs a) {
     int c = 0, stage = 0;
     unsigned phase = 0;
 
-    // [parity of l][Re|Im][m-tile][e]: accumulators; H[parity][m-tile][e] = atten * h_l of the pair
-    double T[2][2][2][2];
-    cplx H[2][2][2];
+    // E[parity of l][Re|Im][m-tile][e]: e_l once finished, before that degree l's accumulator
+    double E[2][2][2][2];
+    cplx A[2][2];               // atten * exp(-i k r) / (k r) of the pair
     double xinv[2][2];          // 1 / (k r) of the pair
     cplx P[2] = {cmake(0.0, 0.0), cmake(0.0, 0.0)};      // [e], summed over this thread's images
 
-    // one degree l of parity PAR = l & 1 (compile-time roles of the two register sets).
-    // Row block of degree l: a_0, a_1, b_1, ..., a_l, b_l (2l + 1 real rows).  For ODD l that is
-    // 3 mod 4: one zero pad row completes the last DMMA k-step.  For EVEN l the 2l rows behind a_0
-    // are whole k-steps, and the a_0 row is a rank-one update done in plain multiplies: it starts
-    // the accumulator (T = Y_l^0 x B[l,0]) — 8 DMUL instead of a mostly empty k-step of 4 DMMAs.
+    // one degree l of parity PAR = l & 1 (compile-time roles of the two register sets): on entry
+    // E[PAR] = e_{l+2} (finished) and E[PAR^1] = degree l+1's accumulator, its DMMAs possibly still
+    // in flight.  Row block of degree l: a_0, a_1, b_1, ..., a_l, b_l (2l + 1 real rows).  For ODD l
+    // that is 3 mod 4: one zero pad row completes the last DMMA k-step.  For EVEN l the 2l rows
+    // behind a_0 are whole k-steps, and the a_0 row is a rank-one update done in plain FMAs — 8 DFMA
+    // instead of a mostly empty k-step of 4 DMMAs.
     auto degree = [&](auto par_tag, const int l, const double *Bs, const double *Ys, const int row0) {
         constexpr int PAR = decltype(par_tag)::value;
         const int row = c_org_rowoff[l] - row0 + (PAR == 0 ? 1 : 0);      // first row of the k-steps
@@ -893,25 +904,17 @@ org_consume_kernel(OrgConsumeArgs a) {
         const double *Yw = Ys + (row + t4) * ORG_OS + wm * 16 + g;
         const double *Bw = Bs + (row + t4) * 2 * ORG_BS + wn * 8 + g;
         auto load_frag = [&](int ks, double (&af)[2], double (&bf)[2]) {
-#ifndef ORG_KO_LDS
             af[0] = Yw[ks * 4 * ORG_OS];
             af[1] = Yw[ks * 4 * ORG_OS + 8];
             bf[0] = Bw[ks * 8 * ORG_BS];
             bf[1] = Bw[ks * 8 * ORG_BS + ORG_BS];
-#else
-            af[0] = (double)ks; af[1] = xinv[0][0]; bf[0] = xinv[1][1]; bf[1] = (double)l;
-#endif
         };
+        double acc[2][2][2];   // [Re|Im][m-tile][e]
         auto mma_frag = [&](const double (&af)[2], const double (&bf)[2]) {
-#ifndef ORG_KO_MMA
 #pragma unroll
             for (int p = 0; p < 2; ++p)
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
-                    dmma884(T[PAR][p][mt][0], T[PAR][p][mt][1], af[mt], bf[p]);
-#else
-            T[PAR][0][0][0] += af[0] * bf[0]; T[PAR][1][1][1] += af[1] * bf[1];
-#endif
+                for (int mt = 0; mt < 2; ++mt) dmma884(acc[p][mt][0], acc[p][mt][1], af[mt], bf[p]);
         };
         double af[2], bf[2];
         int ks = 0;            // k-steps issued so far
@@ -924,8 +927,8 @@ org_consume_kernel(OrgConsumeArgs a) {
             const double2 bim = *reinterpret_cast<const double2 *>(b0 + ORG_BS);
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
-                T[0][0][mt][0] = ya[mt] * bre.x; T[0][0][mt][1] = ya[mt] * bre.y;
-                T[0][1][mt][0] = ya[mt] * bim.x; T[0][1][mt][1] = ya[mt] * bim.y;
+                acc[0][mt][0] = fma(ya[mt], bre.x, E[0][0][mt][0]); acc[0][mt][1] = fma(ya[mt], bre.y, E[0][0][mt][1]);
+                acc[1][mt][0] = fma(ya[mt], bim.x, E[0][1][mt][0]); acc[1][mt][1] = fma(ya[mt], bim.y, E[0][1][mt][1]);
             }
             if (ksn > 0) {
                 load_frag(0, af, bf);
@@ -934,35 +937,24 @@ org_consume_kernel(OrgConsumeArgs a) {
             }
         } else {
             load_frag(0, af, bf);
-#ifndef ORG_KO_MMA
 #pragma unroll
             for (int p = 0; p < 2; ++p)
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt)
-                    dmma884_z(T[PAR][p][mt][0], T[PAR][p][mt][1], af[mt], bf[p]);
-#else
-#pragma unroll
-            for (int p = 0; p < 2; ++p)
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt) { T[PAR][p][mt][0] = af[mt]; T[PAR][p][mt][1] = bf[p]; }
-#endif
+                    dmma884_c(acc[p][mt][0], acc[p][mt][1], af[mt], bf[p], E[1][p][mt][0], E[1][p][mt][1]);
             ks = 1;
         }
-        // degree l-1: P += H_{l-1} T_{l-1}; then H_l = (2l-1)/(kr) H_{l-1} - H_{l-2} overwrites H_{l-2}
-#ifdef ORG_KO_SCALAR
-        if (l == 12345) P[0].x += T[PAR ^ 1][0][0][0] + T[PAR ^ 1][1][1][1] + T[PAR ^ 1][0][1][0] + T[PAR ^ 1][1][0][1] + T[PAR ^ 1][0][0][1] + T[PAR ^ 1][1][1][0] + T[PAR ^ 1][0][1][1] + T[PAR ^ 1][1][0][0];
-        else
-#endif
+        // finish degree l+1 in the shadow of the k-step above: e_{l+1} += (+-a_{l+1}) e_{l+2}, the sign
+        // + for even l+1 (s_{l+1} s_{l+2})
         {
-            const double cl = (double)(2 * l - 1);
+            const double cl = PAR == 1 ? (double)(2 * l + 3) : -(double)(2 * l + 3);
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const cplx hp = H[PAR ^ 1][mt][e];
-                    cfma(P[e], hp, cmake(T[PAR ^ 1][0][mt][e], T[PAR ^ 1][1][mt][e]));
                     const double cf = cl * xinv[mt][e];
-                    H[PAR][mt][e] = cmake(fma(cf, hp.x, -H[PAR][mt][e].x), fma(cf, hp.y, -H[PAR][mt][e].y));
+                    E[PAR ^ 1][0][mt][e] = fma(cf, E[PAR][0][mt][e], E[PAR ^ 1][0][mt][e]);
+                    E[PAR ^ 1][1][mt][e] = fma(cf, E[PAR][1][mt][e], E[PAR ^ 1][1][mt][e]);
                 }
         }
         // remaining k-steps, two per trip with ping-pong fragment registers: the loads of one step
@@ -986,6 +978,10 @@ org_consume_kernel(OrgConsumeArgs a) {
                 mma_frag(af, bf);
             }
         }
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) { E[PAR][p][mt][0] = acc[p][mt][0]; E[PAR][p][mt][1] = acc[p][mt][1]; }
     };
     using Even = std::integral_constant<int, 0>;
     using Odd = std::integral_constant<int, 1>;
@@ -994,11 +990,8 @@ org_consume_kernel(OrgConsumeArgs a) {
     for (int tt = 0; tt < n_tiles; ++tt) {
         const int rb = tt & 1;
         mbar_wait(&sm.recfull[rb], (unsigned)((tt >> 1) & 1));
-        // Spherical Hankel recurrence of this thread's DMMA-mapped pairs (pb:86-118), h = (j, -y).
-        // It is started two orders early, from h_{-2} and h_{-1} (j_{-1} = cos x / x, y_{-1} =
-        // sin x / x, f_{l-2} = (2l-1)/x f_{l-1} - f_l), so that every degree, 0 and 1 included,
-        // takes the same branch-free step h_l = (2l-1)/x h_{l-1} - h_{l-2}; both start values carry
-        // the pair's attenuation.
+        // A = atten * h_{-1}(kr) = atten * exp(-i k r) / (k r) of this thread's DMMA-mapped pairs
+        // (pb:86-118, h = j - i y; h_0 = i h_{-1}), and the empty sums e_L = e_{L+1} = 0
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
             const OrgImage &rec = sm.rec[rb][wm * 16 + mt * 8 + g];
@@ -1042,10 +1035,9 @@ org_consume_kernel(OrgConsumeArgs a) {
                 cs0 = cs; sn0 = sn;
                 const double i1 = sm.invk[fq] * ir;
                 xinv[mt][e] = i1;
-                const double ci = cs * i1, si = sn * i1;
-                H[1][mt][e] = cmul(att, cmake(ci, -si));                                   // h_{-1}
-                H[0][mt][e] = cmul(att, cmake(fma(-ci, i1, -si), fma(si, i1, -ci)));       // h_{-2}
-                T[1][0][mt][e] = 0.0; T[1][1][mt][e] = 0.0;     // degree 0 adds H_{-1} * 0
+                A[mt][e] = cmul(att, cmake(cs * i1, -sn * i1));
+#pragma unroll
+                for (int par = 0; par < 2; ++par) { E[par][0][mt][e] = 0.0; E[par][1][mt][e] = 0.0; }
             }
         }
         __syncwarp();
@@ -1056,18 +1048,18 @@ org_consume_kernel(OrgConsumeArgs a) {
         }
 #pragma unroll 1
         for (int local = 0; local < ncpt; ++local) {
-            const int4 ch = c_org_chunks[local];
+            const int4 ch = c_org_chunks[local];          // chunks and degrees run downwards
             mbar_wait(&sm.full[stage], phase);
             const double *Bs = reinterpret_cast<const double *>(stages + (unsigned)stage * stage_bytes);
             const double *Ys = Bs + a.rc * 2 * ORG_BS;
-            int l = ch.z;
-            if (l & 1) { degree(Odd{}, l, Bs, Ys, ch.x); ++l; }
+            int l = ch.w - 1;
+            if (!(l & 1)) { degree(Even{}, l, Bs, Ys, ch.x); --l; }
 #pragma unroll 1
-            for (; l + 1 < ch.w; l += 2) {
-                degree(Even{}, l, Bs, Ys, ch.x);
-                degree(Odd{}, l + 1, Bs, Ys, ch.x);
+            for (; l - 1 >= ch.z; l -= 2) {
+                degree(Odd{}, l, Bs, Ys, ch.x);
+                degree(Even{}, l - 1, Bs, Ys, ch.x);
             }
-            if (l < ch.w) degree(Even{}, l, Bs, Ys, ch.x);
+            if (l >= ch.z) degree(Odd{}, l, Bs, Ys, ch.x);
             __syncwarp();
 #ifdef ORG_LDGSTS
             {
@@ -1090,20 +1082,16 @@ org_consume_kernel(OrgConsumeArgs a) {
             if (++stage == nst) { stage = 0; phase ^= 1u; }
             if (++pl == ncpt) { pl = 0; ++pt; }
         }
-        // the last degree of the tile
-        if ((a.Lmax - 1) & 1) {
+        // degree 0 was the last one issued: E[1] = e_1 (finished in its shadow), E[0] its accumulator.
+        // e_0 = acc_0 + a_0 e_1;  P += A (i e_0 - e_1)
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                for (int e = 0; e < 2; ++e)
-                    cfma(P[e], H[1][mt][e], cmake(T[1][0][mt][e], T[1][1][mt][e]));
-        } else {
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int e = 0; e < 2; ++e)
-                    cfma(P[e], H[0][mt][e], cmake(T[0][0][mt][e], T[0][1][mt][e]));
-        }
+            for (int e = 0; e < 2; ++e) {
+                const double e0r = fma(xinv[mt][e], E[1][0][mt][e], E[0][0][mt][e]);
+                const double e0i = fma(xinv[mt][e], E[1][1][mt][e], E[0][1][mt][e]);
+                cfma(P[e], A[mt][e], cmake(-e0i - E[1][0][mt][e], e0r - E[1][1][mt][e]));
+            }
     }
 
     // ---- reduce over the 8 row groups x ORG_WM image warps that share a frequency (aliases the stages) ----
@@ -1207,7 +1195,8 @@ __global__ void __launch_bounds__(32 * ORG_SMALL_LANES) org_small_kernel(OrgSmal
                 tx = fma(y0, __ldg(Brow + (long)r * 2 * ORG_BS), tx);
                 ty = fma(y0, __ldg(Brow + (long)r * 2 * ORG_BS + ORG_BS), ty);
             }
-            cfma(P, h, cmake(tx + ux, ty + uy));
+            const double sg = (l & 2) ? -1.0 : 1.0;      // the rows carry the Clenshaw sign s_l
+            cfma(P, h, cmake(sg * (tx + ux), sg * (ty + uy)));
         }
     }
     red[j][q] = P;
@@ -1559,12 +1548,13 @@ static int org_shoebox_impl(int64_t n_images, int64_t K, int N, int V, const voi
         R_tot += rows;
     }
     rowoff[Lmax] = R_tot;
-    for (int l = 0; l < Lmax;) {
+    // chunks from the top degree downwards (the consume kernel's Clenshaw sum runs that way)
+    for (int l1 = Lmax; l1 > 0;) {
         if (ncpt >= ORG_MAXCHUNKS) return set_error(DEISM_ERR_INVALID, "too many (l,mu) chunks");
-        int l1 = l + 1;
-        while (l1 < Lmax && rowoff[l1 + 1] - rowoff[l] <= rc_rows) ++l1;
-        chunks[ncpt++] = make_int4(rowoff[l], rowoff[l1] - rowoff[l], l, l1);
-        l = l1;
+        int l0 = l1 - 1;
+        while (l0 > 0 && rowoff[l1] - rowoff[l0 - 1] <= rc_rows) --l0;
+        chunks[ncpt++] = make_int4(rowoff[l0], rowoff[l1] - rowoff[l0], l0, l1);
+        l1 = l0;
     }
     {   // the tables depend on Lmax only: upload (and synchronise on the stack copies) once per change
         static std::mutex geom_mu;
@@ -1580,7 +1570,10 @@ static int org_shoebox_impl(int64_t n_images, int64_t K, int N, int V, const voi
                 for (int am = 0; am <= l; ++am) {
                     double ratio = 1.0;
                     for (int i = l - am + 1; i <= l + am; ++i) ratio *= (double)i;
-                    norm[l * (l + 1) / 2 + am] = sqrt((double)(2 * l + 1) / (4.0 * 3.14159265358979323846) / ratio);
+                    // signed with s_l = + + - - ...: the harmonic rows feed the Clenshaw recurrence
+                    // of org_consume_kernel (org_small_kernel takes the sign back out)
+                    norm[l * (l + 1) / 2 + am] = ((l & 2) ? -1.0 : 1.0) *
+                                                 sqrt((double)(2 * l + 1) / (4.0 * 3.14159265358979323846) / ratio);
                 }
             DEISM_CUDA_TRY(cudaMemcpyToSymbolAsync(g_org_norm, norm, (size_t)Lmax * (Lmax + 1) / 2 * sizeof(double), 0,
                                                    cudaMemcpyHostToDevice, st));
