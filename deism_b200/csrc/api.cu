@@ -2,6 +2,9 @@
 // scratch, launch counting and the FP64 roofline micro-benchmarks (DFMA / DMMA).
 #include <mutex>
 #include <vector>
+#include <cmath>
+#include <algorithm>
+#include <stdlib.h>
 #include <stdarg.h>
 #include <string.h>
 
@@ -337,6 +340,94 @@ dmma_fed_kernel(int iters, double seed, double *sink) {
             for (int b = 0; b < 2; ++b) s += T[p][a][b][0] + T[p][a][b][1];
     if (s == 123.456) sink[0] = s;
 }
+
+// ---------------------------------------------------------------------------------------
+// Image-chunk schedule of lc_main_kernel / org_consume_kernel.  grid = (frequency tiles, image chunks); CTAs start in
+// launch order (x fastest) on whichever SM slot frees up first.  With equal chunks the last wave is
+// as long as every other one and partly empty; with chunks that shrink towards the end of the launch
+// the tail is short.  The plan is chosen by simulating that greedy hand-out (cost of a CTA = its
+// tiles + ~1/2 tile of prologue) for a few shrink rates and kept only if it beats the uniform cut.
+// ---------------------------------------------------------------------------------------
+static double simulate_handout(const int *sizes, int n, long n_ftiles, long slots) {
+    // min-heap of slot finish times
+    std::vector<double> h((size_t)slots, 0.0);
+    auto sift = [&](size_t i) {
+        const size_t m = h.size();
+        for (;;) {
+            size_t l = 2 * i + 1, r = l + 1, s_ = i;
+            if (l < m && h[l] < h[s_]) s_ = l;
+            if (r < m && h[r] < h[s_]) s_ = r;
+            if (s_ == i) break;
+            std::swap(h[i], h[s_]);
+            i = s_;
+        }
+    };
+    for (int c = 0; c < n; ++c)
+        for (long x = 0; x < n_ftiles; ++x) {
+            h[0] += (double)sizes[c] + 0.5;
+            sift(0);
+        }
+    double mx = 0.0;
+    for (double t : h) mx = t > mx ? t : mx;
+    return mx;
+}
+bool guided_chunks(long n_img_tiles, long n_ftiles, long slots, long uni_chunks, long uni_tpc,
+                          long max_tiles_per_chunk, GuidedPlan &out) {
+    static const bool off = getenv("DEISM_UNIFORM_CHUNKS") != nullptr;
+    if (off || n_ftiles > 2048 || n_img_tiles < 16 || uni_chunks > DEISM_MAXCHUNKS || n_img_tiles > 2000000000L)
+        return false;
+    struct Key { long t, f, s; };
+    struct Entry { Key k; bool use; GuidedPlan plan; };
+    static std::mutex mu;
+    static std::vector<Entry> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    for (const Entry &e : cache)
+        if (e.k.t == n_img_tiles && e.k.f == n_ftiles && e.k.s == slots) {
+            if (e.use) out = e.plan;
+            return e.use;
+        }
+    if (cache.size() > 64) cache.clear();
+    Entry ent;
+    ent.k = {n_img_tiles, n_ftiles, slots};
+    ent.use = false;
+    // the uniform cut
+    std::vector<int> sizes;
+    for (long c = 0; c < uni_chunks; ++c) {
+        const long lo = c * uni_tpc, hi = lo + uni_tpc < n_img_tiles ? lo + uni_tpc : n_img_tiles;
+        sizes.push_back((int)(hi - lo));
+    }
+    double best = simulate_handout(sizes.data(), (int)sizes.size(), n_ftiles, slots);
+    const double per = (double)slots / (double)n_ftiles;        // CTAs of one frequency tile per wave
+    static const double divs[] = {1.25, 1.5, 2.0, 3.0};
+    static const int mins[] = {1, 2, 4, 8};
+    for (double div : divs)
+        for (int minc : mins) {
+            sizes.clear();
+            long rem = n_img_tiles;
+            bool ok = true;
+            while (rem > 0) {
+                long c = (long)ceil((double)rem / (div * per));
+                if (c < minc) c = minc;
+                if (c > rem) c = rem;
+                if (c > max_tiles_per_chunk || (int)sizes.size() >= DEISM_MAXCHUNKS) { ok = false; break; }
+                sizes.push_back((int)c);
+                rem -= c;
+            }
+            if (!ok) continue;
+            const double t = simulate_handout(sizes.data(), (int)sizes.size(), n_ftiles, slots);
+            if (t < best * 0.998) {
+                best = t;
+                ent.use = true;
+                ent.plan.n = (int)sizes.size();
+                ent.plan.lo[0] = 0;
+                for (int c = 0; c < ent.plan.n; ++c) ent.plan.lo[c + 1] = ent.plan.lo[c] + sizes[c];
+            }
+        }
+    cache.push_back(ent);
+    if (ent.use) out = ent.plan;
+    return ent.use;
+}
+
 
 }  // namespace deism
 

@@ -18,6 +18,15 @@ namespace deism {
 // ---------------------------------------------------------------------------------------
 int set_error(int code, const char *fmt, ...);
 void count_launch(int n = 1);
+// Image-chunk schedule with chunks of decreasing size (api.cu): filled in and true when a simulation of
+// the block scheduler's greedy hand-out says it beats `uni_chunks` equal chunks of `uni_tpc` tiles.
+constexpr int DEISM_MAXCHUNKS = 96;
+struct GuidedPlan {
+    int n;
+    int lo[DEISM_MAXCHUNKS + 1];
+};
+bool guided_chunks(long n_img_tiles, long n_ftiles, long slots, long uni_chunks, long uni_tpc,
+                   long max_tiles_per_chunk, GuidedPlan &out);
 void bump_generation();                   // scratch pointers or __constant__ tables changed
 int check_device();                       // DEISM_OK iff current device is sm_100
 void *workspace(int slot, size_t bytes);  // cached device scratch; nullptr on failure

@@ -29,6 +29,9 @@
 //   reduce_partials  deterministic sum of the per-chunk partials into out[K].
 #include <cstring>
 #include <mutex>
+#include <vector>
+#include <cmath>
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -48,6 +51,7 @@ __host__ __device__ constexpr int lc_jcmax(bool cres_on) { return cres_on ? 36 :
 #endif
 constexpr int LC_YS = LC_TI + 4; // Y row stride (doubles): 68 = 4 mod 16 -> conflict-free fragments
 constexpr int LC_MAXST = 16;     // most ring stages
+constexpr int LC_MAXCHUNKS = DEISM_MAXCHUNKS; // most image chunks (grid.y) of a guided schedule
 // A CTA is 4 (image) x WN (frequency) warps: tile = 64 images x TF = 16 WN frequencies.
 //   WN = 4 (512 threads, 1 CTA/SM): the ftile's coefficient planes stay RESIDENT in shared memory
 //          for the CTA's lifetime and only the Y chunks stream through a deep ring;
@@ -296,7 +300,9 @@ struct LcMainArgs {
     const void *atten;       // modes C64/C128
     const cplx *Z;           // fused modes
     const int *flags;        // flags[0]: impedance is frequency-flat
-    long tiles_per_chunk;    // image tiles (of LC_TI) per CTA chunk
+    long tiles_per_chunk;    // image tiles (of LC_TI) per CTA chunk: uniform chunks ...
+    int n_guided;            // ... or, when > 0, that many chunks of DEcreasing size:
+    int chunk_lo[LC_MAXCHUNKS + 1];   // image tiles [chunk_lo[c], chunk_lo[c+1]) of chunk c
     cplx *partial;           // [n_chunks, K]
 };
 
@@ -399,12 +405,12 @@ lc_main_kernel(LcMainArgs a) {
     const long f0 = (long)blockIdx.x * TF;
     const long chunk = blockIdx.y;
     const long n_img_tiles = a.n_pad / LC_TI;
-    long tile_lo = chunk * a.tiles_per_chunk;
-    long tile_hi = tile_lo + a.tiles_per_chunk;
+    const long tile_lo = a.n_guided ? (long)a.chunk_lo[chunk] : chunk * a.tiles_per_chunk;
+    long tile_hi = a.n_guided ? (long)a.chunk_lo[chunk + 1] : tile_lo + a.tiles_per_chunk;
     if (tile_hi > n_img_tiles) tile_hi = n_img_tiles;
     const int n_tiles = tile_hi > tile_lo ? (int)(tile_hi - tile_lo) : 0;
     const int npt = a.ncs + a.ncr;                         // chunks per tile
-    const int total = n_tiles * npt;                       // < 2^31: host caps tiles_per_chunk
+    const int total = n_tiles * npt;                       // < 2^31: host caps the chunk sizes
     const int nst = a.nst;
 
     const int jc_rows = a.JCs > a.JCr ? a.JCs : a.JCr;    // harmonics a ring stage holds
@@ -1217,6 +1223,14 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
         }
     }
 
+    // Chunks of DEcreasing size ("guided" schedule: the block scheduler hands out CTAs in launch
+    // order, so the last ones to start should be the shortest) when a simulation of that greedy
+    // hand-out says they finish earlier than the uniform cut above; cached per problem shape.
+    GuidedPlan gplan;
+    const bool guided = !monopole && guided_chunks(n_img_tiles, n_ftiles, slots, n_chunks, tiles_per_chunk,
+                                                   ((1L << 30) - 1) / (ncs + ncr), gplan);
+    if (guided) n_chunks = gplan.n;
+
     LcImage *img = (LcImage *)workspace(WS_LC_IMG, (size_t)n_pad * sizeof(LcImage));
     double *Ys = (double *)workspace(WS_LC_YS, (size_t)n_img_tiles * Js_pad * LC_YS * sizeof(double));
     double *Yr = (double *)workspace(WS_LC_YR, (size_t)n_img_tiles * Jr_pad * LC_YS * sizeof(double));
@@ -1303,6 +1317,12 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
     ma.mode = atten->mode; ma.atten = atten->d_atten; ma.Z = (const cplx *)atten->d_Z_S;
     ma.flags = flags; ma.tiles_per_chunk = tiles_per_chunk; ma.partial = partial;
     ma.nst = nst;
+    ma.n_guided = 0;
+    memset(ma.chunk_lo, 0, sizeof(ma.chunk_lo));
+    if (guided) {
+        ma.n_guided = gplan.n;
+        memcpy(ma.chunk_lo, gplan.lo, sizeof(int) * (gplan.n + 1));
+    }
     dim3 grid((unsigned)n_ftiles, (unsigned)n_chunks);
     if ((int)carve.total > smem_max)
         return set_error(DEISM_ERR_INVALID, "LC kernel needs %u B of shared memory, device has %d",

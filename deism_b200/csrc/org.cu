@@ -715,8 +715,10 @@ struct OrgConsumeArgs {
     const void *atten;
     const cplx *Z;
     const int *flags;
-    long tiles_per_chunk;
+    long tiles_per_chunk;     // uniform image-tile chunks ...
     cplx *partial;            // [n_chunks][K]
+    int n_guided;             // ... or, when > 0, that many chunks of decreasing size (common.cuh)
+    int chunk_lo[DEISM_MAXCHUNKS + 1];
 };
 
 // fixed part of the shared memory; the operand stages (rc rows of B then rc rows of Y each) follow
@@ -767,8 +769,8 @@ org_consume_kernel(OrgConsumeArgs a) {
     const int wm = warp / ORG_WN, wn = warp % ORG_WN;   // warp tile: 16 images x 8 frequencies
     const long f0 = (long)blockIdx.x * ORG_TF;
     const long n_tiles_all = a.meta[8] / ORG_TI;
-    long tile_lo = (long)blockIdx.y * a.tiles_per_chunk;
-    long tile_hi = tile_lo + a.tiles_per_chunk;
+    long tile_lo = a.n_guided ? (long)a.chunk_lo[blockIdx.y] : (long)blockIdx.y * a.tiles_per_chunk;
+    long tile_hi = a.n_guided ? (long)a.chunk_lo[blockIdx.y + 1] : tile_lo + a.tiles_per_chunk;
     if (tile_hi > n_tiles_all) tile_hi = n_tiles_all;
     const int n_tiles = tile_hi > tile_lo ? (int)(tile_hi - tile_lo) : 0;
     const int ncpt = a.ncpt, nst = a.nst;
@@ -1777,6 +1779,16 @@ static int org_shoebox_impl(int64_t n_images, int64_t K, int N, int V, const voi
         tiles_per_chunk = (n_tiles_cap + n_chunks - 1) / n_chunks;
         n_chunks = (n_tiles_cap + tiles_per_chunk - 1) / tiles_per_chunk;
     }
+    // chunks of decreasing size when the simulated hand-out of CTAs says they finish earlier (the
+    // tile count is the host's estimate; the last chunk runs to the capacity bound and the kernel
+    // clips it to the device-side count)
+    GuidedPlan gplan;
+    const bool guided = guided_chunks(n_tiles_est, n_ftiles, sm_count(), (n_tiles_est + tiles_per_chunk - 1) / tiles_per_chunk,
+                                      tiles_per_chunk, (1L << 24), gplan);
+    if (guided) {
+        gplan.lo[gplan.n] = (int)(n_tiles_cap > gplan.lo[gplan.n] ? n_tiles_cap : gplan.lo[gplan.n]);
+        n_chunks = gplan.n;
+    }
     cplx *partial = (cplx *)workspace(WS_ORG_PARTIAL, (size_t)n_chunks * K * sizeof(cplx));
     if (!partial) return DEISM_ERR_NOMEM;
 
@@ -1786,6 +1798,12 @@ static int org_shoebox_impl(int64_t n_images, int64_t K, int N, int V, const voi
     ca.Bp = Bp; ca.Yp = Yp; ca.rec = rec; ca.meta = meta; ca.k = d_k; ca.mode = atten->mode;
     ca.atten = atten->d_atten; ca.Z = (const cplx *)atten->d_Z_S; ca.flags = flags;
     ca.tiles_per_chunk = tiles_per_chunk; ca.partial = partial;
+    ca.n_guided = 0;
+    memset(ca.chunk_lo, 0, sizeof(ca.chunk_lo));
+    if (guided) {
+        ca.n_guided = gplan.n;
+        memcpy(ca.chunk_lo, gplan.lo, sizeof(int) * (gplan.n + 1));
+    }
     const size_t consume_smem = sizeof(OrgSmem) + (size_t)nst * stage_bytes;
     DEISM_CUDA_TRY(cudaFuncSetAttribute(org_consume_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)consume_smem));
