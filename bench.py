@@ -489,7 +489,7 @@ def measure_shoebox(c, name, steps, warmup, general=False, sharding="frequency",
 
     for _ in range(2):
         step_e2e()
-    if os.environ.get("DEISM_BENCH_PROFILE") == name and rank == 0:      # debugging aid
+    if os.environ.get("DEISM_BENCH_PROFILE") == name and world == 1:     # debugging aid (single process only)
         import cProfile
         import pstats
 
@@ -500,11 +500,13 @@ def measure_shoebox(c, name, steps, warmup, general=False, sharding="frequency",
         pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(25)
     e2e_ms, _ = timed(c, step_e2e, steps)
     e2e_ms = max_over_ranks(c, e2e_ms) / steps
-    # the end-to-end path must return what the device-resident one returned (rank 0 holds both)
+    # the end-to-end path must return what the device-resident one returned.  step_e2e() holds a
+    # collective when N > 1: EVERY rank calls it, rank 0 (which holds both results) compares.
     e2e_diff = None
+    got_e2e = step_e2e()
     if rank == 0:
-        got_e2e, got_dev = step_e2e().numpy(), result.cpu().numpy()
-        e2e_diff = float(np.linalg.norm(got_e2e - got_dev) / np.linalg.norm(got_dev))
+        got_dev = result.cpu().numpy()
+        e2e_diff = float(np.linalg.norm(got_e2e.numpy() - got_dev) / np.linalg.norm(got_dev))
     pg_ms = None
     if pageable:
         for _ in range(2):

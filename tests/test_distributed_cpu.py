@@ -163,3 +163,53 @@ def test_slab_bounds_cover_everything():
             assert prev == n
             c = D.slab_counts(n, world)
             assert sum(c) == n and max(c) - min(c) <= 1
+
+
+def test_bench_has_no_rank_conditional_collectives():
+    """bench.py runs one process per GPU; a step (which ends in an all_gather / all_reduce), a timed
+    loop or a barrier executed by some ranks only deadlocks the job until NCCL's watchdog fires.
+    Static guard: none of those calls may sit under an `if` whose test mentions the rank (or in a
+    function only reached from such a branch: the step helpers are closures called by name)."""
+    import ast
+    import os
+
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
+    tree = ast.parse(src)
+    collective = {"step_device", "step_e2e", "step_pageable", "combine", "timed", "max_over_ranks", "barrier",
+                  "measure_shoebox", "measure_convex", "all_reduce", "all_gather_into_tensor",
+                  "gather_frequency_slabs", "reduce_image_slabs", "replicate_images"}
+
+    def mentions_rank(node):
+        return any(isinstance(n, ast.Name) and n.id == "rank" or isinstance(n, ast.Attribute) and n.attr == "rank"
+                   for n in ast.walk(node))
+
+    def world_is_one(node):
+        # `world == 1` / `c.world == 1` anywhere in the test: a single process cannot deadlock itself
+        for n in ast.walk(node):
+            if isinstance(n, ast.Compare) and len(n.ops) == 1 and isinstance(n.ops[0], ast.Eq):
+                left, right = n.left, n.comparators[0]
+                name = left.id if isinstance(left, ast.Name) else getattr(left, "attr", None)
+                if name == "world" and isinstance(right, ast.Constant) and right.value == 1:
+                    return True
+        return False
+
+    bad = []
+
+    def visit(node, guarded):
+        if isinstance(node, (ast.If, ast.IfExp)):
+            g = guarded or (mentions_rank(node.test) and not world_is_one(node.test))
+            for child in (node.body if isinstance(node.body, list) else [node.body]):
+                visit(child, g)
+            for child in (node.orelse if isinstance(node.orelse, list) else [node.orelse]):
+                visit(child, g)
+            return
+        if guarded and isinstance(node, ast.Call):
+            f = node.func
+            name = f.id if isinstance(f, ast.Name) else getattr(f, "attr", None)
+            if name in collective:
+                bad.append((name, node.lineno))
+        for child in ast.iter_child_nodes(node):
+            visit(child, guarded)
+
+    visit(tree, False)
+    assert not bad, f"collective call(s) under a rank-dependent branch in bench.py: {bad}"
