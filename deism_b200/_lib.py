@@ -58,6 +58,7 @@ _SIGNATURES = {
     "deism_device_info": (C.c_int, [_i32, _vp, _vp, _vp, _vp]),
     "deism_release_workspace": (C.c_int, []),
     "deism_kernel_launch_count": (C.c_uint64, []),
+    "deism_chunk_plan": (C.c_int, [C.c_int64] * 6 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "deism_state_generation": (C.c_uint64, []),
     "deism_graph_replayed": (C.c_int, [_i32, _vp]),
     "deism_profile_enable": (C.c_int, [_i32]),

@@ -376,19 +376,20 @@ bool guided_chunks(long n_img_tiles, long n_ftiles, long slots, long uni_chunks,
     static const bool off = getenv("DEISM_UNIFORM_CHUNKS") != nullptr;
     if (off || n_ftiles > 2048 || n_img_tiles < 16 || uni_chunks > DEISM_MAXCHUNKS || n_img_tiles > 2000000000L)
         return false;
-    struct Key { long t, f, s; };
+    struct Key { long t, f, s, uc, ut, mx; };
     struct Entry { Key k; bool use; GuidedPlan plan; };
     static std::mutex mu;
     static std::vector<Entry> cache;
     std::lock_guard<std::mutex> lk(mu);
     for (const Entry &e : cache)
-        if (e.k.t == n_img_tiles && e.k.f == n_ftiles && e.k.s == slots) {
+        if (e.k.t == n_img_tiles && e.k.f == n_ftiles && e.k.s == slots && e.k.uc == uni_chunks &&
+            e.k.ut == uni_tpc && e.k.mx == max_tiles_per_chunk) {
             if (e.use) out = e.plan;
             return e.use;
         }
     if (cache.size() > 64) cache.clear();
     Entry ent;
-    ent.k = {n_img_tiles, n_ftiles, slots};
+    ent.k = {n_img_tiles, n_ftiles, slots, uni_chunks, uni_tpc, max_tiles_per_chunk};
     ent.use = false;
     // the uniform cut
     std::vector<int> sizes;
@@ -441,6 +442,16 @@ extern "C" const char *deism_last_error(void) { return g_err; }
 // whether the binary is stale)
 static const char g_src_marker[] = "DEISM_SRC_HASH=" DEISM_SRC_HASH;
 extern "C" const char *deism_b200_source_hash(void) { return g_src_marker + 15; }
+
+extern "C" int deism_chunk_plan(int64_t n_tiles, int64_t n_ftiles, int64_t slots, int64_t uni_chunks,
+                                int64_t uni_tpc, int64_t max_tiles_per_chunk, int32_t *lo, int32_t *n) {
+    if (!lo || !n || n_tiles < 1 || n_ftiles < 1 || slots < 1 || uni_chunks < 1 || uni_tpc < 1) return 0;
+    GuidedPlan plan;
+    if (!guided_chunks(n_tiles, n_ftiles, slots, uni_chunks, uni_tpc, max_tiles_per_chunk, plan)) return 0;
+    *n = plan.n;
+    for (int c = 0; c <= plan.n; ++c) lo[c] = plan.lo[c];
+    return 1;
+}
 
 extern "C" uint64_t deism_kernel_launch_count(void) {
     return __atomic_load_n(&g_launches, __ATOMIC_RELAXED);

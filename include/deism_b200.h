@@ -87,6 +87,14 @@ DEISM_API uint64_t deism_state_generation(void);
 DEISM_API int deism_graph_replayed(int n_kernels, void *stream);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 DEISM_API uint64_t deism_kernel_launch_count(void);
+/* Host-only view of the image-chunk schedule the two tensor-core kernels use (no GPU needed; for
+ * tests and tuning): n_tiles image tiles per frequency tile, n_ftiles frequency tiles, `slots` CTAs
+ * resident at a time, against `uni_chunks` equal chunks of `uni_tpc` tiles.  Returns 1 and fills
+ * lo[0..*n] (chunk c = tiles [lo[c], lo[c+1]), at most 96 chunks, sizes non-increasing) when a
+ * schedule of shrinking chunks finishes earlier under the block scheduler's in-order hand-out,
+ * else 0 (the uniform cut stays). */
+DEISM_API int deism_chunk_plan(int64_t n_tiles, int64_t n_ftiles, int64_t slots, int64_t uni_chunks,
+                               int64_t uni_tpc, int64_t max_tiles_per_chunk, int32_t *lo, int32_t *n);
 /* Per-kernel device timing for the roofline report: when enabled, the accumulation entry points
  * bracket their dominant kernels with CUDA events on the launching stream.
  * deism_profile_get("lc_main" | "org_consume" | "org_btable" | "org_direct" | "arg_lc" |

@@ -126,3 +126,58 @@ def test_generation_counter_and_graph_hooks_exist_without_a_gpu():
     assert g >= 1
     assert handle.deism_graph_replayed(0, None) == 2       # no device: DEISM_ERR_CUDA, loudly
     assert b"no CPU fallback" in handle.deism_last_error()
+
+
+def _simulate_handout(sizes, n_ftiles, slots, fixed=0.5):
+    """The block scheduler's hand-out as api.cu models it: CTAs in launch order (frequency tile
+    fastest) to whichever slot frees up first; returns the makespan in tiles."""
+    import heapq
+
+    h = [0.0] * slots
+    heapq.heapify(h)
+    for c in sizes:
+        for _ in range(n_ftiles):
+            heapq.heappush(h, heapq.heappop(h) + c + fixed)
+    return max(h)
+
+
+def test_chunk_plan_invariants_and_benefit():
+    """deism_chunk_plan (host logic, no GPU): whatever the shape, a plan it returns covers every image
+    tile exactly once, in at most 96 non-empty chunks of non-increasing size below the caller's bound,
+    and finishes earlier than the uniform cut under the modelled hand-out; shapes it should not touch
+    (tiny lists, too many chunks) come back as 'keep the uniform cut'."""
+    from deism_b200 import _lib
+
+    h = _lib.lib()
+    rng = np.random.default_rng(5)
+    shapes = [(1386, 250, 148), (1386, 32, 148), (1386, 63, 148), (1386, 125, 148), (181, 125, 148),
+              (326, 63, 148), (322, 188, 148), (1386, 500, 296), (16, 1, 148), (40, 3, 148), (5000, 7, 148)]
+    shapes += [(int(rng.integers(16, 4000)), int(rng.integers(1, 600)), int(rng.choice([148, 296, 132])))
+               for _ in range(40)]
+    used = 0
+    for n_tiles, n_ftiles, slots in shapes:
+        for waves in (4, 8, 16):
+            n = max(1, min(n_tiles, slots * waves // n_ftiles))
+            tpc = -(-n_tiles // n)
+            n = -(-n_tiles // tpc)
+            lo = (C.c_int32 * 97)()
+            cnt = C.c_int32(0)
+            bound = 1 << 20
+            got = h.deism_chunk_plan(n_tiles, n_ftiles, slots, n, tpc, bound, lo, C.byref(cnt))
+            if n > 96:
+                assert got == 0
+            if not got:
+                continue
+            used += 1
+            b = np.array(lo[: cnt.value + 1])
+            sizes = np.diff(b)
+            assert 1 <= cnt.value <= 96 and b[0] == 0 and b[-1] == n_tiles, (n_tiles, n_ftiles, slots, b)
+            assert np.all(sizes >= 1) and np.all(np.diff(sizes) <= 0) and sizes.max() <= bound
+            uniform = [tpc] * (n - 1) + [n_tiles - tpc * (n - 1)]
+            assert _simulate_handout(sizes.tolist(), n_ftiles, slots) < _simulate_handout(uniform, n_ftiles, slots)
+    assert used >= 10        # the C5 / C3 / C2 shapes above do take a shrinking schedule
+    lo = (C.c_int32 * 97)()
+    cnt = C.c_int32(0)
+    assert h.deism_chunk_plan(8, 4, 148, 2, 4, 1 << 20, lo, C.byref(cnt)) == 0          # tiny image list
+    assert h.deism_chunk_plan(1386, 250, 148, 13, 107, 50, lo, C.byref(cnt)) == 0 or \
+        np.diff(np.array(lo[: cnt.value + 1])).max() <= 50                                # chunk bound respected
