@@ -213,3 +213,127 @@ def test_bench_has_no_rank_conditional_collectives():
 
     visit(tree, False)
     assert not bad, f"collective call(s) under a rank-dependent branch in bench.py: {bad}"
+
+
+# ---------------------------------------------------------------------------------------
+# bench.py's rank logic, dry: two gloo ranks run bench.main() itself with the device mocked out (the
+# per-slab compute is the CPU oracle on a small fixture, CUDA events / pinning / the L2 flush are
+# stand-ins).  What is under test is the control flow every rank walks through — the timed loops,
+# barriers, max-over-ranks reductions, the end-to-end result check, the `configs` block and the final
+# JSON line — which must neither deadlock nor diverge between ranks.
+# ---------------------------------------------------------------------------------------
+def _bench_worker(rank, world, port, out_dir, sharding):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import contextlib
+    import datetime
+    import io
+    import types
+
+    import bench
+    from conftest import Golden as G
+    from deism_b200 import _lib, backend, images as gimages
+    from oracle import oracle
+
+    oracle.set_num_threads(1)
+
+    class FakeEvent:
+        def __init__(self, enable_timing=False):
+            pass
+
+        def record(self, stream=None):
+            pass
+
+        def elapsed_time(self, other):
+            return 1.0 + 0.25 * rank          # ranks disagree: max_over_ranks has something to do
+
+    torch.cuda.synchronize = lambda *a, **k: None
+    torch.cuda.Event = FakeEvent
+    torch.cuda.set_device = lambda *a, **k: None
+    torch.Tensor.pin_memory = lambda self, *a, **k: self
+
+    class FakeLib:
+        def __getattr__(self, name):          # deism_profile_enable / _reset / _get: nothing recorded
+            return lambda *a, **k: 0
+
+    def make_ctx(args):
+        c = bench.Ctx()
+        c.rank, c.world, c.local_rank = rank, world, rank
+        c.dev = torch.device("cpu")
+        dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=120))
+        c.lib = FakeLib()
+        c.flush = torch.empty(16, dtype=torch.uint8)
+        c.peaks = {"dfma": 34.0, "dmma_m8n8k4": 37.0}
+        c.traffic = {}
+        return c
+
+    fixtures = {"c5": "s4_shoebox_rir_mix_o9_N2", "c3": "s3_shoebox_rtf_org_o4_N3V2"}
+
+    def build_case(name, general=False):
+        g = G(fixtures[name])
+        p = g.params()
+        p.pop("images", None)
+        class Fx(dict):
+            files = ["RTF"]
+
+        return p, Fx(RTF=g.rtf), f"dry run of {name} on {fixtures[name]}"
+
+    state = {}
+
+    def fake_images(p):
+        state["k"] = np.asarray(p["waveNumbers"])
+        return oracle.shoebox_images(p)       # reference layout, materialised attenuation [I, K]
+
+    def run_device(params, dev=None):
+        q = dict(params)
+        for k, v in list(q.items()):
+            if isinstance(v, torch.Tensor):
+                q[k] = v.numpy()
+        ks = np.asarray(q["waveNumbers"])
+        lo = int(np.argmin(np.abs(state["k"] - ks[0])))          # this rank's frequency slab
+        q["images"] = {}
+        for k, v in params["images"].items():
+            v = v.numpy() if isinstance(v, torch.Tensor) else v
+            if k.startswith("atten") and v.shape[1] != len(ks):
+                v = v[:, lo:lo + len(ks)]
+            q["images"][k] = v
+        return torch.from_numpy(np.asarray(oracle.run_DEISM(q)))
+
+    bench.make_ctx = make_ctx
+    bench.build_case = build_case
+    bench.clocks_sampler = lambda stop, out, idx: None
+    gimages.pre_calc_images_src_rec_optimized_nofs_v2_numba = fake_images
+    backend.run_DEISM_device = run_device
+    _lib.launch_count = lambda: 7
+    argv = ["bench.py", "--gpus", str(world), "--steps", "2", "--warmup", "1"]
+    if sharding == "image":
+        argv += ["--workload", "c3", "--sharding", "image"]
+    sys.argv = argv
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        rc = bench.main()
+    assert rc == 0
+    with open(os.path.join(out_dir, f"r{rank}.txt"), "w") as fh:
+        fh.write(buf.getvalue())
+
+
+@pytest.mark.parametrize("sharding", ["frequency", "image"])
+@pytest.mark.timeout(300)
+def test_bench_main_two_ranks_dry_run(tmp_path, sharding):
+    import json
+
+    port = _free_port()
+    mp.spawn(_bench_worker, args=(2, port, str(tmp_path), sharding), nprocs=2, join=True)
+    assert (tmp_path / "r1.txt").read_text().strip() == ""          # rank 0 alone prints
+    lines = [ln for ln in (tmp_path / "r0.txt").read_text().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["steps"] == 2 and d["unit"] == "terms/s"
+    assert abs(d["ms_per_step"] - 1.25) < 1e-9                      # the slower rank's time
+    assert d["e2e"]["rel_diff_vs_device_resident_result"] == 0.0
+    assert d["parity_rel_l2_vs_reference"] < 1e-12                  # slabs stitched back in order
+    if sharding == "frequency":
+        assert "c3" in d["configs"] and "error" not in d["configs"]["c3"], d["configs"]
+        assert d["configs"]["c3"]["parity_rel_l2_vs_reference"] < 1e-12
