@@ -17,11 +17,15 @@
 //   B[par][l,mu][k] = (i/k) sum_{(n,m,v,u): m'-u = mu} mirror*G * C_s[k,n,m] * C_r[k,v,-u]
 //
 // Kernels:
-//   org_btable_kernel   B for the 8 parity classes (image independent)          [algo 1]
-//   org_sort/prep       images grouped by parity class, Y_l^mu(img) table, attenuation geometry
-//   org_consume_kernel  32 freq x 32 image CTA tile on the FP64 tensor cores; per l: a (2l+1)-row
-//                       real x complex contraction (real-harmonic rows) from TMA-staged shared
-//                       memory, h_l recurrence in registers
+//   org_btable2_kernel  B for the 8 parity classes (image independent): CTA = a tile of frequencies
+//                       x all (l, |mu|) jobs, coefficient tile in shared memory      [algo 1]
+//                       (org_btable_kernel: the earlier form, kept behind ORG_BTABLE_V1)
+//   org_sort/prep       images grouped by parity class, Y_l^mu(img) rows (real harmonics, signed for
+//                       the Clenshaw sum), attenuation geometry
+//   org_consume_kernel  64 image x 32 freq CTA tile on the FP64 tensor cores; per l a (2l+1)-row
+//                       real x complex contraction from TMA-staged shared memory; the sum over l by
+//                       Clenshaw's recurrence with the tensor core adding e_{l+2}
+//   org_small_kernel    the same factorised sum in plain FMAs for a few images (MIX early images)
 //   org_direct_kernel   the quintuple sum done per (image, frequency) pair with per-image
 //                       source coefficients: the ARG form (pb:388-460) and the shoebox
 //                       cross-check [algo 2]
