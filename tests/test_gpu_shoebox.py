@@ -125,6 +125,38 @@ def test_frequency_dependent_impedance_fused_vs_materialised(name, kind):
     assert rel_l2(got, want) < RTF_TOL
 
 
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU minutes were spent: not yet run on a GPU")
+@pytest.mark.parametrize("kind", ["real_same_opposite_walls", "real_plus_1e-16j", "complex"])
+@pytest.mark.parametrize("name", ["s2_shoebox_rtf_lc_o6_N3", "s4_shoebox_rir_mix_o9_N2",
+                                  "s5_shoebox_rtf_lc_o7_mono_noang"])
+def test_frequency_dependent_impedance_compact_storage(name, kind):
+    """The reference's compact image storage (no attenuation array; beta rebuilt per batch from the
+    float32 angles, pb:140-186, NOT rounded to complex64) with an impedance that varies with
+    frequency: the kernels' unrounded per-term chains (two Newton steps) against the CPU oracle."""
+    from deism_b200 import backend, images as im
+    from oracle import oracle
+
+    p = Golden(name).params()
+    p.pop("images")
+    K = len(p["waveNumbers"])
+    Z = np.asarray(p["impedance"], dtype=np.complex128) * (1.0 + 0.3 * np.linspace(0.0, 1.0, K))[None, :]
+    Z = Z * (1.0 + 0.1 * np.arange(6))[:, None] + 1j * (2.0 - 3.0 * np.linspace(0, 1, K))[None, :]
+    if kind == "real_plus_1e-16j":
+        Z = Z.real + 1e-16j
+    elif kind == "real_same_opposite_walls":
+        Z = Z.real[[0, 0, 2, 2, 4, 4]] + 0j
+    p["impedance"] = np.ascontiguousarray(Z)
+    p["shoeboxCompactImages"] = True
+    images = im.pre_calc_images_src_rec_optimized_nofs_v2_numba(p)
+    if p["DEISM_method"] in ("ORG", "LC"):
+        images = im.merge_images(images)
+    assert images["storage"] == "compact"
+    p["images"] = images
+    got = backend.run_DEISM(p)
+    want = oracle.run_DEISM(p)
+    assert rel_l2(got, want) < RTF_TOL
+
+
 def test_lc_vs_oracle_random_inputs():
     """Seeded random geometry / coefficients / complex frequency-dependent impedance, ragged
     sizes (K and I not multiples of the tile sizes), against the CPU oracle."""
