@@ -371,25 +371,48 @@ static double simulate_handout(const int *sizes, int n, long n_ftiles, long slot
     for (double t : h) mx = t > mx ? t : mx;
     return mx;
 }
-bool guided_chunks(long n_img_tiles, long n_ftiles, long slots, long uni_chunks, long uni_tpc,
-                          long max_tiles_per_chunk, GuidedPlan &out) {
+bool guided_chunks_possible(long n_img_tiles, long n_ftiles, long uni_chunks) {
     static const bool off = getenv("DEISM_UNIFORM_CHUNKS") != nullptr;
-    if (off || n_ftiles > 2048 || n_img_tiles < 16 || uni_chunks > DEISM_MAXCHUNKS || n_img_tiles > 2000000000L)
-        return false;
+    return !(off || n_ftiles > 2048 || n_img_tiles < 16 || uni_chunks > DEISM_MAXCHUNKS || n_img_tiles > 2000000000L);
+}
+
+// The simulations cost 0.3-0.7 ms of host time per problem shape: more than the schedule saves on one
+// call of anything but the largest workloads.  So a shape is only RECORDED the first time it is seen
+// (that call keeps the uniform cut), planned when it comes a second time, and served from the cache
+// afterwards: sweeps over ever-changing image counts never pay, repeated shapes pay once.  (Callers
+// size the partial-sum scratch for DEISM_MAXCHUNKS rows from the first call on, so the switch to a
+// plan with more chunks allocates nothing — the second call may be a CUDA-graph capture.)
+bool guided_chunks(long n_img_tiles, long n_ftiles, long slots, long uni_chunks, long uni_tpc,
+                   long max_tiles_per_chunk, GuidedPlan &out) {
+    if (!guided_chunks_possible(n_img_tiles, n_ftiles, uni_chunks)) return false;
     struct Key { long t, f, s, uc, ut, mx; };
-    struct Entry { Key k; bool use; GuidedPlan plan; };
+    struct Entry { Key k; int state; bool use; GuidedPlan plan; };     // state 1: seen once, 2: planned
     static std::mutex mu;
     static std::vector<Entry> cache;
     std::lock_guard<std::mutex> lk(mu);
-    for (const Entry &e : cache)
+    Entry *hit = nullptr;
+    for (Entry &e : cache)
         if (e.k.t == n_img_tiles && e.k.f == n_ftiles && e.k.s == slots && e.k.uc == uni_chunks &&
             e.k.ut == uni_tpc && e.k.mx == max_tiles_per_chunk) {
-            if (e.use) out = e.plan;
-            return e.use;
+            hit = &e;
+            break;
         }
-    if (cache.size() > 64) cache.clear();
-    Entry ent;
-    ent.k = {n_img_tiles, n_ftiles, slots, uni_chunks, uni_tpc, max_tiles_per_chunk};
+    if (hit && hit->state == 2) {
+        if (hit->use) out = hit->plan;
+        return hit->use;
+    }
+    if (!hit) {
+        if (cache.size() > 64) cache.clear();
+        Entry seen;
+        seen.k = {n_img_tiles, n_ftiles, slots, uni_chunks, uni_tpc, max_tiles_per_chunk};
+        seen.state = 1;
+        seen.use = false;
+        seen.plan.n = 0;
+        cache.push_back(seen);
+        return false;
+    }
+    Entry &ent = *hit;
+    ent.state = 2;
     ent.use = false;
     // the uniform cut
     std::vector<int> sizes;
@@ -424,7 +447,6 @@ bool guided_chunks(long n_img_tiles, long n_ftiles, long slots, long uni_chunks,
                 for (int c = 0; c < ent.plan.n; ++c) ent.plan.lo[c + 1] = ent.plan.lo[c] + sizes[c];
             }
         }
-    cache.push_back(ent);
     if (ent.use) out = ent.plan;
     return ent.use;
 }

@@ -19,7 +19,8 @@ namespace deism {
 int set_error(int code, const char *fmt, ...);
 void count_launch(int n = 1);
 // Image-chunk schedule with chunks of decreasing size (api.cu): filled in and true when a simulation of
-// the block scheduler's greedy hand-out says it beats `uni_chunks` equal chunks of `uni_tpc` tiles.
+// the block scheduler's greedy hand-out says it beats `uni_chunks` equal chunks of `uni_tpc` tiles
+// (from the SECOND call with a given shape on: see api.cu).
 constexpr int DEISM_MAXCHUNKS = 96;
 struct GuidedPlan {
     int n;
@@ -27,6 +28,9 @@ struct GuidedPlan {
 };
 bool guided_chunks(long n_img_tiles, long n_ftiles, long slots, long uni_chunks, long uni_tpc,
                    long max_tiles_per_chunk, GuidedPlan &out);
+// whether a later call with this shape may come back with a plan (of up to DEISM_MAXCHUNKS chunks):
+// scratch that depends on the chunk count is sized for that from the first call on
+bool guided_chunks_possible(long n_img_tiles, long n_ftiles, long uni_chunks);
 void bump_generation();                   // scratch pointers or __constant__ tables changed
 int check_device();                       // DEISM_OK iff current device is sm_100
 void *workspace(int slot, size_t bytes);  // cached device scratch; nullptr on failure

@@ -1227,16 +1227,20 @@ extern "C" int deism_lc_shoebox(int64_t n_images, int64_t K, int Js, int Jr, con
     // order, so the last ones to start should be the shortest) when a simulation of that greedy
     // hand-out says they finish earlier than the uniform cut above; cached per problem shape.
     GuidedPlan gplan;
-    const bool guided = !monopole && guided_chunks(n_img_tiles, n_ftiles, slots, n_chunks, tiles_per_chunk,
+    // (the plan arrives with the second call of a shape; the partial sums are sized for it from the
+    // first call on, so that call — possibly a graph capture — allocates nothing)
+    const bool may_guide = !monopole && guided_chunks_possible(n_img_tiles, n_ftiles, n_chunks);
+    const bool guided = may_guide && guided_chunks(n_img_tiles, n_ftiles, slots, n_chunks, tiles_per_chunk,
                                                    ((1L << 30) - 1) / (ncs + ncr), gplan);
     if (guided) n_chunks = gplan.n;
+    const long partial_rows = may_guide && n_chunks < DEISM_MAXCHUNKS ? DEISM_MAXCHUNKS : n_chunks;
 
     LcImage *img = (LcImage *)workspace(WS_LC_IMG, (size_t)n_pad * sizeof(LcImage));
     double *Ys = (double *)workspace(WS_LC_YS, (size_t)n_img_tiles * Js_pad * LC_YS * sizeof(double));
     double *Yr = (double *)workspace(WS_LC_YR, (size_t)n_img_tiles * Jr_pad * LC_YS * sizeof(double));
     double *CT = (double *)workspace(WS_SMALL,
                                      (size_t)n_ftiles * (Js_pad + Jr_pad) * 2 * CS * sizeof(double));
-    cplx *partial = (cplx *)workspace(WS_PARTIAL, (size_t)n_chunks * K * sizeof(cplx));
+    cplx *partial = (cplx *)workspace(WS_PARTIAL, (size_t)partial_rows * K * sizeof(cplx));
     int *flags = (int *)workspace(WS_FLAGS, 64);
     if (!img || !Ys || !Yr || !CT || !partial || !flags) return DEISM_ERR_NOMEM;
     double *CTs = CT, *CTr = CT + (size_t)n_ftiles * Js_pad * 2 * CS;

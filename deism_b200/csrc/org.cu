@@ -1786,14 +1786,19 @@ static int org_shoebox_impl(int64_t n_images, int64_t K, int N, int V, const voi
     // chunks of decreasing size when the simulated hand-out of CTAs says they finish earlier (the
     // tile count is the host's estimate; the last chunk runs to the capacity bound and the kernel
     // clips it to the device-side count)
+    // (the plan arrives with the second call of a shape; the partial sums are sized for it from the
+    // first call on, so that call — possibly a graph capture — allocates nothing)
     GuidedPlan gplan;
-    const bool guided = guided_chunks(n_tiles_est, n_ftiles, sm_count(), (n_tiles_est + tiles_per_chunk - 1) / tiles_per_chunk,
-                                      tiles_per_chunk, (1L << 24), gplan);
+    const long uni_chunks_est = (n_tiles_est + tiles_per_chunk - 1) / tiles_per_chunk;
+    const bool may_guide = guided_chunks_possible(n_tiles_est, n_ftiles, uni_chunks_est);
+    const bool guided = may_guide && guided_chunks(n_tiles_est, n_ftiles, sm_count(), uni_chunks_est,
+                                                   tiles_per_chunk, (1L << 24), gplan);
     if (guided) {
         gplan.lo[gplan.n] = (int)(n_tiles_cap > gplan.lo[gplan.n] ? n_tiles_cap : gplan.lo[gplan.n]);
         n_chunks = gplan.n;
     }
-    cplx *partial = (cplx *)workspace(WS_ORG_PARTIAL, (size_t)n_chunks * K * sizeof(cplx));
+    const long partial_rows = may_guide && n_chunks < DEISM_MAXCHUNKS ? DEISM_MAXCHUNKS : n_chunks;
+    cplx *partial = (cplx *)workspace(WS_ORG_PARTIAL, (size_t)partial_rows * K * sizeof(cplx));
     if (!partial) return DEISM_ERR_NOMEM;
 
     OrgConsumeArgs ca;

@@ -142,7 +142,8 @@ def _simulate_handout(sizes, n_ftiles, slots, fixed=0.5):
 
 
 def test_chunk_plan_invariants_and_benefit():
-    """deism_chunk_plan (host logic, no GPU): whatever the shape, a plan it returns covers every image
+    """deism_chunk_plan (host logic, no GPU): a shape gets its plan when it is seen the second time (the
+    simulations cost more host time than one call saves); whatever the shape, a plan covers every image
     tile exactly once, in at most 96 non-empty chunks of non-increasing size below the caller's bound,
     and finishes earlier than the uniform cut under the modelled hand-out; shapes it should not touch
     (tiny lists, too many chunks) come back as 'keep the uniform cut'."""
@@ -154,7 +155,7 @@ def test_chunk_plan_invariants_and_benefit():
               (326, 63, 148), (322, 188, 148), (1386, 500, 296), (16, 1, 148), (40, 3, 148), (5000, 7, 148)]
     shapes += [(int(rng.integers(16, 4000)), int(rng.integers(1, 600)), int(rng.choice([148, 296, 132])))
                for _ in range(40)]
-    used = 0
+    used, seen = 0, set()
     for n_tiles, n_ftiles, slots in shapes:
         for waves in (4, 8, 16):
             n = max(1, min(n_tiles, slots * waves // n_ftiles))
@@ -163,7 +164,14 @@ def test_chunk_plan_invariants_and_benefit():
             lo = (C.c_int32 * 97)()
             cnt = C.c_int32(0)
             bound = 1 << 20
+            key = (n_tiles, n_ftiles, slots, n, tpc)
+            if key in seen:
+                continue
+            seen.add(key)
+            first = h.deism_chunk_plan(n_tiles, n_ftiles, slots, n, tpc, bound, lo, C.byref(cnt))
+            assert first == 0                 # a shape is only recorded the first time it is seen
             got = h.deism_chunk_plan(n_tiles, n_ftiles, slots, n, tpc, bound, lo, C.byref(cnt))
+            assert got == h.deism_chunk_plan(n_tiles, n_ftiles, slots, n, tpc, bound, lo, C.byref(cnt))
             if n > 96:
                 assert got == 0
             if not got:
@@ -178,6 +186,8 @@ def test_chunk_plan_invariants_and_benefit():
     assert used >= 10        # the C5 / C3 / C2 shapes above do take a shrinking schedule
     lo = (C.c_int32 * 97)()
     cnt = C.c_int32(0)
-    assert h.deism_chunk_plan(8, 4, 148, 2, 4, 1 << 20, lo, C.byref(cnt)) == 0          # tiny image list
+    for _ in range(3):
+        assert h.deism_chunk_plan(8, 4, 148, 2, 4, 1 << 20, lo, C.byref(cnt)) == 0      # tiny image list
+    h.deism_chunk_plan(1386, 250, 148, 13, 107, 50, lo, C.byref(cnt))
     assert h.deism_chunk_plan(1386, 250, 148, 13, 107, 50, lo, C.byref(cnt)) == 0 or \
         np.diff(np.array(lo[: cnt.value + 1])).max() <= 50                                # chunk bound respected
